@@ -1,0 +1,615 @@
+// Host side of the batched LP solver + its C ABI (include/lpbox_b200.h).
+// Plain CUDA runtime; no torch types cross this boundary.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/lpbox_b200.h"
+#include "lp_fix_kernel.cuh"
+#include "lp_kernels.cuh"
+
+using namespace lpb;
+
+static thread_local std::string g_err;
+static void set_err(const std::string &s) { g_err = s; }
+extern "C" const char *lpbox_last_error(void) { return g_err.c_str(); }
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            set_err(std::string(#call) + ": " + cudaGetErrorString(e_));                                \
+            return LPBOX_E_CUDA;                                                                        \
+        }                                                                                               \
+    } while (0)
+
+extern "C" int lpbox_device_count(void) {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) return 0;
+    return c;
+}
+
+extern "C" void lpbox_params_lp(lpbox_params *p) {  // LP.cpp:491-507
+    p->stop_threshold = 1e-4; p->std_threshold = 1e-12; p->max_iters = (int)2e4; p->initial_rho = 25;
+    p->rho_change_step = 25; p->gamma_val = 1.6; p->learning_fact = 1 + 1.0 / 100; p->history_size = 10;
+    p->projection_lp = 2; p->gamma_factor = 0.95; p->pcg_tol = 1e-3; p->pcg_maxiters = (int)1e3;
+}
+extern "C" void lpbox_params_seg(lpbox_params *p) {  // SEG.cpp:659-672
+    p->stop_threshold = 1e-3; p->std_threshold = 1e-6; p->max_iters = (int)1e4; p->initial_rho = 5;
+    p->rho_change_step = 5; p->gamma_val = 1.0; p->learning_fact = 1 + 3.0 / 100; p->history_size = 5;
+    p->projection_lp = 2; p->gamma_factor = 0.99; p->pcg_tol = 1e-3; p->pcg_maxiters = (int)1e3;
+}
+
+template <typename Tp>
+struct DevBuf {
+    Tp *p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        n = count;
+        return cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(Tp));
+    }
+    void free_() { if (p) cudaFree(p); p = nullptr; }
+};
+
+struct lpbox_batch {
+    int device = 0, B = 0, hist_cap = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<int> n0, m0, nnz0;
+    std::vector<long long> off_n, off_m, off_pat, off_val, off_hist;
+    // host copy of the original problem (check_infeasible_l2f uses org_E_ptr, LP.cpp:1593-1612)
+    std::vector<int> h_colptr, h_rowidx;
+    std::vector<long long> h_nnz_off, h_cp_off;
+    std::vector<double> h_val;
+    bool all_unit = true;
+    int max_n = 0, max_m = 0, max_nnz = 0, max_pat = 0;
+    Params pr{};
+    BatchView bv{};
+    DevBuf<long long> d_off_n, d_off_m, d_off_pat, d_off_val, d_off_hist, d_off_vec;
+    DevBuf<double> d_x, d_y1, d_y2, d_z1, d_z2, d_b, d_Pd, d_Esq, d_y3, d_z4, d_f, d_val_r, d_val_c, d_r4v, d_hist,
+        d_ret_val, d_pow, d_vec;
+    DevBuf<unsigned char> d_pat;
+    DevBuf<InstState> d_st;
+    DevBuf<int> d_left, d_ret_idx, d_counter, d_num;
+    std::vector<InstState> h_st;
+    bool inited = false;
+    int tcfg = 0;  // 0: <128,4>  1: <256,4>  2: <512,4>
+    int grid = 0;
+    size_t smem = 0, fix_smem = 0;
+    double last_ms = 0;
+    int64_t launches = 0;
+};
+
+template <int T, int EPT, bool UNIT>
+static cudaError_t prep_kernel(size_t smem, int *occ) {
+    cudaError_t e = cudaFuncSetAttribute(lp_admm_window_kernel<T, EPT, UNIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, lp_admm_window_kernel<T, EPT, UNIT>, T, smem);
+}
+template <int T, int EPT, bool UNIT>
+static void launch_window(lpbox_batch *h, const Launch &la, int grid) {
+    lp_admm_window_kernel<T, EPT, UNIT><<<grid, T, h->smem, h->stream>>>(h->bv, h->pr, la);
+}
+
+static int configure(lpbox_batch *h) {
+    int dim = std::max(h->max_n, h->max_m);
+    if (dim <= 512) h->tcfg = 0;
+    else if (dim <= 1024) h->tcfg = 1;
+    else if (dim <= 2048) h->tcfg = 2;
+    else { set_err("max(n, m) > 2048 is not supported by the on-chip kernel"); return LPBOX_E_UNSUPPORTED; }
+    if (h->max_nnz > 65535) { set_err("nnz > 65535 is not supported by the on-chip kernel"); return LPBOX_E_UNSUPPORTED; }
+    int np = (h->max_n + 1) & ~1, mp = (h->max_m + 1) & ~1;
+    int val_elems = h->all_unit ? 0 : ((h->max_nnz + 1) & ~1);
+    h->smem = smem_bytes(np, mp, h->max_pat, val_elems);
+    h->fix_smem = fix_smem_bytes(np, mp, h->max_pat, val_elems);
+    int dev_smem = 0, sms = 0;
+    CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    if ((int)h->smem > dev_smem || (int)h->fix_smem > dev_smem) {
+        set_err("instance does not fit in shared memory"); return LPBOX_E_UNSUPPORTED;
+    }
+    int occ = 1;
+    bool u = h->all_unit;
+    cudaError_t e;
+    switch (h->tcfg) {
+        case 0: e = u ? prep_kernel<128, 4, true>(h->smem, &occ) : prep_kernel<128, 4, false>(h->smem, &occ); break;
+        case 1: e = u ? prep_kernel<256, 4, true>(h->smem, &occ) : prep_kernel<256, 4, false>(h->smem, &occ); break;
+        default: e = u ? prep_kernel<512, 4, true>(h->smem, &occ) : prep_kernel<512, 4, false>(h->smem, &occ); break;
+    }
+    CK(e);
+    CK(cudaFuncSetAttribute(lp_fix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fix_smem));
+    if (occ < 1) occ = 1;
+    h->grid = std::max(1, std::min(h->B, sms * occ));
+    return 0;
+}
+
+static int run_window(lpbox_batch *h, int iter_start, int iter_end, int l2f, int skip_done) {
+    Launch la{};
+    la.iter_start = iter_start; la.iter_end = iter_end; la.l2f = l2f; la.skip_done = skip_done;
+    la.n_work = h->B; la.work = nullptr; la.counter = h->d_counter.p;
+    la.np = (h->max_n + 1) & ~1; la.mp = (h->max_m + 1) & ~1; la.pat_bytes = h->max_pat;
+    la.val_elems = h->all_unit ? 0 : ((h->max_nnz + 1) & ~1);
+    CK(cudaMemsetAsync(h->d_counter.p, 0, sizeof(int), h->stream));
+    bool u = h->all_unit;
+    switch (h->tcfg) {
+        case 0: u ? launch_window<128, 4, true>(h, la, h->grid) : launch_window<128, 4, false>(h, la, h->grid); break;
+        case 1: u ? launch_window<256, 4, true>(h, la, h->grid) : launch_window<256, 4, false>(h, la, h->grid); break;
+        default: u ? launch_window<512, 4, true>(h, la, h->grid) : launch_window<512, 4, false>(h, la, h->grid); break;
+    }
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
+static int sync_states(lpbox_batch *h) {
+    CK(cudaMemcpyAsync(h->h_st.data(), h->d_st.p, sizeof(InstState) * (size_t)h->B, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" lpbox_batch *lpbox_batch_create(int device, int B, const int32_t *m, const int32_t *n, const int32_t *colptr_all,
+                                           const int32_t *rowidx_all, const double *val_all, const double *b_all,
+                                           const double *f_all, int hist_cap) {
+    if (B <= 0 || !m || !n || !colptr_all || !rowidx_all || !b_all || hist_cap < 0) { set_err("invalid argument"); return nullptr; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { set_err("no CUDA device (there is no CPU fallback)"); return nullptr; }
+    if (device < 0 || device >= ndev) { set_err("bad device index"); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { set_err("cudaSetDevice failed"); return nullptr; }
+    lpbox_batch *h = new lpbox_batch();
+    h->device = device; h->B = B; h->hist_cap = hist_cap;
+    h->n0.assign(n, n + B); h->m0.assign(m, m + B); h->nnz0.resize(B);
+    h->off_n.assign(B + 1, 0); h->off_m.assign(B + 1, 0); h->off_pat.assign(B + 1, 0); h->off_val.assign(B + 1, 0);
+    h->off_hist.assign(B + 1, 0); h->h_nnz_off.assign(B + 1, 0); h->h_cp_off.assign(B + 1, 0);
+    for (int i = 0; i < B; ++i) {
+        if (n[i] <= 0 || m[i] < 0) { set_err("instance with n <= 0"); delete h; return nullptr; }
+        const int32_t *cp = colptr_all + h->h_cp_off[i];
+        h->nnz0[i] = cp[n[i]];
+        h->h_cp_off[i + 1] = h->h_cp_off[i] + n[i] + 1;
+        h->h_nnz_off[i + 1] = h->h_nnz_off[i] + h->nnz0[i];
+        h->off_n[i + 1] = h->off_n[i] + ((n[i] + 1) & ~1);
+        h->off_m[i + 1] = h->off_m[i] + ((m[i] + 1) & ~1);
+        PatLayout PL = pat_layout(n[i], m[i], h->nnz0[i]);
+        h->off_pat[i + 1] = h->off_pat[i] + PL.bytes;
+        h->off_val[i + 1] = h->off_val[i] + ((h->nnz0[i] + 1) & ~1);
+        h->off_hist[i + 1] = h->off_hist[i] + (long long)hist_cap * n[i];
+        h->max_n = std::max(h->max_n, n[i]); h->max_m = std::max(h->max_m, m[i]); h->max_nnz = std::max(h->max_nnz, h->nnz0[i]);
+        h->max_pat = std::max(h->max_pat, PL.bytes);
+    }
+    long long tot_nnz = h->h_nnz_off[B];
+    h->h_colptr.assign(colptr_all, colptr_all + h->h_cp_off[B]);
+    h->h_rowidx.assign(rowidx_all, rowidx_all + tot_nnz);
+    if (val_all) {
+        h->h_val.assign(val_all, val_all + tot_nnz);
+        h->all_unit = true;
+        for (long long k = 0; k < tot_nnz; ++k) if (val_all[k] != 1.0) { h->all_unit = false; break; }
+    }
+    // build pattern blobs (+ values in both orders) on the host
+    std::vector<unsigned char> pat((size_t)h->off_pat[B], 0);
+    std::vector<double> val_r, val_c;
+    if (!h->all_unit) { val_r.assign((size_t)h->off_val[B], 0.0); val_c.assign((size_t)h->off_val[B], 0.0); }
+    std::vector<double> fvec((size_t)h->off_m[B], 1.0), bvec((size_t)h->off_n[B], 0.0);
+    std::vector<InstState> st(B);
+    long long boff = 0, foff = 0;
+    for (int i = 0; i < B; ++i) {
+        const int ni = n[i], mi = m[i], nz = h->nnz0[i];
+        const int32_t *cp = colptr_all + h->h_cp_off[i];
+        const int32_t *ri = rowidx_all + h->h_nnz_off[i];
+        const double *va = val_all ? val_all + h->h_nnz_off[i] : nullptr;
+        PatLayout PL = pat_layout(ni, mi, nz);
+        unsigned char *blob = pat.data() + h->off_pat[i];
+        uint16_t *rowptr = (uint16_t *)(blob + PL.o_rowptr), *colptr = (uint16_t *)(blob + PL.o_colptr);
+        uint16_t *colidx = (uint16_t *)(blob + PL.o_colidx), *rowidx = (uint16_t *)(blob + PL.o_rowidx);
+        std::vector<int> rcount(mi + 1, 0);
+        for (int j = 0; j < ni; ++j) {
+            if (cp[j] > cp[j + 1] || cp[0] != 0) { set_err("bad colptr"); delete h; return nullptr; }
+            colptr[j] = (uint16_t)cp[j];
+            for (int k = cp[j]; k < cp[j + 1]; ++k) {
+                if (ri[k] < 0 || ri[k] >= mi || (k > cp[j] && ri[k] <= ri[k - 1])) {
+                    set_err("row indices must be in range and strictly ascending within each column"); delete h; return nullptr;
+                }
+                rowidx[k] = (uint16_t)ri[k];
+                rcount[ri[k] + 1]++;
+            }
+        }
+        colptr[ni] = (uint16_t)nz;
+        for (int r = 0; r < mi; ++r) rcount[r + 1] += rcount[r];
+        for (int r = 0; r <= mi; ++r) rowptr[r] = (uint16_t)rcount[r];
+        std::vector<int> pos(rcount.begin(), rcount.end() - 1);
+        for (int j = 0; j < ni; ++j)
+            for (int k = cp[j]; k < cp[j + 1]; ++k) {
+                int q = pos[ri[k]]++;
+                colidx[q] = (uint16_t)j;
+                if (!h->all_unit) { val_r[(size_t)h->off_val[i] + q] = va[k]; val_c[(size_t)h->off_val[i] + k] = va[k]; }
+            }
+        memcpy(bvec.data() + h->off_n[i], b_all + boff, sizeof(double) * (size_t)ni);
+        if (f_all) memcpy(fvec.data() + h->off_m[i], f_all + foff, sizeof(double) * (size_t)mi);
+        boff += ni; foff += mi;
+        InstState &s = st[i];
+        memset(&s, 0, sizeof(s));
+        s.n0 = s.n = ni; s.m0 = s.m = mi; s.nnz0 = s.nnz = nz; s.unit = h->all_unit ? 1 : 0; s.std_obj = 1.0; s.rhoUpdated = 1;
+    }
+    h->h_st = st;
+    lpbox_params lp; lpbox_params_lp(&lp);
+    h->pr.stop_threshold = lp.stop_threshold; h->pr.std_threshold = lp.std_threshold; h->pr.max_iters = lp.max_iters;
+    h->pr.initial_rho = lp.initial_rho; h->pr.rho_change_step = lp.rho_change_step; h->pr.gamma_val = lp.gamma_val;
+    h->pr.learning_fact = lp.learning_fact; h->pr.history_size = (int)lp.history_size; h->pr.gamma_factor = lp.gamma_factor;
+    h->pr.pcg_tol = lp.pcg_tol; h->pr.pcg_maxiters = lp.pcg_maxiters; h->pr.guard_first_iter = 1; h->pr.alpha_bailout = 1;
+
+    bool ok = true;
+    auto A = [&](cudaError_t e) { if (e != cudaSuccess) { if (ok) set_err(cudaGetErrorString(e)); ok = false; } };
+    A(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    A(cudaEventCreate(&h->ev0)); A(cudaEventCreate(&h->ev1));
+    size_t NN = (size_t)h->off_n[B], MM = (size_t)h->off_m[B];
+    A(h->d_off_n.alloc(B + 1)); A(h->d_off_m.alloc(B + 1)); A(h->d_off_pat.alloc(B + 1)); A(h->d_off_val.alloc(B + 1));
+    A(h->d_off_hist.alloc(B + 1)); A(h->d_off_vec.alloc(B + 1));
+    A(h->d_x.alloc(NN)); A(h->d_y1.alloc(NN)); A(h->d_y2.alloc(NN)); A(h->d_z1.alloc(NN)); A(h->d_z2.alloc(NN));
+    A(h->d_b.alloc(NN)); A(h->d_Pd.alloc(NN)); A(h->d_Esq.alloc(NN)); A(h->d_ret_val.alloc(NN)); A(h->d_vec.alloc(NN));
+    A(h->d_left.alloc(NN)); A(h->d_ret_idx.alloc(NN));
+    A(h->d_y3.alloc(MM)); A(h->d_z4.alloc(MM)); A(h->d_f.alloc(MM));
+    A(h->d_pat.alloc((size_t)h->off_pat[B]));
+    if (!h->all_unit) { A(h->d_val_r.alloc((size_t)h->off_val[B])); A(h->d_val_c.alloc((size_t)h->off_val[B])); A(h->d_r4v.alloc((size_t)h->off_val[B])); }
+    A(h->d_hist.alloc((size_t)h->off_hist[B]));
+    A(h->d_st.alloc(B)); A(h->d_counter.alloc(1)); A(h->d_num.alloc(B));
+    A(h->d_pow.alloc((size_t)h->max_n + 1));
+    if (!ok) { lpbox_batch_destroy(h); return nullptr; }
+    std::vector<double> powtab((size_t)h->max_n + 1);
+    for (int k = 0; k <= h->max_n; ++k) powtab[k] = pow((double)k, 1.0 / 2);   // std::pow(n, 1.0/p), LP.cpp:427 (host libm)
+    auto H2D = [&](void *d, const void *s, size_t bytes) { if (bytes) A(cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, h->stream)); };
+    H2D(h->d_off_n.p, h->off_n.data(), sizeof(long long) * (B + 1));
+    H2D(h->d_off_m.p, h->off_m.data(), sizeof(long long) * (B + 1));
+    H2D(h->d_off_pat.p, h->off_pat.data(), sizeof(long long) * (B + 1));
+    H2D(h->d_off_val.p, h->off_val.data(), sizeof(long long) * (B + 1));
+    H2D(h->d_off_hist.p, h->off_hist.data(), sizeof(long long) * (B + 1));
+    H2D(h->d_b.p, bvec.data(), sizeof(double) * NN);
+    H2D(h->d_f.p, fvec.data(), sizeof(double) * MM);
+    H2D(h->d_pat.p, pat.data(), pat.size());
+    if (!h->all_unit) { H2D(h->d_val_r.p, val_r.data(), sizeof(double) * val_r.size()); H2D(h->d_val_c.p, val_c.data(), sizeof(double) * val_c.size()); }
+    H2D(h->d_st.p, st.data(), sizeof(InstState) * (size_t)B);
+    H2D(h->d_pow.p, powtab.data(), sizeof(double) * powtab.size());
+    A(cudaStreamSynchronize(h->stream));
+    if (!ok) { lpbox_batch_destroy(h); return nullptr; }
+    BatchView &v = h->bv;
+    v.B = B; v.hist_cap = hist_cap;
+    v.off_n = h->d_off_n.p; v.off_m = h->d_off_m.p; v.off_pat = h->d_off_pat.p; v.off_val = h->d_off_val.p; v.off_hist = h->d_off_hist.p;
+    v.x = h->d_x.p; v.y1 = h->d_y1.p; v.y2 = h->d_y2.p; v.z1 = h->d_z1.p; v.z2 = h->d_z2.p; v.b = h->d_b.p; v.Pd = h->d_Pd.p; v.Esq = h->d_Esq.p;
+    v.y3 = h->d_y3.p; v.z4 = h->d_z4.p; v.f = h->d_f.p; v.pat = h->d_pat.p;
+    v.val_r = h->d_val_r.p; v.val_c = h->d_val_c.p; v.r4v = h->d_r4v.p; v.st = h->d_st.p; v.hist = h->d_hist.p;
+    v.left_idx = h->d_left.p; v.ret_idx = h->d_ret_idx.p; v.ret_val = h->d_ret_val.p; v.pow_tab = h->d_pow.p;
+    if (configure(h) != 0) { lpbox_batch_destroy(h); return nullptr; }
+    return h;
+}
+
+extern "C" void lpbox_batch_destroy(lpbox_batch *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    h->d_off_n.free_(); h->d_off_m.free_(); h->d_off_pat.free_(); h->d_off_val.free_(); h->d_off_hist.free_(); h->d_off_vec.free_();
+    h->d_x.free_(); h->d_y1.free_(); h->d_y2.free_(); h->d_z1.free_(); h->d_z2.free_(); h->d_b.free_(); h->d_Pd.free_(); h->d_Esq.free_();
+    h->d_y3.free_(); h->d_z4.free_(); h->d_f.free_(); h->d_val_r.free_(); h->d_val_c.free_(); h->d_r4v.free_(); h->d_hist.free_();
+    h->d_ret_val.free_(); h->d_pow.free_(); h->d_vec.free_(); h->d_pat.free_(); h->d_st.free_(); h->d_left.free_(); h->d_ret_idx.free_();
+    h->d_counter.free_(); h->d_num.free_();
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int lpbox_batch_set_params(lpbox_batch *h, const lpbox_params *p, int variant) {
+    if (!h || !p) return LPBOX_E_INVALID;
+    if (p->history_size < 2 || p->history_size > 16 || p->history_size != floor(p->history_size)) { set_err("history_size must be an integer in [2,16]"); return LPBOX_E_INVALID; }
+    if (p->projection_lp != 2) { set_err("projection_lp must be 2 (the reference always uses the 2-norm, LP.cpp:423-428)"); return LPBOX_E_INVALID; }
+    if (p->rho_change_step <= 0) return LPBOX_E_INVALID;
+    h->pr.stop_threshold = p->stop_threshold; h->pr.std_threshold = p->std_threshold; h->pr.max_iters = p->max_iters;
+    h->pr.initial_rho = p->initial_rho; h->pr.rho_change_step = p->rho_change_step; h->pr.gamma_val = p->gamma_val;
+    h->pr.learning_fact = p->learning_fact; h->pr.history_size = (int)p->history_size; h->pr.gamma_factor = p->gamma_factor;
+    h->pr.pcg_tol = p->pcg_tol; h->pr.pcg_maxiters = p->pcg_maxiters;
+    h->pr.guard_first_iter = (variant & 1) ? 1 : 0; h->pr.alpha_bailout = (variant & 2) ? 1 : 0;
+    return 0;
+}
+
+static void time_begin(lpbox_batch *h) { cudaEventRecord(h->ev0, h->stream); }
+static int time_end(lpbox_batch *h) {
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaEventSynchronize(h->ev1));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_ms = ms;
+    return 0;
+}
+
+extern "C" int lpbox_batch_init(lpbox_batch *h, const double *x0_all) {
+    if (!h) return LPBOX_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    // reset current sizes / patterns are only valid for a never-compacted batch
+    for (int i = 0; i < h->B; ++i) if (h->inited && h->h_st[i].n != h->h_st[i].n0) { set_err("re-init after early fixing is not supported; create a new batch"); return LPBOX_E_INVALID; }
+    if (x0_all) {
+        std::vector<double> xs((size_t)h->off_n[h->B], 0.0);
+        long long o = 0;
+        for (int i = 0; i < h->B; ++i) { memcpy(xs.data() + h->off_n[i], x0_all + o, sizeof(double) * (size_t)h->n0[i]); o += h->n0[i]; }
+        CK(cudaMemcpyAsync(h->d_x.p, xs.data(), sizeof(double) * xs.size(), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    lp_setup_kernel<<<h->B, 128, 0, h->stream>>>(h->bv, h->pr, 3, x0_all ? 1 : 0);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    { int rc = sync_states(h); if (rc) return rc; }
+    h->inited = true;
+    return 1;   // ADMM_lp_iters_init returns 1 (LP.cpp:762)
+}
+
+extern "C" int lpbox_batch_iters(lpbox_batch *h, int iter_start, int iter_end, int32_t *ret) {
+    if (!h || !h->inited) { set_err("call lpbox_batch_init first"); return LPBOX_E_INVALID; }
+    CK(cudaSetDevice(h->device));
+    time_begin(h);
+    if (iter_start == 0 && iter_end > 0) {   // update_expression(0) inside iteration 0 (LP.cpp:833)
+        lp_setup_kernel<<<h->B, 128, 0, h->stream>>>(h->bv, h->pr, 2, 0);
+        CK(cudaGetLastError());
+        h->launches += 1;
+    }
+    int rc = run_window(h, iter_start, iter_end, 0, h->B > 1 ? 1 : 0);
+    if (rc) return rc;
+    rc = time_end(h); if (rc) return rc;
+    rc = sync_states(h); if (rc) return rc;
+    if (ret) for (int i = 0; i < h->B; ++i) ret[i] = h->h_st[i].last_ret;
+    return h->h_st[0].last_ret;
+}
+
+extern "C" int lpbox_batch_iters_l2f(lpbox_batch *h, int iter_start, int iter_end, const double *vec_all, const int32_t *num,
+                                     int32_t *ret) {
+    if (!h || !h->inited) { set_err("call lpbox_batch_init first"); return LPBOX_E_INVALID; }
+    CK(cudaSetDevice(h->device));
+    const int skip_done = h->B > 1 ? 1 : 0;
+    bool any = false;
+    if (num) for (int i = 0; i < h->B; ++i) if (num[i] != 0) any = true;
+    if (any && !vec_all) { set_err("vec_all is NULL but some num[i] != 0"); return LPBOX_E_INVALID; }
+    time_begin(h);
+    if (any) {
+        std::vector<long long> off_vec(h->B + 1, 0);
+        for (int i = 0; i < h->B; ++i) off_vec[i + 1] = off_vec[i] + h->h_st[i].n;
+        // validate: num[i] must equal the number of entries in {0,1} (the reference prints an error and corrupts memory otherwise)
+        for (int i = 0; i < h->B; ++i) {
+            if (num[i] == 0) continue;
+            int c = 0;
+            const double *v = vec_all + off_vec[i];
+            for (int k = 0; k < h->h_st[i].n; ++k) if (v[k] == 1.0 || v[k] == 0.0) c++;
+            if (c != num[i]) { set_err("num[i] does not match the number of fixed entries in vec"); return LPBOX_E_INVALID; }
+        }
+        CK(cudaMemcpyAsync(h->d_off_vec.p, off_vec.data(), sizeof(long long) * (h->B + 1), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_vec.p, vec_all, sizeof(double) * (size_t)off_vec[h->B], cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_num.p, num, sizeof(int) * (size_t)h->B, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        CK(cudaMemsetAsync(h->d_num.p, 0, sizeof(int) * (size_t)h->B, h->stream));
+    }
+    int np = (h->max_n + 1) & ~1, mp = (h->max_m + 1) & ~1;
+    int val_elems = h->all_unit ? 0 : ((h->max_nnz + 1) & ~1);
+    lp_fix_kernel<<<h->B, FIX_T, h->fix_smem, h->stream>>>(h->bv, h->pr, h->d_vec.p, h->d_off_vec.p, h->d_num.p, skip_done, np, mp,
+                                                          h->max_pat, val_elems);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    if (iter_start == 0 && iter_end > 0) {   // `if(iter==0) update_expression(0)` (LP.cpp:1380-1381)
+        lp_setup_kernel<<<h->B, 128, 0, h->stream>>>(h->bv, h->pr, 2, 0);
+        CK(cudaGetLastError());
+        h->launches += 1;
+    }
+    int rc = run_window(h, iter_start, iter_end, 1, skip_done);
+    if (rc) return rc;
+    rc = time_end(h); if (rc) return rc;
+    rc = sync_states(h); if (rc) return rc;
+    if (ret) for (int i = 0; i < h->B; ++i) ret[i] = h->h_st[i].last_ret;
+    return h->h_st[0].last_ret;
+}
+
+extern "C" int lpbox_batch_solve(lpbox_batch *h, int max_iters, lpbox_log_row *log) {
+    if (!h || !h->inited) { set_err("call lpbox_batch_init first"); return LPBOX_E_INVALID; }
+    CK(cudaSetDevice(h->device));
+    time_begin(h);
+    lp_setup_kernel<<<h->B, 128, 0, h->stream>>>(h->bv, h->pr, 2, 0);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    int rc = run_window(h, 0, max_iters, 0, 1);
+    if (rc) return rc;
+    rc = time_end(h); if (rc) return rc;
+    rc = sync_states(h); if (rc) return rc;
+    if (log) return lpbox_batch_results(h, log, nullptr, 0);
+    return 0;
+}
+
+extern "C" int lpbox_batch_size(const lpbox_batch *h) { return h ? h->B : LPBOX_E_INVALID; }
+#define CHK_I(h, i) if (!(h) || (i) < 0 || (i) >= (h)->B) return LPBOX_E_INVALID
+extern "C" int lpbox_batch_get_n(lpbox_batch *h, int i) { CHK_I(h, i); return h->h_st[i].n; }
+extern "C" int lpbox_batch_get_m(lpbox_batch *h, int i) { CHK_I(h, i); return h->h_st[i].m; }
+extern "C" int lpbox_batch_get_org_n(lpbox_batch *h, int i) { CHK_I(h, i); return h->h_st[i].n0; }
+extern "C" int lpbox_batch_get_iter(lpbox_batch *h, int i) { CHK_I(h, i); return h->h_st[i].iter; }
+extern "C" double lpbox_batch_cal_obj(lpbox_batch *h, int i) {
+    if (!h || i < 0 || i >= h->B) return NAN;
+    const InstState &s = h->h_st[i];
+    return s.n != 0 ? s.sum_fix_obj + s.cur_obj : s.sum_fix_obj;   // LP.cpp:1630-1642
+}
+extern "C" double lpbox_batch_get_cur_bin_obj(lpbox_batch *h, int i) { if (!h || i < 0 || i >= h->B) return NAN; return h->h_st[i].cur_obj; }
+
+static int d2h(lpbox_batch *h, void *dst, const void *src, size_t bytes) {
+    if (!bytes) return 0;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int lpbox_batch_get_state(lpbox_batch *h, int i, double *x, double *y1, double *y2, double *z1, double *z2, double *y3, double *z4) {
+    CHK_I(h, i);
+    const InstState &s = h->h_st[i];
+    size_t nb = sizeof(double) * (size_t)s.n, mb = sizeof(double) * (size_t)s.m;
+    long long on = h->off_n[i], om = h->off_m[i];
+    int rc = 0;
+    if (x) rc |= d2h(h, x, h->d_x.p + on, nb);
+    if (y1) rc |= d2h(h, y1, h->d_y1.p + on, nb);
+    if (y2) rc |= d2h(h, y2, h->d_y2.p + on, nb);
+    if (z1) rc |= d2h(h, z1, h->d_z1.p + on, nb);
+    if (z2) rc |= d2h(h, z2, h->d_z2.p + on, nb);
+    if (y3) rc |= d2h(h, y3, h->d_y3.p + om, mb);
+    if (z4) rc |= d2h(h, z4, h->d_z4.p + om, mb);
+    return rc ? LPBOX_E_CUDA : 0;
+}
+
+extern "C" int lpbox_batch_get_final_x_sol(lpbox_batch *h, int i, double *out) {
+    CHK_I(h, i);
+    if (!out) return LPBOX_E_INVALID;
+    return d2h(h, out, h->d_x.p + h->off_n[i], sizeof(double) * (size_t)h->h_st[i].n) ? LPBOX_E_CUDA : h->h_st[i].n;
+}
+
+// get_x_sol (LP.cpp:1648-1665)
+static int assemble_x(lpbox_batch *h, int i, double *out) {
+    const InstState &s = h->h_st[i];
+    long long on = h->off_n[i];
+    std::vector<int> ridx(s.n_ret), left(s.n);
+    std::vector<double> rval(s.n_ret), x(s.n);
+    if (d2h(h, ridx.data(), h->d_ret_idx.p + on, sizeof(int) * (size_t)s.n_ret)) return LPBOX_E_CUDA;
+    if (d2h(h, rval.data(), h->d_ret_val.p + on, sizeof(double) * (size_t)s.n_ret)) return LPBOX_E_CUDA;
+    if (d2h(h, left.data(), h->d_left.p + on, sizeof(int) * (size_t)s.n)) return LPBOX_E_CUDA;
+    if (d2h(h, x.data(), h->d_x.p + on, sizeof(double) * (size_t)s.n)) return LPBOX_E_CUDA;
+    for (int q = 0; q < s.n_ret; ++q) out[ridx[q]] = rval[q];
+    for (int q = 0; q < s.n; ++q) out[left[q]] = (x[q] >= 0.5) ? 1.0 : 0.0;
+    return s.n0;
+}
+extern "C" int lpbox_batch_get_x_sol(lpbox_batch *h, int i, double *out) {
+    CHK_I(h, i);
+    if (!out) return LPBOX_E_INVALID;
+    return assemble_x(h, i, out);
+}
+
+extern "C" int lpbox_batch_get_x_iters(lpbox_batch *h, int i, int ws, double *out) {
+    CHK_I(h, i);
+    if (!out || ws <= 0) return LPBOX_E_INVALID;
+    const InstState &s = h->h_st[i];
+    int rows = s.xit_rows, cols = std::min(std::min(s.xit_cols, ws), h->hist_cap);
+    std::vector<double> buf((size_t)std::max(cols, 0) * s.n0);
+    if (cols > 0 && d2h(h, buf.data(), h->d_hist.p + h->off_hist[i], sizeof(double) * buf.size())) return LPBOX_E_CUDA;
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < ws; ++c) out[(size_t)r * ws + c] = (c < cols) ? buf[(size_t)c * s.n0 + r] : 0.0;   // x_iters is zero-initialised (LP.cpp:1113)
+    return rows;
+}
+
+extern "C" int lpbox_batch_check_infeasible_lpbox(lpbox_batch *h, int i) {   // LP.cpp:1577-1591: current E, relaxed x
+    CHK_I(h, i);
+    const InstState &s = h->h_st[i];
+    PatLayout PL = pat_layout(s.n0, s.m0, s.nnz0);
+    std::vector<unsigned char> blob(PL.bytes);
+    std::vector<double> x(s.n), vr;
+    if (d2h(h, blob.data(), h->d_pat.p + h->off_pat[i], blob.size())) return LPBOX_E_CUDA;
+    if (d2h(h, x.data(), h->d_x.p + h->off_n[i], sizeof(double) * (size_t)s.n)) return LPBOX_E_CUDA;
+    if (!s.unit) { vr.resize(s.nnz); if (d2h(h, vr.data(), h->d_val_r.p + h->off_val[i], sizeof(double) * (size_t)s.nnz)) return LPBOX_E_CUDA; }
+    const uint16_t *rowptr = (const uint16_t *)(blob.data() + PL.o_rowptr), *colidx = (const uint16_t *)(blob.data() + PL.o_colidx);
+    int inf = 0;
+    for (int r = 0; r < s.m; ++r) {
+        double acc = 0.0;
+        for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) acc = acc + (s.unit ? 1.0 : vr[k]) * x[colidx[k]];
+        if (!(acc <= 1.0)) inf++;
+    }
+    return inf;
+}
+
+extern "C" int lpbox_batch_check_infeasible_l2f(lpbox_batch *h, int i) {     // LP.cpp:1593-1612: original E, assembled binary x
+    CHK_I(h, i);
+    const InstState &s = h->h_st[i];
+    std::vector<double> xs(s.n0, 0.0);
+    int rc = assemble_x(h, i, xs.data());
+    if (rc < 0) return rc;
+    std::vector<double> acc(s.m0, 0.0);
+    const int *cp = h->h_colptr.data() + h->h_cp_off[i];
+    const int *ri = h->h_rowidx.data() + h->h_nnz_off[i];
+    const double *va = h->h_val.empty() ? nullptr : h->h_val.data() + h->h_nnz_off[i];
+    for (int j = 0; j < s.n0; ++j)
+        for (int k = cp[j]; k < cp[j + 1]; ++k) acc[ri[k]] = acc[ri[k]] + (va ? va[k] : 1.0) * xs[j];
+    int inf = 0;
+    for (int r = 0; r < s.m0; ++r) if (!(acc[r] <= 1.0)) inf++;
+    return inf;
+}
+
+extern "C" int lpbox_batch_results(lpbox_batch *h, lpbox_log_row *log, uint8_t *x_bits, int row_stride_bytes) {
+    if (!h) return LPBOX_E_INVALID;
+    int rc = sync_states(h); if (rc) return rc;
+    size_t NN = (size_t)h->off_n[h->B];
+    std::vector<double> x(NN), rval(NN);
+    std::vector<int> left(NN), ridx(NN);
+    if (d2h(h, x.data(), h->d_x.p, sizeof(double) * NN) || d2h(h, rval.data(), h->d_ret_val.p, sizeof(double) * NN) ||
+        d2h(h, left.data(), h->d_left.p, sizeof(int) * NN) || d2h(h, ridx.data(), h->d_ret_idx.p, sizeof(int) * NN)) return LPBOX_E_CUDA;
+    std::vector<double> xs, acc;
+    for (int i = 0; i < h->B; ++i) {
+        const InstState &s = h->h_st[i];
+        long long on = h->off_n[i];
+        xs.assign(s.n0, 0.0);
+        for (int q = 0; q < s.n_ret; ++q) xs[ridx[on + q]] = rval[on + q];
+        for (int q = 0; q < s.n; ++q) xs[left[on + q]] = (x[on + q] >= 0.5) ? 1.0 : 0.0;
+        if (x_bits) {
+            uint8_t *row = x_bits + (size_t)i * row_stride_bytes;
+            memset(row, 0, row_stride_bytes);
+            for (int j = 0; j < s.n0 && (j >> 3) < row_stride_bytes; ++j) if (xs[j] >= 0.5) row[j >> 3] |= (uint8_t)(1u << (j & 7));
+        }
+        if (log) {
+            acc.assign(s.m0, 0.0);
+            const int *cp = h->h_colptr.data() + h->h_cp_off[i];
+            const int *ri = h->h_rowidx.data() + h->h_nnz_off[i];
+            const double *va = h->h_val.empty() ? nullptr : h->h_val.data() + h->h_nnz_off[i];
+            for (int j = 0; j < s.n0; ++j)
+                for (int k = cp[j]; k < cp[j + 1]; ++k) acc[ri[k]] = acc[ri[k]] + (va ? va[k] : 1.0) * xs[j];
+            int inf = 0;
+            for (int r = 0; r < s.m0; ++r) if (!(acc[r] <= 1.0)) inf++;
+            lpbox_log_row &L = log[i];
+            L.iters = (int32_t)s.admm_iters; L.status = s.status; L.cg_iters = s.cg_iters;
+            L.obj = s.n != 0 ? s.sum_fix_obj + s.cur_obj : s.sum_fix_obj; L.cur_bin_obj = s.cur_obj; L.n_left = s.n; L.infeasible = inf;
+        }
+    }
+    return 0;
+}
+
+extern "C" double lpbox_batch_last_kernel_ms(const lpbox_batch *h) { return h ? h->last_ms : -1.0; }
+extern "C" int64_t lpbox_batch_launch_count(const lpbox_batch *h) { return h ? h->launches : -1; }
+
+// ---- file format of the reference (readFile / readSparseMat / readDenseVec, LP.cpp:2407-2545) ----------------------
+extern "C" void lpbox_free(void *p) { free(p); }
+extern "C" int lpbox_read_instance(const char *root, int i, int k, int j, int32_t *m_out, int32_t *n_out, int32_t **colptr_out,
+                                   int32_t **rowidx_out, double **val_out, double **b_out) {
+    if (!root || !m_out || !n_out || !colptr_out || !rowidx_out || !val_out || !b_out) return LPBOX_E_INVALID;
+    char pc[1024], pb[1024];
+    snprintf(pc, sizeof(pc), "%s/instance/%d_%d/instance_%d_C.txt", root, k, j, i);   // :2462
+    snprintf(pb, sizeof(pb), "%s/instance/%d_%d/instance_%d_b.txt", root, k, j, i);   // :2463
+    FILE *fc = fopen(pc, "r");
+    if (!fc) { set_err(std::string("cannot open ") + pc); return LPBOX_E_IO; }
+    struct Trip { int r, c; double v; };
+    std::vector<Trip> tr;
+    int row, col, max_row = 0, max_col = 0;
+    double val;
+    while (fscanf(fc, "%d,%d,%lf\n", &row, &col, &val) == 3) {                       // :2422
+        max_row = std::max(max_row, row); max_col = std::max(max_col, col);
+        tr.push_back({row - 1, col - 1, (k == 2) ? -1.0 * val : val});                // :2433-2436
+    }
+    fclose(fc);
+    const int m = max_row, n = max_col;
+    // setFromTriplets: column-major, duplicates summed, inner indices ascending
+    std::stable_sort(tr.begin(), tr.end(), [](const Trip &a, const Trip &b) { return a.c != b.c ? a.c < b.c : a.r < b.r; });
+    std::vector<Trip> u;
+    for (const Trip &t : tr) {
+        if (t.r < 0 || t.c < 0) { set_err("bad triplet"); return LPBOX_E_IO; }
+        if (!u.empty() && u.back().r == t.r && u.back().c == t.c) u.back().v += t.v; else u.push_back(t);
+    }
+    int32_t *cp = (int32_t *)calloc((size_t)n + 1, sizeof(int32_t));
+    int32_t *ri = (int32_t *)malloc(sizeof(int32_t) * std::max<size_t>(u.size(), 1));
+    double *va = (double *)malloc(sizeof(double) * std::max<size_t>(u.size(), 1));
+    double *b = (double *)malloc(sizeof(double) * std::max<size_t>((size_t)n, 1));
+    for (size_t q = 0; q < u.size(); ++q) { cp[u[q].c + 1]++; ri[q] = u[q].r; va[q] = u[q].v; }
+    for (int c = 0; c < n; ++c) cp[c + 1] += cp[c];
+    FILE *fb = fopen(pb, "r");
+    if (!fb) { free(cp); free(ri); free(va); free(b); set_err(std::string("cannot open ") + pb); return LPBOX_E_IO; }
+    for (int q = 0; q < n; ++q) {
+        if (fscanf(fb, "%lf\n", &b[q]) != 1) { fclose(fb); free(cp); free(ri); free(va); free(b); set_err("error when reading dense vector"); return LPBOX_E_IO; }
+        b[q] = -1.0 * b[q];                                                          // :2520
+    }
+    fclose(fb);
+    *m_out = m; *n_out = n; *colptr_out = cp; *rowidx_out = ri; *val_out = va; *b_out = b;
+    return 0;
+}

@@ -1,0 +1,623 @@
+// Persistent on-chip Lp-Box ADMM kernels for the inequality-constrained LP form (sm_100a).
+//
+// One CTA owns one problem instance for a whole window of ADMM iterations:
+//   * the sparsity pattern of E (both orientations, uint16) is staged into shared memory with one 1-D TMA bulk copy
+//     (cp.async.bulk + mbarrier),
+//   * x, y1, y2, z1, z2, r, p, 1/diag live in REGISTERS of the thread that owns the element (EPT elements / thread),
+//     y3, z4, f in registers of the thread that owns the constraint row,
+//   * only vectors that other threads gather from (x or p for E v, E v for E^T, the reduction operands) go through
+//     shared memory,
+//   * projections, rhs assembly, the whole PCG solve, dual / rho updates and both stop tests are fused: nothing
+//     touches HBM between iterations except the optional iterate history.
+//
+// PARITY MODE (the only mode in this file): every floating-point operation is issued in the order of the
+// reference's compiled Eigen code: no FMA (explicit __dmul_rn/__dadd_rn), SpMV with one sequential
+// accumulator per output row in ascending inner index, reductions as Eigen's SSE2 redux (four interleaved sequential
+// chains).  Reference lines are cited at each step (LP.cpp = LinerProgramming/.../cython_solver/LPboxADMMsolver.cpp).
+#pragma once
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "lp_types.h"
+
+namespace lpb {
+
+typedef uint16_t u16;
+
+#define LPB_FOR_E _Pragma("unroll") for (int e = 0; e < EPT; ++e)
+
+__device__ __forceinline__ double dM(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dA(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dS(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dD(double a, double b) { return __ddiv_rn(a, b); }
+
+// ---- mbarrier / TMA bulk copy helpers (PTX) -----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk copy global -> shared (TMA engine; SASS UBLKCP).  dst/src 16-byte aligned, bytes % 16 == 0.
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- Eigen-order reduction ----------------------------------------------------------------------------------------
+// Executed by ONE warp.  Up to 8 independent reductions run side by side: lane l works on array q = l/4 as chain
+// k = l%4 (Eigen's packet lanes: packet0 = {chain0, chain1}, packet1 = {chain2, chain3}).  Restates Eigen's
+// redux_impl<..., LinearVectorizedTraversal, NoUnrolling> for Packet2d (call sites LP.cpp:277,288,300,306,311,323,425,
+// 455,931-933).  Result of array q is returned in every lane of its group.
+template <int R>
+__device__ __forceinline__ double warp_redux_eigen(const double *red, int stride, int n) {
+    const int lane = threadIdx.x & 31;
+    const int q = lane >> 2, k = lane & 3;
+    const double *v = red + (q < R ? q : 0) * stride;
+    const int a2 = n & ~3, a1 = n & ~1;
+    double res;
+    if (a1 > 2) {
+        double acc = v[k];
+        int i = 4 + k;
+        // software-pipelined: the loads are independent, only the adds form the chain
+        for (; i + 28 < a2; i += 32) {
+            double t0 = v[i], t1 = v[i + 4], t2 = v[i + 8], t3 = v[i + 12], t4 = v[i + 16], t5 = v[i + 20], t6 = v[i + 24],
+                   t7 = v[i + 28];
+            acc = dA(acc, t0); acc = dA(acc, t1); acc = dA(acc, t2); acc = dA(acc, t3);
+            acc = dA(acc, t4); acc = dA(acc, t5); acc = dA(acc, t6); acc = dA(acc, t7);
+        }
+        for (; i < a2; i += 4) acc = dA(acc, v[i]);
+        // packet_res0 = packet_res0 + packet_res1 : chain0+chain2 , chain1+chain3
+        double hi = __shfl_down_sync(0xffffffffu, acc, 2);
+        double l = dA(acc, hi);                       // valid in k = 0,1
+        if (a1 > a2 && k < 2) l = dA(l, v[a2 + k]);   // one more packet
+        double l1 = __shfl_down_sync(0xffffffffu, l, 1);
+        res = dA(l, l1);                              // predux: lane0 + lane1 (valid in k = 0)
+    } else if (a1 == 2) {
+        res = dA(v[0], v[1]);
+    } else {
+        res = (n > 0) ? v[0] : 0.0;                   // n == 1 (coeff(0)); n == 0 -> 0
+    }
+    if ((n & 1) && n > 1) res = dA(res, v[n - 1]);    // scalar tail (valid in k = 0)
+    return __shfl_sync(0xffffffffu, res, lane & ~3);  // broadcast chain-0 lane's value to its group
+}
+
+// ---- sequential sparse dot products -------------------------------------------------------------------------------
+// acc[e] = ((0 + c_1 v[i_1]) + c_2 v[i_2]) + ...  over the stored entries of outer index o_e = tid + e*T, ascending
+// inner index.  Coefficient: COEF 0 -> 1 (unit E), 1 -> scale (unit rho4 E^T), 2 -> val[pos].
+// The EPT chains of a thread are advanced in lock step so that their (dependent) adds overlap.
+template <int T, int EPT, int COEF>
+__device__ __forceinline__ void seq_spmv(const u16 *__restrict__ ptr, const u16 *__restrict__ idx, const double *__restrict__ val,
+                                         double scale, const double *__restrict__ v, int count, double (&acc)[EPT]) {
+    int pos[EPT], end[EPT];
+    int maxlen = 0;
+    LPB_FOR_E {
+        int o = threadIdx.x + e * T;
+        if (o < count) { pos[e] = ptr[o]; end[e] = ptr[o + 1]; } else { pos[e] = 0; end[e] = 0; }
+        maxlen = max(maxlen, end[e] - pos[e]);
+        acc[e] = 0.0;
+    }
+    for (int k = 0; k < maxlen; ++k) {
+        LPB_FOR_E {
+            if (pos[e] < end[e]) {
+                double t = v[idx[pos[e]]];
+                if (COEF == 1) t = dM(scale, t);
+                if (COEF == 2) t = dM(val[pos[e]], t);
+                acc[e] = dA(acc[e], t);
+                pos[e]++;
+            }
+        }
+    }
+}
+
+// shared-memory carve-up -----------------------------------------------------------------------------------------------
+struct Smem {
+    double *gv;      // [np]   vector being gathered by E v (x or p)
+    double *red;     // [5][np] reduction operands
+    double *t1;      // [mp]   E v
+    double *wa;      // [mp]   f - y3
+    double *wb;      // [mp]   z4
+    double *sc;      // [8]    reduction results / broadcast scalars
+    double *ring;    // [16]   tail of obj_list
+    double *val_r, *val_c, *r4v;  // [val_elems] each (non-unit only)
+    unsigned char *pat;
+    uint64_t *bar;
+};
+__host__ __device__ inline size_t smem_bytes(int np, int mp, int pat_bytes, int val_elems) {
+    size_t d = (size_t)np * 6 + (size_t)mp * 3 + 8 + 16 + (size_t)val_elems * 3;
+    return d * sizeof(double) + (size_t)pat_bytes + 16;
+}
+__device__ __forceinline__ Smem carve(unsigned char *base, int np, int mp, int pat_bytes, int val_elems) {
+    Smem s;
+    double *d = reinterpret_cast<double *>(base);
+    s.gv = d; d += np;
+    s.red = d; d += 5 * (size_t)np;
+    s.t1 = d; d += mp;
+    s.wa = d; d += mp;
+    s.wb = d; d += mp;
+    s.sc = d; d += 8;
+    s.ring = d; d += 16;
+    s.val_r = d; d += val_elems;
+    s.val_c = d; d += val_elems;
+    s.r4v = d; d += val_elems;
+    s.pat = reinterpret_cast<unsigned char *>(d);
+    s.bar = reinterpret_cast<uint64_t *>(s.pat + pat_bytes);
+    return s;
+}
+
+// std_dev (LP.cpp:358-377) / compute_std_obj (:459-469) over the tail of obj_list kept in `ring`, with `obj` as the
+// value about to be pushed (obj_len counts entries BEFORE the push).  pow(., 1/2) -> IEEE sqrt.
+__device__ __forceinline__ double std_obj_after_push(const double *ring, long long obj_len, double obj, int history) {
+    long long s = obj_len + 1;
+    long long begin = (s <= history) ? 0 : s - history;
+    int size = (int)(s - begin);
+    double mean = 0.0;
+    for (int i = 0; i < size; ++i) {
+        long long idx = begin + i;
+        double v = (idx == s - 1) ? obj : ring[idx & 15];
+        mean = dA(mean, v);
+    }
+    mean = dD(mean, (double)size);
+    double sd = 0.0;
+    for (int i = 0; i < size; ++i) {
+        long long idx = begin + i;
+        double v = (idx == s - 1) ? obj : ring[idx & 15];
+        double d = dS(v, mean);
+        sd = dA(sd, dM(d, d));
+    }
+    sd = dD(sd, (double)(size - 1));
+    double r = (sd == 0.0) ? 0.0 : sqrt(sd);
+    return dD(r, fabs(obj));
+}
+
+// =====================================================================================================================
+// The window kernel.  T threads, EPT elements (and rows) per thread: max(n, m) <= T*EPT.
+// UNIT: all stored values of E are 1.0 (pattern-only matrices; rho4*E^T is one scalar).
+// =====================================================================================================================
+template <int T, int EPT, bool UNIT>
+__global__ void __launch_bounds__(T, (T <= 128 ? 4 : (T <= 256 ? 2 : 1)))
+lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem S = carve(smem_raw, la.np, la.mp, la.pat_bytes, la.val_elems);
+    __shared__ int s_work;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    constexpr int RW = T / 32 - 1;  // the warp that runs the reductions (owns the fewest rows)
+    const int np = la.np;
+    uint32_t tma_phase = 0;
+
+    if (tid == 0) { mbar_init(S.bar, 1); fence_mbar_init(); }
+    __syncthreads();
+
+    for (;;) {
+        if (tid == 0) s_work = atomicAdd(la.counter, 1);
+        __syncthreads();
+        const int w = s_work;
+        __syncthreads();
+        if (w >= la.n_work) break;
+        const int inst = la.work ? la.work[w] : w;
+        InstState *stp = bv.st + inst;
+        if ((la.skip_done && stp->done) || stp->n == 0) continue;   // uniform per CTA
+
+        // ---------------- stage the instance --------------------------------------------------------------------
+        const int n = stp->n, m = stp->m;
+        const PatLayout PL = pat_layout(stp->n0, stp->m0, stp->nnz0);
+        if (tid == 0) {
+            fence_proxy_async();  // order earlier generic-proxy reads of the previous instance's blob before the overwrite
+            mbar_expect_tx(S.bar, (uint32_t)PL.bytes);
+            tma_load_1d(S.pat, bv.pat + bv.off_pat[inst], (uint32_t)PL.bytes, S.bar);
+        }
+        const long long on = bv.off_n[inst], om = bv.off_m[inst];
+        double x[EPT], y1[EPT], y2[EPT], z1[EPT], z2[EPT], r[EPT], p[EPT], invd[EPT], bb[EPT];
+        double y3[EPT], z4[EPT], ff[EPT];
+        LPB_FOR_E {
+            int j = tid + e * T;
+            bool in = j < n;
+            x[e] = in ? bv.x[on + j] : 0.0;   y1[e] = in ? bv.y1[on + j] : 0.0; y2[e] = in ? bv.y2[on + j] : 0.0;
+            z1[e] = in ? bv.z1[on + j] : 0.0; z2[e] = in ? bv.z2[on + j] : 0.0; bb[e] = in ? bv.b[on + j] : 0.0;
+            double pd = in ? bv.Pd[on + j] : 1.0;
+            invd[e] = (pd != 0.0) ? dD(1.0, pd) : 1.0;   // value in use when rhoUpdated == 0 (Eigen: zero diagonal -> 1)
+            r[e] = 0.0; p[e] = 0.0;
+            bool rin = j < m;
+            y3[e] = rin ? bv.y3[om + j] : 0.0; z4[e] = rin ? bv.z4[om + j] : 0.0; ff[e] = rin ? bv.f[om + j] : 0.0;
+        }
+        double rho1 = stp->rho1, rho2 = stp->rho2, rho4 = stp->rho4, prho1 = stp->prho1, prho2 = stp->prho2,
+               prho4 = stp->prho4, gamma = stp->gamma, ratio = stp->ratio, D = stp->D, r4s = stp->r4s,
+               std_obj = stp->std_obj, cur_obj = stp->cur_obj, best_bin_obj = stp->best_bin_obj;
+        int rhoUpdated = stp->rhoUpdated;
+        long long obj_len = stp->obj_len, cg_total = 0, admm_total = 0;
+        if (tid < 16) S.ring[tid] = stp->obj_ring[tid];
+        if (!UNIT) {
+            const long long ov = bv.off_val[inst];
+            for (int k = tid; k < stp->nnz; k += T) {
+                S.val_r[k] = bv.val_r[ov + k]; S.val_c[k] = bv.val_c[ov + k]; S.r4v[k] = bv.r4v[ov + k];
+            }
+        }
+        mbar_wait(S.bar, tma_phase); tma_phase ^= 1;
+        __syncthreads();
+        const u16 *rowptr = reinterpret_cast<const u16 *>(S.pat + PL.o_rowptr);
+        const u16 *colptr = reinterpret_cast<const u16 *>(S.pat + PL.o_colptr);
+        const u16 *colidx = reinterpret_cast<const u16 *>(S.pat + PL.o_colidx);
+        const u16 *rowidx = reinterpret_cast<const u16 *>(S.pat + PL.o_rowidx);
+        const double pow_n = bv.pow_tab[n];               // std::pow(n, 1.0/p), p = 2 (LP.cpp:427)
+        double *red0 = S.red, *red1 = S.red + np, *red2 = S.red + 2 * np, *red3 = S.red + 3 * np, *red4 = S.red + 4 * np;
+
+        int status = RUNNING;
+        int iter = la.iter_start;
+        int cc = 0;
+        const bool lp_plain = (!la.l2f) && pr.guard_first_iter;
+
+        for (; iter < la.iter_end; ++iter) {
+            double acc[EPT];
+            // ---- y1 (LP.cpp:806-809), y2 pre-image (:815, :424), gather x -------------------------------------
+            LPB_FOR_E {
+                int j = tid + e * T;
+                double t = dA(x[e], dD(z1[e], rho1));
+                y1[e] = (t > 1.0) ? 1.0 : ((t < 0.0) ? 0.0 : t);
+                y2[e] = dS(dA(x[e], dD(z2[e], rho2)), 0.5);
+                if (j < n) { red0[j] = dM(y2[e], y2[e]); S.gv[j] = x[e]; }
+            }
+            __syncthreads();
+            // ---- ||y|| (:425) on the reduction warp, E x (:825) on the row owners ------------------------------
+            if (warp == RW) {
+                double v = warp_redux_eigen<1>(red0, np, n);
+                if ((tid & 31) == 0) S.sc[0] = v;
+            }
+            seq_spmv<T, EPT, UNIT ? 0 : 2>(rowptr, colidx, S.val_r, 0.0, S.gv, m, acc);
+            __syncthreads();
+            {
+                const double nrm = sqrt(S.sc[0]);
+                const double den = dM(2.0, nrm);
+                LPB_FOR_E y2[e] = dA(dD(dM(y2[e], pow_n), den), 0.5);       // :427
+            }
+            // ---- y3 (:826-827) -------------------------------------------------------------------------------
+            LPB_FOR_E {
+                int i = tid + e * T;
+                double t = dS(dS(ff[e], acc[e]), dD(z4[e], rho4));
+                y3[e] = (t < 0.0) ? 0.0 : t;
+                if (i < m) { S.wa[i] = dS(ff[e], y3[e]); S.wb[i] = z4[e]; }
+            }
+            // ---- operator patch after a rho step (:851-866) and preconditioner refresh (:883-890) --------------
+            if (iter != 0 && rhoUpdated) {
+                const double c12 = dM(ratio, dA(prho1, prho2));
+                const double c4 = dM(ratio, prho4);
+                D = dA(D, c12);
+                LPB_FOR_E {
+                    int j = tid + e * T;
+                    if (j < n) {
+                        double pd = bv.Pd[on + j];
+                        pd = dA(pd, c12);
+                        pd = dA(pd, dM(c4, bv.Esq[on + j]));
+                        bv.Pd[on + j] = pd;
+                    }
+                }
+                if (UNIT) r4s = dM(pr.learning_fact, r4s);
+                else for (int k = tid; k < stp->nnz; k += T) S.r4v[k] = dM(pr.learning_fact, S.r4v[k]);
+            }
+            if (rhoUpdated) {
+                LPB_FOR_E {
+                    int j = tid + e * T;
+                    double pd = (j < n) ? bv.Pd[on + j] : 1.0;
+                    invd[e] = (pd != 0.0) ? dD(1.0, pd) : 1.0;
+                }
+                rhoUpdated = 0;
+            }
+            __syncthreads();
+            // ---- rhs (:872-878) -------------------------------------------------------------------------------
+            double rhs[EPT];
+            LPB_FOR_E rhs[e] = dS(dA(dM(rho1, y1[e]), dM(rho2, y2[e])), dA(dA(bb[e], z1[e]), z2[e]));
+            seq_spmv<T, EPT, UNIT ? 1 : 2>(colptr, rowidx, S.r4v, r4s, S.wa, n, acc);
+            LPB_FOR_E rhs[e] = dA(rhs[e], acc[e]);
+            seq_spmv<T, EPT, UNIT ? 0 : 2>(colptr, rowidx, S.val_c, 0.0, S.wb, n, acc);
+            LPB_FOR_E rhs[e] = dS(rhs[e], acc[e]);
+            // ---- PCG (:251-335), warm start x = y1 (:892) ------------------------------------------------------
+            double xc[EPT];
+            LPB_FOR_E {
+                int j = tid + e * T;
+                xc[e] = y1[e];
+                if (j < n) { S.gv[j] = xc[e]; red0[j] = dM(rhs[e], rhs[e]); }
+            }
+            __syncthreads();
+            if (warp == RW) {
+                double v = warp_redux_eigen<1>(red0, np, n);               // rhs.squaredNorm() :277
+                if ((tid & 31) == 0) S.sc[0] = v;
+            }
+            seq_spmv<T, EPT, UNIT ? 0 : 2>(rowptr, colidx, S.val_r, 0.0, S.gv, m, acc);
+            LPB_FOR_E { int i = tid + e * T; if (i < m) S.t1[i] = acc[e]; }
+            __syncthreads();
+            const double rhsNorm2 = S.sc[0];
+            seq_spmv<T, EPT, UNIT ? 1 : 2>(colptr, rowidx, S.r4v, r4s, S.t1, n, acc);
+            LPB_FOR_E {
+                int j = tid + e * T;
+                double mv = dA(dA(0.0, dM(D, xc[e])), acc[e]);               // D v (+) R4ET (E v)   :115-162
+                r[e] = dS(rhs[e], mv);                                       // :273
+                p[e] = dM(invd[e], r[e]);                                    // :297
+                if (j < n) { red1[j] = dM(r[e], r[e]); red2[j] = dM(r[e], p[e]); }
+            }
+            __syncthreads();
+            if (warp == RW) {
+                double v = warp_redux_eigen<2>(red1, np, n);               // :288, :300
+                int lane = tid & 31;
+                if (lane == 0) S.sc[1] = v;
+                if (lane == 4) S.sc[2] = v;
+            }
+            __syncthreads();
+            int cg_it = 0;
+            bool cg_fail = false;
+            if (rhsNorm2 == 0.0) {                                           // :279-284
+                LPB_FOR_E xc[e] = 0.0;
+            } else {
+                double threshold = dM(dM(pr.pcg_tol, pr.pcg_tol), rhsNorm2); // :287
+                if (!(threshold > DBL_MIN)) threshold = DBL_MIN;
+                double r2 = S.sc[1];
+                double absNew = S.sc[2];
+                if (!(r2 < threshold)) {                                     // :290-295
+                    while (cg_it < pr.pcg_maxiters) {
+                        LPB_FOR_E { int j = tid + e * T; if (j < n) S.gv[j] = p[e]; }
+                        __syncthreads();
+                        seq_spmv<T, EPT, UNIT ? 0 : 2>(rowptr, colidx, S.val_r, 0.0, S.gv, m, acc);
+                        LPB_FOR_E { int i = tid + e * T; if (i < m) S.t1[i] = acc[e]; }
+                        __syncthreads();
+                        seq_spmv<T, EPT, UNIT ? 1 : 2>(colptr, rowidx, S.r4v, r4s, S.t1, n, acc);
+                        double tmp[EPT];
+                        LPB_FOR_E {
+                            int j = tid + e * T;
+                            tmp[e] = dA(dA(0.0, dM(D, p[e])), acc[e]);       // :304
+                            if (j < n) red0[j] = dM(p[e], tmp[e]);
+                        }
+                        __syncthreads();
+                        if (warp == RW) {
+                            double v = warp_redux_eigen<1>(red0, np, n);     // p.dot(tmp) :306
+                            if ((tid & 31) == 0) S.sc[0] = v;
+                        }
+                        __syncthreads();
+                        const double alpha = dD(absNew, S.sc[0]);
+                        if (pr.alpha_bailout && alpha < 0.0) { cg_fail = true; break; }  // :307
+                        double zz[EPT];
+                        LPB_FOR_E {
+                            int j = tid + e * T;
+                            xc[e] = dA(xc[e], dM(alpha, p[e]));               // :308
+                            r[e] = dS(r[e], dM(alpha, tmp[e]));               // :310
+                            zz[e] = dM(invd[e], r[e]);                        // :320
+                            if (j < n) { red1[j] = dM(r[e], r[e]); red2[j] = dM(r[e], zz[e]); }
+                        }
+                        __syncthreads();
+                        if (warp == RW) {
+                            double v = warp_redux_eigen<2>(red1, np, n);     // :311, :323
+                            int lane = tid & 31;
+                            if (lane == 0) S.sc[1] = v;
+                            if (lane == 4) S.sc[2] = v;
+                        }
+                        __syncthreads();
+                        r2 = S.sc[1];
+                        if (r2 < threshold) { cg_it++; break; }              // :315-318
+                        const double absOld = absNew;
+                        absNew = S.sc[2];
+                        const double beta = dD(absNew, absOld);              // :324
+                        LPB_FOR_E p[e] = dA(zz[e], dM(beta, p[e]));           // :325
+                        cg_it++;
+                    }
+                }
+            }
+            cg_total += cg_it;
+            if (cg_fail) {
+                if (la.l2f) { status = STOP_CG; break; }                    // :1450-1454 (x_sol keeps its old value)
+                // plain loop ignores the return value: x_sol holds the partially updated iterate (:894)
+            }
+            LPB_FOR_E x[e] = xc[e];
+            admm_total += 1;
+            // ---- iterate history (:1472-1475) ----------------------------------------------------------------
+            if (la.l2f && bv.hist_cap > 0) {
+                if (cc < bv.hist_cap) {
+                    double *h = bv.hist + bv.off_hist[inst] + (long long)cc * stp->n0;
+                    LPB_FOR_E { int j = tid + e * T; if (j < n) h[j] = x[e]; }
+                }
+                cc++;
+            }
+            // ---- duals (:917-924) and stop-test operands (:931-933, :972, :1001-1011) ---------------------------
+            {
+                const double g1 = dM(gamma, rho1), g2 = dM(gamma, rho2);
+                LPB_FOR_E {
+                    int j = tid + e * T;
+                    const double d1 = dS(x[e], y1[e]), d2 = dS(x[e], y2[e]);
+                    z1[e] = dA(z1[e], dM(g1, d1));
+                    z2[e] = dA(z2[e], dM(g2, d2));
+                    if (j < n) {
+                        S.gv[j] = x[e];
+                        red0[j] = dM(x[e], x[e]);
+                        red1[j] = dM(d1, d1);
+                        red2[j] = dM(d2, d2);
+                        red3[j] = dM(bb[e], x[e]);
+                        red4[j] = dM(bb[e], (x[e] >= 0.5) ? 1.0 : 0.0);
+                    }
+                }
+            }
+            __syncthreads();
+            seq_spmv<T, EPT, UNIT ? 0 : 2>(rowptr, colidx, S.val_r, 0.0, S.gv, m, acc);
+            {
+                const double g4 = dM(gamma, rho4);
+                const bool assign = lp_plain && (iter == la.iter_start);    // :920-921
+                LPB_FOR_E {
+                    double t = dM(g4, dS(dA(acc[e], y3[e]), ff[e]));
+                    z4[e] = assign ? t : dA(z4[e], t);
+                }
+            }
+            if (warp == RW) {
+                double v = warp_redux_eigen<5>(red0, np, n);
+                int lane = tid & 31;
+                if ((lane & 3) == 0 && lane < 20) S.sc[lane >> 2] = v;
+                __syncwarp();
+                if (lane == 0) {
+                    const double obj = S.sc[3];
+                    double so = std_obj;
+                    if (obj_len + 1 >= (long long)pr.history_size) so = std_obj_after_push(S.ring, obj_len, obj, pr.history_size);
+                    S.sc[5] = so;
+                }
+            }
+            __syncthreads();
+            {
+                double temp0 = sqrt(S.sc[0]);                                // :931
+                if (!(temp0 > 2.2204e-16)) temp0 = 2.2204e-16;
+                const double c1 = dD(sqrt(S.sc[1]), temp0), c2 = dD(sqrt(S.sc[2]), temp0);
+                const bool guard = lp_plain ? (iter != la.iter_start) : true;
+                if (c1 <= pr.stop_threshold && c2 <= pr.stop_threshold && guard) { status = STOP_Y; break; }  // :934 / :1504
+            }
+            if ((iter + 1) % pr.rho_change_step == 0) {                      // :951-970
+                prho1 = rho1; prho2 = rho2; prho4 = rho4;
+                rho1 = dM(pr.learning_fact, rho1); rho2 = dM(pr.learning_fact, rho2); rho4 = dM(pr.learning_fact, rho4);
+                double g = dM(gamma, pr.gamma_factor);
+                gamma = (g < 1.0) ? 1.0 : g;
+                rhoUpdated = 1;
+                ratio = dS(pr.learning_fact, 1.0);
+            }
+            {
+                const double obj = S.sc[3];                                  // :972-973
+                if (tid == RW * 32) S.ring[obj_len & 15] = obj;              // written and read by the same thread only
+                obj_len++;
+                std_obj = S.sc[5];                                           // :974-976 (unchanged while size < history)
+                if (std_obj <= pr.std_threshold) { status = STOP_STD; break; }   // :977
+            }
+            cur_obj = S.sc[4];                                               // :1001-1005
+            if (best_bin_obj >= cur_obj) best_bin_obj = cur_obj;             // :1006-1009
+            // all reads of S.sc / red* of this iteration are complete before the next iteration's first barrier
+        }
+
+        // ---------------- write the instance back ---------------------------------------------------------------
+        __syncthreads();
+        LPB_FOR_E {
+            int j = tid + e * T;
+            if (j < n) {
+                bv.x[on + j] = x[e]; bv.y1[on + j] = y1[e]; bv.y2[on + j] = y2[e];
+                bv.z1[on + j] = z1[e]; bv.z2[on + j] = z2[e];
+            }
+            if (j < m) { bv.y3[om + j] = y3[e]; bv.z4[om + j] = z4[e]; }
+        }
+        if (!UNIT) {
+            const long long ov = bv.off_val[inst];
+            for (int k = tid; k < stp->nnz; k += T) bv.r4v[ov + k] = S.r4v[k];
+        }
+        if (tid < 16) stp->obj_ring[tid] = S.ring[tid];
+        if (tid == 0) {
+            stp->rho1 = rho1; stp->rho2 = rho2; stp->rho4 = rho4; stp->prho1 = prho1; stp->prho2 = prho2; stp->prho4 = prho4;
+            stp->gamma = gamma; stp->ratio = ratio; stp->D = D; stp->r4s = r4s; stp->std_obj = std_obj;
+            stp->cur_obj = cur_obj; stp->best_bin_obj = best_bin_obj; stp->rhoUpdated = rhoUpdated;
+            stp->obj_len = obj_len; stp->cg_iters += cg_total; stp->admm_iters += admm_total;
+            stp->iter = iter; stp->status = status;
+            int ret;
+            if (la.l2f) ret = (status != RUNNING || stp->norm_small) ? 1 : 0;    // :1505, :1542, :1452, :1223
+            else ret = (status == STOP_STD) ? 1 : 0;                             // :978
+            stp->last_ret = ret;
+            // the window driver stops calling once a call returned 1 (LP.trainer:521); the plain driver calls once
+            stp->done = la.l2f ? ret : (status != RUNNING);
+            if (la.l2f) { stp->xit_cols = cc; }
+        }
+        __syncthreads();
+    }
+}
+
+// =====================================================================================================================
+// Set-up kernel: ADMM_lp_iters_init (LP.cpp:489-763) and/or update_expression (LP.cpp:2289-2404) for every instance.
+// One CTA per instance, operating in HBM.  mode bit 0: initialise the iterate state; bit 1: rebuild the operator.
+// =====================================================================================================================
+__global__ void lp_setup_kernel(BatchView bv, Params pr, int mode, int use_x0) {
+    const int inst = blockIdx.x;
+    InstState *st = bv.st + inst;
+    const int n = st->n, m = st->m;
+    const PatLayout PL = pat_layout(st->n0, st->m0, st->nnz0);
+    const unsigned char *pat = bv.pat + bv.off_pat[inst];
+    const u16 *rowptr = reinterpret_cast<const u16 *>(pat + PL.o_rowptr);
+    const u16 *colptr = reinterpret_cast<const u16 *>(pat + PL.o_colptr);
+    const u16 *colidx = reinterpret_cast<const u16 *>(pat + PL.o_colidx);
+    const long long on = bv.off_n[inst], om = bv.off_m[inst], ov = bv.off_val ? bv.off_val[inst] : 0;
+    const bool unit = st->unit != 0;
+    const int tid = threadIdx.x, T = blockDim.x;
+    __shared__ double s_best;
+    if (mode & 1) {
+        for (int j = tid; j < n; j += T) {
+            double x0 = use_x0 ? bv.x[on + j] : 1.0;                         // :583-586
+            bv.x[on + j] = x0; bv.y1[on + j] = x0; bv.y2[on + j] = x0;       // :714-715
+            bv.z1[on + j] = 0.0; bv.z2[on + j] = 0.0;
+            bv.left_idx[on + j] = j;
+        }
+        __syncthreads();
+        for (int i = tid; i < m; i += T) {                                   // y3 = f - E x  (:720), z4 = 0 (:648)
+            double acc = 0.0;
+            for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+                double v = bv.x[on + colidx[k]];
+                acc = dA(acc, unit ? v : dM(bv.val_r[ov + k], v));
+            }
+            bv.y3[om + i] = dS(bv.f[om + i], acc);
+            bv.z4[om + i] = 0.0;
+        }
+        // best_bin_obj = b.dot(x_sol) (:726) in Eigen order -- one warp
+        if (tid < 32) {
+            // products staged through the (not yet used) history-free y1 copy is avoided: recompute per lane chain
+            const int lane = tid, k = lane & 3;
+            const int a2 = n & ~3, a1 = n & ~1;
+            double res = 0.0;
+            if (lane < 4) {
+                if (a1 > 2) {
+                    double acc = dM(bv.b[on + k], bv.x[on + k]);
+                    for (int i = 4 + k; i < a2; i += 4) acc = dA(acc, dM(bv.b[on + i], bv.x[on + i]));
+                    double hi = __shfl_down_sync(0xfu, acc, 2);
+                    double l = dA(acc, hi);
+                    if (a1 > a2 && k < 2) l = dA(l, dM(bv.b[on + a2 + k], bv.x[on + a2 + k]));
+                    double l1 = __shfl_down_sync(0xfu, l, 1);
+                    res = dA(l, l1);
+                } else if (a1 == 2) {
+                    res = dA(dM(bv.b[on], bv.x[on]), dM(bv.b[on + 1], bv.x[on + 1]));
+                } else if (n == 1) {
+                    res = dM(bv.b[on], bv.x[on]);
+                }
+                if ((n & 1) && n > 1) res = dA(res, dM(bv.b[on + n - 1], bv.x[on + n - 1]));
+                if (lane == 0) s_best = res;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            st->rho1 = st->rho2 = st->rho4 = pr.initial_rho;                 // :629-636
+            st->prho1 = st->prho2 = st->prho4 = pr.initial_rho;
+            st->gamma = pr.gamma_val; st->ratio = 0.0;
+            st->rhoUpdated = 1; st->std_obj = 1.0; st->cur_obj = 0.0; st->best_bin_obj = s_best;
+            st->sum_fix_obj = 0.0; st->fix_obj = 0.0; st->prev_obj = 0.0; st->prev_sum = 0.0;
+            st->obj_len = 0; st->cg_iters = 0; st->admm_iters = 0; st->iter = 0; st->status = RUNNING; st->done = 0;
+            st->last_ret = 0; st->n_ret = 0; st->fix_sum = 0; st->xit_rows = 0; st->xit_cols = 0; st->norm_small = 0;
+            for (int k = 0; k < 16; ++k) st->obj_ring[k] = 0.0;
+        }
+        __syncthreads();
+    }
+    if (mode & 2) {
+        const double rho1 = st->rho1, rho2 = st->rho2, rho4 = st->rho4;
+        const double D = dA(0.0, dA(rho1, rho2));                            // :2339-2343
+        for (int j = tid; j < n; j += T) {
+            double e = 0.0;                                                  // :2379-2390
+            for (int k = colptr[j]; k < colptr[j + 1]; ++k) {
+                if (unit) e = dA(e, 1.0);
+                else { double v = bv.val_c[ov + k]; if (v != 0.0) e = dA(e, dM(v, v)); }
+            }
+            bv.Esq[on + j] = e;
+            bv.Pd[on + j] = dA(D, dM(rho4, e));                              // :2351, :2391
+        }
+        if (!unit) for (int k = tid; k < st->nnz; k += T) bv.r4v[ov + k] = dM(rho4, bv.val_c[ov + k]);   // :2292-2293
+        __syncthreads();
+        if (tid == 0) { st->D = D; st->r4s = dM(rho4, 1.0); }
+    }
+}
+
+}  // namespace lpb

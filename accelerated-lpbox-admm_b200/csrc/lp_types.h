@@ -1,0 +1,106 @@
+// Shared host/device data layout of the batched LP (inequality) Lp-Box ADMM solver.
+//
+// Everything an instance owns lives in HBM between kernel launches (this is the reference's "solver state lives in
+// the C++ object between solve_iter_l2f calls", LP.h:199-262); a window kernel pulls one instance on chip, runs
+// its iterations entirely in registers / shared memory and writes the state back.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define LPB_HD __host__ __device__ __forceinline__
+#else
+#define LPB_HD inline
+#endif
+
+namespace lpb {
+
+// Hyper-parameters (LP.h:115-146) + loop-variant switches.
+struct Params {
+    double stop_threshold, std_threshold;
+    int max_iters;
+    double initial_rho;
+    int rho_change_step;
+    double gamma_val, learning_fact;
+    int history_size;        // compared as `obj_list.size() >= history_size` (double in the reference; integral values only)
+    double gamma_factor, pcg_tol;
+    int pcg_maxiters;
+    int guard_first_iter;    // LP.cpp:934 + :920-921 (plain LP loop)
+    int alpha_bailout;       // LP.cpp:307
+};
+
+enum Status : int { RUNNING = 0, STOP_Y = 1, STOP_STD = 2, STOP_CG = 3, STOP_EMPTY = 4 };
+
+// Per-instance scalars.  One struct per instance in HBM.
+struct InstState {
+    int n0, m0, nnz0;        // capacities (original problem)
+    int n, m, nnz;           // current (after early fixing) -- get_n()
+    int iter;                // loop variable `iter` as left by the last window (get_iter())
+    int status;              // Status of the last window
+    int done;                // != 0: the reference driver would have stopped calling (ret == 1)
+    int last_ret;            // return value of the last ADMM_lp_iters / _l2f call
+    int rhoUpdated;          // LP.h:208
+    int unit;                // all stored values of E are 1.0
+    int n_ret;               // length of ret_idx_prev / ret_val_prev
+    int fix_sum;
+    int xit_rows, xit_cols;  // shape of x_iters of the last l2f window (LP.cpp:1113), cols actually recorded
+    int norm_small;          // LP.cpp:1223 flag (x_sol.norm() < 1e-3 after a fix)
+    int pad0;
+    double rho1, rho2, rho4, prho1, prho2, prho4, gamma, ratio;
+    double D;                // every diagonal entry of _2A_plus_rho1_rho2 (identical for all j)
+    double r4s;              // unit case: the single value stored in rho4_E_transpose
+    double std_obj, cur_obj, best_bin_obj, sum_fix_obj, fix_obj, prev_obj, prev_sum;
+    long long obj_len;       // obj_list.size()
+    double obj_ring[16];     // last 16 entries of obj_list (history_size <= 16)
+    long long cg_iters, admm_iters;
+};
+
+// Byte layout of one instance's sparsity pattern blob (uint16 indices; both orientations of E).  The blob is the
+// exact shared-memory image, so that one 1-D TMA bulk copy stages it.
+struct PatLayout {
+    int o_rowptr, o_colptr, o_colidx, o_rowidx, bytes;
+};
+LPB_HD int a16(int x) { return (x + 15) & ~15; }
+LPB_HD PatLayout pat_layout(int n0, int m0, int nnz0) {
+    PatLayout L;
+    L.o_rowptr = 0;
+    L.o_colptr = a16(2 * (m0 + 1));
+    L.o_colidx = L.o_colptr + a16(2 * (n0 + 1));
+    L.o_rowidx = L.o_colidx + a16(2 * nnz0);
+    L.bytes = L.o_rowidx + a16(2 * nnz0);
+    return L;
+}
+
+// Device view of a batch.
+struct BatchView {
+    int B;
+    int hist_cap;
+    const long long *off_n;    // [B+1] element offsets of the n-vectors (stride n0 rounded up to 2)
+    const long long *off_m;    // [B+1]
+    const long long *off_pat;  // [B+1] byte offsets of the pattern blobs (16-byte aligned)
+    const long long *off_val;  // [B+1] element offsets of the value arrays (nnz0 each); unused when all unit
+    const long long *off_hist; // [B+1] element offsets of the iterate history (hist_cap * n0 each)
+    double *x, *y1, *y2, *z1, *z2, *b, *Pd, *Esq;  // n-vectors
+    double *y3, *z4, *f;                           // m-vectors
+    unsigned char *pat;
+    double *val_r, *val_c, *r4v;                   // CSR-order values, CSC-order values, CSC-order rho4*E^T values
+    InstState *st;
+    double *hist;                                  // [cc][n0] per instance (iteration-major, coalesced writes)
+    int *left_idx;                                 // [off_n] current -> original variable id
+    int *ret_idx;                                  // [off_n] fixed original ids (ret_idx_prev)
+    double *ret_val;                               // [off_n]
+    const double *pow_tab;                         // pow_tab[k] = pow((double)k, 0.5) from the host libm
+};
+
+struct Launch {
+    int iter_start, iter_end;
+    int l2f;                 // 1: ADMM_lp_iters_l2f semantics (record history, ret=1 on either stop, CG bail-out returns)
+    int skip_done;           // 1: skip instances whose previous call returned "stop" (batch drivers)
+    int n_work;              // number of work items
+    const int *work;         // instance ids (NULL: identity)
+    int *counter;            // atomic work counter (device)
+    int np, mp;              // shared-memory vector strides (>= max n0, m0 of the batch; even)
+    int pat_bytes;           // shared-memory bytes reserved for the pattern blob
+    int val_elems;           // shared-memory doubles reserved per value array (0 when unit)
+};
+
+}  // namespace lpb

@@ -1,0 +1,271 @@
+"""LP (inequality-constrained) solver objects over the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _capi
+from ._capi import check, ptr
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def read_instance(root, i, k, j):
+    """`readFile` (LP.cpp:2446-2545): root/instance/<k>_<j>/instance_<i>_{C,b}.txt -> (m, n, colptr, rowidx, val, b)."""
+    L = _capi.lib()
+    m, n = C.c_int32(), C.c_int32()
+    cp, ri = C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)()
+    va, b = C.POINTER(C.c_double)(), C.POINTER(C.c_double)()
+    check(L.lpbox_read_instance(os.fsencode(root), int(i), int(k), int(j), C.byref(m), C.byref(n), C.byref(cp),
+                                C.byref(ri), C.byref(va), C.byref(b)), "read_instance")
+    try:
+        colptr = np.ctypeslib.as_array(cp, shape=(n.value + 1,)).copy()
+        nnz = int(colptr[-1])
+        rowidx = np.ctypeslib.as_array(ri, shape=(max(nnz, 1),))[:nnz].copy()
+        val = np.ctypeslib.as_array(va, shape=(max(nnz, 1),))[:nnz].copy()
+        bb = np.ctypeslib.as_array(b, shape=(max(n.value, 1),))[:n.value].copy()
+    finally:
+        for p in (cp, ri, va, b):
+            L.lpbox_free(C.cast(p, C.c_void_p))
+    return m.value, n.value, colptr, rowidx, val, bb
+
+
+class LPBatch:
+    """B independent instances `min b'x s.t. Ex<=f, x in {0,1}^n` resident on one GPU.
+
+    `problems`: list of (m, n, colptr, rowidx, val_or_None, b[, f]) with E column-compressed, b as the solver sees it
+    (already negated bid prices, LP.cpp:2520).
+    """
+
+    def __init__(self, problems, device=0, hist_cap=0):
+        L = _capi.lib()
+        self.L = L
+        self.B = len(problems)
+        ms = _i32([p[0] for p in problems])
+        ns = _i32([p[1] for p in problems])
+        colptr = _i32(np.concatenate([np.asarray(p[2]) for p in problems]))
+        rowidx = _i32(np.concatenate([np.asarray(p[3]) for p in problems]))
+        has_val = any(p[4] is not None for p in problems)
+        val = None
+        if has_val:
+            val = _f64(np.concatenate([np.ones(len(p[3])) if p[4] is None else np.asarray(p[4]) for p in problems]))
+        b = _f64(np.concatenate([np.asarray(p[5]) for p in problems]))
+        f = None
+        if any(len(p) > 6 and p[6] is not None for p in problems):
+            f = _f64(np.concatenate([np.ones(p[0]) if (len(p) <= 6 or p[6] is None) else np.asarray(p[6]) for p in problems]))
+        self.org_n = ns.copy()
+        self.h = L.lpbox_batch_create(int(device), self.B, ptr(ms), ptr(ns), ptr(colptr), ptr(rowidx), ptr(val), ptr(b),
+                                      ptr(f), int(hist_cap))
+        if not self.h:
+            raise RuntimeError("lpbox_batch_create failed: " + _capi.last_error())
+        self.h = C.c_void_p(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.lpbox_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, variant=3, **kw):
+        p = _capi.Params()
+        self.L.lpbox_params_lp(C.byref(p))
+        for k, v in kw.items():
+            if not hasattr(p, k):
+                raise TypeError(k)
+            setattr(p, k, v)
+        check(self.L.lpbox_batch_set_params(self.h, C.byref(p), int(variant)), "set_params")
+
+    def init(self, x0=None):
+        x0 = None if x0 is None else _f64(np.concatenate([np.asarray(v) for v in x0]))
+        return check(self.L.lpbox_batch_init(self.h, ptr(x0)), "init")
+
+    def iters(self, start, end):
+        ret = np.zeros(self.B, dtype=np.int32)
+        check(self.L.lpbox_batch_iters(self.h, int(start), int(end), ptr(ret)), "iters")
+        return ret
+
+    def iters_l2f(self, start, end, vecs=None, nums=None):
+        """vecs: list of per-instance fix vectors over the CURRENT variables (or None), nums: per-instance #fixed."""
+        ret = np.zeros(self.B, dtype=np.int32)
+        if nums is None:
+            nums = np.zeros(self.B, dtype=np.int32)
+        nums = _i32(nums)
+        vec = None
+        if vecs is not None and np.any(nums != 0):
+            parts = []
+            for i in range(self.B):
+                n = self.get_n(i)
+                v = np.full(n, -1.0) if (vecs[i] is None or nums[i] == 0) else _f64(vecs[i])[:n]
+                parts.append(v)
+            vec = _f64(np.concatenate(parts))
+        check(self.L.lpbox_batch_iters_l2f(self.h, int(start), int(end), ptr(vec), ptr(nums), ptr(ret)), "iters_l2f")
+        return ret
+
+    def solve(self, max_iters=20000):
+        log = np.zeros(self.B, dtype=_capi.LOG_DTYPE)
+        check(self.L.lpbox_batch_solve(self.h, int(max_iters), ptr(log)), "solve")
+        return log
+
+    def results(self, want_bits=True):
+        log = np.zeros(self.B, dtype=_capi.LOG_DTYPE)
+        stride = (int(self.org_n.max()) + 7) // 8
+        bits = np.zeros((self.B, stride), dtype=np.uint8) if want_bits else None
+        check(self.L.lpbox_batch_results(self.h, ptr(log), ptr(bits), stride), "results")
+        return log, bits
+
+    def get_n(self, i=0):
+        return check(self.L.lpbox_batch_get_n(self.h, i))
+
+    def get_m(self, i=0):
+        return check(self.L.lpbox_batch_get_m(self.h, i))
+
+    def get_iter(self, i=0):
+        return check(self.L.lpbox_batch_get_iter(self.h, i))
+
+    def cal_obj(self, i=0):
+        return self.L.lpbox_batch_cal_obj(self.h, i)
+
+    def cur_bin_obj(self, i=0):
+        return self.L.lpbox_batch_get_cur_bin_obj(self.h, i)
+
+    def x_sol(self, i=0, out=None):
+        out = np.zeros(int(self.org_n[i])) if out is None else out
+        check(self.L.lpbox_batch_get_x_sol(self.h, i, ptr(out)), "get_x_sol")
+        return out
+
+    def final_x_sol(self, i=0):
+        out = np.zeros(max(self.get_n(i), 1))
+        n = check(self.L.lpbox_batch_get_final_x_sol(self.h, i, ptr(out)), "get_final_x_sol")
+        return out[:n]
+
+    def x_iters(self, i, ws):
+        rows = self.get_n(i)
+        out = np.zeros((max(rows, 1), int(ws)))
+        r = check(self.L.lpbox_batch_get_x_iters(self.h, i, int(ws), ptr(out)), "get_x_iters")
+        return out[:r]
+
+    def state(self, i=0):
+        n, m = self.get_n(i), self.get_m(i)
+        vs = [np.zeros(max(n, 1)) for _ in range(5)] + [np.zeros(max(m, 1)) for _ in range(2)]
+        check(self.L.lpbox_batch_get_state(self.h, i, *[ptr(v) for v in vs]), "get_state")
+        names = ("x", "y1", "y2", "z1", "z2", "y3", "z4")
+        return {k: (v[:n] if j < 5 else v[:m]) for j, (k, v) in enumerate(zip(names, vs))}
+
+    def check_infeasible_lpbox(self, i=0):
+        return check(self.L.lpbox_batch_check_infeasible_lpbox(self.h, i))
+
+    def check_infeasible_l2f(self, i=0):
+        return check(self.L.lpbox_batch_check_infeasible_l2f(self.h, i))
+
+    def last_kernel_ms(self):
+        return self.L.lpbox_batch_last_kernel_ms(self.h)
+
+    def launch_count(self):
+        return self.L.lpbox_batch_launch_count(self.h)
+
+
+class PyLPboxADMMsolver:
+    """Drop-in for `lpbox.PyLPboxADMMsolver` of the LP experiment (LP.pyx:7-76).
+
+    Same methods, argument meaning and return values; callers may pass float-valued ints (`solve_iter(0, 1e4)`,
+    test.py:10).  In addition to `read_File`, `set_problem` accepts an in-memory problem.  The data root that
+    `readFile` hard-codes as "../cython_solver/data" (LP.cpp:2451) can be overridden with $LPBOX_DATA_ROOT.
+    """
+
+    def __init__(self, print_info=0, fix_threshold=None):
+        # LP.pyx:10-14: the (consistency, fix_threshold) constructor is shadowed by the (print_info) one
+        self.print_info = int(print_info)
+        self._batch = None
+        self._problem = None
+        self._device = int(os.environ.get("LPBOX_DEVICE", "0"))
+        self._hist_cap = 500    # x_iters = Zero(n, 500)  (LP.cpp:1113)
+
+    # -- problem in ------------------------------------------------------------------------------------------
+    def read_File(self, i, k, j):
+        root = os.environ.get("LPBOX_DATA_ROOT", "../cython_solver/data")
+        m, n, colptr, rowidx, val, b = read_instance(root, int(i), int(k), int(j))
+        self._problem = (m, n, colptr, rowidx, val, b, np.ones(m))     # f = 1 (LP.cpp:2522)
+        self._batch = None
+
+    def set_problem(self, m, n, colptr, rowidx, val, b, f=None):
+        """In-memory alternative to read_File: E column-compressed, b as the solver sees it (negated bids)."""
+        self._problem = (int(m), int(n), _i32(colptr), _i32(rowidx), None if val is None else _f64(val), _f64(b),
+                         None if f is None else _f64(f))
+        self._batch = None
+
+    def _need(self):
+        if self._batch is None:
+            raise RuntimeError("solve_init() has not been called")
+        return self._batch
+
+    # -- solve ------------------------------------------------------------------------------------------------
+    def solve_init(self):
+        if self._problem is None:
+            raise RuntimeError("no problem loaded (read_File / set_problem)")
+        if self._batch is not None:
+            self._batch.close()
+        self._batch = LPBatch([self._problem], device=self._device, hist_cap=self._hist_cap)
+        return self._batch.init()
+
+    def solve_iter(self, i, j):
+        return int(self._need().iters(int(i), int(j))[0])
+
+    def solve_iter_l2f(self, i, j, vec, num):
+        vec = _f64(vec)
+        return int(self._need().iters_l2f(int(i), int(j), [vec], [int(num)])[0])
+
+    # -- results ----------------------------------------------------------------------------------------------
+    def cal_Obj(self):
+        return self._need().cal_obj(0)
+
+    def get_curBinObj(self):
+        return self._need().cur_bin_obj(0)
+
+    def get_x_iters_2d(self, ws):
+        return self._need().x_iters(0, int(ws))
+
+    def get_x_iters_1d(self, ws):
+        # LP.pyx:35-41 returns the first n*20 entries of the row-major (n x ws) buffer as a column
+        n = self.get_n()
+        flat = self._need().x_iters(0, int(ws)).reshape(-1)
+        out = np.zeros((n * 20, 1))
+        k = min(n * 20, flat.size)
+        out[:k, 0] = flat[:k]
+        return out
+
+    def get_n(self):
+        return self._need().get_n(0)
+
+    def get_iter(self):
+        return self._need().get_iter(0)
+
+    def get_x_sol(self, n):
+        out = np.zeros(max(int(n), int(self._batch.org_n[0])))
+        self._need().x_sol(0, out)
+        return out[:int(n)].reshape(-1, 1)
+
+    def get_final_x_sol(self, n):
+        x = self._need().final_x_sol(0)
+        out = np.zeros((int(n), 1))
+        k = min(int(n), x.size)
+        out[:k, 0] = x[:k]
+        return out
+
+    def check_infeasible_lpbox(self):
+        return self._need().check_infeasible_lpbox(0)
+
+    def check_infeasible_l2f(self):
+        return self._need().check_infeasible_l2f(0)

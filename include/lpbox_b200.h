@@ -1,0 +1,149 @@
+/*
+ * lpbox_b200 -- C ABI of the B200-native Lp-Box ADMM solver (drop-in for the reference's solver objects).
+ *
+ * Reference aliases (all under the upstream tree):
+ *   LP.cpp / LP.h / LP.pxd / LP.pyx = LinerProgramming/LinearProgramming/cython_solver/{LPboxADMMsolver.cpp,.h,.pxd,lpbox.pyx}
+ *   SEG.cpp / SEG.pxd / SEG.pyx     = Segmentation/Segmentation/cython/src/{LPboxADMMsolver.cpp,.pxd,lpbox.pyx}
+ *
+ * Every entry point below replaces one method the reference's Cython layer binds (LP.pxd:4-21, SEG.pxd:4-17);
+ * the method it replaces is cited next to it.  Plain pointers and sizes only; all buffers are HOST memory owned by
+ * the caller unless the name says `_dev`.  Functions return >= 0 on success (the reference's own return value where
+ * it has one) and a negative LPBOX_E_* code on error.  There is no CPU fallback: if no CUDA device is usable the
+ * create functions fail with LPBOX_E_CUDA.
+ *
+ * Threading: a handle is stateful and not re-entrant (like the reference object); different handles may be used
+ * from different threads.  One handle = one CUDA stream.
+ */
+#ifndef LPBOX_B200_H
+#define LPBOX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LPBOX_E_INVALID      (-1)  /* bad argument / wrong call order */
+#define LPBOX_E_CUDA         (-2)  /* CUDA runtime error (see lpbox_last_error) */
+#define LPBOX_E_UNSUPPORTED  (-3)  /* problem too large for the on-chip kernels */
+#define LPBOX_E_IO           (-4)  /* file could not be read */
+
+typedef struct lpbox_batch lpbox_batch;   /* B independent instances resident in HBM */
+
+/* hyper-parameters of the iteration (LP.h:115-146).  lpbox_params_lp() = LP.cpp:491-507,
+ * lpbox_params_seg() = SEG.cpp:659-672. */
+typedef struct lpbox_params {
+    double stop_threshold;
+    double std_threshold;
+    int    max_iters;
+    double initial_rho;
+    int    rho_change_step;
+    double gamma_val;
+    double learning_fact;
+    double history_size;
+    double projection_lp;
+    double gamma_factor;
+    double pcg_tol;
+    int    pcg_maxiters;
+} lpbox_params;
+
+void lpbox_params_lp(lpbox_params *p);
+void lpbox_params_seg(lpbox_params *p);
+
+/* per-instance result row ("iteration log out"; the reference writes file_idx,-obj,iters,seconds to allres.csv,
+ * LP.cpp:1081) */
+typedef struct lpbox_log_row {
+    int32_t iters;        /* ADMM iterations executed */
+    int32_t status;       /* 0 = ran to iter_end, 1 = ||x-y1||,||x-y2|| stop, 2 = objective-std stop, 3 = CG alpha<0, 4 = all variables fixed */
+    int64_t cg_iters;     /* total CG iterations */
+    double  obj;          /* cal_obj(): sum_fix_obj + cur_obj (minimised, i.e. -revenue)  LP.cpp:1630-1642 */
+    double  cur_bin_obj;  /* get_curBinObj()  LP.cpp:1644 */
+    int32_t n_left;       /* variables still free */
+    int32_t infeasible;   /* violated rows of E_orig x <= 1 for the assembled binary x (check_infeasible_l2f, LP.cpp:1593-1612) */
+} lpbox_log_row;
+
+const char *lpbox_last_error(void);
+int  lpbox_device_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Batched LP (inequality-constrained) solver:   min b'x  s.t.  E x <= f,  x in {0,1}^n        (configs 1, 2, 5)
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* Creates B instances on `device`.  Instance i has m[i] rows, n[i] columns; its matrix is column-compressed
+ * (what readFile/readSparseMat build, LP.cpp:2416-2444): colptr_all holds the B colptr arrays back to back
+ * (n[i]+1 entries each, each starting at 0), rowidx_all / val_all the concatenated row indices (strictly ascending
+ * inside a column) / values.  val_all == NULL means all stored entries are 1.0 (auction instances,
+ * generate_instances.py:359).  b_all: concatenated objective vectors as the SOLVER sees them (readFile negates the
+ * bid prices, LP.cpp:2520).  f_all == NULL means f = 1 (LP.cpp:2522).  hist_cap = number of iterates per window
+ * kept for get_x_iters (the reference keeps 500 columns, LP.cpp:1113); 0 disables the history.
+ * Replaces: LPboxADMMsolver(int) + readFile  (LP.pxd:7,9). */
+lpbox_batch *lpbox_batch_create(int device, int B, const int32_t *m, const int32_t *n, const int32_t *colptr_all,
+                                const int32_t *rowidx_all, const double *val_all, const double *b_all,
+                                const double *f_all, int hist_cap);
+void lpbox_batch_destroy(lpbox_batch *h);
+
+/* Overrides the hyper-parameters that lpbox_batch_init() would set (header setters LP.h:511-575).
+ * variant bit 0: keep the plain loop's `iter != iter_start` guard + z4 assignment (LP.cpp:934,:920-921);
+ * variant bit 1: keep the CG alpha<0 bail-out (LP.cpp:307).  Default after create: both set (LP behaviour);
+ * 0 reproduces the generic ADMM_bqp loop of SEG.cpp:1590-1760. */
+int lpbox_batch_set_params(lpbox_batch *h, const lpbox_params *p, int variant);
+
+/* ADMM_lp_iters_init (LP.cpp:489-763) for every instance; x0_all == NULL means x = 1 (LP.cpp:583-586). */
+int lpbox_batch_init(lpbox_batch *h, const double *x0_all);
+
+/* ADMM_lp_iters(iter_start, iter_end) (LP.cpp:766-1095) for every instance that has not stopped.
+ * ret[i] (may be NULL) receives the reference's return value (1 only for the objective-std stop). */
+int lpbox_batch_iters(lpbox_batch *h, int iter_start, int iter_end, int32_t *ret);
+
+/* ADMM_lp_iters_l2f(iter_start, iter_end, vec, num) (LP.cpp:1098-1574).  vec_all: concatenated fix vectors over the
+ * CURRENT variables of each instance (n_cur[i] entries in {1,0,-1}); num[i] = number of entries != -1 (0 = no fix;
+ * vec of that instance is then ignored, as in the reference).  vec_all may be NULL if every num[i] is 0.
+ * Instances whose previous call returned 1 are skipped (the reference driver stops calling, LP.trainer:521). */
+int lpbox_batch_iters_l2f(lpbox_batch *h, int iter_start, int iter_end, const double *vec_all, const int32_t *num,
+                          int32_t *ret);
+
+/* Whole window loop on the device (LP.trainer:510-535) with fix vectors produced by thresholding caller-supplied
+ * scores: after each window of `ws` iterations the callback-free variant below applies
+ * deter_fix_2 (LP.trainer:101-135: p>0.9 -> 1, p<0.1 -> 0, else -1; fewer than 11 fixes -> none) to scores computed
+ * by the built-in policy kernel (lpbox_batch_set_policy) -- see lpbox_batch_solve_l2f. */
+int lpbox_batch_solve(lpbox_batch *h, int max_iters, lpbox_log_row *log /* B rows, may be NULL */);
+
+/* getters; `i` = instance index ---------------------------------------------------------------------------------- */
+int lpbox_batch_size(const lpbox_batch *h);
+int lpbox_batch_get_n(lpbox_batch *h, int i);            /* get_n()      LP.h:392 */
+int lpbox_batch_get_m(lpbox_batch *h, int i);
+int lpbox_batch_get_org_n(lpbox_batch *h, int i);
+int lpbox_batch_get_iter(lpbox_batch *h, int i);         /* get_iter()   LP.h:357 */
+double lpbox_batch_cal_obj(lpbox_batch *h, int i);       /* cal_obj()    LP.cpp:1630-1642 */
+double lpbox_batch_get_cur_bin_obj(lpbox_batch *h, int i); /* get_curBinObj() LP.cpp:1644 */
+/* get_x_sol(): binary solution in original indexing, out has org_n entries; entries the reference leaves
+ * uninitialised keep the caller's value  (LP.cpp:1648-1665) */
+int lpbox_batch_get_x_sol(lpbox_batch *h, int i, double *out);
+/* get_final_x_sol(): relaxed x of the current (compacted) problem, n entries  (LP.cpp:1668-1685) */
+int lpbox_batch_get_final_x_sol(lpbox_batch *h, int i, double *out);
+/* get_x_iters_d(ws): row-major (n_cur x ws) window history  (LP.cpp:1616-1627).  Returns n_cur. */
+int lpbox_batch_get_x_iters(lpbox_batch *h, int i, int ws, double *out);
+int lpbox_batch_check_infeasible_lpbox(lpbox_batch *h, int i);  /* LP.cpp:1577-1591 */
+int lpbox_batch_check_infeasible_l2f(lpbox_batch *h, int i);    /* LP.cpp:1593-1612 */
+/* full iterate state of instance i (any pointer may be NULL): x,y1,y2,z1,z2 (n), y3,z4 (m) -- parity sweeps */
+int lpbox_batch_get_state(lpbox_batch *h, int i, double *x, double *y1, double *y2, double *z1, double *z2,
+                          double *y3, double *z4);
+/* one log row per instance, plus packed binary solutions (bit j of byte j/8 of row i; row stride = (max org_n+7)/8)
+ * -- the "final gather" payload of SURVEY.md §8e.  Either pointer may be NULL. */
+int lpbox_batch_results(lpbox_batch *h, lpbox_log_row *log, uint8_t *x_bits, int row_stride_bytes);
+/* device time (ms, CUDA events on the handle's stream) and number of kernel launches of the last solve/iters call */
+double lpbox_batch_last_kernel_ms(const lpbox_batch *h);
+int64_t lpbox_batch_launch_count(const lpbox_batch *h);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * File format of the reference: data/instance/<k>_<j>/instance_<i>_{C,b}.txt under `root`
+ * (readFile, LP.cpp:2446-2545).  Arrays are malloc()ed by the library; release with lpbox_free().
+ * ------------------------------------------------------------------------------------------------------------- */
+int lpbox_read_instance(const char *root, int i, int k, int j, int32_t *m, int32_t *n, int32_t **colptr,
+                        int32_t **rowidx, double **val, double **b);
+void lpbox_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LPBOX_B200_H */
