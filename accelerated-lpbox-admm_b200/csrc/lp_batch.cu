@@ -227,6 +227,17 @@ extern "C" lpbox_batch *lpbox_batch_create(int device, int B, const int32_t *m, 
                 colidx[q] = (uint16_t)j;
                 if (!h->all_unit) { val_r[(size_t)h->off_val[i] + q] = va[k]; val_c[(size_t)h->off_val[i] + k] = va[k]; }
             }
+        {   // SpMV work assignment: slots sorted by descending stored length (stable)
+            uint16_t *rowperm = (uint16_t *)(blob + PL.o_rowperm), *colperm = (uint16_t *)(blob + PL.o_colperm);
+            std::vector<int> ord(mi);
+            for (int r = 0; r < mi; ++r) ord[r] = r;
+            std::stable_sort(ord.begin(), ord.end(), [&](int a, int b2) { return (rcount[a + 1] - rcount[a]) > (rcount[b2 + 1] - rcount[b2]); });
+            for (int r = 0; r < mi; ++r) rowperm[r] = (uint16_t)ord[r];
+            ord.resize(ni);
+            for (int j = 0; j < ni; ++j) ord[j] = j;
+            std::stable_sort(ord.begin(), ord.end(), [&](int a, int b2) { return (cp[a + 1] - cp[a]) > (cp[b2 + 1] - cp[b2]); });
+            for (int j = 0; j < ni; ++j) colperm[j] = (uint16_t)ord[j];
+        }
         memcpy(bvec.data() + h->off_n[i], b_all + boff, sizeof(double) * (size_t)ni);
         if (f_all) memcpy(fvec.data() + h->off_m[i], f_all + foff, sizeof(double) * (size_t)mi);
         boff += ni; foff += mi;

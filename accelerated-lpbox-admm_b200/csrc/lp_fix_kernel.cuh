@@ -188,6 +188,16 @@ lp_fix_kernel(BatchView bv, Params pr, const double *__restrict__ vec, const lon
     }
     if (tid == 0) g_colptr[k_tot] = (u16)nnz_new;
     __syncthreads();
+    // column work assignment: stable filter of the old (length-sorted) slot order, renumbered
+    {
+        const u16 *colperm = reinterpret_cast<const u16 *>(spat + PL.o_colperm);
+        u16 *g_colperm = reinterpret_cast<u16 *>(gpat + PL.o_colperm);
+        for (int s2 = tid; s2 < n; s2 += FIX_T) cnt[s2] = is_fixed(colperm[s2]) ? 0 : 1;
+        __syncthreads();
+        block_exscan(cnt, n, part);
+        for (int s2 = tid; s2 < n; s2 += FIX_T) { int c = colperm[s2]; if (!is_fixed(c)) g_colperm[cnt[s2]] = (u16)kidx[c]; }
+    }
+    __syncthreads();
     __threadfence_block();
     // 9. update_expression with the current rho (:1329, :2289-2404) on the new column-compressed pattern
     const double rho1 = st->rho1, rho2 = st->rho2, rho4 = st->rho4;

@@ -99,30 +99,40 @@ __device__ __forceinline__ double warp_redux_eigen(const double *red, int stride
 }
 
 // ---- sequential sparse dot products -------------------------------------------------------------------------------
-// acc[e] = ((0 + c_1 v[i_1]) + c_2 v[i_2]) + ...  over the stored entries of outer index o_e = tid + e*T, ascending
-// inner index.  Coefficient: COEF 0 -> 1 (unit E), 1 -> scale (unit rho4 E^T), 2 -> val[pos].
-// The EPT chains of a thread are advanced in lock step so that their (dependent) adds overlap.
-template <int T, int EPT, int COEF>
-__device__ __forceinline__ void seq_spmv(const u16 *__restrict__ ptr, const u16 *__restrict__ idx, const double *__restrict__ val,
-                                         double scale, const double *__restrict__ v, int count, double (&acc)[EPT]) {
-    int pos[EPT], end[EPT];
-    int maxlen = 0;
-    LPB_FOR_E {
-        int o = threadIdx.x + e * T;
-        if (o < count) { pos[e] = ptr[o]; end[e] = ptr[o + 1]; } else { pos[e] = 0; end[e] = 0; }
-        maxlen = max(maxlen, end[e] - pos[e]);
-        acc[e] = 0.0;
+// acc = ((0 + c_1 v[i_1]) + c_2 v[i_2]) + ...  over the stored entries [beg, end) of ONE row (or column), ascending
+// inner index.  Coefficient: COEF 0 -> 1 (unit E), 1 -> scale (unit rho4 E^T), 2 -> val[k].
+// Loads are batched four at a time (independent), only the adds form the dependent chain.
+template <int COEF>
+__device__ __forceinline__ double seq_dot(const u16 *__restrict__ idx, const double *__restrict__ val, double scale,
+                                          const double *__restrict__ v, int beg, int end) {
+    double acc = 0.0;
+    int k = beg;
+#pragma unroll 1
+    for (; k + 4 <= end; k += 4) {
+        const int i0 = idx[k], i1 = idx[k + 1], i2 = idx[k + 2], i3 = idx[k + 3];
+        double t0 = v[i0], t1 = v[i1], t2 = v[i2], t3 = v[i3];
+        if (COEF == 1) { t0 = dM(scale, t0); t1 = dM(scale, t1); t2 = dM(scale, t2); t3 = dM(scale, t3); }
+        if (COEF == 2) { t0 = dM(val[k], t0); t1 = dM(val[k + 1], t1); t2 = dM(val[k + 2], t2); t3 = dM(val[k + 3], t3); }
+        acc = dA(acc, t0); acc = dA(acc, t1); acc = dA(acc, t2); acc = dA(acc, t3);
     }
-    for (int k = 0; k < maxlen; ++k) {
-        LPB_FOR_E {
-            if (pos[e] < end[e]) {
-                double t = v[idx[pos[e]]];
-                if (COEF == 1) t = dM(scale, t);
-                if (COEF == 2) t = dM(val[pos[e]], t);
-                acc[e] = dA(acc[e], t);
-                pos[e]++;
-            }
-        }
+#pragma unroll 1
+    for (; k < end; ++k) {
+        double t = v[idx[k]];
+        if (COEF == 1) t = dM(scale, t);
+        if (COEF == 2) t = dM(val[k], t);
+        acc = dA(acc, t);
+    }
+    return acc;
+}
+// out[o] = seq_dot(outer index o) for every o < count; slot s = tid + e*T handles o = perm[s] (length-sorted).
+template <int T, int EPT, int COEF>
+__device__ __forceinline__ void seq_spmv_to_smem(const u16 *__restrict__ perm, const u16 *__restrict__ ptr,
+                                                 const u16 *__restrict__ idx, const double *__restrict__ val, double scale,
+                                                 const double *__restrict__ v, int count, double *__restrict__ out) {
+#pragma unroll 1
+    for (int s = threadIdx.x; s < count; s += T) {
+        const int o = perm[s];
+        out[o] = seq_dot<COEF>(idx, val, scale, v, ptr[o], ptr[o + 1]);
     }
 }
 
@@ -130,6 +140,7 @@ __device__ __forceinline__ void seq_spmv(const u16 *__restrict__ ptr, const u16 
 struct Smem {
     double *gv;      // [np]   vector being gathered by E v (x or p)
     double *red;     // [5][np] reduction operands
+    double *oc;      // [np]   result of a column-wise (E^T-type) product, read back by the element owners
     double *t1;      // [mp]   E v
     double *wa;      // [mp]   f - y3
     double *wb;      // [mp]   z4
@@ -140,7 +151,7 @@ struct Smem {
     uint64_t *bar;
 };
 __host__ __device__ inline size_t smem_bytes(int np, int mp, int pat_bytes, int val_elems) {
-    size_t d = (size_t)np * 6 + (size_t)mp * 3 + 8 + 16 + (size_t)val_elems * 3;
+    size_t d = (size_t)np * 7 + (size_t)mp * 3 + 8 + 16 + (size_t)val_elems * 3;
     return d * sizeof(double) + (size_t)pat_bytes + 16;
 }
 __device__ __forceinline__ Smem carve(unsigned char *base, int np, int mp, int pat_bytes, int val_elems) {
@@ -148,6 +159,7 @@ __device__ __forceinline__ Smem carve(unsigned char *base, int np, int mp, int p
     double *d = reinterpret_cast<double *>(base);
     s.gv = d; d += np;
     s.red = d; d += 5 * (size_t)np;
+    s.oc = d; d += np;
     s.t1 = d; d += mp;
     s.wa = d; d += mp;
     s.wb = d; d += mp;
@@ -198,7 +210,9 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
     __shared__ int s_work;
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
-    constexpr int RW = T / 32 - 1;  // the warp that runs the reductions (owns the fewest rows)
+    constexpr int RW = T / 32 - 1;  // the warp that runs the reductions (its SpMV slots hold the shortest rows)
+    constexpr int CE = UNIT ? 0 : 2;   // coefficient mode of products with E / E^T
+    constexpr int CR = UNIT ? 1 : 2;   // coefficient mode of products with rho4 E^T
     const int np = la.np;
     uint32_t tma_phase = 0;
 
@@ -224,18 +238,20 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
             tma_load_1d(S.pat, bv.pat + bv.off_pat[inst], (uint32_t)PL.bytes, S.bar);
         }
         const long long on = bv.off_n[inst], om = bv.off_m[inst];
-        double x[EPT], y1[EPT], y2[EPT], z1[EPT], z2[EPT], r[EPT], p[EPT], invd[EPT], bb[EPT];
-        double y3[EPT], z4[EPT], ff[EPT];
+        const double *__restrict__ gb = bv.b + on;    // read-only during a window
+        const double *__restrict__ gf = bv.f + om;
+        double x[EPT], y1[EPT], y2[EPT], z1[EPT], z2[EPT], r[EPT], p[EPT], invd[EPT];
+        double y3[EPT], z4[EPT];
         LPB_FOR_E {
             int j = tid + e * T;
             bool in = j < n;
             x[e] = in ? bv.x[on + j] : 0.0;   y1[e] = in ? bv.y1[on + j] : 0.0; y2[e] = in ? bv.y2[on + j] : 0.0;
-            z1[e] = in ? bv.z1[on + j] : 0.0; z2[e] = in ? bv.z2[on + j] : 0.0; bb[e] = in ? bv.b[on + j] : 0.0;
+            z1[e] = in ? bv.z1[on + j] : 0.0; z2[e] = in ? bv.z2[on + j] : 0.0;
             double pd = in ? bv.Pd[on + j] : 1.0;
             invd[e] = (pd != 0.0) ? dD(1.0, pd) : 1.0;   // value in use when rhoUpdated == 0 (Eigen: zero diagonal -> 1)
             r[e] = 0.0; p[e] = 0.0;
             bool rin = j < m;
-            y3[e] = rin ? bv.y3[om + j] : 0.0; z4[e] = rin ? bv.z4[om + j] : 0.0; ff[e] = rin ? bv.f[om + j] : 0.0;
+            y3[e] = rin ? bv.y3[om + j] : 0.0; z4[e] = rin ? bv.z4[om + j] : 0.0;
         }
         double rho1 = stp->rho1, rho2 = stp->rho2, rho4 = stp->rho4, prho1 = stp->prho1, prho2 = stp->prho2,
                prho4 = stp->prho4, gamma = stp->gamma, ratio = stp->ratio, D = stp->D, r4s = stp->r4s,
@@ -255,6 +271,8 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
         const u16 *colptr = reinterpret_cast<const u16 *>(S.pat + PL.o_colptr);
         const u16 *colidx = reinterpret_cast<const u16 *>(S.pat + PL.o_colidx);
         const u16 *rowidx = reinterpret_cast<const u16 *>(S.pat + PL.o_rowidx);
+        const u16 *rowperm = reinterpret_cast<const u16 *>(S.pat + PL.o_rowperm);
+        const u16 *colperm = reinterpret_cast<const u16 *>(S.pat + PL.o_colperm);
         const double pow_n = bv.pow_tab[n];               // std::pow(n, 1.0/p), p = 2 (LP.cpp:427)
         double *red0 = S.red, *red1 = S.red + np, *red2 = S.red + 2 * np, *red3 = S.red + 3 * np, *red4 = S.red + 4 * np;
 
@@ -264,7 +282,6 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
         const bool lp_plain = (!la.l2f) && pr.guard_first_iter;
 
         for (; iter < la.iter_end; ++iter) {
-            double acc[EPT];
             // ---- y1 (LP.cpp:806-809), y2 pre-image (:815, :424), gather x -------------------------------------
             LPB_FOR_E {
                 int j = tid + e * T;
@@ -274,12 +291,12 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                 if (j < n) { red0[j] = dM(y2[e], y2[e]); S.gv[j] = x[e]; }
             }
             __syncthreads();
-            // ---- ||y|| (:425) on the reduction warp, E x (:825) on the row owners ------------------------------
+            // ---- ||y|| (:425) on the reduction warp, E x (:825) on the row slots -------------------------------
             if (warp == RW) {
                 double v = warp_redux_eigen<1>(red0, np, n);
                 if ((tid & 31) == 0) S.sc[0] = v;
             }
-            seq_spmv<T, EPT, UNIT ? 0 : 2>(rowptr, colidx, S.val_r, 0.0, S.gv, m, acc);
+            seq_spmv_to_smem<T, EPT, CE>(rowperm, rowptr, colidx, S.val_r, 0.0, S.gv, m, S.t1);
             __syncthreads();
             {
                 const double nrm = sqrt(S.sc[0]);
@@ -289,9 +306,12 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
             // ---- y3 (:826-827) -------------------------------------------------------------------------------
             LPB_FOR_E {
                 int i = tid + e * T;
-                double t = dS(dS(ff[e], acc[e]), dD(z4[e], rho4));
-                y3[e] = (t < 0.0) ? 0.0 : t;
-                if (i < m) { S.wa[i] = dS(ff[e], y3[e]); S.wb[i] = z4[e]; }
+                if (i < m) {
+                    const double fi = gf[i];
+                    double t = dS(dS(fi, S.t1[i]), dD(z4[e], rho4));
+                    y3[e] = (t < 0.0) ? 0.0 : t;
+                    S.wa[i] = dS(fi, y3[e]); S.wb[i] = z4[e];
+                }
             }
             // ---- operator patch after a rho step (:851-866) and preconditioner refresh (:883-890) --------------
             if (iter != 0 && rhoUpdated) {
@@ -319,36 +339,40 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                 rhoUpdated = 0;
             }
             __syncthreads();
-            // ---- rhs (:872-878) -------------------------------------------------------------------------------
-            double rhs[EPT];
-            LPB_FOR_E rhs[e] = dS(dA(dM(rho1, y1[e]), dM(rho2, y2[e])), dA(dA(bb[e], z1[e]), z2[e]));
-            seq_spmv<T, EPT, UNIT ? 1 : 2>(colptr, rowidx, S.r4v, r4s, S.wa, n, acc);
-            LPB_FOR_E rhs[e] = dA(rhs[e], acc[e]);
-            seq_spmv<T, EPT, UNIT ? 0 : 2>(colptr, rowidx, S.val_c, 0.0, S.wb, n, acc);
-            LPB_FOR_E rhs[e] = dS(rhs[e], acc[e]);
+            // ---- rhs (:872-878): two column-wise products, results through shared memory ------------------------
+            seq_spmv_to_smem<T, EPT, CR>(colperm, colptr, rowidx, S.r4v, r4s, S.wa, n, S.oc);      // R4ET (f - y3)
+            seq_spmv_to_smem<T, EPT, CE>(colperm, colptr, rowidx, S.val_c, 0.0, S.wb, n, red4);   // ET z4
+            __syncthreads();
             // ---- PCG (:251-335), warm start x = y1 (:892) ------------------------------------------------------
-            double xc[EPT];
+            double rhs[EPT], xc[EPT];
             LPB_FOR_E {
                 int j = tid + e * T;
-                xc[e] = y1[e];
-                if (j < n) { S.gv[j] = xc[e]; red0[j] = dM(rhs[e], rhs[e]); }
+                if (j < n) {
+                    double t = dS(dA(dM(rho1, y1[e]), dM(rho2, y2[e])), dA(dA(gb[j], z1[e]), z2[e]));
+                    t = dA(t, S.oc[j]);
+                    rhs[e] = dS(t, red4[j]);
+                    xc[e] = y1[e];
+                    S.gv[j] = xc[e]; red0[j] = dM(rhs[e], rhs[e]);
+                } else { rhs[e] = 0.0; xc[e] = 0.0; }
             }
             __syncthreads();
             if (warp == RW) {
                 double v = warp_redux_eigen<1>(red0, np, n);               // rhs.squaredNorm() :277
                 if ((tid & 31) == 0) S.sc[0] = v;
             }
-            seq_spmv<T, EPT, UNIT ? 0 : 2>(rowptr, colidx, S.val_r, 0.0, S.gv, m, acc);
-            LPB_FOR_E { int i = tid + e * T; if (i < m) S.t1[i] = acc[e]; }
+            seq_spmv_to_smem<T, EPT, CE>(rowperm, rowptr, colidx, S.val_r, 0.0, S.gv, m, S.t1);
             __syncthreads();
             const double rhsNorm2 = S.sc[0];
-            seq_spmv<T, EPT, UNIT ? 1 : 2>(colptr, rowidx, S.r4v, r4s, S.t1, n, acc);
+            seq_spmv_to_smem<T, EPT, CR>(colperm, colptr, rowidx, S.r4v, r4s, S.t1, n, S.oc);
+            __syncthreads();
             LPB_FOR_E {
                 int j = tid + e * T;
-                double mv = dA(dA(0.0, dM(D, xc[e])), acc[e]);               // D v (+) R4ET (E v)   :115-162
-                r[e] = dS(rhs[e], mv);                                       // :273
-                p[e] = dM(invd[e], r[e]);                                    // :297
-                if (j < n) { red1[j] = dM(r[e], r[e]); red2[j] = dM(r[e], p[e]); }
+                if (j < n) {
+                    double mv = dA(dA(0.0, dM(D, xc[e])), S.oc[j]);          // D v (+) R4ET (E v)   :115-162
+                    r[e] = dS(rhs[e], mv);                                   // :273
+                    p[e] = dM(invd[e], r[e]);                                // :297
+                    red1[j] = dM(r[e], r[e]); red2[j] = dM(r[e], p[e]);
+                }
             }
             __syncthreads();
             if (warp == RW) {
@@ -371,15 +395,17 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                     while (cg_it < pr.pcg_maxiters) {
                         LPB_FOR_E { int j = tid + e * T; if (j < n) S.gv[j] = p[e]; }
                         __syncthreads();
-                        seq_spmv<T, EPT, UNIT ? 0 : 2>(rowptr, colidx, S.val_r, 0.0, S.gv, m, acc);
-                        LPB_FOR_E { int i = tid + e * T; if (i < m) S.t1[i] = acc[e]; }
+                        seq_spmv_to_smem<T, EPT, CE>(rowperm, rowptr, colidx, S.val_r, 0.0, S.gv, m, S.t1);
                         __syncthreads();
-                        seq_spmv<T, EPT, UNIT ? 1 : 2>(colptr, rowidx, S.r4v, r4s, S.t1, n, acc);
+                        seq_spmv_to_smem<T, EPT, CR>(colperm, colptr, rowidx, S.r4v, r4s, S.t1, n, S.oc);
+                        __syncthreads();
                         double tmp[EPT];
                         LPB_FOR_E {
                             int j = tid + e * T;
-                            tmp[e] = dA(dA(0.0, dM(D, p[e])), acc[e]);       // :304
-                            if (j < n) red0[j] = dM(p[e], tmp[e]);
+                            if (j < n) {
+                                tmp[e] = dA(dA(0.0, dM(D, p[e])), S.oc[j]);   // :304
+                                red0[j] = dM(p[e], tmp[e]);
+                            } else tmp[e] = 0.0;
                         }
                         __syncthreads();
                         if (warp == RW) {
@@ -439,25 +465,18 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                     z1[e] = dA(z1[e], dM(g1, d1));
                     z2[e] = dA(z2[e], dM(g2, d2));
                     if (j < n) {
+                        const double bj = gb[j];
                         S.gv[j] = x[e];
                         red0[j] = dM(x[e], x[e]);
                         red1[j] = dM(d1, d1);
                         red2[j] = dM(d2, d2);
-                        red3[j] = dM(bb[e], x[e]);
-                        red4[j] = dM(bb[e], (x[e] >= 0.5) ? 1.0 : 0.0);
+                        red3[j] = dM(bj, x[e]);
+                        red4[j] = dM(bj, (x[e] >= 0.5) ? 1.0 : 0.0);
                     }
                 }
             }
             __syncthreads();
-            seq_spmv<T, EPT, UNIT ? 0 : 2>(rowptr, colidx, S.val_r, 0.0, S.gv, m, acc);
-            {
-                const double g4 = dM(gamma, rho4);
-                const bool assign = lp_plain && (iter == la.iter_start);    // :920-921
-                LPB_FOR_E {
-                    double t = dM(g4, dS(dA(acc[e], y3[e]), ff[e]));
-                    z4[e] = assign ? t : dA(z4[e], t);
-                }
-            }
+            seq_spmv_to_smem<T, EPT, CE>(rowperm, rowptr, colidx, S.val_r, 0.0, S.gv, m, S.t1);
             if (warp == RW) {
                 double v = warp_redux_eigen<5>(red0, np, n);
                 int lane = tid & 31;
@@ -471,6 +490,17 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                 }
             }
             __syncthreads();
+            {
+                const double g4 = dM(gamma, rho4);
+                const bool assign = lp_plain && (iter == la.iter_start);    // :920-921
+                LPB_FOR_E {
+                    int i = tid + e * T;
+                    if (i < m) {
+                        double t = dM(g4, dS(dA(S.t1[i], y3[e]), gf[i]));
+                        z4[e] = assign ? t : dA(z4[e], t);
+                    }
+                }
+            }
             {
                 double temp0 = sqrt(S.sc[0]);                                // :931
                 if (!(temp0 > 2.2204e-16)) temp0 = 2.2204e-16;
@@ -495,7 +525,7 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
             }
             cur_obj = S.sc[4];                                               // :1001-1005
             if (best_bin_obj >= cur_obj) best_bin_obj = cur_obj;             // :1006-1009
-            // all reads of S.sc / red* of this iteration are complete before the next iteration's first barrier
+            // all reads of S.sc / red* / t1 of this iteration are complete before the next iteration's first barrier
         }
 
         // ---------------- write the instance back ---------------------------------------------------------------

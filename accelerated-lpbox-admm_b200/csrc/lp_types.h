@@ -56,8 +56,11 @@ struct InstState {
 
 // Byte layout of one instance's sparsity pattern blob (uint16 indices; both orientations of E).  The blob is the
 // exact shared-memory image, so that one 1-D TMA bulk copy stages it.
+// rowperm / colperm: work assignment of the sequential SpMVs -- slot s (thread s % T) processes row rowperm[s] /
+// column colperm[s]; slots are sorted by descending stored length so that the lanes of a warp run loops of similar
+// trip count (the ARITHMETIC of each row/column is unchanged, only which thread performs it).
 struct PatLayout {
-    int o_rowptr, o_colptr, o_colidx, o_rowidx, bytes;
+    int o_rowptr, o_colptr, o_colidx, o_rowidx, o_rowperm, o_colperm, bytes;
 };
 LPB_HD int a16(int x) { return (x + 15) & ~15; }
 LPB_HD PatLayout pat_layout(int n0, int m0, int nnz0) {
@@ -66,7 +69,9 @@ LPB_HD PatLayout pat_layout(int n0, int m0, int nnz0) {
     L.o_colptr = a16(2 * (m0 + 1));
     L.o_colidx = L.o_colptr + a16(2 * (n0 + 1));
     L.o_rowidx = L.o_colidx + a16(2 * nnz0);
-    L.bytes = L.o_rowidx + a16(2 * nnz0);
+    L.o_rowperm = L.o_rowidx + a16(2 * nnz0);
+    L.o_colperm = L.o_rowperm + a16(2 * m0);
+    L.bytes = L.o_colperm + a16(2 * n0);
     return L;
 }
 
