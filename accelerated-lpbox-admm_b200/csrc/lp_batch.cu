@@ -84,6 +84,7 @@ struct lpbox_batch {
     size_t smem = 0, fix_smem = 0;
     double last_ms = 0;
     int64_t launches = 0;
+    int64_t h2d_bytes = 0, d2h_bytes = 0;
 };
 
 template <int T, int EPT, bool UNIT>
@@ -148,6 +149,7 @@ static int run_window(lpbox_batch *h, int iter_start, int iter_end, int l2f, int
 }
 
 static int sync_states(lpbox_batch *h) {
+    h->d2h_bytes += (int64_t)(sizeof(InstState) * (size_t)h->B);
     CK(cudaMemcpyAsync(h->h_st.data(), h->d_st.p, sizeof(InstState) * (size_t)h->B, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
@@ -271,7 +273,7 @@ extern "C" lpbox_batch *lpbox_batch_create(int device, int B, const int32_t *m, 
     if (!ok) { lpbox_batch_destroy(h); return nullptr; }
     std::vector<double> powtab((size_t)h->max_n + 1);
     for (int k = 0; k <= h->max_n; ++k) powtab[k] = pow((double)k, 1.0 / 2);   // std::pow(n, 1.0/p), LP.cpp:427 (host libm)
-    auto H2D = [&](void *d, const void *s, size_t bytes) { if (bytes) A(cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, h->stream)); };
+    auto H2D = [&](void *d, const void *s, size_t bytes) { if (bytes) { A(cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, h->stream)); h->h2d_bytes += (int64_t)bytes; } };
     H2D(h->d_off_n.p, h->off_n.data(), sizeof(long long) * (B + 1));
     H2D(h->d_off_m.p, h->off_m.data(), sizeof(long long) * (B + 1));
     H2D(h->d_off_pat.p, h->off_pat.data(), sizeof(long long) * (B + 1));
@@ -345,9 +347,11 @@ extern "C" int lpbox_batch_init(lpbox_batch *h, const double *x0_all) {
         CK(cudaMemcpyAsync(h->d_x.p, xs.data(), sizeof(double) * xs.size(), cudaMemcpyHostToDevice, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
+    time_begin(h);
     lp_setup_kernel<<<h->B, 128, 0, h->stream>>>(h->bv, h->pr, 3, x0_all ? 1 : 0);
     CK(cudaGetLastError());
     h->launches += 1;
+    { int rc = time_end(h); if (rc) return rc; }
     { int rc = sync_states(h); if (rc) return rc; }
     h->inited = true;
     return 1;   // ADMM_lp_iters_init returns 1 (LP.cpp:762)
@@ -445,6 +449,7 @@ extern "C" double lpbox_batch_get_cur_bin_obj(lpbox_batch *h, int i) { if (!h ||
 
 static int d2h(lpbox_batch *h, void *dst, const void *src, size_t bytes) {
     if (!bytes) return 0;
+    h->d2h_bytes += (int64_t)bytes;
     CK(cudaSetDevice(h->device));
     CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -579,6 +584,8 @@ extern "C" int lpbox_batch_results(lpbox_batch *h, lpbox_log_row *log, uint8_t *
 }
 
 extern "C" double lpbox_batch_last_kernel_ms(const lpbox_batch *h) { return h ? h->last_ms : -1.0; }
+extern "C" int64_t lpbox_batch_h2d_bytes(const lpbox_batch *h) { return h ? h->h2d_bytes : -1; }
+extern "C" int64_t lpbox_batch_d2h_bytes(const lpbox_batch *h) { return h ? h->d2h_bytes : -1; }
 extern "C" int64_t lpbox_batch_launch_count(const lpbox_batch *h) { return h ? h->launches : -1; }
 
 // ---- file format of the reference (readFile / readSparseMat / readDenseVec, LP.cpp:2407-2545) ----------------------

@@ -5,5 +5,5 @@ Reference surface being mirrored (same names, argument meaning and return values
   * batched entry points (new; the reference solves one instance per object) -> :class:`LPBatch`
 All compute happens in hand-written sm_100a CUDA behind the C ABI of `include/lpbox_b200.h`.
 """
-from .lp import LPBatch, PyLPboxADMMsolver, read_instance  # noqa: F401
+from .lp import LPBatch, PyLPboxADMMsolver, gen_auctions, read_instance  # noqa: F401
 from . import _capi  # noqa: F401

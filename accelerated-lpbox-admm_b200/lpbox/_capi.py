@@ -67,9 +67,13 @@ SIGNATURES = {
     "lpbox_batch_results": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "lpbox_batch_last_kernel_ms": (C.c_double, [_vp]),
     "lpbox_batch_launch_count": (C.c_int64, [_vp]),
+    "lpbox_batch_h2d_bytes": (C.c_int64, [_vp]),
+    "lpbox_batch_d2h_bytes": (C.c_int64, [_vp]),
     "lpbox_read_instance": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, _ip, _ip, C.POINTER(_ip), C.POINTER(_ip),
                                       C.POINTER(_dp), C.POINTER(_dp)]),
     "lpbox_free": (None, [_vp]),
+    "lpbox_gen_auctions": (C.c_int, [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(_ip),
+                                     C.POINTER(_ip), C.POINTER(_ip), C.POINTER(_dp)]),
 }
 
 _lib = None

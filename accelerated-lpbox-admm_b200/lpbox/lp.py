@@ -176,6 +176,12 @@ class LPBatch:
     def launch_count(self):
         return self.L.lpbox_batch_launch_count(self.h)
 
+    def h2d_bytes(self):
+        return self.L.lpbox_batch_h2d_bytes(self.h)
+
+    def d2h_bytes(self):
+        return self.L.lpbox_batch_d2h_bytes(self.h)
+
 
 class PyLPboxADMMsolver:
     """Drop-in for `lpbox.PyLPboxADMMsolver` of the LP experiment (LP.pyx:7-76).
@@ -269,3 +275,29 @@ class PyLPboxADMMsolver:
 
     def check_infeasible_l2f(self):
         return self._need().check_infeasible_l2f(0)
+
+
+def gen_auctions(seed, count, n_items=100, n_bids=500, add_item_prob=0.7, threads=0):
+    """`count` synthetic auction instances from the native generator (csrc/auction_gen.cpp).
+
+    Returns a list of problem tuples (m, n, colptr, rowidx, None, b, None) with b = -price (readFile, LP.cpp:2520)."""
+    L = _capi.lib()
+    m_p, cp_p, ri_p = C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)()
+    pr_p = C.POINTER(C.c_double)()
+    check(L.lpbox_gen_auctions(int(seed), int(count), int(n_items), int(n_bids), float(add_item_prob), int(threads),
+                               C.byref(m_p), C.byref(cp_p), C.byref(ri_p), C.byref(pr_p)), "gen_auctions")
+    try:
+        ms = np.ctypeslib.as_array(m_p, shape=(count,)).copy()
+        cps = np.ctypeslib.as_array(cp_p, shape=(count, n_bids + 1)).copy()
+        tot = int(cps[:, -1].sum())
+        ris = np.ctypeslib.as_array(ri_p, shape=(max(tot, 1),))[:tot].copy()
+        prs = np.ctypeslib.as_array(pr_p, shape=(count, n_bids)).copy()
+    finally:
+        for p in (m_p, cp_p, ri_p, pr_p):
+            L.lpbox_free(C.cast(p, C.c_void_p))
+    out, o = [], 0
+    for i in range(count):
+        nz = int(cps[i, -1])
+        out.append((int(ms[i]), n_bids, cps[i], ris[o:o + nz], None, -prs[i], None))
+        o += nz
+    return out

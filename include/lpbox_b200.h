@@ -134,6 +134,9 @@ int lpbox_batch_results(lpbox_batch *h, lpbox_log_row *log, uint8_t *x_bits, int
 /* device time (ms, CUDA events on the handle's stream) and number of kernel launches of the last solve/iters call */
 double lpbox_batch_last_kernel_ms(const lpbox_batch *h);
 int64_t lpbox_batch_launch_count(const lpbox_batch *h);
+/* bytes copied host->device / device->host by this handle so far (counted from the buffers actually copied) */
+int64_t lpbox_batch_h2d_bytes(const lpbox_batch *h);
+int64_t lpbox_batch_d2h_bytes(const lpbox_batch *h);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * File format of the reference: data/instance/<k>_<j>/instance_<i>_{C,b}.txt under `root`
@@ -142,6 +145,14 @@ int64_t lpbox_batch_launch_count(const lpbox_batch *h);
 int lpbox_read_instance(const char *root, int i, int k, int j, int32_t *m, int32_t *n, int32_t **colptr,
                         int32_t **rowidx, double **val, double **b);
 void lpbox_free(void *p);
+
+/* Synthetic instances: `count` auctions from the "arbitrary" scheme of Leyton-Brown et al. (EC-00 §4.3) with the
+ * parameterisation of the reference generator (generate_instances.py:137-140; add_item_prob as passed at :396 = 0.7).
+ * Own random stream (not numpy's): same distribution, different instances.  Outputs are malloc()ed, concatenated in
+ * the layout lpbox_batch_create takes (colptr: count x (n_bids+1); price: count x n_bids, POSITIVE bid prices --
+ * negate for b); release with lpbox_free().  threads <= 0: all host cores. */
+int lpbox_gen_auctions(uint64_t seed, int count, int n_items, int n_bids, double add_item_prob, int threads,
+                       int32_t **m_out, int32_t **colptr_out, int32_t **rowidx_out, double **price_out);
 
 #ifdef __cplusplus
 }
