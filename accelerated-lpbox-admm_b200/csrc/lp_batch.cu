@@ -105,7 +105,7 @@ static int configure(lpbox_batch *h) {
     else if (dim <= 2048) h->tcfg = 2;
     else { set_err("max(n, m) > 2048 is not supported by the on-chip kernel"); return LPBOX_E_UNSUPPORTED; }
     if (h->max_nnz > 65535) { set_err("nnz > 65535 is not supported by the on-chip kernel"); return LPBOX_E_UNSUPPORTED; }
-    int np = (h->max_n + 1) & ~1, mp = (h->max_m + 1) & ~1;
+    int mp = (h->max_m + 1) & ~1, np = std::max((h->max_n + 1) & ~1, mp);   // m-vectors alias n-sized buffers
     int val_elems = h->all_unit ? 0 : ((h->max_nnz + 1) & ~1);
     h->smem = smem_bytes(np, mp, h->max_pat, val_elems);
     h->fix_smem = fix_smem_bytes(np, mp, h->max_pat, val_elems);
@@ -134,7 +134,7 @@ static int run_window(lpbox_batch *h, int iter_start, int iter_end, int l2f, int
     Launch la{};
     la.iter_start = iter_start; la.iter_end = iter_end; la.l2f = l2f; la.skip_done = skip_done;
     la.n_work = h->B; la.work = nullptr; la.counter = h->d_counter.p;
-    la.np = (h->max_n + 1) & ~1; la.mp = (h->max_m + 1) & ~1; la.pat_bytes = h->max_pat;
+    la.mp = (h->max_m + 1) & ~1; la.np = std::max((h->max_n + 1) & ~1, la.mp); la.pat_bytes = h->max_pat;
     la.val_elems = h->all_unit ? 0 : ((h->max_nnz + 1) & ~1);
     CK(cudaMemsetAsync(h->d_counter.p, 0, sizeof(int), h->stream));
     bool u = h->all_unit;

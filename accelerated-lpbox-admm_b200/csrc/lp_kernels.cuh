@@ -107,13 +107,20 @@ __device__ __forceinline__ double seq_dot(const u16 *__restrict__ idx, const dou
                                           const double *__restrict__ v, int beg, int end) {
     double acc = 0.0;
     int k = beg;
+    if (k + 4 <= end) {
+        // software pipeline: the indices of the next batch are fetched while the current batch is gathered and added
+        int i0 = idx[k], i1 = idx[k + 1], i2 = idx[k + 2], i3 = idx[k + 3];
 #pragma unroll 1
-    for (; k + 4 <= end; k += 4) {
-        const int i0 = idx[k], i1 = idx[k + 1], i2 = idx[k + 2], i3 = idx[k + 3];
-        double t0 = v[i0], t1 = v[i1], t2 = v[i2], t3 = v[i3];
-        if (COEF == 1) { t0 = dM(scale, t0); t1 = dM(scale, t1); t2 = dM(scale, t2); t3 = dM(scale, t3); }
-        if (COEF == 2) { t0 = dM(val[k], t0); t1 = dM(val[k + 1], t1); t2 = dM(val[k + 2], t2); t3 = dM(val[k + 3], t3); }
-        acc = dA(acc, t0); acc = dA(acc, t1); acc = dA(acc, t2); acc = dA(acc, t3);
+        for (;;) {
+            double t0 = v[i0], t1 = v[i1], t2 = v[i2], t3 = v[i3];
+            if (COEF == 2) { t0 = dM(val[k], t0); t1 = dM(val[k + 1], t1); t2 = dM(val[k + 2], t2); t3 = dM(val[k + 3], t3); }
+            k += 4;
+            const bool more = (k + 4 <= end);
+            if (more) { i0 = idx[k]; i1 = idx[k + 1]; i2 = idx[k + 2]; i3 = idx[k + 3]; }
+            if (COEF == 1) { t0 = dM(scale, t0); t1 = dM(scale, t1); t2 = dM(scale, t2); t3 = dM(scale, t3); }
+            acc = dA(acc, t0); acc = dA(acc, t1); acc = dA(acc, t2); acc = dA(acc, t3);
+            if (!more) break;
+        }
     }
 #pragma unroll 1
     for (; k < end; ++k) {
@@ -151,7 +158,7 @@ struct Smem {
     uint64_t *bar;
 };
 __host__ __device__ inline size_t smem_bytes(int np, int mp, int pat_bytes, int val_elems) {
-    size_t d = (size_t)np * 7 + (size_t)mp * 3 + 8 + 16 + (size_t)val_elems * 3;
+    size_t d = (size_t)np * 6 + (size_t)mp * 1 + 8 + 16 + (size_t)val_elems * 3;
     return d * sizeof(double) + (size_t)pat_bytes + 16;
 }
 __device__ __forceinline__ Smem carve(unsigned char *base, int np, int mp, int pat_bytes, int val_elems) {
@@ -159,10 +166,10 @@ __device__ __forceinline__ Smem carve(unsigned char *base, int np, int mp, int p
     double *d = reinterpret_cast<double *>(base);
     s.gv = d; d += np;
     s.red = d; d += 5 * (size_t)np;
-    s.oc = d; d += np;
+    s.oc = s.red + 3 * (size_t)np;   // aliases red3: column products are consumed before red3 is next written
     s.t1 = d; d += mp;
-    s.wa = d; d += mp;
-    s.wb = d; d += mp;
+    s.wa = s.red;                     // aliases red0 (m <= np): f - y3 lives only between the y3 step and the rhs products
+    s.wb = s.red + (size_t)np;        // aliases red1: z4 copy, same lifetime
     s.sc = d; d += 8;
     s.ring = d; d += 16;
     s.val_r = d; d += val_elems;
@@ -203,7 +210,7 @@ __device__ __forceinline__ double std_obj_after_push(const double *ring, long lo
 // UNIT: all stored values of E are 1.0 (pattern-only matrices; rho4*E^T is one scalar).
 // =====================================================================================================================
 template <int T, int EPT, bool UNIT>
-__global__ void __launch_bounds__(T, (T <= 128 ? 4 : (T <= 256 ? 2 : 1)))
+__global__ void __launch_bounds__(T, (T <= 128 ? 6 : (T <= 256 ? 3 : 1)))
 lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem S = carve(smem_raw, la.np, la.mp, la.pat_bytes, la.val_elems);
