@@ -62,19 +62,19 @@ struct lpbox_batch {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<int> n0, m0, nnz0;
-    std::vector<long long> off_n, off_m, off_pat, off_val, off_hist;
+    std::vector<long long> off_n, off_m, off_pat, off_csr, off_val, off_evr, off_evc, off_hist;
     // host copy of the original problem (check_infeasible_l2f uses org_E_ptr, LP.cpp:1593-1612)
     std::vector<int> h_colptr, h_rowidx;
     std::vector<long long> h_nnz_off, h_cp_off;
     std::vector<double> h_val;
     bool all_unit = true;
-    int max_n = 0, max_m = 0, max_nnz = 0, max_pat = 0;
+    int max_n = 0, max_m = 0, max_nnz = 0, max_pat = 0, max_csr = 0, max_evr = 0, max_evc = 0;
     Params pr{};
     BatchView bv{};
-    DevBuf<long long> d_off_n, d_off_m, d_off_pat, d_off_val, d_off_hist, d_off_vec;
-    DevBuf<double> d_x, d_y1, d_y2, d_z1, d_z2, d_b, d_Pd, d_Esq, d_y3, d_z4, d_f, d_val_r, d_val_c, d_r4v, d_hist,
+    DevBuf<long long> d_off_n, d_off_m, d_off_pat, d_off_csr, d_off_val, d_off_evr, d_off_evc, d_off_hist, d_off_vec;
+    DevBuf<double> d_x, d_y1, d_y2, d_z1, d_z2, d_b, d_Pd, d_Esq, d_y3, d_z4, d_f, d_val_r, d_val_c, d_ev_r, d_ev_c, d_r4v, d_hist,
         d_ret_val, d_pow, d_vec;
-    DevBuf<unsigned char> d_pat;
+    DevBuf<unsigned char> d_pat, d_csr;
     DevBuf<InstState> d_st;
     DevBuf<int> d_left, d_ret_idx, d_counter, d_num;
     std::vector<InstState> h_st;
@@ -107,8 +107,8 @@ static int configure(lpbox_batch *h) {
     if (h->max_nnz > 65535) { set_err("nnz > 65535 is not supported by the on-chip kernel"); return LPBOX_E_UNSUPPORTED; }
     int mp = (h->max_m + 1) & ~1, np = std::max((h->max_n + 1) & ~1, mp);   // m-vectors alias n-sized buffers
     int val_elems = h->all_unit ? 0 : ((h->max_nnz + 1) & ~1);
-    h->smem = smem_bytes(np, mp, h->max_pat, val_elems);
-    h->fix_smem = fix_smem_bytes(np, mp, h->max_pat, val_elems);
+    h->smem = smem_bytes(np, mp, h->max_pat, h->all_unit ? 0 : h->max_evr, h->all_unit ? 0 : h->max_evc);
+    h->fix_smem = fix_smem_bytes((h->max_n + 1) & ~1, mp, h->max_csr, val_elems);
     int dev_smem = 0, sms = 0;
     CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
@@ -135,7 +135,7 @@ static int run_window(lpbox_batch *h, int iter_start, int iter_end, int l2f, int
     la.iter_start = iter_start; la.iter_end = iter_end; la.l2f = l2f; la.skip_done = skip_done;
     la.n_work = h->B; la.work = nullptr; la.counter = h->d_counter.p;
     la.mp = (h->max_m + 1) & ~1; la.np = std::max((h->max_n + 1) & ~1, la.mp); la.pat_bytes = h->max_pat;
-    la.val_elems = h->all_unit ? 0 : ((h->max_nnz + 1) & ~1);
+    la.evr_elems = h->all_unit ? 0 : h->max_evr; la.evc_elems = h->all_unit ? 0 : h->max_evc;
     CK(cudaMemsetAsync(h->d_counter.p, 0, sizeof(int), h->stream));
     bool u = h->all_unit;
     switch (h->tcfg) {
@@ -167,6 +167,9 @@ extern "C" lpbox_batch *lpbox_batch_create(int device, int B, const int32_t *m, 
     h->device = device; h->B = B; h->hist_cap = hist_cap;
     h->n0.assign(n, n + B); h->m0.assign(m, m + B); h->nnz0.resize(B);
     h->off_n.assign(B + 1, 0); h->off_m.assign(B + 1, 0); h->off_pat.assign(B + 1, 0); h->off_val.assign(B + 1, 0);
+    h->off_csr.assign(B + 1, 0); h->off_evr.assign(B + 1, 0); h->off_evc.assign(B + 1, 0);
+    std::vector<int> rcap(B, 0), ccap(B, 0);
+    std::vector<std::vector<uint16_t>> rperm_all(B), cperm_all(B);
     h->off_hist.assign(B + 1, 0); h->h_nnz_off.assign(B + 1, 0); h->h_cp_off.assign(B + 1, 0);
     for (int i = 0; i < B; ++i) {
         if (n[i] <= 0 || m[i] < 0) { set_err("instance with n <= 0"); delete h; return nullptr; }
@@ -176,12 +179,35 @@ extern "C" lpbox_batch *lpbox_batch_create(int device, int B, const int32_t *m, 
         h->h_nnz_off[i + 1] = h->h_nnz_off[i] + h->nnz0[i];
         h->off_n[i + 1] = h->off_n[i] + ((n[i] + 1) & ~1);
         h->off_m[i + 1] = h->off_m[i] + ((m[i] + 1) & ~1);
-        PatLayout PL = pat_layout(n[i], m[i], h->nnz0[i]);
-        h->off_pat[i + 1] = h->off_pat[i] + PL.bytes;
+        {   // SpMV work assignment: slots sorted by descending stored length (stable); capacities of the sliced-ELL image
+            const int ni = n[i], mi = m[i];
+            const int32_t *ri = rowidx_all + h->h_nnz_off[i];
+            std::vector<int> rl(mi, 0), cl(ni), ord(mi);
+            for (int k = 0; k < h->nnz0[i]; ++k) { if (ri[k] < 0 || ri[k] >= mi) { set_err("row index out of range"); delete h; return nullptr; } rl[ri[k]]++; }
+            for (int j = 0; j < ni; ++j) cl[j] = cp[j + 1] - cp[j];
+            for (int r = 0; r < mi; ++r) ord[r] = r;
+            std::stable_sort(ord.begin(), ord.end(), [&](int a, int b2) { return rl[a] > rl[b2]; });
+            rperm_all[i].resize(mi);
+            for (int r = 0; r < mi; ++r) { rperm_all[i][r] = (uint16_t)ord[r]; if ((r & 31) == 0) rcap[i] += rl[ord[r]]; }
+            ord.resize(ni);
+            for (int j = 0; j < ni; ++j) ord[j] = j;
+            std::stable_sort(ord.begin(), ord.end(), [&](int a, int b2) { return cl[a] > cl[b2]; });
+            cperm_all[i].resize(ni);
+            for (int j = 0; j < ni; ++j) { cperm_all[i][j] = (uint16_t)ord[j]; if ((j & 31) == 0) ccap[i] += cl[ord[j]]; }
+        }
+        EllLayout EL = ell_layout(n[i], m[i], rcap[i], ccap[i]);
+        CsrLayout PL = csr_layout(n[i], m[i], h->nnz0[i]);
+        h->off_pat[i + 1] = h->off_pat[i] + EL.bytes;
+        h->off_csr[i + 1] = h->off_csr[i] + PL.bytes;
         h->off_val[i + 1] = h->off_val[i] + ((h->nnz0[i] + 1) & ~1);
+        h->off_evr[i + 1] = h->off_evr[i] + 32 * rcap[i];
+        h->off_evc[i + 1] = h->off_evc[i] + 32 * ccap[i];
+        h->max_csr = std::max(h->max_csr, PL.bytes);
+        h->max_evr = std::max(h->max_evr, 32 * rcap[i]); h->max_evc = std::max(h->max_evc, 32 * ccap[i]);
+        if (rcap[i] > 2047 || ccap[i] > 2047) { set_err("pattern too large for the on-chip kernel"); delete h; return nullptr; }
         h->off_hist[i + 1] = h->off_hist[i] + (long long)hist_cap * n[i];
         h->max_n = std::max(h->max_n, n[i]); h->max_m = std::max(h->max_m, m[i]); h->max_nnz = std::max(h->max_nnz, h->nnz0[i]);
-        h->max_pat = std::max(h->max_pat, PL.bytes);
+        h->max_pat = std::max(h->max_pat, EL.bytes);
     }
     long long tot_nnz = h->h_nnz_off[B];
     h->h_colptr.assign(colptr_all, colptr_all + h->h_cp_off[B]);
@@ -192,7 +218,7 @@ extern "C" lpbox_batch *lpbox_batch_create(int device, int B, const int32_t *m, 
         for (long long k = 0; k < tot_nnz; ++k) if (val_all[k] != 1.0) { h->all_unit = false; break; }
     }
     // build pattern blobs (+ values in both orders) on the host
-    std::vector<unsigned char> pat((size_t)h->off_pat[B], 0);
+    std::vector<unsigned char> pat((size_t)h->off_pat[B], 0), csr((size_t)h->off_csr[B], 0);
     std::vector<double> val_r, val_c;
     if (!h->all_unit) { val_r.assign((size_t)h->off_val[B], 0.0); val_c.assign((size_t)h->off_val[B], 0.0); }
     std::vector<double> fvec((size_t)h->off_m[B], 1.0), bvec((size_t)h->off_n[B], 0.0);
@@ -203,8 +229,14 @@ extern "C" lpbox_batch *lpbox_batch_create(int device, int B, const int32_t *m, 
         const int32_t *cp = colptr_all + h->h_cp_off[i];
         const int32_t *ri = rowidx_all + h->h_nnz_off[i];
         const double *va = val_all ? val_all + h->h_nnz_off[i] : nullptr;
-        PatLayout PL = pat_layout(ni, mi, nz);
-        unsigned char *blob = pat.data() + h->off_pat[i];
+        CsrLayout PL = csr_layout(ni, mi, nz);
+        unsigned char *blob = csr.data() + h->off_csr[i];
+        {
+            EllLayout EL = ell_layout(ni, mi, rcap[i], ccap[i]);
+            unsigned char *eb = pat.data() + h->off_pat[i];
+            memcpy(eb + EL.o_rperm, rperm_all[i].data(), sizeof(uint16_t) * (size_t)mi);
+            memcpy(eb + EL.o_cperm, cperm_all[i].data(), sizeof(uint16_t) * (size_t)ni);
+        }
         uint16_t *rowptr = (uint16_t *)(blob + PL.o_rowptr), *colptr = (uint16_t *)(blob + PL.o_colptr);
         uint16_t *colidx = (uint16_t *)(blob + PL.o_colidx), *rowidx = (uint16_t *)(blob + PL.o_rowidx);
         std::vector<int> rcount(mi + 1, 0);
@@ -229,23 +261,12 @@ extern "C" lpbox_batch *lpbox_batch_create(int device, int B, const int32_t *m, 
                 colidx[q] = (uint16_t)j;
                 if (!h->all_unit) { val_r[(size_t)h->off_val[i] + q] = va[k]; val_c[(size_t)h->off_val[i] + k] = va[k]; }
             }
-        {   // SpMV work assignment: slots sorted by descending stored length (stable)
-            uint16_t *rowperm = (uint16_t *)(blob + PL.o_rowperm), *colperm = (uint16_t *)(blob + PL.o_colperm);
-            std::vector<int> ord(mi);
-            for (int r = 0; r < mi; ++r) ord[r] = r;
-            std::stable_sort(ord.begin(), ord.end(), [&](int a, int b2) { return (rcount[a + 1] - rcount[a]) > (rcount[b2 + 1] - rcount[b2]); });
-            for (int r = 0; r < mi; ++r) rowperm[r] = (uint16_t)ord[r];
-            ord.resize(ni);
-            for (int j = 0; j < ni; ++j) ord[j] = j;
-            std::stable_sort(ord.begin(), ord.end(), [&](int a, int b2) { return (cp[a + 1] - cp[a]) > (cp[b2 + 1] - cp[b2]); });
-            for (int j = 0; j < ni; ++j) colperm[j] = (uint16_t)ord[j];
-        }
         memcpy(bvec.data() + h->off_n[i], b_all + boff, sizeof(double) * (size_t)ni);
         if (f_all) memcpy(fvec.data() + h->off_m[i], f_all + foff, sizeof(double) * (size_t)mi);
         boff += ni; foff += mi;
         InstState &s = st[i];
         memset(&s, 0, sizeof(s));
-        s.n0 = s.n = ni; s.m0 = s.m = mi; s.nnz0 = s.nnz = nz; s.unit = h->all_unit ? 1 : 0; s.std_obj = 1.0; s.rhoUpdated = 1;
+        s.n0 = s.n = ni; s.m0 = s.m = mi; s.nnz0 = s.nnz = nz; s.rcap = rcap[i]; s.ccap = ccap[i]; s.unit = h->all_unit ? 1 : 0; s.std_obj = 1.0; s.rhoUpdated = 1;
     }
     h->h_st = st;
     lpbox_params lp; lpbox_params_lp(&lp);
@@ -260,13 +281,19 @@ extern "C" lpbox_batch *lpbox_batch_create(int device, int B, const int32_t *m, 
     A(cudaEventCreate(&h->ev0)); A(cudaEventCreate(&h->ev1));
     size_t NN = (size_t)h->off_n[B], MM = (size_t)h->off_m[B];
     A(h->d_off_n.alloc(B + 1)); A(h->d_off_m.alloc(B + 1)); A(h->d_off_pat.alloc(B + 1)); A(h->d_off_val.alloc(B + 1));
+    A(h->d_off_csr.alloc(B + 1)); A(h->d_off_evr.alloc(B + 1)); A(h->d_off_evc.alloc(B + 1)); A(h->d_csr.alloc((size_t)h->off_csr[B]));
     A(h->d_off_hist.alloc(B + 1)); A(h->d_off_vec.alloc(B + 1));
     A(h->d_x.alloc(NN)); A(h->d_y1.alloc(NN)); A(h->d_y2.alloc(NN)); A(h->d_z1.alloc(NN)); A(h->d_z2.alloc(NN));
     A(h->d_b.alloc(NN)); A(h->d_Pd.alloc(NN)); A(h->d_Esq.alloc(NN)); A(h->d_ret_val.alloc(NN)); A(h->d_vec.alloc(NN));
     A(h->d_left.alloc(NN)); A(h->d_ret_idx.alloc(NN));
     A(h->d_y3.alloc(MM)); A(h->d_z4.alloc(MM)); A(h->d_f.alloc(MM));
     A(h->d_pat.alloc((size_t)h->off_pat[B]));
-    if (!h->all_unit) { A(h->d_val_r.alloc((size_t)h->off_val[B])); A(h->d_val_c.alloc((size_t)h->off_val[B])); A(h->d_r4v.alloc((size_t)h->off_val[B])); }
+    if (!h->all_unit) {
+        A(h->d_val_r.alloc((size_t)h->off_val[B])); A(h->d_val_c.alloc((size_t)h->off_val[B]));
+        A(h->d_ev_r.alloc((size_t)h->off_evr[B])); A(h->d_ev_c.alloc((size_t)h->off_evc[B])); A(h->d_r4v.alloc((size_t)h->off_evc[B]));
+        if (ok) { A(cudaMemset(h->d_ev_r.p, 0, sizeof(double) * std::max<size_t>(h->d_ev_r.n, 1))); A(cudaMemset(h->d_ev_c.p, 0, sizeof(double) * std::max<size_t>(h->d_ev_c.n, 1)));
+                  A(cudaMemset(h->d_r4v.p, 0, sizeof(double) * std::max<size_t>(h->d_r4v.n, 1))); }
+    }
     A(h->d_hist.alloc((size_t)h->off_hist[B]));
     A(h->d_st.alloc(B)); A(h->d_counter.alloc(1)); A(h->d_num.alloc(B));
     A(h->d_pow.alloc((size_t)h->max_n + 1));
@@ -278,6 +305,10 @@ extern "C" lpbox_batch *lpbox_batch_create(int device, int B, const int32_t *m, 
     H2D(h->d_off_m.p, h->off_m.data(), sizeof(long long) * (B + 1));
     H2D(h->d_off_pat.p, h->off_pat.data(), sizeof(long long) * (B + 1));
     H2D(h->d_off_val.p, h->off_val.data(), sizeof(long long) * (B + 1));
+    H2D(h->d_off_csr.p, h->off_csr.data(), sizeof(long long) * (B + 1));
+    H2D(h->d_off_evr.p, h->off_evr.data(), sizeof(long long) * (B + 1));
+    H2D(h->d_off_evc.p, h->off_evc.data(), sizeof(long long) * (B + 1));
+    H2D(h->d_csr.p, csr.data(), csr.size());
     H2D(h->d_off_hist.p, h->off_hist.data(), sizeof(long long) * (B + 1));
     H2D(h->d_b.p, bvec.data(), sizeof(double) * NN);
     H2D(h->d_f.p, fvec.data(), sizeof(double) * MM);
@@ -290,11 +321,15 @@ extern "C" lpbox_batch *lpbox_batch_create(int device, int B, const int32_t *m, 
     BatchView &v = h->bv;
     v.B = B; v.hist_cap = hist_cap;
     v.off_n = h->d_off_n.p; v.off_m = h->d_off_m.p; v.off_pat = h->d_off_pat.p; v.off_val = h->d_off_val.p; v.off_hist = h->d_off_hist.p;
+    v.off_csr = h->d_off_csr.p; v.off_evr = h->d_off_evr.p; v.off_evc = h->d_off_evc.p; v.csr = h->d_csr.p; v.ev_r = h->d_ev_r.p; v.ev_c = h->d_ev_c.p;
     v.x = h->d_x.p; v.y1 = h->d_y1.p; v.y2 = h->d_y2.p; v.z1 = h->d_z1.p; v.z2 = h->d_z2.p; v.b = h->d_b.p; v.Pd = h->d_Pd.p; v.Esq = h->d_Esq.p;
     v.y3 = h->d_y3.p; v.z4 = h->d_z4.p; v.f = h->d_f.p; v.pat = h->d_pat.p;
     v.val_r = h->d_val_r.p; v.val_c = h->d_val_c.p; v.r4v = h->d_r4v.p; v.st = h->d_st.p; v.hist = h->d_hist.p;
     v.left_idx = h->d_left.p; v.ret_idx = h->d_ret_idx.p; v.ret_val = h->d_ret_val.p; v.pow_tab = h->d_pow.p;
     if (configure(h) != 0) { lpbox_batch_destroy(h); return nullptr; }
+    lp_setup_kernel<<<B, 128, 0, h->stream>>>(h->bv, h->pr, 4, 0);     // build the sliced-ELL images on the device
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess) { set_err("ELL build kernel failed"); lpbox_batch_destroy(h); return nullptr; }
+    h->launches += 1;
     return h;
 }
 
@@ -303,6 +338,7 @@ extern "C" void lpbox_batch_destroy(lpbox_batch *h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->d_off_n.free_(); h->d_off_m.free_(); h->d_off_pat.free_(); h->d_off_val.free_(); h->d_off_hist.free_(); h->d_off_vec.free_();
+    h->d_off_csr.free_(); h->d_off_evr.free_(); h->d_off_evc.free_(); h->d_csr.free_(); h->d_ev_r.free_(); h->d_ev_c.free_();
     h->d_x.free_(); h->d_y1.free_(); h->d_y2.free_(); h->d_z1.free_(); h->d_z2.free_(); h->d_b.free_(); h->d_Pd.free_(); h->d_Esq.free_();
     h->d_y3.free_(); h->d_z4.free_(); h->d_f.free_(); h->d_val_r.free_(); h->d_val_c.free_(); h->d_r4v.free_(); h->d_hist.free_();
     h->d_ret_val.free_(); h->d_pow.free_(); h->d_vec.free_(); h->d_pat.free_(); h->d_st.free_(); h->d_left.free_(); h->d_ret_idx.free_();
@@ -403,7 +439,7 @@ extern "C" int lpbox_batch_iters_l2f(lpbox_batch *h, int iter_start, int iter_en
     int np = (h->max_n + 1) & ~1, mp = (h->max_m + 1) & ~1;
     int val_elems = h->all_unit ? 0 : ((h->max_nnz + 1) & ~1);
     lp_fix_kernel<<<h->B, FIX_T, h->fix_smem, h->stream>>>(h->bv, h->pr, h->d_vec.p, h->d_off_vec.p, h->d_num.p, skip_done, np, mp,
-                                                          h->max_pat, val_elems);
+                                                          h->max_csr, val_elems);
     CK(cudaGetLastError());
     h->launches += 1;
     if (iter_start == 0 && iter_end > 0) {   // `if(iter==0) update_expression(0)` (LP.cpp:1380-1381)
@@ -513,10 +549,10 @@ extern "C" int lpbox_batch_get_x_iters(lpbox_batch *h, int i, int ws, double *ou
 extern "C" int lpbox_batch_check_infeasible_lpbox(lpbox_batch *h, int i) {   // LP.cpp:1577-1591: current E, relaxed x
     CHK_I(h, i);
     const InstState &s = h->h_st[i];
-    PatLayout PL = pat_layout(s.n0, s.m0, s.nnz0);
+    CsrLayout PL = csr_layout(s.n0, s.m0, s.nnz0);
     std::vector<unsigned char> blob(PL.bytes);
     std::vector<double> x(s.n), vr;
-    if (d2h(h, blob.data(), h->d_pat.p + h->off_pat[i], blob.size())) return LPBOX_E_CUDA;
+    if (d2h(h, blob.data(), h->d_csr.p + h->off_csr[i], blob.size())) return LPBOX_E_CUDA;
     if (d2h(h, x.data(), h->d_x.p + h->off_n[i], sizeof(double) * (size_t)s.n)) return LPBOX_E_CUDA;
     if (!s.unit) { vr.resize(s.nnz); if (d2h(h, vr.data(), h->d_val_r.p + h->off_val[i], sizeof(double) * (size_t)s.nnz)) return LPBOX_E_CUDA; }
     const uint16_t *rowptr = (const uint16_t *)(blob.data() + PL.o_rowptr), *colidx = (const uint16_t *)(blob.data() + PL.o_colidx);

@@ -37,18 +37,21 @@ __device__ __forceinline__ int block_exscan(int *data, int L, int *s_part) {
     return s_part[FIX_T];
 }
 
-// shared memory: int kidx[np+1] | int cnt[max(np,mp)+1] | int part[FIX_T+1] | double stage[max(np, val_elems)] | pattern copy
-__host__ __device__ inline size_t fix_smem_bytes(int np, int mp, int pat_bytes, int val_elems) {
+// shared memory: int kidx[np+2] | int cnt[max(np,mp)+2] | int part[FIX_T+2] | int pold[np+2] | int s_w[80] |
+//                double stage[max(np, val_elems)+2] | copy of the (old) CSR/CSC blob
+__host__ __device__ inline size_t fix_ints(int np, int mp) {
     int L = (np > mp ? np : mp) + 2;
-    size_t ints = (size_t)(np + 2) + (size_t)L + FIX_T + 2;
-    ints = (ints + 3) & ~(size_t)3;
+    size_t ints = (size_t)(np + 2) + (size_t)L + FIX_T + 2 + (size_t)(np + 2) + 80;
+    return (ints + 3) & ~(size_t)3;
+}
+__host__ __device__ inline size_t fix_smem_bytes(int np, int mp, int csr_bytes, int val_elems) {
     size_t dbl = (size_t)(np > val_elems ? np : val_elems) + 2;
-    return ints * 4 + dbl * 8 + (size_t)pat_bytes + 16;
+    return fix_ints(np, mp) * 4 + dbl * 8 + (size_t)csr_bytes + 16;
 }
 
 __global__ void __launch_bounds__(FIX_T)
 lp_fix_kernel(BatchView bv, Params pr, const double *__restrict__ vec, const long long *__restrict__ off_vec,
-              const int *__restrict__ num, int skip_done, int np, int mp, int pat_bytes, int val_elems) {
+              const int *__restrict__ num, int skip_done, int np, int mp, int csr_bytes, int val_elems) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int inst = blockIdx.x;
     InstState *st = bv.st + inst;
@@ -61,19 +64,22 @@ lp_fix_kernel(BatchView bv, Params pr, const double *__restrict__ vec, const lon
         return;
     }
     const int L = (np > mp ? np : mp) + 2;
-    size_t nints = (size_t)(np + 2) + (size_t)L + FIX_T + 2;
-    nints = (nints + 3) & ~(size_t)3;
+    const size_t nints = fix_ints(np, mp);
     int *kidx = reinterpret_cast<int *>(smem_raw);
     int *cnt = kidx + (np + 2);
     int *part = cnt + L;
+    int *pold = part + FIX_T + 2;
+    int *s_w = pold + (np + 2);
     double *stage = reinterpret_cast<double *>(smem_raw + nints * 4);
     unsigned char *spat = reinterpret_cast<unsigned char *>(stage + (size_t)(np > val_elems ? np : val_elems) + 2);
 
     const long long on = bv.off_n[inst], om = bv.off_m[inst], ov = bv.off_val ? bv.off_val[inst] : 0;
     const bool unit = st->unit != 0;
     const double *v = vec + off_vec[inst];
-    const PatLayout PL = pat_layout(st->n0, st->m0, st->nnz0);
-    unsigned char *gpat = bv.pat + bv.off_pat[inst];
+    const CsrLayout PL = csr_layout(st->n0, st->m0, st->nnz0);
+    unsigned char *gpat = bv.csr + bv.off_csr[inst];
+    const EllLayout EL = ell_layout(st->n0, st->m0, st->rcap, st->ccap);
+    unsigned char *gell = bv.pat + bv.off_pat[inst];
 
     // stage the (old) pattern
     for (int k = tid; k < PL.bytes / 16; k += FIX_T)
@@ -190,15 +196,20 @@ lp_fix_kernel(BatchView bv, Params pr, const double *__restrict__ vec, const lon
     __syncthreads();
     // column work assignment: stable filter of the old (length-sorted) slot order, renumbered
     {
-        const u16 *colperm = reinterpret_cast<const u16 *>(spat + PL.o_colperm);
-        u16 *g_colperm = reinterpret_cast<u16 *>(gpat + PL.o_colperm);
-        for (int s2 = tid; s2 < n; s2 += FIX_T) cnt[s2] = is_fixed(colperm[s2]) ? 0 : 1;
+        u16 *g_cperm = reinterpret_cast<u16 *>(gell + EL.o_cperm);
+        for (int s2 = tid; s2 < n; s2 += FIX_T) { int c = g_cperm[s2]; pold[s2] = c; cnt[s2] = is_fixed(c) ? 0 : 1; }
         __syncthreads();
         block_exscan(cnt, n, part);
-        for (int s2 = tid; s2 < n; s2 += FIX_T) { int c = colperm[s2]; if (!is_fixed(c)) g_colperm[cnt[s2]] = (u16)kidx[c]; }
+        for (int s2 = tid; s2 < n; s2 += FIX_T) { int c = pold[s2]; if (!is_fixed(c)) g_cperm[cnt[s2]] = (u16)kidx[c]; }
     }
     __syncthreads();
-    __threadfence_block();
+    // sliced-ELL images of the compacted pattern (rows keep their slots; lengths only shrink)
+    build_ell(g_rowptr, g_colidx, unit ? nullptr : bv.val_r + ov, reinterpret_cast<const u16 *>(gell + EL.o_rperm), m,
+              reinterpret_cast<u16 *>(gell + EL.o_rlen), reinterpret_cast<u16 *>(gell + EL.o_rsptr),
+              reinterpret_cast<u16 *>(gell + EL.o_ridx), unit ? nullptr : bv.ev_r + bv.off_evr[inst], s_w);
+    build_ell(g_colptr, g_rowidx, unit ? nullptr : bv.val_c + ov, reinterpret_cast<const u16 *>(gell + EL.o_cperm), k_tot,
+              reinterpret_cast<u16 *>(gell + EL.o_clen), reinterpret_cast<u16 *>(gell + EL.o_csptr),
+              reinterpret_cast<u16 *>(gell + EL.o_cidx), unit ? nullptr : bv.ev_c + bv.off_evc[inst], s_w);
     // 9. update_expression with the current rho (:1329, :2289-2404) on the new column-compressed pattern
     const double rho1 = st->rho1, rho2 = st->rho2, rho4 = st->rho4;
     const double D = dA(0.0, dA(rho1, rho2));
@@ -212,7 +223,10 @@ lp_fix_kernel(BatchView bv, Params pr, const double *__restrict__ vec, const lon
         bv.Esq[on + j] = e;
         bv.Pd[on + j] = dA(D, dM(rho4, e));
     }
-    if (!unit) for (int k = tid; k < nnz_new; k += FIX_T) bv.r4v[ov + k] = dM(rho4, bv.val_c[ov + k]);
+    if (!unit) {
+        const long long ec = bv.off_evc[inst];
+        for (int k = tid; k < 32 * st->ccap; k += FIX_T) bv.r4v[ec + k] = dM(rho4, bv.ev_c[ec + k]);
+    }
     if (tid == 0) {
         st->D = D; st->r4s = dM(rho4, 1.0);
         st->n = k_tot; st->nnz = nnz_new; st->n_ret = n_ret + j_tot; st->fix_sum += j_tot;

@@ -98,49 +98,75 @@ __device__ __forceinline__ double warp_redux_eigen(const double *red, int stride
     return __shfl_sync(0xffffffffu, res, lane & ~3);  // broadcast chain-0 lane's value to its group
 }
 
-// ---- sequential sparse dot products -------------------------------------------------------------------------------
-// acc = ((0 + c_1 v[i_1]) + c_2 v[i_2]) + ...  over the stored entries [beg, end) of ONE row (or column), ascending
-// inner index.  Coefficient: COEF 0 -> 1 (unit E), 1 -> scale (unit rho4 E^T), 2 -> val[k].
-// Loads are batched four at a time (independent), only the adds form the dependent chain.
-template <int COEF>
-__device__ __forceinline__ double seq_dot(const u16 *__restrict__ idx, const double *__restrict__ val, double scale,
-                                          const double *__restrict__ v, int beg, int end) {
-    double acc = 0.0;
-    int k = beg;
-    if (k + 4 <= end) {
-        // software pipeline: the indices of the next batch are fetched while the current batch is gathered and added
-        int i0 = idx[k], i1 = idx[k + 1], i2 = idx[k + 2], i3 = idx[k + 3];
-#pragma unroll 1
-        for (;;) {
-            double t0 = v[i0], t1 = v[i1], t2 = v[i2], t3 = v[i3];
-            if (COEF == 2) { t0 = dM(val[k], t0); t1 = dM(val[k + 1], t1); t2 = dM(val[k + 2], t2); t3 = dM(val[k + 3], t3); }
-            k += 4;
-            const bool more = (k + 4 <= end);
-            if (more) { i0 = idx[k]; i1 = idx[k + 1]; i2 = idx[k + 2]; i3 = idx[k + 3]; }
-            if (COEF == 1) { t0 = dM(scale, t0); t1 = dM(scale, t1); t2 = dM(scale, t2); t3 = dM(scale, t3); }
-            acc = dA(acc, t0); acc = dA(acc, t1); acc = dA(acc, t2); acc = dA(acc, t3);
-            if (!more) break;
-        }
-    }
-#pragma unroll 1
-    for (; k < end; ++k) {
-        double t = v[idx[k]];
-        if (COEF == 1) t = dM(scale, t);
-        if (COEF == 2) t = dM(val[k], t);
-        acc = dA(acc, t);
-    }
-    return acc;
-}
-// out[o] = seq_dot(outer index o) for every o < count; slot s = tid + e*T handles o = perm[s] (length-sorted).
-template <int T, int EPT, int COEF>
-__device__ __forceinline__ void seq_spmv_to_smem(const u16 *__restrict__ perm, const u16 *__restrict__ ptr,
-                                                 const u16 *__restrict__ idx, const double *__restrict__ val, double scale,
-                                                 const double *__restrict__ v, int count, double *__restrict__ out) {
+// ---- sequential sparse dot products on the sliced-ELL image ---------------------------------------------------------
+// out[perm[s]] = ((0 + c_1 v[i_1]) + c_2 v[i_2]) + ...  over the stored entries of slot s in ascending inner index
+// (the reference's per-row order, SURVEY.md 8c rule 2).  Coefficient: COEF 0 -> 1 (unit E), 1 -> scale (unit rho4 E^T),
+// 2 -> val[pos] (ELL order).  Index loads are warp-coalesced (32 consecutive uint16) and software-pipelined one batch
+// ahead; the gathers of a batch are independent; only the adds form the dependent chain.
+template <int T, int COEF>
+__device__ __forceinline__ void seq_spmv_ell(const u16 *__restrict__ len, const u16 *__restrict__ sptr,
+                                             const u16 *__restrict__ perm, const u16 *__restrict__ idx,
+                                             const double *__restrict__ val, double scale, const double *__restrict__ v,
+                                             int count, double *__restrict__ out) {
 #pragma unroll 1
     for (int s = threadIdx.x; s < count; s += T) {
-        const int o = perm[s];
-        out[o] = seq_dot<COEF>(idx, val, scale, v, ptr[o], ptr[o + 1]);
+        const int L = len[s];
+        int pos = (int)sptr[s >> 5] * 32 + (s & 31);     // entry k lives at pos + 32 k
+        double acc = 0.0;
+        int k = 0;
+        if (L >= 4) {
+            int i0 = idx[pos], i1 = idx[pos + 32], i2 = idx[pos + 64], i3 = idx[pos + 96];
+#pragma unroll 1
+            for (;;) {
+                double t0 = v[i0], t1 = v[i1], t2 = v[i2], t3 = v[i3];
+                if (COEF == 2) { t0 = dM(val[pos], t0); t1 = dM(val[pos + 32], t1); t2 = dM(val[pos + 64], t2); t3 = dM(val[pos + 96], t3); }
+                k += 4; pos += 128;
+                const bool more = (k + 4 <= L);
+                if (more) { i0 = idx[pos]; i1 = idx[pos + 32]; i2 = idx[pos + 64]; i3 = idx[pos + 96]; }
+                if (COEF == 1) { t0 = dM(scale, t0); t1 = dM(scale, t1); t2 = dM(scale, t2); t3 = dM(scale, t3); }
+                acc = dA(acc, t0); acc = dA(acc, t1); acc = dA(acc, t2); acc = dA(acc, t3);
+                if (!more) break;
+            }
+        }
+#pragma unroll 1
+        for (; k < L; ++k, pos += 32) {
+            double t = v[idx[pos]];
+            if (COEF == 1) t = dM(scale, t);
+            if (COEF == 2) t = dM(val[pos], t);
+            acc = dA(acc, t);
+        }
+        out[perm[s]] = acc;
     }
+}
+
+// Builds one orientation of the sliced-ELL image from the compressed one.  Block-cooperative (any blockDim, all
+// threads must call).  ptr/idx(/val): compressed arrays (outer = row for the row image, column for the column image),
+// perm: slot -> outer index.  s_w: shared scratch of >= count/32 + 2 ints.
+__device__ __forceinline__ void build_ell(const u16 *ptr, const u16 *idx, const double *val, const u16 *perm, int count,
+                                          u16 *o_len, u16 *o_sptr, u16 *o_idx, double *o_val, int *s_w) {
+    const int ns = (count + 31) >> 5;
+    for (int w = threadIdx.x; w <= ns; w += blockDim.x) s_w[w] = 0;
+    __syncthreads();
+    for (int s = threadIdx.x; s < count; s += blockDim.x) {
+        const int o = perm[s];
+        const int L = ptr[o + 1] - ptr[o];
+        o_len[s] = (u16)L;
+        atomicMax(&s_w[s >> 5], L);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int w = 0; w < ns; ++w) { int wd = s_w[w]; s_w[w] = run; o_sptr[w] = (u16)run; run += wd; }
+        s_w[ns] = run; o_sptr[ns] = (u16)run;
+    }
+    __syncthreads();
+    for (int s = threadIdx.x; s < count; s += blockDim.x) {
+        const int o = perm[s];
+        const int beg = ptr[o], L = ptr[o + 1] - beg;
+        int pos = s_w[s >> 5] * 32 + (s & 31);
+        for (int k = 0; k < L; ++k, pos += 32) { o_idx[pos] = idx[beg + k]; if (o_val) o_val[pos] = val[beg + k]; }
+    }
+    __syncthreads();
 }
 
 // shared-memory carve-up -----------------------------------------------------------------------------------------------
@@ -153,15 +179,15 @@ struct Smem {
     double *wb;      // [mp]   z4
     double *sc;      // [8]    reduction results / broadcast scalars
     double *ring;    // [16]   tail of obj_list
-    double *val_r, *val_c, *r4v;  // [val_elems] each (non-unit only)
+    double *ev_r, *ev_c, *r4v;    // ELL-order values: [evr_elems], [evc_elems], [evc_elems] (non-unit only)
     unsigned char *pat;
     uint64_t *bar;
 };
-__host__ __device__ inline size_t smem_bytes(int np, int mp, int pat_bytes, int val_elems) {
-    size_t d = (size_t)np * 6 + (size_t)mp * 1 + 8 + 16 + (size_t)val_elems * 3;
+__host__ __device__ inline size_t smem_bytes(int np, int mp, int pat_bytes, int evr_elems, int evc_elems) {
+    size_t d = (size_t)np * 6 + (size_t)mp * 1 + 8 + 16 + (size_t)evr_elems + 2 * (size_t)evc_elems;
     return d * sizeof(double) + (size_t)pat_bytes + 16;
 }
-__device__ __forceinline__ Smem carve(unsigned char *base, int np, int mp, int pat_bytes, int val_elems) {
+__device__ __forceinline__ Smem carve(unsigned char *base, int np, int mp, int pat_bytes, int evr_elems, int evc_elems) {
     Smem s;
     double *d = reinterpret_cast<double *>(base);
     s.gv = d; d += np;
@@ -172,9 +198,9 @@ __device__ __forceinline__ Smem carve(unsigned char *base, int np, int mp, int p
     s.wb = s.red + (size_t)np;        // aliases red1: z4 copy, same lifetime
     s.sc = d; d += 8;
     s.ring = d; d += 16;
-    s.val_r = d; d += val_elems;
-    s.val_c = d; d += val_elems;
-    s.r4v = d; d += val_elems;
+    s.ev_r = d; d += evr_elems;
+    s.ev_c = d; d += evc_elems;
+    s.r4v = d; d += evc_elems;
     s.pat = reinterpret_cast<unsigned char *>(d);
     s.bar = reinterpret_cast<uint64_t *>(s.pat + pat_bytes);
     return s;
@@ -213,7 +239,7 @@ template <int T, int EPT, bool UNIT>
 __global__ void __launch_bounds__(T, (T <= 128 ? 6 : (T <= 256 ? 3 : 1)))
 lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem S = carve(smem_raw, la.np, la.mp, la.pat_bytes, la.val_elems);
+    Smem S = carve(smem_raw, la.np, la.mp, la.pat_bytes, la.evr_elems, la.evc_elems);
     __shared__ int s_work;
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -238,7 +264,7 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
 
         // ---------------- stage the instance --------------------------------------------------------------------
         const int n = stp->n, m = stp->m;
-        const PatLayout PL = pat_layout(stp->n0, stp->m0, stp->nnz0);
+        const EllLayout PL = ell_layout(stp->n0, stp->m0, stp->rcap, stp->ccap);
         if (tid == 0) {
             fence_proxy_async();  // order earlier generic-proxy reads of the previous instance's blob before the overwrite
             mbar_expect_tx(S.bar, (uint32_t)PL.bytes);
@@ -266,20 +292,22 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
         int rhoUpdated = stp->rhoUpdated;
         long long obj_len = stp->obj_len, cg_total = 0, admm_total = 0;
         if (tid < 16) S.ring[tid] = stp->obj_ring[tid];
+        const int evr_used = UNIT ? 0 : 32 * stp->rcap, evc_used = UNIT ? 0 : 32 * stp->ccap;
         if (!UNIT) {
-            const long long ov = bv.off_val[inst];
-            for (int k = tid; k < stp->nnz; k += T) {
-                S.val_r[k] = bv.val_r[ov + k]; S.val_c[k] = bv.val_c[ov + k]; S.r4v[k] = bv.r4v[ov + k];
-            }
+            const long long er = bv.off_evr[inst], ec = bv.off_evc[inst];
+            for (int k = tid; k < evr_used; k += T) S.ev_r[k] = bv.ev_r[er + k];
+            for (int k = tid; k < evc_used; k += T) { S.ev_c[k] = bv.ev_c[ec + k]; S.r4v[k] = bv.r4v[ec + k]; }
         }
         mbar_wait(S.bar, tma_phase); tma_phase ^= 1;
         __syncthreads();
-        const u16 *rowptr = reinterpret_cast<const u16 *>(S.pat + PL.o_rowptr);
-        const u16 *colptr = reinterpret_cast<const u16 *>(S.pat + PL.o_colptr);
-        const u16 *colidx = reinterpret_cast<const u16 *>(S.pat + PL.o_colidx);
-        const u16 *rowidx = reinterpret_cast<const u16 *>(S.pat + PL.o_rowidx);
-        const u16 *rowperm = reinterpret_cast<const u16 *>(S.pat + PL.o_rowperm);
-        const u16 *colperm = reinterpret_cast<const u16 *>(S.pat + PL.o_colperm);
+        const u16 *rlen = reinterpret_cast<const u16 *>(S.pat + PL.o_rlen);
+        const u16 *rsptr = reinterpret_cast<const u16 *>(S.pat + PL.o_rsptr);
+        const u16 *rperm = reinterpret_cast<const u16 *>(S.pat + PL.o_rperm);
+        const u16 *ridx = reinterpret_cast<const u16 *>(S.pat + PL.o_ridx);
+        const u16 *clen = reinterpret_cast<const u16 *>(S.pat + PL.o_clen);
+        const u16 *csptr = reinterpret_cast<const u16 *>(S.pat + PL.o_csptr);
+        const u16 *cperm = reinterpret_cast<const u16 *>(S.pat + PL.o_cperm);
+        const u16 *cidx = reinterpret_cast<const u16 *>(S.pat + PL.o_cidx);
         const double pow_n = bv.pow_tab[n];               // std::pow(n, 1.0/p), p = 2 (LP.cpp:427)
         double *red0 = S.red, *red1 = S.red + np, *red2 = S.red + 2 * np, *red3 = S.red + 3 * np, *red4 = S.red + 4 * np;
 
@@ -303,7 +331,7 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                 double v = warp_redux_eigen<1>(red0, np, n);
                 if ((tid & 31) == 0) S.sc[0] = v;
             }
-            seq_spmv_to_smem<T, EPT, CE>(rowperm, rowptr, colidx, S.val_r, 0.0, S.gv, m, S.t1);
+            seq_spmv_ell<T, CE>(rlen, rsptr, rperm, ridx, S.ev_r, 0.0, S.gv, m, S.t1);
             __syncthreads();
             {
                 const double nrm = sqrt(S.sc[0]);
@@ -335,7 +363,7 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                     }
                 }
                 if (UNIT) r4s = dM(pr.learning_fact, r4s);
-                else for (int k = tid; k < stp->nnz; k += T) S.r4v[k] = dM(pr.learning_fact, S.r4v[k]);
+                else for (int k = tid; k < evc_used; k += T) S.r4v[k] = dM(pr.learning_fact, S.r4v[k]);
             }
             if (rhoUpdated) {
                 LPB_FOR_E {
@@ -347,8 +375,8 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
             }
             __syncthreads();
             // ---- rhs (:872-878): two column-wise products, results through shared memory ------------------------
-            seq_spmv_to_smem<T, EPT, CR>(colperm, colptr, rowidx, S.r4v, r4s, S.wa, n, S.oc);      // R4ET (f - y3)
-            seq_spmv_to_smem<T, EPT, CE>(colperm, colptr, rowidx, S.val_c, 0.0, S.wb, n, red4);   // ET z4
+            seq_spmv_ell<T, CR>(clen, csptr, cperm, cidx, S.r4v, r4s, S.wa, n, S.oc);      // R4ET (f - y3)
+            seq_spmv_ell<T, CE>(clen, csptr, cperm, cidx, S.ev_c, 0.0, S.wb, n, red4);   // ET z4
             __syncthreads();
             // ---- PCG (:251-335), warm start x = y1 (:892) ------------------------------------------------------
             double rhs[EPT], xc[EPT];
@@ -367,10 +395,10 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                 double v = warp_redux_eigen<1>(red0, np, n);               // rhs.squaredNorm() :277
                 if ((tid & 31) == 0) S.sc[0] = v;
             }
-            seq_spmv_to_smem<T, EPT, CE>(rowperm, rowptr, colidx, S.val_r, 0.0, S.gv, m, S.t1);
+            seq_spmv_ell<T, CE>(rlen, rsptr, rperm, ridx, S.ev_r, 0.0, S.gv, m, S.t1);
             __syncthreads();
             const double rhsNorm2 = S.sc[0];
-            seq_spmv_to_smem<T, EPT, CR>(colperm, colptr, rowidx, S.r4v, r4s, S.t1, n, S.oc);
+            seq_spmv_ell<T, CR>(clen, csptr, cperm, cidx, S.r4v, r4s, S.t1, n, S.oc);
             __syncthreads();
             LPB_FOR_E {
                 int j = tid + e * T;
@@ -402,9 +430,9 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                     while (cg_it < pr.pcg_maxiters) {
                         LPB_FOR_E { int j = tid + e * T; if (j < n) S.gv[j] = p[e]; }
                         __syncthreads();
-                        seq_spmv_to_smem<T, EPT, CE>(rowperm, rowptr, colidx, S.val_r, 0.0, S.gv, m, S.t1);
+                        seq_spmv_ell<T, CE>(rlen, rsptr, rperm, ridx, S.ev_r, 0.0, S.gv, m, S.t1);
                         __syncthreads();
-                        seq_spmv_to_smem<T, EPT, CR>(colperm, colptr, rowidx, S.r4v, r4s, S.t1, n, S.oc);
+                        seq_spmv_ell<T, CR>(clen, csptr, cperm, cidx, S.r4v, r4s, S.t1, n, S.oc);
                         __syncthreads();
                         double tmp[EPT];
                         LPB_FOR_E {
@@ -483,7 +511,7 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                 }
             }
             __syncthreads();
-            seq_spmv_to_smem<T, EPT, CE>(rowperm, rowptr, colidx, S.val_r, 0.0, S.gv, m, S.t1);
+            seq_spmv_ell<T, CE>(rlen, rsptr, rperm, ridx, S.ev_r, 0.0, S.gv, m, S.t1);
             if (warp == RW) {
                 double v = warp_redux_eigen<5>(red0, np, n);
                 int lane = tid & 31;
@@ -546,8 +574,8 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
             if (j < m) { bv.y3[om + j] = y3[e]; bv.z4[om + j] = z4[e]; }
         }
         if (!UNIT) {
-            const long long ov = bv.off_val[inst];
-            for (int k = tid; k < stp->nnz; k += T) bv.r4v[ov + k] = S.r4v[k];
+            const long long ec = bv.off_evc[inst];
+            for (int k = tid; k < evc_used; k += T) bv.r4v[ec + k] = S.r4v[k];
         }
         if (tid < 16) stp->obj_ring[tid] = S.ring[tid];
         if (tid == 0) {
@@ -576,15 +604,27 @@ __global__ void lp_setup_kernel(BatchView bv, Params pr, int mode, int use_x0) {
     const int inst = blockIdx.x;
     InstState *st = bv.st + inst;
     const int n = st->n, m = st->m;
-    const PatLayout PL = pat_layout(st->n0, st->m0, st->nnz0);
-    const unsigned char *pat = bv.pat + bv.off_pat[inst];
+    const CsrLayout PL = csr_layout(st->n0, st->m0, st->nnz0);
+    const unsigned char *pat = bv.csr + bv.off_csr[inst];
     const u16 *rowptr = reinterpret_cast<const u16 *>(pat + PL.o_rowptr);
     const u16 *colptr = reinterpret_cast<const u16 *>(pat + PL.o_colptr);
     const u16 *colidx = reinterpret_cast<const u16 *>(pat + PL.o_colidx);
+    const u16 *rowidx = reinterpret_cast<const u16 *>(pat + PL.o_rowidx);
     const long long on = bv.off_n[inst], om = bv.off_m[inst], ov = bv.off_val ? bv.off_val[inst] : 0;
     const bool unit = st->unit != 0;
     const int tid = threadIdx.x, T = blockDim.x;
     __shared__ double s_best;
+    __shared__ int s_w[80];
+    if (mode & 4) {   // (re)build the sliced-ELL image from the compressed one
+        const EllLayout EL = ell_layout(st->n0, st->m0, st->rcap, st->ccap);
+        unsigned char *ell = bv.pat + bv.off_pat[inst];
+        build_ell(rowptr, colidx, unit ? nullptr : bv.val_r + ov, reinterpret_cast<const u16 *>(ell + EL.o_rperm), m,
+                  reinterpret_cast<u16 *>(ell + EL.o_rlen), reinterpret_cast<u16 *>(ell + EL.o_rsptr),
+                  reinterpret_cast<u16 *>(ell + EL.o_ridx), unit ? nullptr : bv.ev_r + bv.off_evr[inst], s_w);
+        build_ell(colptr, rowidx, unit ? nullptr : bv.val_c + ov, reinterpret_cast<const u16 *>(ell + EL.o_cperm), n,
+                  reinterpret_cast<u16 *>(ell + EL.o_clen), reinterpret_cast<u16 *>(ell + EL.o_csptr),
+                  reinterpret_cast<u16 *>(ell + EL.o_cidx), unit ? nullptr : bv.ev_c + bv.off_evc[inst], s_w);
+    }
     if (mode & 1) {
         for (int j = tid; j < n; j += T) {
             double x0 = use_x0 ? bv.x[on + j] : 1.0;                         // :583-586
@@ -651,7 +691,10 @@ __global__ void lp_setup_kernel(BatchView bv, Params pr, int mode, int use_x0) {
             bv.Esq[on + j] = e;
             bv.Pd[on + j] = dA(D, dM(rho4, e));                              // :2351, :2391
         }
-        if (!unit) for (int k = tid; k < st->nnz; k += T) bv.r4v[ov + k] = dM(rho4, bv.val_c[ov + k]);   // :2292-2293
+        if (!unit) {                                                         // :2292-2293 (ELL order; padding is never read)
+            const long long ec = bv.off_evc[inst];
+            for (int k = tid; k < 32 * st->ccap; k += T) bv.r4v[ec + k] = dM(rho4, bv.ev_c[ec + k]);
+        }
         __syncthreads();
         if (tid == 0) { st->D = D; st->r4s = dM(rho4, 1.0); }
     }

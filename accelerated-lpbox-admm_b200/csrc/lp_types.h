@@ -33,6 +33,7 @@ enum Status : int { RUNNING = 0, STOP_Y = 1, STOP_STD = 2, STOP_CG = 3, STOP_EMP
 // Per-instance scalars.  One struct per instance in HBM.
 struct InstState {
     int n0, m0, nnz0;        // capacities (original problem)
+    int rcap, ccap;          // capacities of the sliced-ELL index arrays (32-entry groups)
     int n, m, nnz;           // current (after early fixing) -- get_n()
     int iter;                // loop variable `iter` as left by the last window (get_iter())
     int status;              // Status of the last window
@@ -44,7 +45,6 @@ struct InstState {
     int fix_sum;
     int xit_rows, xit_cols;  // shape of x_iters of the last l2f window (LP.cpp:1113), cols actually recorded
     int norm_small;          // LP.cpp:1223 flag (x_sol.norm() < 1e-3 after a fix)
-    int pad0;
     double rho1, rho2, rho4, prho1, prho2, prho4, gamma, ratio;
     double D;                // every diagonal entry of _2A_plus_rho1_rho2 (identical for all j)
     double r4s;              // unit case: the single value stored in rho4_E_transpose
@@ -54,24 +54,47 @@ struct InstState {
     long long cg_iters, admm_iters;
 };
 
-// Byte layout of one instance's sparsity pattern blob (uint16 indices; both orientations of E).  The blob is the
-// exact shared-memory image, so that one 1-D TMA bulk copy stages it.
-// rowperm / colperm: work assignment of the sequential SpMVs -- slot s (thread s % T) processes row rowperm[s] /
-// column colperm[s]; slots are sorted by descending stored length so that the lanes of a warp run loops of similar
-// trip count (the ARITHMETIC of each row/column is unchanged, only which thread performs it).
-struct PatLayout {
-    int o_rowptr, o_colptr, o_colidx, o_rowidx, o_rowperm, o_colperm, bytes;
+// Two images of the sparsity pattern of E per instance, all uint16:
+//
+// (1) CsrLayout -- both compressed orientations (rowptr/colidx, colptr/rowidx).  Lives in HBM only; used by the
+//     set-up / early-fix kernels and the host getters.
+// (2) EllLayout -- the image the window kernel stages into shared memory with one 1-D TMA bulk copy: both
+//     orientations in SLICED-ELL form.  "Slot" s (work item of thread s % T) holds row rperm[s] (column cperm[s]);
+//     slots are sorted by descending stored length, a slice = 32 consecutive slots, stored column-major:
+//     entry k of the slot with lane l of slice w sits at idx[(sptr[w] + k) * 32 + l].  The 32 lanes of a warp read 32
+//     consecutive uint16 (one conflict-free 64-byte wavefront) and the addresses do not depend on loaded data, so the
+//     next batch of indices can be prefetched.  Only WHO computes a row/column product changes -- the order of
+//     operations inside each product (ascending inner index) is the reference's.
+struct CsrLayout {
+    int o_rowptr, o_colptr, o_colidx, o_rowidx, bytes;
+};
+struct EllLayout {
+    int o_rlen, o_rsptr, o_rperm, o_ridx, o_clen, o_csptr, o_cperm, o_cidx, bytes;
 };
 LPB_HD int a16(int x) { return (x + 15) & ~15; }
-LPB_HD PatLayout pat_layout(int n0, int m0, int nnz0) {
-    PatLayout L;
+LPB_HD CsrLayout csr_layout(int n0, int m0, int nnz0) {
+    CsrLayout L;
     L.o_rowptr = 0;
     L.o_colptr = a16(2 * (m0 + 1));
     L.o_colidx = L.o_colptr + a16(2 * (n0 + 1));
     L.o_rowidx = L.o_colidx + a16(2 * nnz0);
-    L.o_rowperm = L.o_rowidx + a16(2 * nnz0);
-    L.o_colperm = L.o_rowperm + a16(2 * m0);
-    L.bytes = L.o_colperm + a16(2 * n0);
+    L.bytes = L.o_rowidx + a16(2 * nnz0);
+    return L;
+}
+// rcap / ccap: capacity of the row / column ELL index arrays in 32-entry groups (sum of the slice widths at creation;
+// early fixing can only shrink them)
+LPB_HD EllLayout ell_layout(int n0, int m0, int rcap, int ccap) {
+    EllLayout L;
+    const int nsr = (m0 + 31) / 32, nsc = (n0 + 31) / 32;
+    L.o_rlen = 0;
+    L.o_rsptr = a16(2 * m0);
+    L.o_rperm = L.o_rsptr + a16(2 * (nsr + 1));
+    L.o_ridx = L.o_rperm + a16(2 * m0);
+    L.o_clen = L.o_ridx + a16(64 * rcap);
+    L.o_csptr = L.o_clen + a16(2 * n0);
+    L.o_cperm = L.o_csptr + a16(2 * (nsc + 1));
+    L.o_cidx = L.o_cperm + a16(2 * n0);
+    L.bytes = L.o_cidx + a16(64 * ccap);
     return L;
 }
 
@@ -81,13 +104,18 @@ struct BatchView {
     int hist_cap;
     const long long *off_n;    // [B+1] element offsets of the n-vectors (stride n0 rounded up to 2)
     const long long *off_m;    // [B+1]
-    const long long *off_pat;  // [B+1] byte offsets of the pattern blobs (16-byte aligned)
-    const long long *off_val;  // [B+1] element offsets of the value arrays (nnz0 each); unused when all unit
+    const long long *off_pat;  // [B+1] byte offsets of the sliced-ELL blobs (16-byte aligned)
+    const long long *off_csr;  // [B+1] byte offsets of the CSR/CSC blobs
+    const long long *off_val;  // [B+1] element offsets of the compressed-order value arrays (nnz0 each); non-unit only
+    const long long *off_evr;  // [B+1] element offsets of the row-ELL-order value array (32*rcap each)
+    const long long *off_evc;  // [B+1] element offsets of the column-ELL-order value arrays (32*ccap each)
     const long long *off_hist; // [B+1] element offsets of the iterate history (hist_cap * n0 each)
     double *x, *y1, *y2, *z1, *z2, *b, *Pd, *Esq;  // n-vectors
     double *y3, *z4, *f;                           // m-vectors
-    unsigned char *pat;
-    double *val_r, *val_c, *r4v;                   // CSR-order values, CSC-order values, CSC-order rho4*E^T values
+    unsigned char *pat;                            // sliced-ELL blobs (shared-memory images)
+    unsigned char *csr;                            // CSR/CSC blobs
+    double *val_r, *val_c;                         // CSR-order / CSC-order values of E (non-unit only)
+    double *ev_r, *ev_c, *r4v;                     // ELL-order values: E (row slots), E (column slots), rho4*E^T (column slots)
     InstState *st;
     double *hist;                                  // [cc][n0] per instance (iteration-major, coalesced writes)
     int *left_idx;                                 // [off_n] current -> original variable id
@@ -104,8 +132,8 @@ struct Launch {
     const int *work;         // instance ids (NULL: identity)
     int *counter;            // atomic work counter (device)
     int np, mp;              // shared-memory vector strides (>= max n0, m0 of the batch; even)
-    int pat_bytes;           // shared-memory bytes reserved for the pattern blob
-    int val_elems;           // shared-memory doubles reserved per value array (0 when unit)
+    int pat_bytes;           // shared-memory bytes reserved for the sliced-ELL blob
+    int evr_elems, evc_elems; // shared-memory doubles reserved for the ELL-order value arrays (0 when unit)
 };
 
 }  // namespace lpb
