@@ -620,6 +620,11 @@ extern "C" int lpbox_batch_results(lpbox_batch *h, lpbox_log_row *log, uint8_t *
 }
 
 extern "C" double lpbox_batch_last_kernel_ms(const lpbox_batch *h) { return h ? h->last_ms : -1.0; }
+extern "C" int lpbox_batch_config(const lpbox_batch *h, int32_t *out4) {
+    if (!h || !out4) return LPBOX_E_INVALID;
+    out4[0] = h->grid; out4[1] = (int32_t)h->smem; out4[2] = h->tcfg == 0 ? 128 : (h->tcfg == 1 ? 256 : 512); out4[3] = (int32_t)h->fix_smem;
+    return 0;
+}
 extern "C" int64_t lpbox_batch_h2d_bytes(const lpbox_batch *h) { return h ? h->h2d_bytes : -1; }
 extern "C" int64_t lpbox_batch_d2h_bytes(const lpbox_batch *h) { return h ? h->d2h_bytes : -1; }
 extern "C" int64_t lpbox_batch_launch_count(const lpbox_batch *h) { return h ? h->launches : -1; }

@@ -61,10 +61,83 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 }
 
 // ---- Eigen-order reduction ----------------------------------------------------------------------------------------
-// Executed by ONE warp.  Up to 8 independent reductions run side by side: lane l works on array q = l/4 as chain
+// Executed by ONE warp.  Up to 8 independent reductions run side by side: lane l works on reduction q = l/4 as chain
 // k = l%4 (Eigen's packet lanes: packet0 = {chain0, chain1}, packet1 = {chain2, chain3}).  Restates Eigen's
 // redux_impl<..., LinearVectorizedTraversal, NoUnrolling> for Packet2d (call sites LP.cpp:277,288,300,306,311,323,425,
-// 455,931-933).  Result of array q is returned in every lane of its group.
+// 455,931-933).  Reduction q sums the products a_q[i] * c_q[i] formed on the fly (dot / squaredNorm expressions); with
+// `ind` the second operand is the indicator 1[c_q[i] >= 0.5] (LP.cpp:1001-1005).  The per-lane operand pointers are
+// set by the caller.  Result of reduction q is returned in every lane of its group.
+__device__ __forceinline__ double prod_at(const double *a, const double *c, bool ind, int i) {
+    double cv = c[i];
+    if (ind) cv = (cv >= 0.5) ? 1.0 : 0.0;
+    return dM(a[i], cv);
+}
+// mode 0: sum of v[i]   (operand = materialised products)      mode 1: sum of v[i]*v[i]   (squaredNorm)
+__device__ __forceinline__ double term_at(const double *v, int mode, int i) {
+    const double t = v[i];
+    return mode ? dM(t, t) : t;
+}
+// one-operand variant of warp_redux_eigen2: each lane group reduces its own array `v` in mode `mode` (see term_at)
+__device__ __forceinline__ double warp_redux_eigen1(const double *v, int mode, int n) {
+    const int lane = threadIdx.x & 31;
+    const int k = lane & 3;
+    const int a2 = n & ~3, a1 = n & ~1;
+    double res;
+    if (a1 > 2) {
+        double acc = term_at(v, mode, k);
+        int i = 4 + k;
+        for (; i + 28 < a2; i += 32) {
+            double t0 = term_at(v, mode, i), t1 = term_at(v, mode, i + 4), t2 = term_at(v, mode, i + 8), t3 = term_at(v, mode, i + 12),
+                   t4 = term_at(v, mode, i + 16), t5 = term_at(v, mode, i + 20), t6 = term_at(v, mode, i + 24), t7 = term_at(v, mode, i + 28);
+            acc = dA(acc, t0); acc = dA(acc, t1); acc = dA(acc, t2); acc = dA(acc, t3);
+            acc = dA(acc, t4); acc = dA(acc, t5); acc = dA(acc, t6); acc = dA(acc, t7);
+        }
+        for (; i < a2; i += 4) acc = dA(acc, term_at(v, mode, i));
+        double hi = __shfl_down_sync(0xffffffffu, acc, 2);
+        double l = dA(acc, hi);
+        if (a1 > a2 && k < 2) l = dA(l, term_at(v, mode, a2 + k));
+        double l1 = __shfl_down_sync(0xffffffffu, l, 1);
+        res = dA(l, l1);
+    } else if (a1 == 2) {
+        res = dA(term_at(v, mode, 0), term_at(v, mode, 1));
+    } else {
+        res = (n > 0) ? term_at(v, mode, 0) : 0.0;
+    }
+    if ((n & 1) && n > 1) res = dA(res, term_at(v, mode, n - 1));
+    return __shfl_sync(0xffffffffu, res, lane & ~3);
+}
+__device__ __forceinline__ double warp_redux_eigen2(const double *__restrict__ a, const double *__restrict__ c, bool ind, int n) {
+    const int lane = threadIdx.x & 31;
+    const int k = lane & 3;
+    const int a2 = n & ~3, a1 = n & ~1;
+    double res;
+    if (a1 > 2) {
+        double acc = prod_at(a, c, ind, k);
+        int i = 4 + k;
+        // software-pipelined: loads and products are independent, only the adds form the chain
+        for (; i + 28 < a2; i += 32) {
+            double t0 = prod_at(a, c, ind, i), t1 = prod_at(a, c, ind, i + 4), t2 = prod_at(a, c, ind, i + 8),
+                   t3 = prod_at(a, c, ind, i + 12), t4 = prod_at(a, c, ind, i + 16), t5 = prod_at(a, c, ind, i + 20),
+                   t6 = prod_at(a, c, ind, i + 24), t7 = prod_at(a, c, ind, i + 28);
+            acc = dA(acc, t0); acc = dA(acc, t1); acc = dA(acc, t2); acc = dA(acc, t3);
+            acc = dA(acc, t4); acc = dA(acc, t5); acc = dA(acc, t6); acc = dA(acc, t7);
+        }
+        for (; i < a2; i += 4) acc = dA(acc, prod_at(a, c, ind, i));
+        // packet_res0 = packet_res0 + packet_res1 : chain0+chain2 , chain1+chain3
+        double hi = __shfl_down_sync(0xffffffffu, acc, 2);
+        double l = dA(acc, hi);                                          // valid in k = 0,1
+        if (a1 > a2 && k < 2) l = dA(l, prod_at(a, c, ind, a2 + k));     // one more packet
+        double l1 = __shfl_down_sync(0xffffffffu, l, 1);
+        res = dA(l, l1);                                                 // predux: lane0 + lane1 (valid in k = 0)
+    } else if (a1 == 2) {
+        res = dA(prod_at(a, c, ind, 0), prod_at(a, c, ind, 1));
+    } else {
+        res = (n > 0) ? prod_at(a, c, ind, 0) : 0.0;                     // n == 1 (coeff(0)); n == 0 -> 0
+    }
+    if ((n & 1) && n > 1) res = dA(res, prod_at(a, c, ind, n - 1));      // scalar tail (valid in k = 0)
+    return __shfl_sync(0xffffffffu, res, lane & ~3);                     // broadcast chain-0 lane's value to its group
+}
+// single-array sum (used by the early-fix kernel on materialised products)
 template <int R>
 __device__ __forceinline__ double warp_redux_eigen(const double *red, int stride, int n) {
     const int lane = threadIdx.x & 31;
@@ -74,28 +147,19 @@ __device__ __forceinline__ double warp_redux_eigen(const double *red, int stride
     double res;
     if (a1 > 2) {
         double acc = v[k];
-        int i = 4 + k;
-        // software-pipelined: the loads are independent, only the adds form the chain
-        for (; i + 28 < a2; i += 32) {
-            double t0 = v[i], t1 = v[i + 4], t2 = v[i + 8], t3 = v[i + 12], t4 = v[i + 16], t5 = v[i + 20], t6 = v[i + 24],
-                   t7 = v[i + 28];
-            acc = dA(acc, t0); acc = dA(acc, t1); acc = dA(acc, t2); acc = dA(acc, t3);
-            acc = dA(acc, t4); acc = dA(acc, t5); acc = dA(acc, t6); acc = dA(acc, t7);
-        }
-        for (; i < a2; i += 4) acc = dA(acc, v[i]);
-        // packet_res0 = packet_res0 + packet_res1 : chain0+chain2 , chain1+chain3
+        for (int i = 4 + k; i < a2; i += 4) acc = dA(acc, v[i]);
         double hi = __shfl_down_sync(0xffffffffu, acc, 2);
-        double l = dA(acc, hi);                       // valid in k = 0,1
-        if (a1 > a2 && k < 2) l = dA(l, v[a2 + k]);   // one more packet
+        double l = dA(acc, hi);
+        if (a1 > a2 && k < 2) l = dA(l, v[a2 + k]);
         double l1 = __shfl_down_sync(0xffffffffu, l, 1);
-        res = dA(l, l1);                              // predux: lane0 + lane1 (valid in k = 0)
+        res = dA(l, l1);
     } else if (a1 == 2) {
         res = dA(v[0], v[1]);
     } else {
-        res = (n > 0) ? v[0] : 0.0;                   // n == 1 (coeff(0)); n == 0 -> 0
+        res = (n > 0) ? v[0] : 0.0;
     }
-    if ((n & 1) && n > 1) res = dA(res, v[n - 1]);    // scalar tail (valid in k = 0)
-    return __shfl_sync(0xffffffffu, res, lane & ~3);  // broadcast chain-0 lane's value to its group
+    if ((n & 1) && n > 1) res = dA(res, v[n - 1]);
+    return __shfl_sync(0xffffffffu, res, lane & ~3);
 }
 
 // ---- sequential sparse dot products on the sliced-ELL image ---------------------------------------------------------
@@ -170,13 +234,14 @@ __device__ __forceinline__ void build_ell(const u16 *ptr, const u16 *idx, const 
 }
 
 // shared-memory carve-up -----------------------------------------------------------------------------------------------
+// Three n-vectors and two m-vectors are enough: every reduction takes its operands from vectors that are staged anyway
+// (products are formed inside the reduction), and column-product results overwrite operands that are dead by then.
 struct Smem {
-    double *gv;      // [np]   vector being gathered by E v (x or p)
-    double *red;     // [5][np] reduction operands
-    double *oc;      // [np]   result of a column-wise (E^T-type) product, read back by the element owners
+    double *gv;      // [np]   vector being gathered by E v (x or p); second reduction operand (z); E^T z4 result
+    double *a1;      // [np]   y2 pre-image / R4ET(f-y3) result / rhs / r
+    double *a2;      // [np]   f - y3 (m entries) / column-product result / tmp = M p / x - y2
     double *t1;      // [mp]   E v
-    double *wa;      // [mp]   f - y3
-    double *wb;      // [mp]   z4
+    double *wb;      // [mp]   copy of z4 gathered by E^T z4
     double *sc;      // [8]    reduction results / broadcast scalars
     double *ring;    // [16]   tail of obj_list
     double *ev_r, *ev_c, *r4v;    // ELL-order values: [evr_elems], [evc_elems], [evc_elems] (non-unit only)
@@ -184,18 +249,17 @@ struct Smem {
     uint64_t *bar;
 };
 __host__ __device__ inline size_t smem_bytes(int np, int mp, int pat_bytes, int evr_elems, int evc_elems) {
-    size_t d = (size_t)np * 6 + (size_t)mp * 1 + 8 + 16 + (size_t)evr_elems + 2 * (size_t)evc_elems;
+    size_t d = (size_t)np * 3 + (size_t)mp * 2 + 8 + 16 + (size_t)evr_elems + 2 * (size_t)evc_elems;
     return d * sizeof(double) + (size_t)pat_bytes + 16;
 }
 __device__ __forceinline__ Smem carve(unsigned char *base, int np, int mp, int pat_bytes, int evr_elems, int evc_elems) {
     Smem s;
     double *d = reinterpret_cast<double *>(base);
     s.gv = d; d += np;
-    s.red = d; d += 5 * (size_t)np;
-    s.oc = s.red + 3 * (size_t)np;   // aliases red3: column products are consumed before red3 is next written
+    s.a1 = d; d += np;
+    s.a2 = d; d += np;
     s.t1 = d; d += mp;
-    s.wa = s.red;                     // aliases red0 (m <= np): f - y3 lives only between the y3 step and the rhs products
-    s.wb = s.red + (size_t)np;        // aliases red1: z4 copy, same lifetime
+    s.wb = d; d += mp;
     s.sc = d; d += 8;
     s.ring = d; d += 16;
     s.ev_r = d; d += evr_elems;
@@ -309,7 +373,7 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
         const u16 *cperm = reinterpret_cast<const u16 *>(S.pat + PL.o_cperm);
         const u16 *cidx = reinterpret_cast<const u16 *>(S.pat + PL.o_cidx);
         const double pow_n = bv.pow_tab[n];               // std::pow(n, 1.0/p), p = 2 (LP.cpp:427)
-        double *red0 = S.red, *red1 = S.red + np, *red2 = S.red + 2 * np, *red3 = S.red + 3 * np, *red4 = S.red + 4 * np;
+        const int lane = tid & 31, rq = lane >> 2;        // reduction group of this lane (reduction warp only)
 
         int status = RUNNING;
         int iter = la.iter_start;
@@ -323,13 +387,13 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                 double t = dA(x[e], dD(z1[e], rho1));
                 y1[e] = (t > 1.0) ? 1.0 : ((t < 0.0) ? 0.0 : t);
                 y2[e] = dS(dA(x[e], dD(z2[e], rho2)), 0.5);
-                if (j < n) { red0[j] = dM(y2[e], y2[e]); S.gv[j] = x[e]; }
+                if (j < n) { S.a1[j] = y2[e]; S.gv[j] = x[e]; }
             }
             __syncthreads();
             // ---- ||y|| (:425) on the reduction warp, E x (:825) on the row slots -------------------------------
             if (warp == RW) {
-                double v = warp_redux_eigen<1>(red0, np, n);
-                if ((tid & 31) == 0) S.sc[0] = v;
+                double v = warp_redux_eigen1(S.a1, 1, n);
+                if (lane == 0) S.sc[0] = v;
             }
             seq_spmv_ell<T, CE>(rlen, rsptr, rperm, ridx, S.ev_r, 0.0, S.gv, m, S.t1);
             __syncthreads();
@@ -338,14 +402,14 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                 const double den = dM(2.0, nrm);
                 LPB_FOR_E y2[e] = dA(dD(dM(y2[e], pow_n), den), 0.5);       // :427
             }
-            // ---- y3 (:826-827) -------------------------------------------------------------------------------
+            // ---- y3 (:826-827); f - y3 and z4 staged for the two column products of the rhs ----------------------
             LPB_FOR_E {
                 int i = tid + e * T;
                 if (i < m) {
                     const double fi = gf[i];
                     double t = dS(dS(fi, S.t1[i]), dD(z4[e], rho4));
                     y3[e] = (t < 0.0) ? 0.0 : t;
-                    S.wa[i] = dS(fi, y3[e]); S.wb[i] = z4[e];
+                    S.a2[i] = dS(fi, y3[e]); S.wb[i] = z4[e];
                 }
             }
             // ---- operator patch after a rho step (:851-866) and preconditioner refresh (:883-890) --------------
@@ -374,9 +438,9 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                 rhoUpdated = 0;
             }
             __syncthreads();
-            // ---- rhs (:872-878): two column-wise products, results through shared memory ------------------------
-            seq_spmv_ell<T, CR>(clen, csptr, cperm, cidx, S.r4v, r4s, S.wa, n, S.oc);      // R4ET (f - y3)
-            seq_spmv_ell<T, CE>(clen, csptr, cperm, cidx, S.ev_c, 0.0, S.wb, n, red4);   // ET z4
+            // ---- rhs (:872-878): R4ET (f - y3) -> a1, ET z4 -> gv ------------------------------------------------
+            seq_spmv_ell<T, CR>(clen, csptr, cperm, cidx, S.r4v, r4s, S.a2, n, S.a1);
+            seq_spmv_ell<T, CE>(clen, csptr, cperm, cidx, S.ev_c, 0.0, S.wb, n, S.gv);
             __syncthreads();
             // ---- PCG (:251-335), warm start x = y1 (:892) ------------------------------------------------------
             double rhs[EPT], xc[EPT];
@@ -384,35 +448,34 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                 int j = tid + e * T;
                 if (j < n) {
                     double t = dS(dA(dM(rho1, y1[e]), dM(rho2, y2[e])), dA(dA(gb[j], z1[e]), z2[e]));
-                    t = dA(t, S.oc[j]);
-                    rhs[e] = dS(t, red4[j]);
+                    t = dA(t, S.a1[j]);
+                    rhs[e] = dS(t, S.gv[j]);
                     xc[e] = y1[e];
-                    S.gv[j] = xc[e]; red0[j] = dM(rhs[e], rhs[e]);
+                    S.gv[j] = xc[e]; S.a1[j] = rhs[e];
                 } else { rhs[e] = 0.0; xc[e] = 0.0; }
             }
             __syncthreads();
             if (warp == RW) {
-                double v = warp_redux_eigen<1>(red0, np, n);               // rhs.squaredNorm() :277
-                if ((tid & 31) == 0) S.sc[0] = v;
+                double v = warp_redux_eigen1(S.a1, 1, n);                  // rhs.squaredNorm() :277
+                if (lane == 0) S.sc[0] = v;
             }
             seq_spmv_ell<T, CE>(rlen, rsptr, rperm, ridx, S.ev_r, 0.0, S.gv, m, S.t1);
             __syncthreads();
             const double rhsNorm2 = S.sc[0];
-            seq_spmv_ell<T, CR>(clen, csptr, cperm, cidx, S.r4v, r4s, S.t1, n, S.oc);
+            seq_spmv_ell<T, CR>(clen, csptr, cperm, cidx, S.r4v, r4s, S.t1, n, S.a2);
             __syncthreads();
             LPB_FOR_E {
                 int j = tid + e * T;
                 if (j < n) {
-                    double mv = dA(dA(0.0, dM(D, xc[e])), S.oc[j]);          // D v (+) R4ET (E v)   :115-162
+                    double mv = dA(dA(0.0, dM(D, xc[e])), S.a2[j]);          // D v (+) R4ET (E v)   :115-162
                     r[e] = dS(rhs[e], mv);                                   // :273
                     p[e] = dM(invd[e], r[e]);                                // :297
-                    red1[j] = dM(r[e], r[e]); red2[j] = dM(r[e], p[e]);
+                    S.a1[j] = r[e]; S.gv[j] = p[e]; S.a2[j] = dM(r[e], p[e]);
                 }
             }
             __syncthreads();
             if (warp == RW) {
-                double v = warp_redux_eigen<2>(red1, np, n);               // :288, :300
-                int lane = tid & 31;
+                double v = warp_redux_eigen1(rq == 0 ? S.a1 : S.a2, rq == 0, n);       // r.r :288, r.p :300
                 if (lane == 0) S.sc[1] = v;
                 if (lane == 4) S.sc[2] = v;
             }
@@ -427,25 +490,23 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                 double r2 = S.sc[1];
                 double absNew = S.sc[2];
                 if (!(r2 < threshold)) {                                     // :290-295
-                    while (cg_it < pr.pcg_maxiters) {
-                        LPB_FOR_E { int j = tid + e * T; if (j < n) S.gv[j] = p[e]; }
-                        __syncthreads();
+                    while (cg_it < pr.pcg_maxiters) {                        // gv holds p here
                         seq_spmv_ell<T, CE>(rlen, rsptr, rperm, ridx, S.ev_r, 0.0, S.gv, m, S.t1);
                         __syncthreads();
-                        seq_spmv_ell<T, CR>(clen, csptr, cperm, cidx, S.r4v, r4s, S.t1, n, S.oc);
+                        seq_spmv_ell<T, CR>(clen, csptr, cperm, cidx, S.r4v, r4s, S.t1, n, S.a2);
                         __syncthreads();
                         double tmp[EPT];
                         LPB_FOR_E {
                             int j = tid + e * T;
                             if (j < n) {
-                                tmp[e] = dA(dA(0.0, dM(D, p[e])), S.oc[j]);   // :304
-                                red0[j] = dM(p[e], tmp[e]);
+                                tmp[e] = dA(dA(0.0, dM(D, p[e])), S.a2[j]);   // :304
+                                S.a2[j] = dM(p[e], tmp[e]);
                             } else tmp[e] = 0.0;
                         }
                         __syncthreads();
                         if (warp == RW) {
-                            double v = warp_redux_eigen<1>(red0, np, n);     // p.dot(tmp) :306
-                            if ((tid & 31) == 0) S.sc[0] = v;
+                            double v = warp_redux_eigen1(S.a2, 0, n);             // p.dot(tmp) :306
+                            if (lane == 0) S.sc[0] = v;
                         }
                         __syncthreads();
                         const double alpha = dD(absNew, S.sc[0]);
@@ -456,12 +517,11 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                             xc[e] = dA(xc[e], dM(alpha, p[e]));               // :308
                             r[e] = dS(r[e], dM(alpha, tmp[e]));               // :310
                             zz[e] = dM(invd[e], r[e]);                        // :320
-                            if (j < n) { red1[j] = dM(r[e], r[e]); red2[j] = dM(r[e], zz[e]); }
+                            if (j < n) { S.a1[j] = r[e]; S.gv[j] = dM(r[e], zz[e]); }
                         }
                         __syncthreads();
                         if (warp == RW) {
-                            double v = warp_redux_eigen<2>(red1, np, n);     // :311, :323
-                            int lane = tid & 31;
+                            double v = warp_redux_eigen1(rq == 0 ? S.a1 : S.gv, rq == 0, n);       // r.r :311, r.z :323
                             if (lane == 0) S.sc[1] = v;
                             if (lane == 4) S.sc[2] = v;
                         }
@@ -471,8 +531,13 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                         const double absOld = absNew;
                         absNew = S.sc[2];
                         const double beta = dD(absNew, absOld);              // :324
-                        LPB_FOR_E p[e] = dA(zz[e], dM(beta, p[e]));           // :325
+                        LPB_FOR_E {
+                            int j = tid + e * T;
+                            p[e] = dA(zz[e], dM(beta, p[e]));                 // :325
+                            if (j < n) S.gv[j] = p[e];
+                        }
                         cg_it++;
+                        __syncthreads();
                     }
                 }
             }
@@ -499,23 +564,17 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                     const double d1 = dS(x[e], y1[e]), d2 = dS(x[e], y2[e]);
                     z1[e] = dA(z1[e], dM(g1, d1));
                     z2[e] = dA(z2[e], dM(g2, d2));
-                    if (j < n) {
-                        const double bj = gb[j];
-                        S.gv[j] = x[e];
-                        red0[j] = dM(x[e], x[e]);
-                        red1[j] = dM(d1, d1);
-                        red2[j] = dM(d2, d2);
-                        red3[j] = dM(bj, x[e]);
-                        red4[j] = dM(bj, (x[e] >= 0.5) ? 1.0 : 0.0);
-                    }
+                    if (j < n) { S.gv[j] = x[e]; S.a1[j] = d1; S.a2[j] = d2; }
                 }
             }
             __syncthreads();
             seq_spmv_ell<T, CE>(rlen, rsptr, rperm, ridx, S.ev_r, 0.0, S.gv, m, S.t1);
             if (warp == RW) {
-                double v = warp_redux_eigen<5>(red0, np, n);
-                int lane = tid & 31;
-                if ((lane & 3) == 0 && lane < 20) S.sc[lane >> 2] = v;
+                // x.x, (x-y1)^2, (x-y2)^2, b.x, b.1[x>=0.5]  (:931-933, :972, :1001-1005) side by side
+                const double *pa = (rq == 0) ? S.gv : (rq == 1) ? S.a1 : (rq == 2) ? S.a2 : gb;
+                const double *pc = (rq == 1) ? S.a1 : (rq == 2) ? S.a2 : S.gv;
+                double v = warp_redux_eigen2(pa, pc, rq == 4, n);
+                if ((lane & 3) == 0 && lane < 20) S.sc[rq] = v;
                 __syncwarp();
                 if (lane == 0) {
                     const double obj = S.sc[3];
@@ -560,7 +619,7 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
             }
             cur_obj = S.sc[4];                                               // :1001-1005
             if (best_bin_obj >= cur_obj) best_bin_obj = cur_obj;             // :1006-1009
-            // all reads of S.sc / red* / t1 of this iteration are complete before the next iteration's first barrier
+            // all reads of S.sc / gv / a1 / a2 / t1 of this iteration are complete before the next iteration's first barrier
         }
 
         // ---------------- write the instance back ---------------------------------------------------------------

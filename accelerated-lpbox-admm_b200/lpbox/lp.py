@@ -176,6 +176,11 @@ class LPBatch:
     def launch_count(self):
         return self.L.lpbox_batch_launch_count(self.h)
 
+    def config(self):
+        out = np.zeros(4, dtype=np.int32)
+        check(self.L.lpbox_batch_config(self.h, ptr(out)), "config")
+        return dict(grid=int(out[0]), smem_bytes=int(out[1]), threads=int(out[2]), fix_smem_bytes=int(out[3]))
+
     def h2d_bytes(self):
         return self.L.lpbox_batch_h2d_bytes(self.h)
 

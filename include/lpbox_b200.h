@@ -134,6 +134,9 @@ int lpbox_batch_results(lpbox_batch *h, lpbox_log_row *log, uint8_t *x_bits, int
 /* device time (ms, CUDA events on the handle's stream) and number of kernel launches of the last solve/iters call */
 double lpbox_batch_last_kernel_ms(const lpbox_batch *h);
 int64_t lpbox_batch_launch_count(const lpbox_batch *h);
+/* launch configuration of the window kernel: out4 = {grid (persistent CTAs), dynamic shared memory bytes per CTA,
+ * threads per CTA, shared memory bytes of the early-fix kernel} */
+int lpbox_batch_config(const lpbox_batch *h, int32_t *out4);
 /* bytes copied host->device / device->host by this handle so far (counted from the buffers actually copied) */
 int64_t lpbox_batch_h2d_bytes(const lpbox_batch *h);
 int64_t lpbox_batch_d2h_bytes(const lpbox_batch *h);

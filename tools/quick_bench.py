@@ -10,7 +10,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 592
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
 gs = [load_golden(f"auction_100_500_seed{s}.npz") for s in (0, 1, 2)]
 probs = [problem_tuple(gs[i % 3]) for i in range(B)]
-t = time.time(); b = lpbox.LPBatch(probs); b.init(); print("create+init s", time.time() - t)
+t = time.time(); b = lpbox.LPBatch(probs); b.init(); print("create+init s", time.time() - t, b.config())
 t = time.time(); log = b.solve(iters); wall = time.time() - t
 ms = b.last_kernel_ms()
 print(f"B={B} kernel_ms={ms:.1f} wall={wall:.3f}s inst/s={B/(ms/1e3):.1f} admm_it/s={log['iters'].sum()/(ms/1e3):.3e} cg_it/s={log['cg_iters'].sum()/(ms/1e3):.3e}")
