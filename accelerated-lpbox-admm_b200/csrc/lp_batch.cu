@@ -13,6 +13,7 @@
 #include "../../include/lpbox_b200.h"
 #include "lp_fix_kernel.cuh"
 #include "lp_kernels.cuh"
+#include "lp_policy_glue.cuh"
 
 using namespace lpb;
 
@@ -85,6 +86,13 @@ struct lpbox_batch {
     double last_ms = 0;
     int64_t launches = 0;
     int64_t h2d_bytes = 0, d2h_bytes = 0;
+    bool own_stream = true;
+    // device-resident window loop
+    DevBuf<int> d_active;
+    DevBuf<long long> d_row_off;
+    std::vector<int> h_active;
+    std::vector<long long> h_row_off;
+    bool dev_fix_pending = false;
 };
 
 template <int T, int EPT, bool UNIT>
@@ -345,7 +353,8 @@ extern "C" void lpbox_batch_destroy(lpbox_batch *h) {
     h->d_counter.free_(); h->d_num.free_();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
+    h->d_active.free_(); h->d_row_off.free_();
     delete h;
 }
 
@@ -620,6 +629,83 @@ extern "C" int lpbox_batch_results(lpbox_batch *h, lpbox_log_row *log, uint8_t *
 }
 
 extern "C" double lpbox_batch_last_kernel_ms(const lpbox_batch *h) { return h ? h->last_ms : -1.0; }
+// ---- device-resident window loop (no host copies of iterates / scores / fix vectors) ---------------------------------
+extern "C" int lpbox_batch_set_stream(lpbox_batch *h, void *cuda_stream) {
+    if (!h) return LPBOX_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    h->stream = (cudaStream_t)cuda_stream; h->own_stream = false;
+    return 0;
+}
+extern "C" void *lpbox_batch_hist_dev(lpbox_batch *h) { return h ? (void *)h->d_hist.p : nullptr; }
+
+extern "C" int64_t lpbox_batch_policy_input_dev(lpbox_batch *h, int ws, float *out_dev, int64_t capacity_rows) {
+    if (!h || !h->inited || ws <= 0 || ws > h->hist_cap) { set_err("policy_input: bad arguments (ws must be <= hist_cap)"); return LPBOX_E_INVALID; }
+    CK(cudaSetDevice(h->device));
+    h->h_active.clear(); h->h_row_off.assign(1, 0);
+    int max_rows = 0;
+    for (int i = 0; i < h->B; ++i) {
+        const InstState &s = h->h_st[i];
+        if (s.done || s.n == 0) continue;
+        h->h_active.push_back(i);
+        h->h_row_off.push_back(h->h_row_off.back() + s.n);
+        max_rows = std::max(max_rows, s.n);
+    }
+    const int na = (int)h->h_active.size();
+    const int64_t rows = h->h_row_off.back();
+    if (!out_dev || na == 0) return rows;
+    if (rows > capacity_rows) { set_err("policy_input: output buffer too small"); return LPBOX_E_INVALID; }
+    if (!h->d_active.p) { CK(h->d_active.alloc(h->B)); CK(h->d_row_off.alloc((size_t)h->B + 1)); }
+    CK(cudaMemcpyAsync(h->d_active.p, h->h_active.data(), sizeof(int) * (size_t)na, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_row_off.p, h->h_row_off.data(), sizeof(long long) * (size_t)(na + 1), cudaMemcpyHostToDevice, h->stream));
+    dim3 grid((max_rows + 31) / 32, na), block(32, 8);
+    lp_policy_input_kernel<<<grid, block, 0, h->stream>>>(h->bv, h->d_active.p, h->d_row_off.p, ws, out_dev);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    return rows;
+}
+
+extern "C" int lpbox_batch_apply_scores_dev(lpbox_batch *h, const float *scores_dev, double hi, double lo, int min_fix) {
+    if (!h || !h->inited || !scores_dev) return LPBOX_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    const int na = (int)h->h_active.size();
+    CK(cudaMemsetAsync(h->d_num.p, 0, sizeof(int) * (size_t)h->B, h->stream));
+    if (na > 0) {
+        lp_threshold_kernel<<<na, 256, 0, h->stream>>>(h->bv, h->d_active.p, h->d_row_off.p, scores_dev, hi, lo, min_fix, h->d_vec.p,
+                                                      h->d_off_vec.p, h->d_num.p);
+        CK(cudaGetLastError());
+        h->launches += 1;
+    }
+    h->dev_fix_pending = true;
+    return na;
+}
+
+extern "C" int lpbox_batch_iters_l2f_dev(lpbox_batch *h, int iter_start, int iter_end) {
+    if (!h || !h->inited) { set_err("call lpbox_batch_init first"); return LPBOX_E_INVALID; }
+    CK(cudaSetDevice(h->device));
+    time_begin(h);
+    if (!h->dev_fix_pending) CK(cudaMemsetAsync(h->d_num.p, 0, sizeof(int) * (size_t)h->B, h->stream));
+    h->dev_fix_pending = false;
+    int np = (h->max_n + 1) & ~1, mp = (h->max_m + 1) & ~1;
+    int val_elems = h->all_unit ? 0 : ((h->max_nnz + 1) & ~1);
+    lp_fix_kernel<<<h->B, FIX_T, h->fix_smem, h->stream>>>(h->bv, h->pr, h->d_vec.p, h->d_off_vec.p, h->d_num.p, 1, np, mp, h->max_csr, val_elems);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    if (iter_start == 0 && iter_end > 0) {
+        lp_setup_kernel<<<h->B, 128, 0, h->stream>>>(h->bv, h->pr, 2, 0);
+        CK(cudaGetLastError());
+        h->launches += 1;
+    }
+    int rc = run_window(h, iter_start, iter_end, 1, 1);
+    if (rc) return rc;
+    rc = time_end(h); if (rc) return rc;
+    rc = sync_states(h); if (rc) return rc;
+    int active = 0;
+    for (int i = 0; i < h->B; ++i) if (!h->h_st[i].done && h->h_st[i].n != 0) active++;
+    return active;
+}
+
 extern "C" int lpbox_batch_config(const lpbox_batch *h, int32_t *out4) {
     if (!h || !out4) return LPBOX_E_INVALID;
     out4[0] = h->grid; out4[1] = (int32_t)h->smem; out4[2] = h->tcfg == 0 ? 128 : (h->tcfg == 1 ? 256 : 512); out4[3] = (int32_t)h->fix_smem;

@@ -1,0 +1,59 @@
+// Device-side glue between the window kernel and the early-fixing policy (LP.trainer:510-535 without host copies):
+//   * lp_policy_input_kernel: iterate history [iteration][n0] (fp64) -> packed policy input [row][ws] (fp32), i.e. the
+//     reference's `xiters.reshape(n_left, 20, ws/20).astype(float32)` (LP.trainer:524-530) for all active instances;
+//   * lp_threshold_kernel: deter_fix_2 (LP.trainer:101-135) + the "n <= 10 -> no fix" rule (:533-535) on the scores.
+#pragma once
+#include "lp_kernels.cuh"
+
+namespace lpb {
+
+// grid = (ceil(max_rows/32), n_active); block = (32, 8).  Tile transpose through shared memory so that both the reads
+// (along the variable index) and the writes (along the iteration index) are coalesced.
+__global__ void lp_policy_input_kernel(BatchView bv, const int *__restrict__ active, const long long *__restrict__ row_off,
+                                       int ws, float *__restrict__ out) {
+    __shared__ float tile[32][33];
+    const int inst = active[blockIdx.y];
+    const InstState *st = bv.st + inst;
+    const int n = st->n, n0 = st->n0, cols = min(st->xit_cols, min(ws, bv.hist_cap));
+    const int r0 = blockIdx.x * 32;
+    if (r0 >= n) return;
+    const double *h = bv.hist + bv.off_hist[inst];
+    float *o = out + row_off[blockIdx.y] * ws;
+    for (int c0 = 0; c0 < ws; c0 += 32) {
+        for (int cy = threadIdx.y; cy < 32; cy += 8) {
+            const int c = c0 + cy, r = r0 + threadIdx.x;
+            tile[cy][threadIdx.x] = (c < cols && r < n) ? (float)h[(long long)c * n0 + r] : 0.0f;   // x_iters is zero-initialised
+        }
+        __syncthreads();
+        for (int ry = threadIdx.y; ry < 32; ry += 8) {
+            const int r = r0 + ry, c = c0 + threadIdx.x;
+            if (r < n && c < ws) o[(long long)r * ws + c] = tile[threadIdx.x][ry];
+        }
+        __syncthreads();
+    }
+}
+
+// one CTA per active instance: vec[i] = 1 if p > hi, 0 if p < lo, else -1; num = #fixed, or 0 when #fixed <= min_fix
+__global__ void lp_threshold_kernel(BatchView bv, const int *__restrict__ active, const long long *__restrict__ row_off,
+                                    const float *__restrict__ scores, double hi, double lo, int min_fix, double *__restrict__ vec,
+                                    long long *__restrict__ off_vec, int *__restrict__ num) {
+    __shared__ int s_cnt;
+    const int inst = active[blockIdx.x];
+    const int n = bv.st[inst].n;
+    const float *p = scores + row_off[blockIdx.x];
+    double *v = vec + bv.off_n[inst];
+    if (threadIdx.x == 0) { s_cnt = 0; off_vec[inst] = bv.off_n[inst]; }
+    __syncthreads();
+    int c = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double pi = (double)p[i];
+        double f = -1.0;
+        if (pi > hi) { f = 1.0; c++; } else if (pi < lo) { f = 0.0; c++; }
+        v[i] = f;
+    }
+    atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) num[inst] = (s_cnt <= min_fix) ? 0 : s_cnt;
+}
+
+}  // namespace lpb

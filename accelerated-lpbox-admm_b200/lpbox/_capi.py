@@ -68,6 +68,11 @@ SIGNATURES = {
     "lpbox_batch_last_kernel_ms": (C.c_double, [_vp]),
     "lpbox_batch_launch_count": (C.c_int64, [_vp]),
     "lpbox_batch_config": (C.c_int, [_vp, _vp]),
+    "lpbox_batch_set_stream": (C.c_int, [_vp, _vp]),
+    "lpbox_batch_hist_dev": (_vp, [_vp]),
+    "lpbox_batch_policy_input_dev": (C.c_int64, [_vp, C.c_int, _vp, C.c_int64]),
+    "lpbox_batch_apply_scores_dev": (C.c_int, [_vp, _vp, C.c_double, C.c_double, C.c_int]),
+    "lpbox_batch_iters_l2f_dev": (C.c_int, [_vp, C.c_int, C.c_int]),
     "lpbox_batch_h2d_bytes": (C.c_int64, [_vp]),
     "lpbox_batch_d2h_bytes": (C.c_int64, [_vp]),
     "lpbox_read_instance": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, _ip, _ip, C.POINTER(_ip), C.POINTER(_ip),

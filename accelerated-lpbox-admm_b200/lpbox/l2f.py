@@ -1,0 +1,48 @@
+"""The early-fixing window driver (LP.trainer:483-545) with everything on the device.
+
+Per window: ADMM window kernel -> policy input gather -> policy network -> threshold -> compaction kernel, all ordered on
+one CUDA stream; the only host<->device traffic per window is the per-instance state structs (a few hundred bytes per
+instance) that tell the host which instances are still active.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ._capi import check
+
+
+def solve_l2f(batch, score_fn, ws=100, max_iter=10000, tokens=20, hi=0.9, lo=None, min_fix=10, chunk_rows=32768, device=None):
+    """Runs `for i in range(max_iter // ws): solve_iter_l2f(...); policy; deter_fix_2` for every instance of `batch`.
+
+    score_fn: callable (rows, tokens, ws // tokens) float32 CUDA tensor -> (rows,) or (rows, 1) sigmoid scores, e.g.
+    `lambda x: net(x)[1]` with a `lpbox.policy.GraphAttentionEncoder`.  Returns (log rows, packed bits, stats dict).
+    """
+    import torch
+    if lo is None:
+        lo = 1 - hi                                             # `data[i] < 1 - C` (LP.trainer:124)
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    L, h = batch.L, batch.h
+    check(L.lpbox_batch_set_stream(h, torch.cuda.current_stream(dev).cuda_stream), "set_stream")
+    cap = int(batch.org_n.sum())
+    inp = torch.empty((cap, ws), dtype=torch.float32, device=dev)
+    scores = torch.empty((cap,), dtype=torch.float32, device=dev)
+    stats = dict(windows=0, policy_rows=0, window_ms=0.0)
+    for w in range(int(max_iter // ws)):
+        active = check(L.lpbox_batch_iters_l2f_dev(h, ws * w, ws * (w + 1)), "iters_l2f_dev")
+        stats["windows"] += 1
+        stats["window_ms"] += batch.last_kernel_ms()
+        if active == 0:
+            break
+        rows = check(L.lpbox_batch_policy_input_dev(h, ws, inp.data_ptr(), cap), "policy_input_dev")
+        if rows == 0:
+            break
+        x = inp[:rows].view(rows, tokens, ws // tokens)
+        with torch.no_grad():
+            for a in range(0, rows, chunk_rows):
+                b = min(rows, a + chunk_rows)
+                scores[a:b] = score_fn(x[a:b]).reshape(-1).float()
+        stats["policy_rows"] += rows
+        check(L.lpbox_batch_apply_scores_dev(h, scores.data_ptr(), float(hi), float(lo), int(min_fix)), "apply_scores_dev")
+    torch.cuda.current_stream(dev).synchronize()
+    log, bits = batch.results()
+    return log, bits, stats

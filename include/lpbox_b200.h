@@ -108,6 +108,24 @@ int lpbox_batch_iters_l2f(lpbox_batch *h, int iter_start, int iter_end, const do
  * by the built-in policy kernel (lpbox_batch_set_policy) -- see lpbox_batch_solve_l2f. */
 int lpbox_batch_solve(lpbox_batch *h, int max_iters, lpbox_log_row *log /* B rows, may be NULL */);
 
+/* ---- device-resident window loop: window -> policy -> threshold -> compact without host copies of the iterates ----
+ * (LP.trainer:510-535).  The policy network itself runs outside this library on `scores`/`input` DEVICE buffers
+ * (PyTorch or the bf16 policy kernel); everything is ordered on one stream. */
+/* use the caller's CUDA stream (cudaStream_t) for all work of this handle, e.g. torch's current stream */
+int lpbox_batch_set_stream(lpbox_batch *h, void *cuda_stream);
+/* device pointer of the iterate history: instance i at element offset sum_{k<i} hist_cap*n[k], layout [iteration][n[i]] fp64 */
+void *lpbox_batch_hist_dev(lpbox_batch *h);
+/* Packs the last window's history of every still-active instance into out_dev as fp32 rows [row][ws] -- the reference's
+ * `xiters.reshape(n_left, 20, ws/20).astype(float32)` (LP.trainer:524-530) -- rows of the active instances back to
+ * back in instance order.  Returns the number of rows (call with out_dev == NULL to size the buffer). */
+int64_t lpbox_batch_policy_input_dev(lpbox_batch *h, int ws, float *out_dev, int64_t capacity_rows);
+/* deter_fix_2 (LP.trainer:101-135) on device scores laid out like the rows above: p > hi -> fix 1, p < lo -> fix 0,
+ * else keep; instances with <= min_fix fixes get none (LP.trainer:533-535).  The result feeds the next _dev window. */
+int lpbox_batch_apply_scores_dev(lpbox_batch *h, const float *scores_dev, double hi, double lo, int min_fix);
+/* ADMM_lp_iters_l2f for all active instances with the fix vectors produced by lpbox_batch_apply_scores_dev (none if it
+ * was not called since the last window).  Returns the number of instances still active afterwards. */
+int lpbox_batch_iters_l2f_dev(lpbox_batch *h, int iter_start, int iter_end);
+
 /* getters; `i` = instance index ---------------------------------------------------------------------------------- */
 int lpbox_batch_size(const lpbox_batch *h);
 int lpbox_batch_get_n(lpbox_batch *h, int i);            /* get_n()      LP.h:392 */

@@ -1,0 +1,77 @@
+"""GPU test of the device-resident window loop (window kernel -> policy input gather -> scores -> threshold kernel ->
+compaction kernel; LP.trainer:510-535) against the CPU oracle driven by the reference's Python loop shape, with an
+EXACT surrogate policy (score = last iterate of the window as float32) so that fix decisions are identical."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, problem_tuple, synth_auction
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_loop(g, ws, max_iter):
+    """LP.trainer:510-535 on the oracle."""
+    import oracle as orc
+    o = orc.OracleLP()
+    o.set_problem_csc(g["m"], g["n"], g["colptr"], g["rowidx"], np.ones(len(g["rowidx"])), g["b"], g["f"])
+    o.solve_init()
+    vec, n = np.zeros(1), 0
+    for i in range(int(max_iter / ws)):
+        ret = o.solve_iter_l2f(ws * i, ws * (i + 1), vec, n)
+        if ret:
+            break
+        xit = o.get_x_iters_2d(ws)
+        p = xit[:, -1].astype(np.float32).astype(np.float64)          # surrogate score
+        vec = np.where(p > 0.9, 1.0, np.where(p < 1 - 0.9, 0.0, -1.0))
+        n = int((vec != -1.0).sum())
+        if n <= 10:
+            n = 0
+    return o
+
+
+def test_device_window_loop_matches_oracle():
+    import torch
+    import lpbox
+    gs = [load_golden("auction_100_500_seed0.npz"), load_golden("auction_40_200_seed1.npz"),
+          load_golden("auction_20_60_seed0.npz"), load_golden("auction_100_500_seed2.npz")] + [synth_auction(s, 30, 90) for s in range(3)]
+    ws, max_iter = 100, 10000
+    batch = lpbox.LPBatch([problem_tuple(g) for g in gs], hist_cap=ws)
+    batch.init()
+    log, bits, stats = lpbox.solve_l2f(batch, lambda x: x[:, -1, -1], ws=ws, max_iter=max_iter, tokens=20)
+    assert stats["windows"] >= 2
+    fixed_some = False
+    for i, g in enumerate(gs):
+        o = _oracle_loop(g, ws, max_iter)
+        assert log["n_left"][i] == o.get_n(), i
+        fixed_some |= o.get_n() < g["n"]
+        assert log["obj"][i] == o.cal_Obj(), i
+        assert log["iters"][i] == o.admm_iters(), i
+        assert log["cg_iters"][i] == o.cg_iters(), i
+        assert log["infeasible"][i] == o.check_infeasible_l2f(), i
+        assert np.array_equal(batch.x_sol(i), o.get_x_sol(g["n"]).ravel()), i
+        xb = np.unpackbits(bits[i], bitorder="little")[:g["n"]].astype(np.float64)
+        assert np.array_equal(xb, batch.x_sol(i))
+    assert fixed_some
+
+
+def test_policy_input_layout_matches_reference_reshape():
+    """The packed fp32 policy input equals `get_x_iters_2d(ws).reshape(n, 20, 5).astype(float32)` (LP.trainer:524-530)."""
+    import ctypes
+    import torch
+    import lpbox
+    gs = [load_golden("auction_40_200_seed1.npz"), load_golden("auction_20_60_seed0.npz")]
+    ws = 100
+    batch = lpbox.LPBatch([problem_tuple(g) for g in gs], hist_cap=ws)
+    batch.init()
+    batch.iters_l2f(0, ws)
+    rows = batch.L.lpbox_batch_policy_input_dev(batch.h, ws, None, 0)
+    assert rows == sum(g["n"] for g in gs)
+    inp = torch.zeros((rows, ws), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    got = batch.L.lpbox_batch_policy_input_dev(batch.h, ws, ctypes.c_void_p(inp.data_ptr()), rows)
+    assert got == rows
+    import ctypes as C
+    # the library works on its own stream here: synchronise through a getter (stream sync inside)
+    ref = np.concatenate([batch.x_iters(i, ws) for i in range(len(gs))]).astype(np.float32)
+    torch.cuda.synchronize()
+    assert np.array_equal(inp.cpu().numpy(), ref)
