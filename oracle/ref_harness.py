@@ -260,3 +260,50 @@ def mat_mul_vec(M_csr_full, v):
     fn.restype = None
     fn(C.byref(M.s), C.byref(vv.s), C.byref(out.s))
     return out.a.copy()
+
+
+class DenseMatrix(C.Structure):
+    """Eigen::Matrix<double, Dynamic, Dynamic> (column-major): {double* data; long rows; long cols}."""
+    _fields_ = [("data", C.c_void_p), ("rows", C.c_long), ("cols", C.c_long)]
+
+
+def binary_cost(image_colmajor_2d):
+    """`get_binary_cost(image, W)` of the reference binary (SEG.cpp:173-224).  image: (nr, nc) float64 = grey / 263.
+    Returns W as (rowptr, colidx, values) of the RowMajor Eigen matrix it builds."""
+    lib = _load()
+    img = np.asarray(image_colmajor_2d, dtype=np.float64)
+    nr, nc = img.shape
+    buf = _aligned(np.asfortranarray(img).ravel(order="K"), np.float64)       # column-major storage
+    dm = DenseMatrix(buf.ctypes.data, nr, nc)
+    out = SparseMatrixRM()
+    fn = lib._Z15get_binary_costRKN5Eigen6MatrixIdLin1ELin1ELi0ELin1ELin1EEERNS_12SparseMatrixIdLi1EiEE
+    fn.restype = None
+    fn(C.byref(dm), C.byref(out))
+    n = out.outerSize
+    rp = np.ctypeslib.as_array(C.cast(out.outerIndex, C.POINTER(C.c_int)), shape=(n + 1,)).copy()
+    if out.innerNonZeros:
+        nzc = np.ctypeslib.as_array(C.cast(out.innerNonZeros, C.POINTER(C.c_int)), shape=(n,)).copy()
+    else:
+        nzc = np.diff(rp)
+    idx_all = np.ctypeslib.as_array(C.cast(out.indices, C.POINTER(C.c_int)), shape=(int(rp[-1]) if not out.innerNonZeros else int(rp[n - 1] + nzc[n - 1]),))
+    val_all = np.ctypeslib.as_array(C.cast(out.values, C.POINTER(C.c_double)), shape=idx_all.shape)
+    ci = np.concatenate([idx_all[rp[i]:rp[i] + nzc[i]] for i in range(n)])
+    va = np.concatenate([val_all[rp[i]:rp[i] + nzc[i]] for i in range(n)])
+    rp2 = np.zeros(n + 1, dtype=np.int32); rp2[1:] = np.cumsum(nzc)
+    return rp2, ci.astype(np.int32), va.copy()
+
+
+def unary_cost(image_2d, sigma=0.1, b=0.6, f1=0.2, f2=0.2):
+    """`get_unary_cost` of the reference binary (SEG.cpp:55-81): returns the UNROUNDED (2, N) cost matrix."""
+    lib = _load()
+    img = np.asarray(image_2d, dtype=np.float64)
+    nr, nc = img.shape
+    buf = _aligned(np.asfortranarray(img).ravel(order="K"), np.float64)
+    dm = DenseMatrix(buf.ctypes.data, nr, nc)
+    out = DenseMatrix(None, 0, 0)
+    fn = lib._Z14get_unary_costRKN5Eigen6MatrixIdLin1ELin1ELi0ELin1ELin1EEEddddRS1_
+    fn.restype = None
+    fn.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]
+    fn(C.byref(dm), sigma, b, f1, f2, C.byref(out))
+    a = np.ctypeslib.as_array(C.cast(out.data, C.POINTER(C.c_double)), shape=(out.rows * out.cols,)).copy()
+    return a.reshape((out.rows, out.cols), order="F")
