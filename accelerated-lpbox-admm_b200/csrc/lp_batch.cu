@@ -19,6 +19,7 @@ using namespace lpb;
 
 static thread_local std::string g_err;
 static void set_err(const std::string &s) { g_err = s; }
+void lpbox_set_error(const std::string &s) { g_err = s; }   // shared with seg_batch.cu
 extern "C" const char *lpbox_last_error(void) { return g_err.c_str(); }
 
 #define CK(call)                                                                                        \

@@ -659,7 +659,7 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
 // Set-up kernel: ADMM_lp_iters_init (LP.cpp:489-763) and/or update_expression (LP.cpp:2289-2404) for every instance.
 // One CTA per instance, operating in HBM.  mode bit 0: initialise the iterate state; bit 1: rebuild the operator.
 // =====================================================================================================================
-__global__ void lp_setup_kernel(BatchView bv, Params pr, int mode, int use_x0) {
+static __global__ void lp_setup_kernel(BatchView bv, Params pr, int mode, int use_x0) {
     const int inst = blockIdx.x;
     InstState *st = bv.st + inst;
     const int n = st->n, m = st->m;

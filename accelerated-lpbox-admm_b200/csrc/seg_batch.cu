@@ -1,0 +1,394 @@
+// Host side + C ABI of the batched unconstrained (segmentation) solver.  See include/lpbox_b200.h.
+#include <cuda_runtime.h>
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/lpbox_b200.h"
+#include "seg_kernels.cuh"
+
+using namespace lpb;
+
+void lpbox_set_error(const std::string &s);   // lp_batch.cu
+
+#define SCK(call)                                                                      \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess) { lpbox_set_error(std::string(#call) + ": " + cudaGetErrorString(e_)); return LPBOX_E_CUDA; } \
+    } while (0)
+
+template <typename Tp>
+struct SBuf {
+    Tp *p = nullptr;
+    cudaError_t alloc(size_t count) { return cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(Tp)); }
+    void free_() { if (p) cudaFree(p); p = nullptr; }
+};
+
+struct lpbox_seg_batch {
+    int device = 0, B = 0, hist_cap = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<int> n0, nnz0;
+    std::vector<long long> off_n, off_nnz, off_hist;
+    std::vector<double> cconst;
+    Params pr{};
+    SegView sv{};
+    SBuf<long long> d_off_n, d_off_nnz, d_off_hist;
+    SBuf<double> vecs[11], d_b[2], d_val[2], d_hist, d_ret_val, d_powv;
+    SBuf<int> d_rp[2], d_ci[2], d_left, d_ret_idx, d_counter;
+    SBuf<SegInst> d_st;
+    std::vector<SegInst> h_st;
+    bool inited = false;
+    int grid = 0;
+    size_t smem = 0;
+    double last_ms = 0;
+    int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+};
+
+// ---- graph builder (SEG.cpp:55-81, :144-248, :727-758) ------------------------------------------------------------------
+// Grey image (row-major uint8, nr x nc) -> A = D - W (row-compressed, <= 7 stored entries per row, explicit zeros kept),
+// b = U2 - U1, c = sum U1.  Restated from the reference: I = grey/263; unary costs from a Gaussian background model
+// (mean 0.6) and a two-Gaussian foreground model (means 0.2, 0.2), sigma 0.1, rounded half away from zero; pairwise
+// weights round(3 exp(-(Ip - Iq)^2 / sigma_img)) over the offsets (a,b) in {-1,0,1}^2 with a != b (a 6-neighbourhood),
+// sigma_img = sample standard deviation of the image; intensities are looked up through the column-major flattening while
+// p, q are row-major indices (the reference's index mismatch, reproduced literally).
+static double eigen_sum(const double *v, long n) {   // Eigen's linear-vectorised redux order (sum)
+    long a2 = (n / 4) * 4, a1 = (n / 2) * 2;
+    if (!a1) return n ? v[0] : 0.0;
+    double p00 = v[0], p01 = v[1];
+    if (a1 > 2) {
+        double p10 = v[2], p11 = v[3];
+        for (long i = 4; i < a2; i += 4) { p00 += v[i]; p01 += v[i + 1]; p10 += v[i + 2]; p11 += v[i + 3]; }
+        p00 += p10; p01 += p11;
+        if (a1 > a2) { p00 += v[a2]; p01 += v[a2 + 1]; }
+    }
+    double res = p00 + p01;
+    for (long i = a1; i < n; ++i) res += v[i];
+    return res;
+}
+
+extern "C" int lpbox_seg_build_graph(const uint8_t *pixels, int nr, int nc, int32_t *rowptr, int32_t *colidx, double *val, double *b,
+                                     double *c_out) {
+    if (!pixels || nr <= 0 || nc <= 0 || !rowptr || !colidx || !val || !b || !c_out) return LPBOX_E_INVALID;
+    const int n = nr * nc;
+    std::vector<double> I(n), v(n), tmp(n);
+    for (int k = 0; k < n; ++k) I[k] = (double)pixels[k] / 263.0;                                  // SEG.cpp:727
+    for (int c = 0; c < nc; ++c) for (int r = 0; r < nr; ++r) v[(size_t)c * nr + r] = I[(size_t)r * nc + c];   // vectorize :46-53
+    const double sigma = 0.1, bg = 0.6, f1 = 0.2, f2 = 0.2;                                        // :734-737
+    const double cst = log(2.0 * 3.14159265358979323846) / 2.0 + log(sigma);
+    for (int k = 0; k < n; ++k) {
+        const double ab = pow(v[k] - bg, 2.0) / (2 * sigma * sigma) + cst;                         // :58
+        const double aa = exp(-pow(v[k] - f1, 2.0) / (2 * sigma * sigma)) + exp(-pow(v[k] - f2, 2) / (2 * sigma * sigma));
+        const double af = -log(aa + DBL_EPSILON) + cst + log(2.0);                                 // :61
+        const double U1 = round(ab), U2 = round(af);                                               // :743
+        b[k] = U2 - U1;
+        tmp[k] = U1;
+    }
+    *c_out = eigen_sum(tmp.data(), n);
+    const double mean = eigen_sum(v.data(), n) / (double)n;                                        // :181
+    for (int k = 0; k < n; ++k) tmp[k] = (v[k] - mean) * (v[k] - mean);
+    const double sig = sqrt(eigen_sum(tmp.data(), n) / (double)(n - 1));
+    const int oa[7] = {-1, -1, 0, 0, 0, 1, 1}, ob[7] = {0, 1, -1, 0, 1, -1, 0};                    // ascending column order
+    int q = 0;
+    for (int i = 0; i < nr; ++i)
+        for (int j = 0; j < nc; ++j) {
+            const int p = i * nc + j;
+            rowptr[p] = q;
+            int dq = -1;
+            for (int t = 0; t < 7; ++t) {
+                const int a = oa[t], bo = ob[t];
+                if (a == 0 && bo == 0) { dq = q; colidx[q] = p; val[q] = 0.0; q++; continue; }     // explicit diagonal :213-219
+                if (i + a < 0 || i + a >= nr || j + bo < 0 || j + bo >= nc) continue;
+                const int p2 = (i + a) * nc + (j + bo);
+                const double i1 = I[(size_t)(p % nr) * nc + (p / nr)], i2 = I[(size_t)(p2 % nr) * nc + (p2 / nr)];   // :192-193
+                const double wgt = round(3 * exp(-(pow(i1 - i2, 2.0) / sig)));                     // :196-205
+                colidx[q] = p2; val[q] = -wgt; q++;
+            }
+            double wsum = 0.0;
+            for (int e = rowptr[p]; e < q; ++e) wsum = wsum + (-val[e]) * 1.0;                     // We = -A 1  (:234-236)
+            val[dq] = val[dq] + wsum;
+        }
+    rowptr[n] = q;
+    return q;
+}
+
+static int seg_sync_states(lpbox_seg_batch *h) {
+    h->d2h_bytes += (int64_t)(sizeof(SegInst) * (size_t)h->B);
+    SCK(cudaMemcpyAsync(h->h_st.data(), h->d_st.p, sizeof(SegInst) * (size_t)h->B, cudaMemcpyDeviceToHost, h->stream));
+    SCK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" void lpbox_seg_destroy(lpbox_seg_batch *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    h->d_off_n.free_(); h->d_off_nnz.free_(); h->d_off_hist.free_();
+    for (auto &v : h->vecs) v.free_();
+    for (int k = 0; k < 2; ++k) { h->d_b[k].free_(); h->d_val[k].free_(); h->d_rp[k].free_(); h->d_ci[k].free_(); }
+    h->d_hist.free_(); h->d_ret_val.free_(); h->d_powv.free_(); h->d_left.free_(); h->d_ret_idx.free_(); h->d_counter.free_(); h->d_st.free_();
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" lpbox_seg_batch *lpbox_seg_create_csr(int device, int B, const int32_t *n, const int32_t *rowptr_all, const int32_t *colidx_all,
+                                                const double *val_all, const double *b_all, const double *c, int hist_cap) {
+    if (B <= 0 || !n || !rowptr_all || !colidx_all || !val_all || !b_all || hist_cap < 0) { lpbox_set_error("invalid argument"); return nullptr; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { lpbox_set_error("no CUDA device (there is no CPU fallback)"); return nullptr; }
+    if (device < 0 || device >= ndev || cudaSetDevice(device) != cudaSuccess) { lpbox_set_error("bad device"); return nullptr; }
+    lpbox_seg_batch *h = new lpbox_seg_batch();
+    h->device = device; h->B = B; h->hist_cap = hist_cap;
+    h->n0.assign(n, n + B); h->nnz0.resize(B); h->cconst.assign(B, 0.0);
+    h->off_n.assign(B + 1, 0); h->off_nnz.assign(B + 1, 0); h->off_hist.assign(B + 1, 0);
+    long long rpo = 0;
+    std::vector<long long> rp_off(B + 1, 0);
+    for (int i = 0; i < B; ++i) {
+        if (n[i] <= 0) { lpbox_set_error("n <= 0"); delete h; return nullptr; }
+        const int32_t *rp = rowptr_all + rpo;
+        h->nnz0[i] = rp[n[i]];
+        rp_off[i] = rpo; rpo += n[i] + 1;
+        h->off_n[i + 1] = h->off_n[i] + ((n[i] + 3) & ~3);
+        h->off_nnz[i + 1] = h->off_nnz[i] + ((h->nnz0[i] + 3) & ~3);
+        h->off_hist[i + 1] = h->off_hist[i] + (long long)hist_cap * n[i];
+        if (c) h->cconst[i] = c[i];
+    }
+    rp_off[B] = rpo;
+    const size_t NN = (size_t)h->off_n[B], ZZ = (size_t)h->off_nnz[B];
+    std::vector<int> rp_pack(NN + 4 * (size_t)B, 0), ci_pack(ZZ, 0);
+    std::vector<double> va_pack(ZZ, 0.0), b_pack(NN, 0.0), powv(B);
+    std::vector<SegInst> st(B);
+    long long zo = 0, bo = 0;
+    for (int i = 0; i < B; ++i) {
+        const int ni = n[i], nz = h->nnz0[i];
+        const int32_t *rp = rowptr_all + rp_off[i];
+        for (int r = 0; r < ni; ++r) {
+            bool diag = false;
+            if (rp[r] > rp[r + 1]) { lpbox_set_error("bad rowptr"); delete h; return nullptr; }
+            for (int k = rp[r]; k < rp[r + 1]; ++k) {
+                const int cc = colidx_all[zo + k];
+                if (cc < 0 || cc >= ni || (k > rp[r] && cc <= colidx_all[zo + k - 1])) { lpbox_set_error("column indices must be in range and strictly ascending within each row"); delete h; return nullptr; }
+                if (cc == r) diag = true;
+            }
+            if (!diag) { lpbox_set_error("every row of A must store its diagonal entry (explicit zero allowed), as the reference's graph builder does"); delete h; return nullptr; }
+        }
+        memcpy(rp_pack.data() + h->off_n[i] + 4 * (size_t)i, rp, sizeof(int) * ((size_t)ni + 1));
+        memcpy(ci_pack.data() + h->off_nnz[i], colidx_all + zo, sizeof(int) * (size_t)nz);
+        memcpy(va_pack.data() + h->off_nnz[i], val_all + zo, sizeof(double) * (size_t)nz);
+        memcpy(b_pack.data() + h->off_n[i], b_all + bo, sizeof(double) * (size_t)ni);
+        zo += nz; bo += ni;
+        powv[i] = pow((double)ni, 1.0 / 2);
+        SegInst &s = st[i];
+        memset(&s, 0, sizeof(s));
+        s.n0 = s.n = ni; s.nnz0 = s.nnz = nz; s.std_obj = 1.0; s.rhoUpdated = 1; s.cconst = h->cconst[i];
+    }
+    h->h_st = st;
+    lpbox_params sp; lpbox_params_seg(&sp);
+    h->pr.stop_threshold = sp.stop_threshold; h->pr.std_threshold = sp.std_threshold; h->pr.max_iters = sp.max_iters;
+    h->pr.initial_rho = sp.initial_rho; h->pr.rho_change_step = sp.rho_change_step; h->pr.gamma_val = sp.gamma_val;
+    h->pr.learning_fact = sp.learning_fact; h->pr.history_size = (int)sp.history_size; h->pr.gamma_factor = sp.gamma_factor;
+    h->pr.pcg_tol = sp.pcg_tol; h->pr.pcg_maxiters = sp.pcg_maxiters; h->pr.guard_first_iter = 0; h->pr.alpha_bailout = 0;
+    bool ok = true;
+    auto A = [&](cudaError_t e) { if (e != cudaSuccess) { if (ok) lpbox_set_error(cudaGetErrorString(e)); ok = false; } };
+    A(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    A(cudaEventCreate(&h->ev0)); A(cudaEventCreate(&h->ev1));
+    A(h->d_off_n.alloc(B + 1)); A(h->d_off_nnz.alloc(B + 1)); A(h->d_off_hist.alloc(B + 1));
+    for (auto &v : h->vecs) A(v.alloc(NN));
+    for (int k = 0; k < 2; ++k) { A(h->d_b[k].alloc(NN)); A(h->d_val[k].alloc(ZZ)); A(h->d_rp[k].alloc(NN + 4 * (size_t)B)); A(h->d_ci[k].alloc(ZZ)); }
+    A(h->d_hist.alloc((size_t)h->off_hist[B])); A(h->d_ret_val.alloc(NN)); A(h->d_powv.alloc(B)); A(h->d_left.alloc(NN)); A(h->d_ret_idx.alloc(NN));
+    A(h->d_counter.alloc(1)); A(h->d_st.alloc(B));
+    if (!ok) { lpbox_seg_destroy(h); return nullptr; }
+    auto H2D = [&](void *d, const void *s, size_t bytes) { if (bytes) { A(cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, h->stream)); h->h2d_bytes += (int64_t)bytes; } };
+    H2D(h->d_off_n.p, h->off_n.data(), sizeof(long long) * (B + 1));
+    H2D(h->d_off_nnz.p, h->off_nnz.data(), sizeof(long long) * (B + 1));
+    H2D(h->d_off_hist.p, h->off_hist.data(), sizeof(long long) * (B + 1));
+    H2D(h->d_rp[0].p, rp_pack.data(), sizeof(int) * rp_pack.size());
+    H2D(h->d_ci[0].p, ci_pack.data(), sizeof(int) * ZZ);
+    H2D(h->d_val[0].p, va_pack.data(), sizeof(double) * ZZ);
+    H2D(h->d_b[0].p, b_pack.data(), sizeof(double) * NN);
+    H2D(h->d_powv.p, powv.data(), sizeof(double) * (size_t)B);
+    H2D(h->d_st.p, st.data(), sizeof(SegInst) * (size_t)B);
+    A(cudaStreamSynchronize(h->stream));
+    if (!ok) { lpbox_seg_destroy(h); return nullptr; }
+    SegView &v = h->sv;
+    v.B = B; v.hist_cap = hist_cap; v.off_n = h->d_off_n.p; v.off_nnz = h->d_off_nnz.p; v.off_hist = h->d_off_hist.p;
+    double **vp[11] = {&v.x, &v.y1, &v.y2, &v.z1, &v.z2, &v.md, &v.invd, &v.r, &v.p, &v.t, &v.w};
+    for (int k = 0; k < 11; ++k) *vp[k] = h->vecs[k].p;
+    for (int k = 0; k < 2; ++k) { v.b[k] = h->d_b[k].p; v.rowptr[k] = h->d_rp[k].p; v.colidx[k] = h->d_ci[k].p; v.val[k] = h->d_val[k].p; }
+    v.st = h->d_st.p; v.hist = h->d_hist.p; v.left_idx = h->d_left.p; v.ret_idx = h->d_ret_idx.p; v.ret_val = h->d_ret_val.p; v.powv = h->d_powv.p;
+    h->smem = sizeof(double) * (2 * SEG_RMAX * SEG_CH + 8 + 16);
+    int sms = 0, occ = 1;
+    if (cudaFuncSetAttribute(seg_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess ||
+        cudaFuncSetAttribute(seg_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seg_admm_kernel, SEG_T, h->smem) != cudaSuccess) {
+        lpbox_set_error("seg kernel configuration failed"); lpbox_seg_destroy(h); return nullptr;
+    }
+    h->grid = std::max(1, std::min(B, sms * std::max(occ, 1)));
+    return h;
+}
+
+extern "C" lpbox_seg_batch *lpbox_seg_create_images(int device, int B, const uint8_t *pixels_all, const int32_t *nr, const int32_t *nc,
+                                                   int hist_cap) {
+    if (B <= 0 || !pixels_all || !nr || !nc) { lpbox_set_error("invalid argument"); return nullptr; }
+    std::vector<long long> po(B + 1, 0), ro(B + 1, 0), zo(B + 1, 0), no(B + 1, 0);
+    for (int i = 0; i < B; ++i) {
+        const long long n = (long long)nr[i] * nc[i];
+        po[i + 1] = po[i] + n; ro[i + 1] = ro[i] + n + 1; zo[i + 1] = zo[i] + 7 * n; no[i + 1] = no[i] + n;
+    }
+    std::vector<int32_t> rp((size_t)ro[B]), ci((size_t)zo[B]), ns(B);
+    std::vector<double> va((size_t)zo[B]), b((size_t)no[B]), c(B);
+    std::vector<int> nnz(B);
+    std::atomic<int> next(0);
+    int nt = std::max(1, std::min((int)std::thread::hardware_concurrency(), B));
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt; ++t)
+        pool.emplace_back([&]() {
+            for (int i; (i = next.fetch_add(1)) < B;) {
+                nnz[i] = lpbox_seg_build_graph(pixels_all + po[i], nr[i], nc[i], rp.data() + ro[i], ci.data() + zo[i], va.data() + zo[i], b.data() + no[i], &c[i]);
+                ns[i] = nr[i] * nc[i];
+            }
+        });
+    for (auto &th : pool) th.join();
+    // compact colidx / val to the layout lpbox_seg_create_csr takes (concatenated by actual nnz)
+    size_t w = 0;
+    for (int i = 0; i < B; ++i) {
+        if (nnz[i] < 0) { lpbox_set_error("graph builder failed"); return nullptr; }
+        memmove(ci.data() + w, ci.data() + zo[i], sizeof(int32_t) * (size_t)nnz[i]);
+        memmove(va.data() + w, va.data() + zo[i], sizeof(double) * (size_t)nnz[i]);
+        w += (size_t)nnz[i];
+    }
+    return lpbox_seg_create_csr(device, B, ns.data(), rp.data(), ci.data(), va.data(), b.data(), c.data(), hist_cap);
+}
+
+extern "C" int lpbox_seg_set_params(lpbox_seg_batch *h, const lpbox_params *p) {
+    if (!h || !p) return LPBOX_E_INVALID;
+    if (p->history_size < 2 || p->history_size > 16 || p->rho_change_step <= 0) return LPBOX_E_INVALID;
+    h->pr.stop_threshold = p->stop_threshold; h->pr.std_threshold = p->std_threshold; h->pr.max_iters = p->max_iters;
+    h->pr.initial_rho = p->initial_rho; h->pr.rho_change_step = p->rho_change_step; h->pr.gamma_val = p->gamma_val;
+    h->pr.learning_fact = p->learning_fact; h->pr.history_size = (int)p->history_size; h->pr.gamma_factor = p->gamma_factor;
+    h->pr.pcg_tol = p->pcg_tol; h->pr.pcg_maxiters = p->pcg_maxiters;
+    return 0;
+}
+
+extern "C" int lpbox_seg_init(lpbox_seg_batch *h, const double *x0_all) {
+    if (!h) return LPBOX_E_INVALID;
+    SCK(cudaSetDevice(h->device));
+    if (x0_all) {
+        std::vector<double> xs((size_t)h->off_n[h->B], 0.0);
+        long long o = 0;
+        for (int i = 0; i < h->B; ++i) { memcpy(xs.data() + h->off_n[i], x0_all + o, sizeof(double) * (size_t)h->n0[i]); o += h->n0[i]; }
+        SCK(cudaMemcpyAsync(h->sv.x, xs.data(), sizeof(double) * xs.size(), cudaMemcpyHostToDevice, h->stream));
+        SCK(cudaStreamSynchronize(h->stream));
+    }
+    SCK(cudaEventRecord(h->ev0, h->stream));
+    seg_setup_kernel<<<h->B, SEG_T, h->smem, h->stream>>>(h->sv, h->pr, x0_all ? 1 : 0);
+    SCK(cudaGetLastError());
+    h->launches += 1;
+    SCK(cudaEventRecord(h->ev1, h->stream));
+    int rc = seg_sync_states(h); if (rc) return rc;
+    float ms = 0; SCK(cudaEventElapsedTime(&ms, h->ev0, h->ev1)); h->last_ms = ms;
+    h->inited = true;
+    return 0;
+}
+
+static int seg_run(lpbox_seg_batch *h, int iter_start, int iter_end, int l2f, int skip_done) {
+    SegLaunch la{};
+    la.iter_start = iter_start; la.iter_end = iter_end; la.l2f = l2f; la.skip_done = skip_done; la.n_work = h->B; la.counter = h->d_counter.p;
+    SCK(cudaMemsetAsync(h->d_counter.p, 0, sizeof(int), h->stream));
+    SCK(cudaEventRecord(h->ev0, h->stream));
+    seg_admm_kernel<<<h->grid, SEG_T, h->smem, h->stream>>>(h->sv, h->pr, la);
+    SCK(cudaGetLastError());
+    h->launches += 1;
+    SCK(cudaEventRecord(h->ev1, h->stream));
+    int rc = seg_sync_states(h); if (rc) return rc;
+    float ms = 0; SCK(cudaEventElapsedTime(&ms, h->ev0, h->ev1)); h->last_ms = ms;
+    return 0;
+}
+
+// ADMM_bqp_unconstrained_legacy for every image: energy[i] = int(cur_obj + _c)  (SEG.cpp:1200-1380)
+extern "C" int lpbox_seg_solve(lpbox_seg_batch *h, int32_t *energy) {
+    if (!h || !h->inited) { lpbox_set_error("call lpbox_seg_init first"); return LPBOX_E_INVALID; }
+    SCK(cudaSetDevice(h->device));
+    int rc = seg_run(h, 0, h->pr.max_iters, 0, 0);
+    if (rc) return rc;
+    if (energy) for (int i = 0; i < h->B; ++i) energy[i] = (int32_t)(h->h_st[i].cur_obj + h->h_st[i].cconst);
+    return (int)(h->h_st[0].cur_obj + h->h_st[0].cconst);
+}
+
+extern "C" int lpbox_seg_size(const lpbox_seg_batch *h) { return h ? h->B : LPBOX_E_INVALID; }
+#define SCHK(h, i) if (!(h) || (i) < 0 || (i) >= (h)->B) return LPBOX_E_INVALID
+extern "C" int lpbox_seg_get_n(lpbox_seg_batch *h, int i) { SCHK(h, i); return h->h_st[i].n; }
+extern "C" int lpbox_seg_get_org_n(lpbox_seg_batch *h, int i) { SCHK(h, i); return h->h_st[i].n0; }
+extern "C" int lpbox_seg_get_iter(lpbox_seg_batch *h, int i) { SCHK(h, i); return h->h_st[i].iter; }
+static int seg_d2h(lpbox_seg_batch *h, void *dst, const void *src, size_t bytes) {
+    if (!bytes) return 0;
+    h->d2h_bytes += (int64_t)bytes;
+    SCK(cudaSetDevice(h->device));
+    SCK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+    SCK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+extern "C" int lpbox_seg_get_state(lpbox_seg_batch *h, int i, double *x, double *y1, double *y2, double *z1, double *z2) {
+    SCHK(h, i);
+    const size_t nb = sizeof(double) * (size_t)h->h_st[i].n;
+    const long long on = h->off_n[i];
+    int rc = 0;
+    if (x) rc |= seg_d2h(h, x, h->sv.x + on, nb);
+    if (y1) rc |= seg_d2h(h, y1, h->sv.y1 + on, nb);
+    if (y2) rc |= seg_d2h(h, y2, h->sv.y2 + on, nb);
+    if (z1) rc |= seg_d2h(h, z1, h->sv.z1 + on, nb);
+    if (z2) rc |= seg_d2h(h, z2, h->sv.z2 + on, nb);
+    return rc ? LPBOX_E_CUDA : 0;
+}
+// get_x_sol (SEG.cpp:895-915): binary solution in original indexing (no early fixing in this build: left_idx = identity)
+extern "C" int lpbox_seg_get_x_sol(lpbox_seg_batch *h, int i, double *out) {
+    SCHK(h, i);
+    if (!out) return LPBOX_E_INVALID;
+    const SegInst &s = h->h_st[i];
+    if (s.n != s.n0) { lpbox_set_error("early fixing is not built for the segmentation path yet"); return LPBOX_E_UNSUPPORTED; }
+    std::vector<double> x(s.n);
+    if (seg_d2h(h, x.data(), h->sv.x + h->off_n[i], sizeof(double) * (size_t)s.n)) return LPBOX_E_CUDA;
+    for (int q = 0; q < s.n; ++q) out[q] = (x[q] >= 0.5) ? 1.0 : 0.0;
+    return s.n0;
+}
+// get_final_obj (SEG.cpp:868-893): x'Ax + b'x of the assembled binary solution on the original problem, + _c
+extern "C" double lpbox_seg_get_final_obj(lpbox_seg_batch *h, int i) {
+    if (!h || i < 0 || i >= h->B) return NAN;
+    const SegInst &s = h->h_st[i];
+    if (s.n != s.n0) return NAN;
+    std::vector<double> xs(s.n0), ax(s.n0), b(s.n0), va(s.nnz0);
+    std::vector<int> rp(s.n0 + 1), ci(s.nnz0);
+    if (lpbox_seg_get_x_sol(h, i, xs.data()) < 0) return NAN;
+    if (seg_d2h(h, rp.data(), h->sv.rowptr[s.cur] + h->off_n[i] + 4 * (size_t)i, sizeof(int) * ((size_t)s.n0 + 1)) ||
+        seg_d2h(h, ci.data(), h->sv.colidx[s.cur] + h->off_nnz[i], sizeof(int) * (size_t)s.nnz0) ||
+        seg_d2h(h, va.data(), h->sv.val[s.cur] + h->off_nnz[i], sizeof(double) * (size_t)s.nnz0) ||
+        seg_d2h(h, b.data(), h->sv.b[s.cur] + h->off_n[i], sizeof(double) * (size_t)s.n0)) return NAN;
+    for (int r = 0; r < s.n0; ++r) { double acc = 0.0; for (int k = rp[r]; k < rp[r + 1]; ++k) acc = acc + va[k] * xs[ci[k]]; ax[r] = acc; }
+    std::vector<double> pr1(s.n0), pr2(s.n0);
+    for (int r = 0; r < s.n0; ++r) { pr1[r] = xs[r] * ax[r]; pr2[r] = b[r] * xs[r]; }
+    return (eigen_sum(pr1.data(), s.n0) + eigen_sum(pr2.data(), s.n0)) + s.cconst;
+}
+extern "C" int lpbox_seg_results(lpbox_seg_batch *h, lpbox_log_row *log) {
+    if (!h || !log) return LPBOX_E_INVALID;
+    for (int i = 0; i < h->B; ++i) {
+        const SegInst &s = h->h_st[i];
+        log[i].iters = (int32_t)s.admm_iters; log[i].status = s.status; log[i].cg_iters = s.cg_iters;
+        log[i].obj = s.cur_obj + s.cconst; log[i].cur_bin_obj = s.cur_obj; log[i].n_left = s.n; log[i].infeasible = 0;
+    }
+    return 0;
+}
+extern "C" double lpbox_seg_last_kernel_ms(const lpbox_seg_batch *h) { return h ? h->last_ms : -1.0; }
+extern "C" int64_t lpbox_seg_launch_count(const lpbox_seg_batch *h) { return h ? h->launches : -1; }
+extern "C" int64_t lpbox_seg_h2d_bytes(const lpbox_seg_batch *h) { return h ? h->h2d_bytes : -1; }
+extern "C" int64_t lpbox_seg_d2h_bytes(const lpbox_seg_batch *h) { return h ? h->d2h_bytes : -1; }

@@ -1,0 +1,367 @@
+// Unconstrained Lp-Box ADMM (graph-cut segmentation, `min x'Ax + b'x`) for sm_100a -- streaming variant.
+//
+// An image-sized problem (n = 187 500 for 375x500) does not fit on chip: per image ~12 fp64 n-vectors + A (<= 7 stored
+// entries per row).  One CTA owns one image for a whole window and streams its vectors through L2/HBM with coalesced
+// accesses; there is NO inter-CTA synchronisation, so a batch of images fills the GPU with independent CTAs
+// (2 per SM: while one CTA sits in a sequential reduction chain the other streams).
+//
+// PARITY MODE: the arithmetic follows the reference's compiled Eigen code (SEG.cpp =
+// Segmentation/Segmentation/cython/src/LPboxADMMsolver.cpp): no FMA, row-sequential SpMV in ascending column order,
+// reductions in Eigen's SSE2 order.  A reduction over n elements is four dependent chains of n/4 adds; the CTA streams
+// the products into a double-buffered shared-memory ring (all warps) while one warp walks the chains (up to 8
+// reductions side by side, 4 lanes each).
+//
+// The CG matrix `temp_mat = 2A + (rho1+rho2) I` (SEG.cpp:784-786) is never materialised: off-diagonal entries are
+// 2*a_ij (exact), the diagonal lives in `md` and is patched additively like the reference (SEG.cpp:1240-1243).
+#pragma once
+#include "lp_kernels.cuh"
+
+namespace lpb {
+
+struct SegInst {
+    int n0, nnz0;            // capacities
+    int n, nnz;              // current
+    int iter, status, done, last_ret;
+    int rhoUpdated;
+    int n_ret;
+    int xit_rows, xit_cols;
+    int cur;                 // which half of the double-buffered arrays (CSR, b) is current (early fixing ping-pongs)
+    int pad;
+    double rho1, rho2, prho1, prho2, gamma, ratio;
+    double std_obj, cur_obj, best_bin_obj, cconst;
+    long long obj_len;
+    double obj_ring[16];
+    long long cg_iters, admm_iters;
+};
+
+struct SegView {
+    int B, hist_cap;
+    const long long *off_n;    // [B+1] element offsets of n-vectors (n0 rounded up to 4)
+    const long long *off_nnz;  // [B+1] element offsets of colidx / val
+    const long long *off_hist;
+    double *x, *y1, *y2, *z1, *z2, *md, *invd, *r, *p, *t, *w;   // n-vectors
+    double *b[2];              // double-buffered (early fixing rewrites it)
+    int *rowptr[2];            // (off_n + i) offset, n0 + 1 entries per instance (stride n0r + 4 keeps room)
+    int *colidx[2];
+    double *val[2];
+    SegInst *st;
+    double *hist;              // [cc][n0]
+    int *left_idx, *ret_idx;
+    double *ret_val;
+    const double *pow_tab;     // unused for n > table; pow(n, .5) passed per instance in powv
+    double *powv;              // [B] std::pow(n, 0.5) of the CURRENT n (host libm), refreshed after a fix
+};
+
+struct SegLaunch {
+    int iter_start, iter_end;
+    int l2f, skip_done;
+    int n_work;
+    int *counter;
+};
+
+constexpr int SEG_T = 512;
+constexpr int SEG_CH = 512;     // products staged per reduction per chunk
+constexpr int SEG_RMAX = 7;
+
+// y_i = ((0 + m_i1 v_j1) + m_i2 v_j2) + ...  row i of (DIAG ? 2A with the diagonal replaced by md : A)
+template <bool DIAG>
+__device__ __forceinline__ double seg_row_dot(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ av,
+                                              const double *__restrict__ md, const double *__restrict__ v, int i) {
+    double acc = 0.0;
+    const int e = rp[i + 1];
+    for (int k = rp[i]; k < e; ++k) {
+        const int c = ci[k];
+        double m = av[k];
+        if (DIAG) m = (c == i) ? md[i] : dM(2.0, m);
+        acc = dA(acc, dM(m, v[c]));
+    }
+    return acc;
+}
+
+// Block-cooperative Eigen-order reduction of R product streams prod(q, i), i < n.  Results in sc[0..R).
+// buf: shared, 2 * R * SEG_CH doubles.  All SEG_T threads must call.
+template <int R, typename F>
+__device__ __forceinline__ void seg_block_redux(F prod, int n, double *buf, double *sc) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int RW = SEG_T / 32 - 1;
+    const int a2 = n & ~3, a1 = n & ~1;
+    const int q = lane >> 2, k = lane & 3;
+    const int nch = (a2 + SEG_CH - 1) / SEG_CH;
+    auto stage = [&](int c) {
+        double *dst = buf + (size_t)(c & 1) * R * SEG_CH;
+        const int base = c * SEG_CH;
+        const int lim = min(SEG_CH, a2 - base);
+        for (int idx = tid; idx < R * SEG_CH; idx += SEG_T - 32) {      // every warp but the reduction warp
+            const int qq = idx / SEG_CH, i = idx - qq * SEG_CH;
+            if (i < lim) dst[qq * SEG_CH + i] = prod(qq, base + i);
+        }
+    };
+    double acc = 0.0;
+    __syncthreads();   // every reader of the previous results in sc[] is done; operands written by other threads are visible
+    if (a1 > 2) {
+        if (warp != RW) stage(0);
+        __syncthreads();
+        for (int c = 0; c < nch; ++c) {
+            if (warp != RW) { if (c + 1 < nch) stage(c + 1); }
+            else if (q < R) {
+                const double *src = buf + (size_t)(c & 1) * R * SEG_CH + q * SEG_CH;
+                const int lim = min(SEG_CH, a2 - c * SEG_CH);
+                int i = k;
+                if (c == 0) { acc = src[k]; i = 4 + k; }
+                for (; i + 28 < lim; i += 32) {
+                    double t0 = src[i], t1 = src[i + 4], t2 = src[i + 8], t3 = src[i + 12], t4 = src[i + 16], t5 = src[i + 20],
+                           t6 = src[i + 24], t7 = src[i + 28];
+                    acc = dA(acc, t0); acc = dA(acc, t1); acc = dA(acc, t2); acc = dA(acc, t3);
+                    acc = dA(acc, t4); acc = dA(acc, t5); acc = dA(acc, t6); acc = dA(acc, t7);
+                }
+                for (; i < lim; i += 4) acc = dA(acc, src[i]);
+            }
+            __syncthreads();
+        }
+    }
+    if (warp == RW) {
+        const int qq = q < R ? q : 0;
+        double res;
+        if (a1 > 2) {
+            double hi = __shfl_down_sync(0xffffffffu, acc, 2);
+            double l = dA(acc, hi);
+            if (a1 > a2 && k < 2) l = dA(l, prod(qq, a2 + k));
+            double l1 = __shfl_down_sync(0xffffffffu, l, 1);
+            res = dA(l, l1);
+        } else if (a1 == 2) {
+            res = dA(prod(qq, 0), prod(qq, 1));
+        } else {
+            res = (n > 0) ? prod(qq, 0) : 0.0;
+        }
+        if ((n & 1) && n > 1) res = dA(res, prod(qq, n - 1));
+        if (k == 0 && q < R) sc[q] = res;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(SEG_T, 2)
+seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *buf = reinterpret_cast<double *>(smem_raw);                 // [2][SEG_RMAX][SEG_CH]
+    double *sc = buf + 2 * SEG_RMAX * SEG_CH;                           // [8]
+    double *ring = sc + 8;                                              // [16]
+    __shared__ int s_work;
+    const int tid = threadIdx.x;
+    for (;;) {
+        if (tid == 0) s_work = atomicAdd(la.counter, 1);
+        __syncthreads();
+        const int wk = s_work;
+        __syncthreads();
+        if (wk >= la.n_work) break;
+        const int inst = wk;
+        SegInst *st = sv.st + inst;
+        if ((la.skip_done && st->done) || st->n == 0) continue;
+        const int n = st->n, cur = st->cur;
+        const long long on = sv.off_n[inst], oz = sv.off_nnz[inst];
+        double *x = sv.x + on, *y1 = sv.y1 + on, *y2 = sv.y2 + on, *z1 = sv.z1 + on, *z2 = sv.z2 + on, *md = sv.md + on,
+               *invd = sv.invd + on, *r = sv.r + on, *p = sv.p + on, *t = sv.t + on, *w = sv.w + on;
+        const double *__restrict__ b = sv.b[cur] + on;
+        const int *__restrict__ rp = sv.rowptr[cur] + on + 4 * inst;      // n0r + 4 ints reserved per instance
+        const int *__restrict__ ci = sv.colidx[cur] + oz;
+        const double *__restrict__ av = sv.val[cur] + oz;
+        double rho1 = st->rho1, rho2 = st->rho2, prho1 = st->prho1, prho2 = st->prho2, gamma = st->gamma, ratio = st->ratio,
+               std_obj = st->std_obj, cur_obj = st->cur_obj, best_bin_obj = st->best_bin_obj;
+        int rhoUpdated = st->rhoUpdated;
+        long long obj_len = st->obj_len, cg_total = 0, admm_total = 0;
+        if (tid < 16) ring[tid] = st->obj_ring[tid];
+        const double pow_n = sv.powv[inst];
+        __syncthreads();
+
+        int status = RUNNING, iter = la.iter_start, cc = 0;
+        for (; iter < la.iter_end; ++iter) {
+            // ---- y1, y2 pre-image (SEG.cpp:1223-1234) ------------------------------------------------------------
+            for (int i = tid; i < n; i += SEG_T) {
+                const double xi = x[i];
+                double tt = dA(xi, dD(z1[i], rho1));
+                y1[i] = (tt > 1.0) ? 1.0 : ((tt < 0.0) ? 0.0 : tt);
+                y2[i] = dS(dA(xi, dD(z2[i], rho2)), 0.5);
+            }
+            __syncthreads();
+            seg_block_redux<1>([&](int, int i) { const double v = y2[i]; return dM(v, v); }, n, buf, sc);
+            const double den = dM(2.0, sqrt(sc[0]));
+            // ---- diagonal patch (:1240-1243), preconditioner (:1252-1255), y2 (:427 of LP.cpp), rhs (:1246), x = y1 ----
+            const bool patch = (iter != 0 && rhoUpdated);
+            const double dpatch = dM(dA(prho1, prho2), ratio);
+            for (int i = tid; i < n; i += SEG_T) {
+                if (patch) md[i] = dA(md[i], dpatch);
+                if (rhoUpdated) { const double d = md[i]; invd[i] = (d != 0.0) ? dD(1.0, d) : 1.0; }
+                const double y1i = y1[i];
+                const double y2v = dA(dD(dM(y2[i], pow_n), den), 0.5);
+                y2[i] = y2v;
+                w[i] = dS(dA(dM(rho1, y1i), dM(rho2, y2v)), dA(dA(b[i], z1[i]), z2[i]));
+                x[i] = y1i;
+            }
+            rhoUpdated = 0;
+            __syncthreads();
+            // ---- PCG (SEG.cpp:272-342) ---------------------------------------------------------------------------
+            for (int i = tid; i < n; i += SEG_T) {
+                const double rr = dS(w[i], seg_row_dot<true>(rp, ci, av, md, x, i));
+                r[i] = rr; p[i] = dM(invd[i], rr);
+            }
+            __syncthreads();
+            seg_block_redux<3>([&](int q, int i) {
+                const double a = (q == 0) ? w[i] : r[i];
+                const double c = (q == 0) ? a : ((q == 1) ? a : p[i]);
+                return dM(a, c); }, n, buf, sc);
+            const double rhsNorm2 = sc[0];
+            int cg_it = 0;
+            if (rhsNorm2 == 0.0) {
+                for (int i = tid; i < n; i += SEG_T) x[i] = 0.0;
+            } else {
+                double threshold = dM(dM(pr.pcg_tol, pr.pcg_tol), rhsNorm2);
+                if (!(threshold > DBL_MIN)) threshold = DBL_MIN;
+                double r2 = sc[1], absNew = sc[2];
+                if (!(r2 < threshold)) {
+                    while (cg_it < pr.pcg_maxiters) {
+                        for (int i = tid; i < n; i += SEG_T) t[i] = seg_row_dot<true>(rp, ci, av, md, p, i);
+                        __syncthreads();
+                        seg_block_redux<1>([&](int, int i) { return dM(p[i], t[i]); }, n, buf, sc);
+                        const double alpha = dD(absNew, sc[0]);
+                        for (int i = tid; i < n; i += SEG_T) {
+                            const double pi = p[i];
+                            x[i] = dA(x[i], dM(alpha, pi));
+                            const double rr = dS(r[i], dM(alpha, t[i]));
+                            r[i] = rr;
+                            t[i] = dM(invd[i], rr);                      // z
+                        }
+                        __syncthreads();
+                        seg_block_redux<2>([&](int q, int i) { const double a = r[i]; return dM(a, q == 0 ? a : t[i]); }, n, buf, sc);
+                        r2 = sc[0];
+                        if (r2 < threshold) { cg_it++; break; }
+                        const double absOld = absNew;
+                        absNew = sc[1];
+                        const double beta = dD(absNew, absOld);
+                        for (int i = tid; i < n; i += SEG_T) p[i] = dA(t[i], dM(beta, p[i]));
+                        cg_it++;
+                        __syncthreads();
+                    }
+                }
+            }
+            cg_total += cg_it; admm_total += 1;
+            __syncthreads();
+            // ---- history (SEG.cpp:1131-1134), duals (:1280-1281), indicator ----------------------------------------
+            double *h = nullptr;
+            if (la.l2f && sv.hist_cap > 0) { if (cc < sv.hist_cap) h = sv.hist + sv.off_hist[inst] + (long long)cc * st->n0; cc++; }
+            {
+                const double g1 = dM(gamma, rho1), g2 = dM(gamma, rho2);
+                for (int i = tid; i < n; i += SEG_T) {
+                    const double xi = x[i];
+                    if (h) h[i] = xi;
+                    z1[i] = dA(z1[i], dM(g1, dS(xi, y1[i])));
+                    z2[i] = dA(z2[i], dM(g2, dS(xi, y2[i])));
+                    w[i] = (xi >= 0.5) ? 1.0 : 0.0;
+                }
+            }
+            __syncthreads();
+            for (int i = tid; i < n; i += SEG_T) {
+                t[i] = seg_row_dot<false>(rp, ci, av, md, x, i);        // A x
+                r[i] = seg_row_dot<false>(rp, ci, av, md, w, i);        // A 1[x >= 0.5]
+            }
+            __syncthreads();
+            // x.x, (x-y1)^2, (x-y2)^2, x.Ax, b.x, idx.A idx, b.idx   (SEG.cpp:1285-1287, :568-572)
+            seg_block_redux<7>([&](int q, int i) {
+                const double xi = x[i];
+                switch (q) {
+                    case 0: return dM(xi, xi);
+                    case 1: { const double d = dS(xi, y1[i]); return dM(d, d); }
+                    case 2: { const double d = dS(xi, y2[i]); return dM(d, d); }
+                    case 3: return dM(xi, t[i]);
+                    case 4: return dM(b[i], xi);
+                    case 5: return dM(w[i], r[i]);
+                    default: return dM(b[i], w[i]);
+                } }, n, buf, sc);
+            {
+                double temp0 = sqrt(sc[0]);
+                if (!(temp0 > 2.2204e-16)) temp0 = 2.2204e-16;
+                const double c1 = dD(sqrt(sc[1]), temp0), c2 = dD(sqrt(sc[2]), temp0);
+                if (c1 <= pr.stop_threshold && c2 <= pr.stop_threshold) { status = STOP_Y; break; }   // SEG.cpp:1288-1292
+            }
+            if ((iter + 1) % pr.rho_change_step == 0) {                  // :1295-1303
+                prho1 = rho1; prho2 = rho2;
+                rho1 = dM(pr.learning_fact, rho1); rho2 = dM(pr.learning_fact, rho2);
+                double g = dM(gamma, pr.gamma_factor);
+                gamma = (g < 1.0) ? 1.0 : g;
+                rhoUpdated = 1;
+                ratio = dS(pr.learning_fact, 1.0);
+            }
+            {
+                const double obj = dA(sc[3], sc[4]);                     // compute_cost: val + val2
+                double so = std_obj;
+                if (obj_len + 1 >= (long long)pr.history_size) so = std_obj_after_push(ring, obj_len, obj, pr.history_size);
+                __syncthreads();
+                if (tid == 0) ring[obj_len & 15] = obj;
+                obj_len++;
+                std_obj = so;
+                __syncthreads();
+                if (std_obj <= pr.std_threshold) { status = STOP_STD; break; }   // :1313-1319
+            }
+            cur_obj = dA(sc[5], sc[6]);                                  // :1323-1326
+            if (best_bin_obj >= cur_obj) best_bin_obj = cur_obj;
+        }
+        __syncthreads();
+        if (!la.l2f) {
+            // legacy epilogue (SEG.cpp:1366-1367): cur_obj = compute_cost(1[x >= 0.5])
+            for (int i = tid; i < n; i += SEG_T) w[i] = (x[i] >= 0.5) ? 1.0 : 0.0;
+            __syncthreads();
+            for (int i = tid; i < n; i += SEG_T) r[i] = seg_row_dot<false>(rp, ci, av, md, w, i);
+            __syncthreads();
+            seg_block_redux<2>([&](int q, int i) { return dM(q == 0 ? w[i] : b[i], q == 0 ? r[i] : w[i]); }, n, buf, sc);
+            cur_obj = dA(sc[0], sc[1]);
+        }
+        if (tid < 16) st->obj_ring[tid] = ring[tid];
+        if (tid == 0) {
+            st->rho1 = rho1; st->rho2 = rho2; st->prho1 = prho1; st->prho2 = prho2; st->gamma = gamma; st->ratio = ratio;
+            st->std_obj = std_obj; st->cur_obj = cur_obj; st->best_bin_obj = best_bin_obj; st->rhoUpdated = rhoUpdated;
+            st->obj_len = obj_len; st->cg_iters += cg_total; st->admm_iters += admm_total; st->iter = iter; st->status = status;
+            const int ret = la.l2f ? (status != RUNNING ? 1 : 0) : 0;
+            st->last_ret = ret;
+            st->done = (status != RUNNING) ? 1 : 0;
+            if (la.l2f) st->xit_cols = cc;
+        }
+        __syncthreads();
+    }
+}
+
+// ADMM_bqp_unconstrained_init (SEG.cpp:747-810) for every image: x = x0 (zeros), y = x, z = 0, md = 2 a_ii + (rho1+rho2),
+// best_bin_obj = compute_cost(x0).  One CTA per image.
+__global__ void __launch_bounds__(SEG_T)
+seg_setup_kernel(SegView sv, Params pr, int use_x0) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *buf = reinterpret_cast<double *>(smem_raw);
+    double *sc = buf + 2 * SEG_RMAX * SEG_CH;
+    const int inst = blockIdx.x, tid = threadIdx.x;
+    SegInst *st = sv.st + inst;
+    const int n = st->n, cur = st->cur;
+    const long long on = sv.off_n[inst], oz = sv.off_nnz[inst];
+    const int *rp = sv.rowptr[cur] + on + 4 * inst;
+    const int *ci = sv.colidx[cur] + oz;
+    const double *av = sv.val[cur] + oz;
+    const double *b = sv.b[cur] + on;
+    double *x = sv.x + on, *t = sv.t + on;
+    const double rho = pr.initial_rho;
+    for (int i = tid; i < n; i += SEG_T) {
+        const double x0 = use_x0 ? x[i] : 0.0;
+        x[i] = x0; sv.y1[on + i] = x0; sv.y2[on + i] = x0; sv.z1[on + i] = 0.0; sv.z2[on + i] = 0.0;
+        sv.left_idx[on + i] = i;
+        double d = 0.0;
+        for (int k = rp[i]; k < rp[i + 1]; ++k) if (ci[k] == i) d = dM(2.0, av[k]);
+        sv.md[on + i] = dA(d, dA(rho, rho));                             // temp_mat = 2A; diag += rho1 + rho2
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += SEG_T) t[i] = seg_row_dot<false>(rp, ci, av, nullptr, x, i);
+    __syncthreads();
+    seg_block_redux<2>([&](int q, int i) { return dM(q == 0 ? x[i] : b[i], q == 0 ? t[i] : x[i]); }, n, buf, sc);
+    if (tid == 0) {
+        st->rho1 = st->rho2 = st->prho1 = st->prho2 = rho; st->gamma = pr.gamma_val; st->ratio = 0.0; st->rhoUpdated = 1;
+        st->std_obj = 1.0; st->cur_obj = 0.0; st->best_bin_obj = dA(sc[0], sc[1]); st->obj_len = 0; st->cg_iters = 0; st->admm_iters = 0;
+        st->iter = 0; st->status = RUNNING; st->done = 0; st->last_ret = 0; st->n_ret = 0; st->xit_rows = 0; st->xit_cols = 0;
+        for (int k = 0; k < 16; ++k) st->obj_ring[k] = 0.0;
+    }
+}
+
+}  // namespace lpb

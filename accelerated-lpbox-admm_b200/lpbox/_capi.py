@@ -75,6 +75,25 @@ SIGNATURES = {
     "lpbox_batch_iters_l2f_dev": (C.c_int, [_vp, C.c_int, C.c_int]),
     "lpbox_batch_h2d_bytes": (C.c_int64, [_vp]),
     "lpbox_batch_d2h_bytes": (C.c_int64, [_vp]),
+    "lpbox_seg_create_csr": (_vp, [C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
+    "lpbox_seg_create_images": (_vp, [C.c_int, C.c_int, _vp, _vp, _vp, C.c_int]),
+    "lpbox_seg_destroy": (None, [_vp]),
+    "lpbox_seg_build_graph": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "lpbox_seg_set_params": (C.c_int, [_vp, C.POINTER(Params)]),
+    "lpbox_seg_init": (C.c_int, [_vp, _vp]),
+    "lpbox_seg_solve": (C.c_int, [_vp, _vp]),
+    "lpbox_seg_size": (C.c_int, [_vp]),
+    "lpbox_seg_get_n": (C.c_int, [_vp, C.c_int]),
+    "lpbox_seg_get_org_n": (C.c_int, [_vp, C.c_int]),
+    "lpbox_seg_get_iter": (C.c_int, [_vp, C.c_int]),
+    "lpbox_seg_get_x_sol": (C.c_int, [_vp, C.c_int, _vp]),
+    "lpbox_seg_get_final_obj": (C.c_double, [_vp, C.c_int]),
+    "lpbox_seg_get_state": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "lpbox_seg_results": (C.c_int, [_vp, _vp]),
+    "lpbox_seg_last_kernel_ms": (C.c_double, [_vp]),
+    "lpbox_seg_launch_count": (C.c_int64, [_vp]),
+    "lpbox_seg_h2d_bytes": (C.c_int64, [_vp]),
+    "lpbox_seg_d2h_bytes": (C.c_int64, [_vp]),
     "lpbox_read_instance": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, _ip, _ip, C.POINTER(_ip), C.POINTER(_ip),
                                       C.POINTER(_dp), C.POINTER(_dp)]),
     "lpbox_free": (None, [_vp]),

@@ -160,6 +160,45 @@ int64_t lpbox_batch_h2d_bytes(const lpbox_batch *h);
 int64_t lpbox_batch_d2h_bytes(const lpbox_batch *h);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Batched UNCONSTRAINED solver (graph-cut image segmentation):   min x'Ax + b'x,  x in {0,1}^n            (config 3)
+ * Replaces the Segmentation experiment's LPboxADMMsolver (SEG.pxd:4-17).  Problems do not fit on chip; one CTA streams
+ * one image (see csrc/seg_kernels.cuh).
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct lpbox_seg_batch lpbox_seg_batch;
+
+/* B problems given as row-compressed symmetric A (columns strictly ascending inside a row, EVERY row stores its
+ * diagonal entry -- explicit zeros allowed, as the reference's graph builder produces, SEG.cpp:213-219), b and the
+ * constant c (`_c`, SEG.cpp:238).  rowptr_all: the B rowptr arrays back to back (n[i]+1 entries each, starting at 0). */
+lpbox_seg_batch *lpbox_seg_create_csr(int device, int B, const int32_t *n, const int32_t *rowptr_all, const int32_t *colidx_all,
+                                      const double *val_all, const double *b_all, const double *c, int hist_cap);
+/* B grey images (row-major uint8, nr[i] x nc[i], already scaled to the node budget): runs the reference's graph
+ * builder (get_unary_cost / get_binary_cost / get_A_b_from_cost, SEG.cpp:55-81,144-248,727-758) on the host cores and
+ * uploads.  Replaces the image front-end of ADMM_bqp_unconstrained_init (SEG.cpp:705-758) minus imread/resize. */
+lpbox_seg_batch *lpbox_seg_create_images(int device, int B, const uint8_t *pixels_all, const int32_t *nr, const int32_t *nc,
+                                         int hist_cap);
+void lpbox_seg_destroy(lpbox_seg_batch *h);
+/* the graph builder alone: outputs rowptr[n+1], colidx/val[<= 7n], b[n], *c; returns nnz */
+int lpbox_seg_build_graph(const uint8_t *pixels, int nr, int nc, int32_t *rowptr, int32_t *colidx, double *val, double *b,
+                          double *c_out);
+int lpbox_seg_set_params(lpbox_seg_batch *h, const lpbox_params *p);        /* default: lpbox_params_seg() */
+/* ADMM_bqp_unconstrained_init (SEG.cpp:658-810) state part; x0_all == NULL means x = 0 (SEG.cpp:761-762) */
+int lpbox_seg_init(lpbox_seg_batch *h, const double *x0_all);
+/* ADMM_bqp_unconstrained_legacy (SEG.cpp:1200-1380) for every image; energy[i] = int(cur_obj + _c) as it returns */
+int lpbox_seg_solve(lpbox_seg_batch *h, int32_t *energy);
+int lpbox_seg_size(const lpbox_seg_batch *h);
+int lpbox_seg_get_n(lpbox_seg_batch *h, int i);                             /* get_n()      */
+int lpbox_seg_get_org_n(lpbox_seg_batch *h, int i);                         /* get_org_n()  */
+int lpbox_seg_get_iter(lpbox_seg_batch *h, int i);
+int lpbox_seg_get_x_sol(lpbox_seg_batch *h, int i, double *out);            /* get_x_sol()      SEG.cpp:895-915 */
+double lpbox_seg_get_final_obj(lpbox_seg_batch *h, int i);                  /* get_final_obj()  SEG.cpp:868-893 */
+int lpbox_seg_get_state(lpbox_seg_batch *h, int i, double *x, double *y1, double *y2, double *z1, double *z2);
+int lpbox_seg_results(lpbox_seg_batch *h, lpbox_log_row *log);
+double lpbox_seg_last_kernel_ms(const lpbox_seg_batch *h);
+int64_t lpbox_seg_launch_count(const lpbox_seg_batch *h);
+int64_t lpbox_seg_h2d_bytes(const lpbox_seg_batch *h);
+int64_t lpbox_seg_d2h_bytes(const lpbox_seg_batch *h);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * File format of the reference: data/instance/<k>_<j>/instance_<i>_{C,b}.txt under `root`
  * (readFile, LP.cpp:2446-2545).  Arrays are malloc()ed by the library; release with lpbox_free().
  * ------------------------------------------------------------------------------------------------------------- */
