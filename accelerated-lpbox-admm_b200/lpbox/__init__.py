@@ -8,4 +8,5 @@ All compute happens in hand-written sm_100a CUDA behind the C ABI of `include/lp
 from .lp import LPBatch, PyLPboxADMMsolver, gen_auctions, read_instance  # noqa: F401
 from . import _capi  # noqa: F401
 from .l2f import solve_l2f  # noqa: F401
+from . import sparse_attack  # noqa: F401
 from .seg import PySegLPboxADMMsolver, SegBatch, build_graph  # noqa: F401

@@ -228,7 +228,7 @@ def main():
         elog, bits = bb.results()
         if dist is not None:   # the final gather of packed solutions over NVLink
             tb = torch.from_numpy(bits).cuda()
-            out = torch.empty((world,) + tuple(tb.shape), dtype=tb.dtype, device=tb.device)
+            out = torch.empty((world * tb.shape[0],) + tuple(tb.shape[1:]), dtype=tb.dtype, device=tb.device)
             dist.all_gather_into_tensor(out, tb)
             _ = out.cpu()
         barrier()

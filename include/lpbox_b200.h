@@ -199,6 +199,32 @@ int64_t lpbox_seg_h2d_bytes(const lpbox_seg_batch *h);
 int64_t lpbox_seg_d2h_bytes(const lpbox_seg_batch *h);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Sparse adversarial attack: Lp-Box ADMM on the pixel mask G, fp32, batched over images                     (config 4)
+ * Replaces the tensor arithmetic of update_G / loop / update_G_l2f (SparseAttack/main_ori.py:626-743, :502-623,
+ * :376-499); the attacked classifier stays in PyTorch.  ALL pointers are DEVICE pointers (torch CUDA tensors, fp32,
+ * [n_img][n_elem] with n_elem = channels*H*W); `stream` is a cudaStream_t.  Segments (the reference's SLIC blocks B,
+ * main_ori.py:147-158) must partition the elements: seg_of[e] = segment of element e, seg_ptr/seg_elems = elements
+ * grouped by segment (nseg+1 / n_elem entries), shared by all images (seg_per_image = 0) or one set per image.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* steps 1-2 of an iteration (main_ori.py:652-664) + the classifier input (:670-672):
+ * y1 = clamp(G + z1/rho1, 0, 1); y2 = sqrt(n)/2 * s/||s|| + 1/2, s = G + z2/rho2 - 1/2 (utils.py:8-16);
+ * y3 = group-lasso prox of C = G + z3/rho3; image_s = (clamp(images + G*eps, minpix, maxpix) - mean) / std */
+int lpbox_sa_pre_dev(void *stream, int n_img, int n_elem, int n_chan, int nseg, int seg_per_image, const float *G, const float *z1,
+                     const float *z2, const float *z3, const float *images, const float *eps, const int32_t *seg_ptr,
+                     const int32_t *seg_elems, const int32_t *seg_of, const float *mean, const float *stdv, double rho1, double rho2,
+                     double rho3, double lambda2, double minpix, double maxpix, float *y1, float *y2, float *y3, float *image_s);
+/* steps 3-4 (main_ori.py:697-721) given grad_in = dLoss/d image_s from the classifier: chain rule to G, grad_G, gradient
+ * step, z1..z4 updates; writes the new G into hist_slot as well when it is not NULL (G_iters, main_ori.py:586) */
+int lpbox_sa_post_dev(void *stream, int n_img, int n_elem, int n_chan, float *G, float *z1, float *z2, float *z3, float *z4,
+                      const float *y1, const float *y2, const float *y3, const float *grad_in, const float *images, const float *eps,
+                      const float *nw, const float *stdv, double lambda1, double rho1, double rho2, double rho3, double rho4,
+                      double step, double k, double minpix, double maxpix, float *hist_slot);
+/* update_G_l2f's rewrite of G from policy scores (main_ori.py:476-485): p > hi -> 1, p < lo -> 0, else `last`;
+ * counts2[0], counts2[1] receive the number of ones / zeros fixed */
+int lpbox_sa_apply_policy_dev(void *stream, int64_t n, const float *scores, const float *last, double hi, double lo, float *G,
+                              int32_t *counts2);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * File format of the reference: data/instance/<k>_<j>/instance_<i>_{C,b}.txt under `root`
  * (readFile, LP.cpp:2446-2545).  Arrays are malloc()ed by the library; release with lpbox_free().
  * ------------------------------------------------------------------------------------------------------------- */
