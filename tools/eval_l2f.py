@@ -14,7 +14,7 @@ probs = lpbox.gen_auctions(4242, B, 100, 500)
 b = lpbox.LPBatch(probs); b.init()
 t = time.time(); plain = b.solve(20000); torch.cuda.synchronize(); t_plain = time.time() - t
 b.close()
-net = load_policy(os.path.join(ROOT, "accelerated-lpbox-admm_b200", "lpbox", "weights", "lp_mha_policy.pt"))
+net = load_policy(os.path.join(ROOT, "accelerated-lpbox-admm_b200", "lpbox", "weights", os.environ.get("LPBOX_POLICY", "lp_mha_policy.pt")))
 if dtype == "bf16":
     def score(x):
         with torch.autocast("cuda", dtype=torch.bfloat16):
