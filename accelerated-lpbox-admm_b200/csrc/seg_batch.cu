@@ -42,8 +42,10 @@ struct lpbox_seg_batch {
     Params pr{};
     SegView sv{};
     SBuf<long long> d_off_n, d_off_nnz, d_off_hist;
-    SBuf<double> vecs[11], d_b[2], d_val[2], d_hist, d_ret_val, d_powv;
-    SBuf<int> d_rp[2], d_ci[2], d_left, d_ret_idx, d_counter;
+    SBuf<double> vecs[11], d_b[2], d_val[2], d_hist, d_ret_val, d_powv, d_powtab, d_vec, d_b_org, d_val_org;
+    SBuf<int> d_rp[2], d_ci[2], d_left, d_ret_idx, d_counter, d_kidx, d_cnt, d_num, d_rp_org, d_ci_org;
+    SBuf<long long> d_off_vec;
+    int max_n = 0;
     SBuf<SegInst> d_st;
     std::vector<SegInst> h_st;
     bool inited = false;
@@ -134,7 +136,8 @@ extern "C" void lpbox_seg_destroy(lpbox_seg_batch *h) {
     h->d_off_n.free_(); h->d_off_nnz.free_(); h->d_off_hist.free_();
     for (auto &v : h->vecs) v.free_();
     for (int k = 0; k < 2; ++k) { h->d_b[k].free_(); h->d_val[k].free_(); h->d_rp[k].free_(); h->d_ci[k].free_(); }
-    h->d_hist.free_(); h->d_ret_val.free_(); h->d_powv.free_(); h->d_left.free_(); h->d_ret_idx.free_(); h->d_counter.free_(); h->d_st.free_();
+    h->d_hist.free_(); h->d_ret_val.free_(); h->d_powv.free_(); h->d_powtab.free_(); h->d_vec.free_(); h->d_b_org.free_(); h->d_val_org.free_();
+    h->d_kidx.free_(); h->d_cnt.free_(); h->d_num.free_(); h->d_rp_org.free_(); h->d_ci_org.free_(); h->d_off_vec.free_(); h->d_left.free_(); h->d_ret_idx.free_(); h->d_counter.free_(); h->d_st.free_();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -162,6 +165,7 @@ extern "C" lpbox_seg_batch *lpbox_seg_create_csr(int device, int B, const int32_
         h->off_nnz[i + 1] = h->off_nnz[i] + ((h->nnz0[i] + 3) & ~3);
         h->off_hist[i + 1] = h->off_hist[i] + (long long)hist_cap * n[i];
         if (c) h->cconst[i] = c[i];
+        h->max_n = std::max(h->max_n, n[i]);
     }
     rp_off[B] = rpo;
     const size_t NN = (size_t)h->off_n[B], ZZ = (size_t)h->off_nnz[B];
@@ -207,6 +211,8 @@ extern "C" lpbox_seg_batch *lpbox_seg_create_csr(int device, int B, const int32_
     for (int k = 0; k < 2; ++k) { A(h->d_b[k].alloc(NN)); A(h->d_val[k].alloc(ZZ)); A(h->d_rp[k].alloc(NN + 4 * (size_t)B)); A(h->d_ci[k].alloc(ZZ)); }
     A(h->d_hist.alloc((size_t)h->off_hist[B])); A(h->d_ret_val.alloc(NN)); A(h->d_powv.alloc(B)); A(h->d_left.alloc(NN)); A(h->d_ret_idx.alloc(NN));
     A(h->d_counter.alloc(1)); A(h->d_st.alloc(B));
+    A(h->d_kidx.alloc(NN)); A(h->d_cnt.alloc(NN)); A(h->d_num.alloc(B)); A(h->d_off_vec.alloc(B + 1)); A(h->d_vec.alloc(NN)); A(h->d_powtab.alloc((size_t)h->max_n + 1));
+    A(h->d_rp_org.alloc(NN + 4 * (size_t)B)); A(h->d_ci_org.alloc(ZZ)); A(h->d_val_org.alloc(ZZ)); A(h->d_b_org.alloc(NN));
     if (!ok) { lpbox_seg_destroy(h); return nullptr; }
     auto H2D = [&](void *d, const void *s, size_t bytes) { if (bytes) { A(cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, h->stream)); h->h2d_bytes += (int64_t)bytes; } };
     H2D(h->d_off_n.p, h->off_n.data(), sizeof(long long) * (B + 1));
@@ -217,6 +223,13 @@ extern "C" lpbox_seg_batch *lpbox_seg_create_csr(int device, int B, const int32_
     H2D(h->d_val[0].p, va_pack.data(), sizeof(double) * ZZ);
     H2D(h->d_b[0].p, b_pack.data(), sizeof(double) * NN);
     H2D(h->d_powv.p, powv.data(), sizeof(double) * (size_t)B);
+    std::vector<double> powtab((size_t)h->max_n + 1);
+    for (int k = 0; k <= h->max_n; ++k) powtab[k] = pow((double)k, 1.0 / 2);     // std::pow(n, 1.0/p) from the host libm
+    H2D(h->d_powtab.p, powtab.data(), sizeof(double) * powtab.size());
+    H2D(h->d_rp_org.p, rp_pack.data(), sizeof(int) * rp_pack.size());
+    H2D(h->d_ci_org.p, ci_pack.data(), sizeof(int) * ZZ);
+    H2D(h->d_val_org.p, va_pack.data(), sizeof(double) * ZZ);
+    H2D(h->d_b_org.p, b_pack.data(), sizeof(double) * NN);
     H2D(h->d_st.p, st.data(), sizeof(SegInst) * (size_t)B);
     A(cudaStreamSynchronize(h->stream));
     if (!ok) { lpbox_seg_destroy(h); return nullptr; }
@@ -225,6 +238,7 @@ extern "C" lpbox_seg_batch *lpbox_seg_create_csr(int device, int B, const int32_
     double **vp[11] = {&v.x, &v.y1, &v.y2, &v.z1, &v.z2, &v.md, &v.invd, &v.r, &v.p, &v.t, &v.w};
     for (int k = 0; k < 11; ++k) *vp[k] = h->vecs[k].p;
     for (int k = 0; k < 2; ++k) { v.b[k] = h->d_b[k].p; v.rowptr[k] = h->d_rp[k].p; v.colidx[k] = h->d_ci[k].p; v.val[k] = h->d_val[k].p; }
+    v.kidx = h->d_kidx.p; v.cnt = h->d_cnt.p; v.pow_tab = h->d_powtab.p;
     v.st = h->d_st.p; v.hist = h->d_hist.p; v.left_idx = h->d_left.p; v.ret_idx = h->d_ret_idx.p; v.ret_val = h->d_ret_val.p; v.powv = h->d_powv.p;
     h->smem = sizeof(double) * (2 * SEG_RMAX * SEG_CH + 8 + 16);
     int sms = 0, occ = 1;
@@ -326,6 +340,56 @@ extern "C" int lpbox_seg_solve(lpbox_seg_batch *h, int32_t *energy) {
     return (int)(h->h_st[0].cur_obj + h->h_st[0].cconst);
 }
 
+// ADMM_bqp_unconstrained_l2f(iter_start, iter_end, vec, num) for every image (SEG.cpp:917-1195)
+extern "C" int lpbox_seg_iters_l2f(lpbox_seg_batch *h, int iter_start, int iter_end, const double *vec_all, const int32_t *num, int32_t *ret) {
+    if (!h || !h->inited) { lpbox_set_error("call lpbox_seg_init first"); return LPBOX_E_INVALID; }
+    SCK(cudaSetDevice(h->device));
+    const int skip_done = h->B > 1 ? 1 : 0;
+    bool any = false;
+    if (num) for (int i = 0; i < h->B; ++i) if (num[i] != 0) any = true;
+    if (any && !vec_all) { lpbox_set_error("vec_all is NULL but some num[i] != 0"); return LPBOX_E_INVALID; }
+    if (any) {
+        std::vector<long long> off_vec(h->B + 1, 0);
+        for (int i = 0; i < h->B; ++i) off_vec[i + 1] = off_vec[i] + h->h_st[i].n;
+        for (int i = 0; i < h->B; ++i) {
+            if (num[i] == 0) continue;
+            int c = 0;
+            const double *v = vec_all + off_vec[i];
+            for (int k = 0; k < h->h_st[i].n; ++k) if (v[k] == 1.0 || v[k] == 0.0) c++;
+            if (c != num[i]) { lpbox_set_error("num[i] does not match the number of fixed entries in vec"); return LPBOX_E_INVALID; }
+        }
+        SCK(cudaMemcpyAsync(h->d_off_vec.p, off_vec.data(), sizeof(long long) * (h->B + 1), cudaMemcpyHostToDevice, h->stream));
+        SCK(cudaMemcpyAsync(h->d_vec.p, vec_all, sizeof(double) * (size_t)off_vec[h->B], cudaMemcpyHostToDevice, h->stream));
+        SCK(cudaMemcpyAsync(h->d_num.p, num, sizeof(int) * (size_t)h->B, cudaMemcpyHostToDevice, h->stream));
+        h->h2d_bytes += (int64_t)(sizeof(double) * (size_t)off_vec[h->B]);
+    } else {
+        SCK(cudaMemsetAsync(h->d_num.p, 0, sizeof(int) * (size_t)h->B, h->stream));
+    }
+    seg_fix_kernel<<<h->B, SEG_T, 0, h->stream>>>(h->sv, h->pr, h->d_vec.p, h->d_off_vec.p, h->d_num.p, skip_done);
+    SCK(cudaGetLastError());
+    h->launches += 1;
+    int rc = seg_run(h, iter_start, iter_end, 1, skip_done);
+    if (rc) return rc;
+    if (ret) for (int i = 0; i < h->B; ++i) ret[i] = h->h_st[i].last_ret;
+    return h->h_st[0].last_ret;
+}
+
+// get_x_iters_d(ws) (SEG.cpp:833-845): row-major (n_cur x ws); the reference keeps 10 columns (SEG.cpp:924)
+extern "C" int lpbox_seg_get_x_iters(lpbox_seg_batch *h, int i, int ws, double *out) {
+    if (!h || i < 0 || i >= h->B || !out || ws <= 0) return LPBOX_E_INVALID;
+    const SegInst &s = h->h_st[i];
+    const int rows = s.xit_rows, cols = std::min(std::min(s.xit_cols, ws), h->hist_cap);
+    std::vector<double> buf((size_t)std::max(cols, 0) * s.n0);
+    if (cols > 0) {
+        h->d2h_bytes += (int64_t)(sizeof(double) * buf.size());
+        SCK(cudaMemcpyAsync(buf.data(), h->sv.hist + h->off_hist[i], sizeof(double) * buf.size(), cudaMemcpyDeviceToHost, h->stream));
+        SCK(cudaStreamSynchronize(h->stream));
+    }
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < ws; ++c) out[(size_t)r * ws + c] = (c < cols) ? buf[(size_t)c * s.n0 + r] : 0.0;
+    return rows;
+}
+
 extern "C" int lpbox_seg_size(const lpbox_seg_batch *h) { return h ? h->B : LPBOX_E_INVALID; }
 #define SCHK(h, i) if (!(h) || (i) < 0 || (i) >= (h)->B) return LPBOX_E_INVALID
 extern "C" int lpbox_seg_get_n(lpbox_seg_batch *h, int i) { SCHK(h, i); return h->h_st[i].n; }
@@ -351,29 +415,32 @@ extern "C" int lpbox_seg_get_state(lpbox_seg_batch *h, int i, double *x, double 
     if (z2) rc |= seg_d2h(h, z2, h->sv.z2 + on, nb);
     return rc ? LPBOX_E_CUDA : 0;
 }
-// get_x_sol (SEG.cpp:895-915): binary solution in original indexing (no early fixing in this build: left_idx = identity)
+// get_x_sol (SEG.cpp:895-915): fixed values + 1[x >= 0.5] of the remaining variables, original indexing
 extern "C" int lpbox_seg_get_x_sol(lpbox_seg_batch *h, int i, double *out) {
     SCHK(h, i);
     if (!out) return LPBOX_E_INVALID;
     const SegInst &s = h->h_st[i];
-    if (s.n != s.n0) { lpbox_set_error("early fixing is not built for the segmentation path yet"); return LPBOX_E_UNSUPPORTED; }
-    std::vector<double> x(s.n);
-    if (seg_d2h(h, x.data(), h->sv.x + h->off_n[i], sizeof(double) * (size_t)s.n)) return LPBOX_E_CUDA;
-    for (int q = 0; q < s.n; ++q) out[q] = (x[q] >= 0.5) ? 1.0 : 0.0;
+    const long long on = h->off_n[i];
+    std::vector<double> x(s.n), rval(s.n_ret);
+    std::vector<int> left(s.n), ridx(s.n_ret);
+    if (seg_d2h(h, x.data(), h->sv.x + on, sizeof(double) * (size_t)s.n) || seg_d2h(h, left.data(), h->sv.left_idx + on, sizeof(int) * (size_t)s.n) ||
+        seg_d2h(h, ridx.data(), h->sv.ret_idx + on, sizeof(int) * (size_t)s.n_ret) || seg_d2h(h, rval.data(), h->sv.ret_val + on, sizeof(double) * (size_t)s.n_ret))
+        return LPBOX_E_CUDA;
+    for (int q = 0; q < s.n_ret; ++q) out[ridx[q]] = rval[q];
+    for (int q = 0; q < s.n; ++q) out[left[q]] = (x[q] >= 0.5) ? 1.0 : 0.0;
     return s.n0;
 }
-// get_final_obj (SEG.cpp:868-893): x'Ax + b'x of the assembled binary solution on the original problem, + _c
+// get_final_obj (SEG.cpp:868-893): x'Ax + b'x of the assembled binary solution on the ORIGINAL problem, + _c
 extern "C" double lpbox_seg_get_final_obj(lpbox_seg_batch *h, int i) {
     if (!h || i < 0 || i >= h->B) return NAN;
     const SegInst &s = h->h_st[i];
-    if (s.n != s.n0) return NAN;
-    std::vector<double> xs(s.n0), ax(s.n0), b(s.n0), va(s.nnz0);
+    std::vector<double> xs(s.n0, 0.0), ax(s.n0), b(s.n0), va(s.nnz0);
     std::vector<int> rp(s.n0 + 1), ci(s.nnz0);
     if (lpbox_seg_get_x_sol(h, i, xs.data()) < 0) return NAN;
-    if (seg_d2h(h, rp.data(), h->sv.rowptr[s.cur] + h->off_n[i] + 4 * (size_t)i, sizeof(int) * ((size_t)s.n0 + 1)) ||
-        seg_d2h(h, ci.data(), h->sv.colidx[s.cur] + h->off_nnz[i], sizeof(int) * (size_t)s.nnz0) ||
-        seg_d2h(h, va.data(), h->sv.val[s.cur] + h->off_nnz[i], sizeof(double) * (size_t)s.nnz0) ||
-        seg_d2h(h, b.data(), h->sv.b[s.cur] + h->off_n[i], sizeof(double) * (size_t)s.n0)) return NAN;
+    if (seg_d2h(h, rp.data(), h->d_rp_org.p + h->off_n[i] + 4 * (size_t)i, sizeof(int) * ((size_t)s.n0 + 1)) ||
+        seg_d2h(h, ci.data(), h->d_ci_org.p + h->off_nnz[i], sizeof(int) * (size_t)s.nnz0) ||
+        seg_d2h(h, va.data(), h->d_val_org.p + h->off_nnz[i], sizeof(double) * (size_t)s.nnz0) ||
+        seg_d2h(h, b.data(), h->d_b_org.p + h->off_n[i], sizeof(double) * (size_t)s.n0)) return NAN;
     for (int r = 0; r < s.n0; ++r) { double acc = 0.0; for (int k = rp[r]; k < rp[r + 1]; ++k) acc = acc + va[k] * xs[ci[k]]; ax[r] = acc; }
     std::vector<double> pr1(s.n0), pr2(s.n0);
     for (int r = 0; r < s.n0; ++r) { pr1[r] = xs[r] * ax[r]; pr2[r] = b[r] * xs[r]; }

@@ -48,8 +48,10 @@ struct SegView {
     double *hist;              // [cc][n0]
     int *left_idx, *ret_idx;
     double *ret_val;
-    const double *pow_tab;     // unused for n > table; pow(n, .5) passed per instance in powv
-    double *powv;              // [B] std::pow(n, 0.5) of the CURRENT n (host libm), refreshed after a fix
+    const double *pow_tab;     // pow_tab[k] = std::pow(k, 0.5) from the host libm, k <= max n0
+    double *powv;              // [B] std::pow(n, 0.5) of the CURRENT n, refreshed by the early-fix kernel
+    int *kidx;                 // [off_n] scratch: new index of a kept variable
+    int *cnt;                  // [off_n] scratch: kept entries per new row / misc
 };
 
 struct SegLaunch {
@@ -361,6 +363,111 @@ seg_setup_kernel(SegView sv, Params pr, int use_x0) {
         st->std_obj = 1.0; st->cur_obj = 0.0; st->best_bin_obj = dA(sc[0], sc[1]); st->obj_len = 0; st->cg_iters = 0; st->admm_iters = 0;
         st->iter = 0; st->status = RUNNING; st->done = 0; st->last_ret = 0; st->n_ret = 0; st->xit_rows = 0; st->xit_cols = 0;
         for (int k = 0; k < 16; ++k) st->obj_ring[k] = 0.0;
+    }
+}
+
+
+// ---- device-side early fixing for the unconstrained form: ADMM_bqp_unconstrained_l2f prologue (SEG.cpp:932-1090) -------
+// One CTA per image.  A <- A[keep,keep] (Ma), b <- 2 A[keep,fix] x_fix + b[keep] (:1044-1052), x,y1,y2,z1,z2 gathered,
+// left_idx / ret_idx / ret_val bookkeeping, temp_mat diagonal rebuilt at the CURRENT rho (:1054-1057).  The compressed
+// arrays and b ping-pong between two buffers (no in-place hazards); n-vectors are gathered through the scratch vector r.
+__device__ __forceinline__ int seg_block_exscan_global(int *data, int n, int *s_part) {
+    // in-place exclusive scan of a global int array by the whole CTA; returns the total
+    const int tid = threadIdx.x;
+    constexpr int ITEMS = 8;
+    int carry = 0;
+    for (int base = 0; base < n; base += SEG_T * ITEMS) {
+        int v[ITEMS], sum = 0;
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) { const int i = base + tid * ITEMS + k; v[k] = (i < n) ? data[i] : 0; sum += v[k]; }
+        s_part[tid] = sum;
+        __syncthreads();
+        if (tid == 0) { int run = 0; for (int t2 = 0; t2 < SEG_T; ++t2) { const int q = s_part[t2]; s_part[t2] = run; run += q; } s_part[SEG_T] = run; }
+        __syncthreads();
+        int run = carry + s_part[tid];
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) { const int i = base + tid * ITEMS + k; if (i < n) data[i] = run; run += v[k]; }
+        carry += s_part[SEG_T];
+        __syncthreads();
+    }
+    return carry;
+}
+
+__global__ void __launch_bounds__(SEG_T)
+seg_fix_kernel(SegView sv, Params pr, const double *__restrict__ vec, const long long *__restrict__ off_vec, const int *__restrict__ num,
+               int skip_done) {
+    __shared__ int s_part[SEG_T + 1];
+    const int inst = blockIdx.x, tid = threadIdx.x;
+    SegInst *st = sv.st + inst;
+    if (skip_done && st->done) return;
+    const int n = st->n;
+    const int fn = num ? num[inst] : 0;
+    if (fn == 0 || n == 0) { if (tid == 0) { st->xit_rows = n; st->xit_cols = 0; } return; }
+    const int cur = st->cur, nxt = cur ^ 1;
+    const long long on = sv.off_n[inst], oz = sv.off_nnz[inst];
+    const double *v = vec + off_vec[inst];
+    const int *rp = sv.rowptr[cur] + on + 4 * inst, *ci = sv.colidx[cur] + oz;
+    const double *av = sv.val[cur] + oz, *b = sv.b[cur] + on;
+    int *rp2 = sv.rowptr[nxt] + on + 4 * inst, *ci2 = sv.colidx[nxt] + oz;
+    double *av2 = sv.val[nxt] + oz, *b2 = sv.b[nxt] + on;
+    int *kidx = sv.kidx + on, *cnt = sv.cnt + on;
+    auto is_fixed = [&](int i) { const double t = v[i]; return t == 1.0 || t == 0.0; };
+    for (int i = tid; i < n; i += SEG_T) kidx[i] = is_fixed(i) ? 0 : 1;
+    __syncthreads();
+    const int k_tot = seg_block_exscan_global(kidx, n, s_part);
+    const int j_tot = n - k_tot, n_ret = st->n_ret;
+    // bookkeeping (SEG.cpp:1017-1026): left_idx compacted through cnt as scratch
+    for (int i = tid; i < n; i += SEG_T) cnt[i] = sv.left_idx[on + i];
+    __syncthreads();
+    for (int i = tid; i < n; i += SEG_T) {
+        if (is_fixed(i)) { const int q = n_ret + (i - kidx[i]); sv.ret_idx[on + q] = cnt[i]; sv.ret_val[on + q] = v[i]; }
+        else sv.left_idx[on + kidx[i]] = cnt[i];
+    }
+    __syncthreads();
+    if (k_tot == 0) {                                                         // :1028-1032
+        if (tid == 0) { st->n = 0; st->nnz = 0; st->n_ret = n_ret + j_tot; st->status = STOP_EMPTY; st->last_ret = 1; st->done = 1; st->xit_rows = 0; st->xit_cols = 0; }
+        return;
+    }
+    // gathers (:1035-1041) through the scratch vector r
+    double *vecs[5] = {sv.x + on, sv.y1 + on, sv.y2 + on, sv.z1 + on, sv.z2 + on};
+    double *scr = sv.r + on;
+    for (int a = 0; a < 5; ++a) {
+        for (int i = tid; i < n; i += SEG_T) scr[i] = vecs[a][i];
+        __syncthreads();
+        for (int i = tid; i < n; i += SEG_T) if (!is_fixed(i)) vecs[a][kidx[i]] = scr[i];
+        __syncthreads();
+    }
+    // Ma = A[keep,keep], b = 2 (Mb x2) + b1 (:973-1015, :1044-1052); md = 2 a_ii + (rho1 + rho2) (:1054-1057)
+    for (int i = tid; i < n; i += SEG_T) cnt[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += SEG_T) {
+        if (is_fixed(i)) continue;
+        int c = 0;
+        for (int k = rp[i]; k < rp[i + 1]; ++k) c += is_fixed(ci[k]) ? 0 : 1;
+        cnt[kidx[i]] = c;
+    }
+    __syncthreads();
+    const int nnz_new = seg_block_exscan_global(cnt, k_tot, s_part);
+    const double rr = dA(st->rho1, st->rho2);
+    for (int i = tid; i < n; i += SEG_T) {
+        if (is_fixed(i)) continue;
+        const int r = kidx[i];
+        int q = cnt[r];
+        rp2[r] = q;
+        double acc = 0.0, dg = 0.0;
+        for (int k = rp[i]; k < rp[i + 1]; ++k) {
+            const int c = ci[k];
+            const double a = av[k];
+            if (is_fixed(c)) acc = dA(acc, dM(a, v[c]));
+            else { ci2[q] = kidx[c]; av2[q] = a; q++; if (c == i) dg = dM(2.0, a); }
+        }
+        b2[r] = dA(dM(2.0, acc), b[i]);
+        sv.md[on + r] = dA(dg, rr);
+    }
+    if (tid == 0) {
+        rp2[k_tot] = nnz_new;
+        st->n = k_tot; st->nnz = nnz_new; st->n_ret = n_ret + j_tot; st->cur = nxt; st->xit_rows = k_tot; st->xit_cols = 0;
+        sv.powv[inst] = sv.pow_tab[k_tot];
     }
 }
 

@@ -82,6 +82,8 @@ SIGNATURES = {
     "lpbox_seg_set_params": (C.c_int, [_vp, C.POINTER(Params)]),
     "lpbox_seg_init": (C.c_int, [_vp, _vp]),
     "lpbox_seg_solve": (C.c_int, [_vp, _vp]),
+    "lpbox_seg_iters_l2f": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "lpbox_seg_get_x_iters": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "lpbox_seg_size": (C.c_int, [_vp]),
     "lpbox_seg_get_n": (C.c_int, [_vp, C.c_int]),
     "lpbox_seg_get_org_n": (C.c_int, [_vp, C.c_int]),

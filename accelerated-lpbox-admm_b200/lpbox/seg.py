@@ -86,6 +86,25 @@ class SegBatch:
             raise RuntimeError("lpbox_seg_solve failed: " + _capi.last_error())
         return e
 
+    def iters_l2f(self, start, end, vecs=None, nums=None):
+        ret = np.zeros(self.B, dtype=np.int32)
+        nums = _i32(np.zeros(self.B) if nums is None else nums)
+        vec = None
+        if vecs is not None and np.any(nums != 0):
+            parts = []
+            for i in range(self.B):
+                n = self.get_n(i)
+                parts.append(np.full(n, -1.0) if (vecs[i] is None or nums[i] == 0) else _f64(vecs[i])[:n])
+            vec = _f64(np.concatenate(parts))
+        check(self.L.lpbox_seg_iters_l2f(self.h, int(start), int(end), ptr(vec), ptr(nums), ptr(ret)), "seg_iters_l2f")
+        return ret
+
+    def x_iters(self, i, ws):
+        rows = self.get_n(i)
+        out = np.zeros((max(rows, 1), int(ws)))
+        r = check(self.L.lpbox_seg_get_x_iters(self.h, i, int(ws), ptr(out)), "seg_get_x_iters")
+        return out[:r]
+
     def results(self):
         log = np.zeros(self.B, dtype=_capi.LOG_DTYPE)
         check(self.L.lpbox_seg_results(self.h, ptr(log)), "seg_results")
@@ -155,7 +174,7 @@ class PySegLPboxADMMsolver:
             self._load()
         if self._b is not None:
             self._b.close()
-        self._b = SegBatch([self._img], device=self._device)
+        self._b = SegBatch([self._img], device=self._device, hist_cap=10)       # x_iters = Zero(n, 10)  (SEG.cpp:924)
         self._b.init()
 
     def solve_iter(self):
@@ -174,7 +193,10 @@ class PySegLPboxADMMsolver:
         return self._b.x_sol(0).reshape(-1, 1)
 
     def solve_iter_l2f(self, i, j, vec, num):
-        raise NotImplementedError("early fixing for the segmentation path (ADMM_bqp_unconstrained_l2f, SEG.cpp:917-1195) is not built yet")
+        return int(self._b.iters_l2f(int(i), int(j), [_f64(vec)], [int(num)])[0])
+
+    def get_x_iters_2d(self, ws):
+        return self._b.x_iters(0, int(ws))
 
     def save_img(self, path=None):
         """SEG.cpp:812-831: reshape the solution column-major to (rows, cols), 1 -> white, write ../result/output_<i>.png."""

@@ -185,6 +185,10 @@ int lpbox_seg_set_params(lpbox_seg_batch *h, const lpbox_params *p);        /* d
 int lpbox_seg_init(lpbox_seg_batch *h, const double *x0_all);
 /* ADMM_bqp_unconstrained_legacy (SEG.cpp:1200-1380) for every image; energy[i] = int(cur_obj + _c) as it returns */
 int lpbox_seg_solve(lpbox_seg_batch *h, int32_t *energy);
+/* ADMM_bqp_unconstrained_l2f(iter_start, iter_end, vec, num) (SEG.cpp:917-1195), argument conventions as
+ * lpbox_batch_iters_l2f; the compaction A <- A[keep,keep], b <- 2 A[keep,fix] x_fix + b[keep] runs on the device */
+int lpbox_seg_iters_l2f(lpbox_seg_batch *h, int iter_start, int iter_end, const double *vec_all, const int32_t *num, int32_t *ret);
+int lpbox_seg_get_x_iters(lpbox_seg_batch *h, int i, int ws, double *out);   /* get_x_iters_d(ws)  SEG.cpp:833-845 */
 int lpbox_seg_size(const lpbox_seg_batch *h);
 int lpbox_seg_get_n(lpbox_seg_batch *h, int i);                             /* get_n()      */
 int lpbox_seg_get_org_n(lpbox_seg_batch *h, int i);                         /* get_org_n()  */

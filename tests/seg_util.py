@@ -59,6 +59,17 @@ class OracleSeg:
         if max_iters is not None:
             self.L.sego_set_params(self.h, 1e-3, 1e-6, int(max_iters), 5.0, 5, 1.0, 1.03, 5.0, 0.99, 1e-3, 1000)
 
+    def l2f(self, a, b, vec, num):
+        return self.L.sego_l2f(self.h, int(a), int(b), np.ascontiguousarray(vec, dtype=np.float64), int(num))
+
+    def x_iters(self, ws):
+        self.L.sego_get_x_iters.restype = C.c_int
+        self.L.sego_get_x_iters.argtypes = [C.c_void_p, C.c_int, _dp]
+        n = self.L.sego_get_n(self.h)
+        out = np.zeros((max(n, 1), ws))
+        r = self.L.sego_get_x_iters(self.h, ws, out.reshape(-1))
+        return out[:r]
+
     def legacy(self):
         return self.L.sego_legacy(self.h)
 

@@ -65,3 +65,36 @@ def test_python_mirror_class():
     assert s.get_n() == s.get_org_n() == 1200
     assert s.get_x_sol().shape == (1200, 1)
     assert s.get_obj() == o.L.sego_get_final_obj(o.h)
+
+
+def test_l2f_windows_match_oracle():
+    """ADMM_bqp_unconstrained_l2f with injected fix vectors (SEG.trainer:699-752 shape: windows of 10 iterations):
+    device-side compaction A[keep,keep], b update, history, getters -- bit-exact vs the oracle."""
+    import lpbox
+    img = synth_image(7, 28, 36)
+    o = OracleSeg(); o.set_problem(*o.build_graph(img)); o.init()
+    s = lpbox.PySegLPboxADMMsolver(0, 28 * 36, 0)
+    s.set_image(img); s.solve_init()
+    ws = 10
+    vec, num = np.zeros(1), 0
+    for w in range(8):
+        ro = o.l2f(ws * w, ws * (w + 1), vec, num)
+        rg = s.solve_iter_l2f(ws * w, ws * (w + 1), vec if num else np.zeros(1), num)
+        assert ro == rg, w
+        assert o.L.sego_get_n(o.h) == s.get_n()
+        xo, xg = o.x_iters(ws), s.get_x_iters_2d(ws)
+        assert xo.shape == xg.shape and np.array_equal(xo, xg), w
+        so = o.state(); sg = s._b.state(0)
+        for k in so:
+            assert np.array_equal(so[k], sg[k]), (w, k)
+        assert np.array_equal(o.x_sol(), s.get_x_sol().ravel())
+        assert o.L.sego_get_final_obj(o.h) == s.get_obj()
+        if ro:
+            break
+        if w in (1, 3, 5):
+            x = so["x"]
+            idx = np.argsort(-np.abs(x - 0.5))[: max(11, len(x) // 4)]
+            vec = -np.ones(len(x)); vec[idx] = (x[idx] >= 0.5) * 1.0; num = len(idx)
+        else:
+            vec, num = np.zeros(1), 0
+    assert s.get_n() < 28 * 36
