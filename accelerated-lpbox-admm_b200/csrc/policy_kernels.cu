@@ -1,0 +1,404 @@
+// Early-fixing policy network as bf16 tensor-core kernels for sm_100a.
+//
+// GraphAttentionEncoder / MLPEncoder forward (LP.mha:202-304) in eval mode for R variables x T tokens:
+//   embed (CUDA cores, K = 10) -> per layer { QKV GEMM -> attention (T <= 32, 8 heads, d_k = 16; CUDA cores)
+//   -> out-proj GEMM (+skip, BatchNorm folded) -> FF1 GEMM (+bias, ReLU) -> FF2 GEMM (+bias, +skip, BatchNorm folded) }
+//   -> fc1 GEMM (K = T*128) -> fc2 GEMM -> head (fc3, fc4, sigmoid; CUDA cores).
+// 97 % of the MACs are in the GEMMs, which run on the 5th-generation tensor cores: tcgen05.mma (kind::f16, bf16 x bf16
+// -> fp32 in TMEM) issued by one elected thread, operands staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) through
+// a 4-stage mbarrier ring, accumulators read back with tcgen05.ld and a fused epilogue
+//   out = [ (acc + bias[n]) (+ residual[m][n]) ] -> [ReLU] -> [* scale[n] + shift[n]] -> bf16.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/lpbox_b200.h"
+
+void lpbox_set_error(const std::string &s);
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 4;
+constexpr int GEMM_THREADS = 192;          // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..5: epilogue
+constexpr uint32_t TMEM_COLS = 128;        // 128 lanes x 128 fp32 columns = one 128 x 128 accumulator tile
+constexpr size_t STAGE_BYTES = (size_t)(BM + BN) * BK * 2;
+constexpr size_t GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t s2u(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint64_t *b, int c) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s2u(b)), "r"(c)); }
+__device__ __forceinline__ void mb_expect(uint64_t *b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s2u(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_wait(uint64_t *b, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "LW:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra LD;\n\t"
+        "bra LW;\n\t"
+        "LD:\n\t}" ::"r"(s2u(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(s2u(dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(s2u(bar)) : "memory");
+}
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
+// start address >> 4 in [0,14), LBO (16-byte units) in [16,30) = 1, SBO in [32,46) = 8 rows * 128 B = 1024 B,
+// version = 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): D = fp32 (c_format 1, bits [4,6)), A = B = bf16
+// (format 1, bits [7,10) and [10,13)), both K-major (bits 15, 16 = 0), N >> 3 in [17,23), M >> 4 in [24,29)
+__device__ __forceinline__ uint32_t make_idesc() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+struct Epi {
+    const float *bias;            // [N] or NULL
+    const __nv_bfloat16 *resid;   // [M][ldc] or NULL
+    const float *scale, *shift;   // [N] or NULL (folded BatchNorm, applied after the residual add)
+    int relu;
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, __nv_bfloat16 *__restrict__ C, int M,
+                  int N, int K, int ldc, Epi ep) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1024 B
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    uint64_t *empty = full + STAGES;
+    uint64_t *acc_full = empty + STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int nk = K / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mb_init(&full[s], 1); mb_init(&empty[s], 1); }
+        mb_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // TMEM allocation by one warp (it also owns the deallocation)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_slot)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ---- TMA producer ----
+        for (int kb = 0; kb < nk; ++kb) {
+            const int s = kb % STAGES;
+            if (kb >= STAGES) mb_wait(&empty[s], ((kb / STAGES) - 1) & 1);
+            unsigned char *a = smem + (size_t)s * STAGE_BYTES, *b = a + (size_t)BM * BK * 2;
+            mb_expect(&full[s], (uint32_t)STAGE_BYTES);
+            tma_2d(a, &mapA, kb * BK, m0, &full[s]);
+            tma_2d(b, &mapB, kb * BK, n0, &full[s]);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---- MMA issuer ----
+        const uint32_t idesc = make_idesc();
+        for (int kb = 0; kb < nk; ++kb) {
+            const int s = kb % STAGES;
+            mb_wait(&full[s], (kb / STAGES) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_addr = s2u(smem + (size_t)s * STAGE_BYTES), b_addr = a_addr + BM * BK * 2;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {     // UMMA_K = 16 for bf16: advance 32 bytes inside the swizzled row
+                const uint64_t da = make_desc(a_addr + k * 32), db = make_desc(b_addr + k * 32);
+                const uint32_t accum = (kb | k) ? 1u : 0u;
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "setp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+            }
+            // frees the smem stage once the MMAs that read it have completed (implies fence::before_thread_sync)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s2u(&empty[s])) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s2u(acc_full)) : "memory");
+    } else if (warp >= 2) {
+        // ---- epilogue: warp w may touch TMEM lanes [32 (w % 4), +32) ----
+        mb_wait(acc_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;
+        const int m = m0 + q * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+                "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                  "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                  "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                  "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (m < M) {
+                const int nb = n0 + c0;
+                __nv_bfloat16 *crow = C + (size_t)m * ldc + nb;
+                const __nv_bfloat16 *rrow = ep.resid ? ep.resid + (size_t)m * ldc + nb : nullptr;
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    float v0 = __uint_as_float(r[j]), v1 = __uint_as_float(r[j + 1]);
+                    if (ep.bias) { v0 += ep.bias[nb + j]; v1 += ep.bias[nb + j + 1]; }
+                    if (rrow) { const __nv_bfloat162 rr = *reinterpret_cast<const __nv_bfloat162 *>(rrow + j); v0 += __low2float(rr); v1 += __high2float(rr); }
+                    if (ep.relu) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
+                    if (ep.scale) { v0 = v0 * ep.scale[nb + j] + ep.shift[nb + j]; v1 = v1 * ep.scale[nb + j + 1] + ep.shift[nb + j + 1]; }
+                    *reinterpret_cast<__nv_bfloat162 *>(crow + j) = __floats2bfloat162_rn(v0, v1);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+}
+
+// ---- small CUDA-core kernels ----------------------------------------------------------------------------------------------
+// embedding: h0[m][j] = sum_f We[j][f] x[m][f] + c[t][j],  c[t] = We[:,5:10] pe[t] + b  (LP.mha:229-235)
+__global__ void embed_kernel(const float *__restrict__ x, long long Mtok, int T, const float *__restrict__ We5 /*[128][5]*/,
+                             const float *__restrict__ cpos /*[T][128]*/, __nv_bfloat16 *__restrict__ h) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= Mtok * 128) return;
+    const long long m = idx >> 7;
+    const int j = (int)(idx & 127), t = (int)(m % T);
+    const float *xm = x + m * 5;
+    float acc = cpos[t * 128 + j];
+#pragma unroll
+    for (int f = 0; f < 5; ++f) acc += We5[j * 5 + f] * xm[f];
+    h[idx] = __float2bfloat16(acc);
+}
+
+// attention for one variable per CTA: qkv [T][384] (q | k | v, head-major inside each third) -> heads [T][128]
+// softmax(q k' / sqrt(16)) v per head (LP.mha:83-104).  blockDim = 8 heads * 32; thread (head, i) handles query i < T.
+__global__ void __launch_bounds__(256) attention_kernel(const __nv_bfloat16 *__restrict__ qkv, int T, __nv_bfloat16 *__restrict__ heads) {
+    __shared__ float s[32 * 384];
+    const long long var = blockIdx.x;
+    const __nv_bfloat16 *src = qkv + var * T * 384;
+    for (int i = threadIdx.x; i < T * 384; i += 256) s[i] = __bfloat162float(src[i]);
+    __syncthreads();
+    const int hd = threadIdx.x >> 5, i = threadIdx.x & 31;
+    if (i >= T) return;
+    const float *q = s + i * 384 + hd * 16;
+    float sc[32], mx = -INFINITY;
+    for (int j = 0; j < T; ++j) {
+        const float *k = s + j * 384 + 128 + hd * 16;
+        float d = 0.0f;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) d += q[e] * k[e];
+        sc[j] = d * 0.25f;
+        mx = fmaxf(mx, sc[j]);
+    }
+    float den = 0.0f;
+    for (int j = 0; j < T; ++j) { sc[j] = __expf(sc[j] - mx); den += sc[j]; }
+    const float inv = 1.0f / den;
+    float o[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) o[e] = 0.0f;
+    for (int j = 0; j < T; ++j) {
+        const float *v = s + j * 384 + 256 + hd * 16;
+        const float p = sc[j] * inv;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) o[e] += p * v[e];
+    }
+    __nv_bfloat16 *dst = heads + (var * T + i) * 128 + hd * 16;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) dst[e] = __float2bfloat16(o[e]);
+}
+
+// head: a2 [R][128] (after fc2 + ReLU) -> fc3 (16) ReLU -> fc4 (1) -> sigmoid  (LP.mha:185-199)
+__global__ void head_kernel(const __nv_bfloat16 *__restrict__ a2, long long R, const float *__restrict__ w3 /*[16][128]*/, const float *__restrict__ b3,
+                            const float *__restrict__ w4 /*[16]*/, float b4, float *__restrict__ scores) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    float in[128];
+    const __nv_bfloat16 *src = a2 + r * 128;
+#pragma unroll
+    for (int k = 0; k < 128; ++k) in[k] = __bfloat162float(src[k]);
+    float logit = b4;
+    for (int o = 0; o < 16; ++o) {
+        float acc = b3[o];
+#pragma unroll
+        for (int k = 0; k < 128; ++k) acc += w3[o * 128 + k] * in[k];
+        logit += w4[o] * fmaxf(acc, 0.0f);
+    }
+    scores[r] = 1.0f / (1.0f + __expf(-logit));
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                             const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn get_encode() {
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeFn)p;
+    }
+    return fn;
+}
+// row-major [rows][cols] bf16 matrix, box = [box_rows][64 cols], 128-byte swizzle, OOB -> zeros
+bool make_map(CUtensorMap *map, const void *ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    EncodeFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {cols, rows}, strides[1] = {cols * 2};
+    cuuint32_t box[2] = {BK, box_rows}, estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int launch_gemm(cudaStream_t st, const __nv_bfloat16 *A, const __nv_bfloat16 *W, __nv_bfloat16 *C, long long M, int N, int K, const Epi &ep) {
+    if (M <= 0) return 0;
+    if (N % BN || K % BK) { lpbox_set_error("policy GEMM: N must be a multiple of 128 and K of 64"); return LPBOX_E_INVALID; }
+    CUtensorMap ma, mb;
+    if (!make_map(&ma, A, (uint64_t)M, (uint64_t)K, BM) || !make_map(&mb, W, (uint64_t)N, (uint64_t)K, BN)) { lpbox_set_error("cuTensorMapEncodeTiled failed"); return LPBOX_E_CUDA; }
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(gemm_bf16_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM); attr = true; }
+    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)(N / BN));
+    gemm_bf16_tcgen05<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ma, mb, C, (int)M, N, K, N, ep);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { lpbox_set_error(std::string("policy GEMM launch: ") + cudaGetErrorString(e)); return LPBOX_E_CUDA; }
+    return 0;
+}
+
+template <typename Tp>
+Tp *dalloc(size_t n) { Tp *p = nullptr; return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(Tp)) == cudaSuccess ? p : nullptr; }
+
+}  // namespace
+
+struct lpbox_policy {
+    int device = 0, T = 0, L = 0;
+    long long chunk = 0;     // variables per pass
+    std::vector<void *> owned;
+    float *We5 = nullptr, *cpos = nullptr, *w3 = nullptr, *b3 = nullptr, *w4 = nullptr;
+    float b4 = 0;
+    struct Layer { __nv_bfloat16 *Wqkv, *Wo, *W1, *W2; float *b1, *b2, *s1, *t1, *s2, *t2; };
+    std::vector<Layer> layers;
+    __nv_bfloat16 *Wfc1 = nullptr, *Wfc2 = nullptr;
+    float *bfc1 = nullptr, *bfc2 = nullptr;
+    __nv_bfloat16 *h = nullptr, *h2 = nullptr, *qkv = nullptr, *ff = nullptr, *a1 = nullptr, *a2 = nullptr;
+    int64_t launches = 0;
+};
+
+static __nv_bfloat16 *upload_bf16(lpbox_policy *p, const float *src, size_t n) {
+    std::vector<__nv_bfloat16> tmp(n);
+    for (size_t i = 0; i < n; ++i) tmp[i] = __float2bfloat16(src[i]);
+    __nv_bfloat16 *d = dalloc<__nv_bfloat16>(n);
+    if (d) { cudaMemcpy(d, tmp.data(), n * 2, cudaMemcpyHostToDevice); p->owned.push_back(d); }
+    return d;
+}
+static float *upload_f32(lpbox_policy *p, const float *src, size_t n) {
+    float *d = dalloc<float>(n);
+    if (d) { cudaMemcpy(d, src, n * 4, cudaMemcpyHostToDevice); p->owned.push_back(d); }
+    return d;
+}
+
+// Packed fp32 weights (see lpbox/policy_kernel.py: pack_policy): embed_w[128][10], embed_b[128], pe[T][5], per layer
+// { Wqkv[384][128], Wo[128][128], bn1_scale[128], bn1_shift[128], W1[512][128], b1[512], W2[128][512], b2[128], bn2_scale[128],
+// bn2_shift[128] }, fc1_w[256][T*128], fc1_b[256], fc2_w[128][256], fc2_b[128], fc3_w[16][128], fc3_b[16], fc4_w[16], fc4_b[1].
+extern "C" lpbox_policy *lpbox_policy_create(int device, int tokens, int n_layers, const float *packed, int64_t n_packed, int64_t chunk_rows) {
+    if (tokens <= 0 || tokens > 32 || n_layers < 0 || !packed) { lpbox_set_error("policy_create: bad arguments (tokens <= 32)"); return nullptr; }
+    const int64_t per_layer = 384 * 128 + 128 * 128 + 256 + 512 * 128 + 512 + 128 * 512 + 128 + 256;
+    const int64_t need = 128 * 10 + 128 + tokens * 5 + n_layers * per_layer + 256LL * tokens * 128 + 256 + 128 * 256 + 128 + 16 * 128 + 16 + 16 + 1;
+    if (n_packed != need) { lpbox_set_error("policy_create: packed weight buffer has the wrong size"); return nullptr; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { lpbox_set_error("no CUDA device (there is no CPU fallback)"); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { lpbox_set_error("bad device"); return nullptr; }
+    if (!get_encode()) { lpbox_set_error("cuTensorMapEncodeTiled not available"); return nullptr; }
+    lpbox_policy *p = new lpbox_policy();
+    p->device = device; p->T = tokens; p->L = n_layers; p->chunk = chunk_rows > 0 ? chunk_rows : 16384;
+    const float *w = packed;
+    const float *ew = w; w += 128 * 10;
+    const float *eb = w; w += 128;
+    const float *pe = w; w += tokens * 5;
+    std::vector<float> we5(128 * 5), cpos((size_t)tokens * 128);
+    for (int j = 0; j < 128; ++j) {
+        for (int f = 0; f < 5; ++f) we5[j * 5 + f] = ew[j * 10 + f];
+        for (int t = 0; t < tokens; ++t) { float a = eb[j]; for (int f = 0; f < 5; ++f) a += ew[j * 10 + 5 + f] * pe[t * 5 + f]; cpos[(size_t)t * 128 + j] = a; }
+    }
+    p->We5 = upload_f32(p, we5.data(), we5.size()); p->cpos = upload_f32(p, cpos.data(), cpos.size());
+    for (int l = 0; l < n_layers; ++l) {
+        lpbox_policy::Layer L;
+        L.Wqkv = upload_bf16(p, w, 384 * 128); w += 384 * 128;
+        L.Wo = upload_bf16(p, w, 128 * 128); w += 128 * 128;
+        L.s1 = upload_f32(p, w, 128); w += 128; L.t1 = upload_f32(p, w, 128); w += 128;
+        L.W1 = upload_bf16(p, w, 512 * 128); w += 512 * 128; L.b1 = upload_f32(p, w, 512); w += 512;
+        L.W2 = upload_bf16(p, w, 128 * 512); w += 128 * 512; L.b2 = upload_f32(p, w, 128); w += 128;
+        L.s2 = upload_f32(p, w, 128); w += 128; L.t2 = upload_f32(p, w, 128); w += 128;
+        p->layers.push_back(L);
+    }
+    p->Wfc1 = upload_bf16(p, w, (size_t)256 * tokens * 128); w += (size_t)256 * tokens * 128; p->bfc1 = upload_f32(p, w, 256); w += 256;
+    p->Wfc2 = upload_bf16(p, w, 128 * 256); w += 128 * 256; p->bfc2 = upload_f32(p, w, 128); w += 128;
+    p->w3 = upload_f32(p, w, 16 * 128); w += 16 * 128; p->b3 = upload_f32(p, w, 16); w += 16;
+    p->w4 = upload_f32(p, w, 16); w += 16; p->b4 = w[0];
+    const size_t Mt = (size_t)p->chunk * tokens;
+    p->h = dalloc<__nv_bfloat16>(Mt * 128); p->h2 = dalloc<__nv_bfloat16>(Mt * 128); p->qkv = dalloc<__nv_bfloat16>(Mt * 384);
+    p->ff = dalloc<__nv_bfloat16>(Mt * 512); p->a1 = dalloc<__nv_bfloat16>((size_t)p->chunk * 256); p->a2 = dalloc<__nv_bfloat16>((size_t)p->chunk * 128);
+    for (void *q : {(void *)p->h, (void *)p->h2, (void *)p->qkv, (void *)p->ff, (void *)p->a1, (void *)p->a2}) { if (!q) { lpbox_set_error("policy_create: out of device memory"); return nullptr; } p->owned.push_back(q); }
+    return p;
+}
+
+extern "C" void lpbox_policy_destroy(lpbox_policy *p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaDeviceSynchronize();
+    for (void *q : p->owned) cudaFree(q);
+    delete p;
+}
+
+// scores_dev[r] = sigmoid(policy(input_dev[r])) for r < rows; input_dev: fp32 [rows][T*5] (the packed window history)
+extern "C" int lpbox_policy_forward_dev(lpbox_policy *p, void *stream, const float *input_dev, int64_t rows, float *scores_dev) {
+    if (!p || !input_dev || !scores_dev || rows < 0) return LPBOX_E_INVALID;
+    if (cudaSetDevice(p->device) != cudaSuccess) return LPBOX_E_CUDA;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int T = p->T;
+    for (int64_t r0 = 0; r0 < rows; r0 += p->chunk) {
+        const long long R = std::min<long long>(p->chunk, rows - r0), Mt = R * T;
+        embed_kernel<<<(unsigned)((Mt * 128 + 255) / 256), 256, 0, st>>>(input_dev + r0 * T * 5, Mt, T, p->We5, p->cpos, p->h);
+        p->launches++;
+        __nv_bfloat16 *h = p->h, *h2 = p->h2;
+        for (auto &L : p->layers) {
+            int rc = launch_gemm(st, h, L.Wqkv, p->qkv, Mt, 384, 128, Epi{nullptr, nullptr, nullptr, nullptr, 0}); if (rc) return rc;
+            attention_kernel<<<(unsigned)R, 256, 0, st>>>(p->qkv, T, h2);                                  // heads -> h2
+            rc = launch_gemm(st, h2, L.Wo, p->qkv /*reuse as [Mt][128] scratch*/, Mt, 128, 128, Epi{nullptr, h, L.s1, L.t1, 0}); if (rc) return rc;
+            // NOTE: the out-proj result (h + MHA(h), BatchNorm folded) lives in the first Mt*128 elements of qkv
+            __nv_bfloat16 *hn = p->qkv;
+            rc = launch_gemm(st, hn, L.W1, p->ff, Mt, 512, 128, Epi{L.b1, nullptr, nullptr, nullptr, 1}); if (rc) return rc;
+            rc = launch_gemm(st, p->ff, L.W2, h2, Mt, 128, 512, Epi{L.b2, hn, L.s2, L.t2, 0}); if (rc) return rc;
+            std::swap(h, h2);
+            p->launches += 5;
+        }
+        int rc = launch_gemm(st, h, p->Wfc1, p->a1, R, 256, T * 128, Epi{p->bfc1, nullptr, nullptr, nullptr, 1}); if (rc) return rc;
+        rc = launch_gemm(st, p->a1, p->Wfc2, p->a2, R, 128, 256, Epi{p->bfc2, nullptr, nullptr, nullptr, 1}); if (rc) return rc;
+        head_kernel<<<(unsigned)((R + 127) / 128), 128, 0, st>>>(p->a2, R, p->w3, p->b3, p->w4, p->b4, scores_dev + r0);
+        p->launches += 3;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { lpbox_set_error(std::string("policy forward: ") + cudaGetErrorString(e)); return LPBOX_E_CUDA; }
+    }
+    return 0;
+}
+
+extern "C" int64_t lpbox_policy_launch_count(const lpbox_policy *p) { return p ? p->launches : -1; }
+
+// plain GEMM entry for tests: C[M][N] (bf16) = A[M][K] (bf16) . W[N][K]^T (+ bias, ReLU)
+extern "C" int lpbox_gemm_bf16_dev(void *stream, const void *A, const void *W, void *C, int64_t M, int N, int K, const float *bias, int relu) {
+    if (!get_encode()) { lpbox_set_error("cuTensorMapEncodeTiled not available"); return LPBOX_E_CUDA; }
+    return launch_gemm((cudaStream_t)stream, (const __nv_bfloat16 *)A, (const __nv_bfloat16 *)W, (__nv_bfloat16 *)C, M, N, K,
+                       Epi{bias, nullptr, nullptr, nullptr, relu});
+}

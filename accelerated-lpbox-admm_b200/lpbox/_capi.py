@@ -99,6 +99,11 @@ SIGNATURES = {
     "lpbox_sa_pre_dev": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int] + [_vp] * 11 + [C.c_double] * 6 + [_vp] * 4),
     "lpbox_sa_post_dev": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int] + [_vp] * 13 + [C.c_double] * 9 + [_vp]),
     "lpbox_sa_apply_policy_dev": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_double, C.c_double, _vp, _vp]),
+    "lpbox_policy_create": (_vp, [C.c_int, C.c_int, C.c_int, _vp, C.c_int64, C.c_int64]),
+    "lpbox_policy_destroy": (None, [_vp]),
+    "lpbox_policy_forward_dev": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp]),
+    "lpbox_policy_launch_count": (C.c_int64, [_vp]),
+    "lpbox_gemm_bf16_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, C.c_int]),
     "lpbox_read_instance": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, _ip, _ip, C.POINTER(_ip), C.POINTER(_ip),
                                       C.POINTER(_dp), C.POINTER(_dp)]),
     "lpbox_free": (None, [_vp]),

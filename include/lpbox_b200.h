@@ -229,6 +229,21 @@ int lpbox_sa_apply_policy_dev(void *stream, int64_t n, const float *scores, cons
                               int32_t *counts2);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Early-fixing policy network on the tensor cores (GraphAttentionEncoder / MLPEncoder forward, LP.mha:202-304, eval
+ * mode): bf16 tcgen05 GEMMs with fp32 TMEM accumulators + small CUDA-core kernels (csrc/policy_kernels.cu).
+ * `packed`: fp32 host buffer in the layout written by lpbox/policy_kernel.py:pack_policy.  tokens <= 32.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct lpbox_policy lpbox_policy;
+lpbox_policy *lpbox_policy_create(int device, int tokens, int n_layers, const float *packed, int64_t n_packed, int64_t chunk_rows);
+void lpbox_policy_destroy(lpbox_policy *p);
+/* scores_dev[r] = sigmoid(net(input_dev[r])), input_dev: DEVICE fp32 [rows][tokens*5] (= the packed window history of
+ * lpbox_batch_policy_input_dev), scores_dev: DEVICE fp32 [rows]; ordered on `stream` (cudaStream_t) */
+int lpbox_policy_forward_dev(lpbox_policy *p, void *stream, const float *input_dev, int64_t rows, float *scores_dev);
+int64_t lpbox_policy_launch_count(const lpbox_policy *p);
+/* the tcgen05 GEMM alone (tests): C[M][N] = A[M][K] . W[N][K]^T (+ bias[n]) (ReLU); bf16 DEVICE row-major; N % 128 == 0, K % 64 == 0 */
+int lpbox_gemm_bf16_dev(void *stream, const void *A, const void *W, void *C, int64_t M, int N, int K, const float *bias, int relu);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * File format of the reference: data/instance/<k>_<j>/instance_<i>_{C,b}.txt under `root`
  * (readFile, LP.cpp:2446-2545).  Arrays are malloc()ed by the library; release with lpbox_free().
  * ------------------------------------------------------------------------------------------------------------- */

@@ -1,0 +1,48 @@
+"""GPU tests of the tensor-core policy path (D1): the tcgen05 bf16 GEMM against torch, and the whole network against the
+fp32 PyTorch module (tolerance: bf16 activations/weights with fp32 accumulation -> |d sigmoid| <= 0.02)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from policy_weights import fill_deterministic
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 384, 128), (1000, 128, 512), (77, 256, 2560), (4096, 512, 128)])
+def test_tcgen05_gemm_matches_torch(M, N, K):
+    import lpbox
+    L = lpbox._capi.lib()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.1).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    Cc = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = L.lpbox_gemm_bf16_dev(st, C.c_void_p(A.data_ptr()), C.c_void_p(W.data_ptr()), C.c_void_p(Cc.data_ptr()), M, N, K, C.c_void_p(bias.data_ptr()), 1)
+    assert rc == 0, lpbox._capi.last_error()
+    torch.cuda.synchronize()
+    ref = torch.relu(A.float() @ W.float().t() + bias)
+    err = (Cc.float() - ref).abs().max().item()
+    assert err <= 0.02 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("kind,T", [("GraphAttentionEncoder", 20), ("MLPEncoder", 20), ("GraphAttentionEncoder", 5), ("GraphAttentionEncoder", 10)])
+def test_policy_kernel_matches_torch_module(kind, T):
+    from lpbox import policy
+    from lpbox.policy_kernel import PolicyKernel
+    torch.manual_seed(7)
+    net = getattr(policy, kind)(tokens=T).cuda().eval()
+    fill_deterministic(net)
+    g = torch.Generator(device="cuda").manual_seed(T)
+    x = torch.rand(3000, T, 5, device="cuda", generator=g)
+    with torch.no_grad():
+        ref = net(x)[1].reshape(-1)
+    pk = PolicyKernel(net, chunk_rows=1024)
+    got = pk(x)
+    torch.cuda.synchronize()
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() <= 0.02
+    assert pk.launch_count() > 0
