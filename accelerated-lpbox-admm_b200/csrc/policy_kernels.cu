@@ -23,7 +23,7 @@ void lpbox_set_error(const std::string &s);
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 4;
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 2;   // K is 128..2560: 2 stages x 32 KB -> 3 CTAs per SM overlap load / MMA / epilogue
 constexpr int GEMM_THREADS = 192;          // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..5: epilogue
 constexpr uint32_t TMEM_COLS = 128;        // 128 lanes x 128 fp32 columns = one 128 x 128 accumulator tile
 constexpr size_t STAGE_BYTES = (size_t)(BM + BN) * BK * 2;
@@ -72,7 +72,7 @@ struct Epi {
     int relu;
 };
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 3)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, __nv_bfloat16 *__restrict__ C, int M,
                   int N, int K, int ldc, Epi ep) {
     extern __shared__ unsigned char smem_raw[];
@@ -186,24 +186,29 @@ __global__ void embed_kernel(const float *__restrict__ x, long long Mtok, int T,
 }
 
 // attention for one variable per CTA: qkv [T][384] (q | k | v, head-major inside each third) -> heads [T][128]
-// softmax(q k' / sqrt(16)) v per head (LP.mha:83-104).  blockDim = 8 heads * 32; thread (head, i) handles query i < T.
+// softmax(q k' / sqrt(16)) v per head (LP.mha:83-104).  Thread t < 8*T handles (head, query) = (t / T, t % T).
 __global__ void __launch_bounds__(256) attention_kernel(const __nv_bfloat16 *__restrict__ qkv, int T, __nv_bfloat16 *__restrict__ heads) {
-    __shared__ float s[32 * 384];
+    __shared__ __align__(16) __nv_bfloat16 s[32 * 384];
     const long long var = blockIdx.x;
-    const __nv_bfloat16 *src = qkv + var * T * 384;
-    for (int i = threadIdx.x; i < T * 384; i += 256) s[i] = __bfloat162float(src[i]);
+    const uint4 *src = reinterpret_cast<const uint4 *>(qkv + var * T * 384);      // T*384*2 bytes, 16-byte aligned (384*2 = 768)
+    for (int i = threadIdx.x; i < T * 48; i += blockDim.x) reinterpret_cast<uint4 *>(s)[i] = src[i];
     __syncthreads();
-    const int hd = threadIdx.x >> 5, i = threadIdx.x & 31;
-    if (i >= T) return;
-    const float *q = s + i * 384 + hd * 16;
+    if (threadIdx.x >= 8 * T) return;
+    const int hd = threadIdx.x / T, i = threadIdx.x - hd * T;
+    float q[16];
+    {
+        const __nv_bfloat162 *qp = reinterpret_cast<const __nv_bfloat162 *>(s + i * 384 + hd * 16);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float2 f = __bfloat1622float2(qp[e]); q[2 * e] = f.x * 0.25f; q[2 * e + 1] = f.y * 0.25f; }
+    }
     float sc[32], mx = -INFINITY;
     for (int j = 0; j < T; ++j) {
-        const float *k = s + j * 384 + 128 + hd * 16;
+        const __nv_bfloat162 *kp = reinterpret_cast<const __nv_bfloat162 *>(s + j * 384 + 128 + hd * 16);
         float d = 0.0f;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) d += q[e] * k[e];
-        sc[j] = d * 0.25f;
-        mx = fmaxf(mx, sc[j]);
+        for (int e = 0; e < 8; ++e) { const float2 f = __bfloat1622float2(kp[e]); d += q[2 * e] * f.x + q[2 * e + 1] * f.y; }
+        sc[j] = d;
+        mx = fmaxf(mx, d);
     }
     float den = 0.0f;
     for (int j = 0; j < T; ++j) { sc[j] = __expf(sc[j] - mx); den += sc[j]; }
@@ -212,14 +217,14 @@ __global__ void __launch_bounds__(256) attention_kernel(const __nv_bfloat16 *__r
 #pragma unroll
     for (int e = 0; e < 16; ++e) o[e] = 0.0f;
     for (int j = 0; j < T; ++j) {
-        const float *v = s + j * 384 + 256 + hd * 16;
+        const __nv_bfloat162 *vp = reinterpret_cast<const __nv_bfloat162 *>(s + j * 384 + 256 + hd * 16);
         const float p = sc[j] * inv;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) o[e] += p * v[e];
+        for (int e = 0; e < 8; ++e) { const float2 f = __bfloat1622float2(vp[e]); o[2 * e] += p * f.x; o[2 * e + 1] += p * f.y; }
     }
-    __nv_bfloat16 *dst = heads + (var * T + i) * 128 + hd * 16;
+    __nv_bfloat162 *dst = reinterpret_cast<__nv_bfloat162 *>(heads + (var * T + i) * 128 + hd * 16);
 #pragma unroll
-    for (int e = 0; e < 16; ++e) dst[e] = __float2bfloat16(o[e]);
+    for (int e = 0; e < 8; ++e) dst[e] = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
 }
 
 // head: a2 [R][128] (after fc2 + ReLU) -> fc3 (16) ReLU -> fc4 (1) -> sigmoid  (LP.mha:185-199)
@@ -375,7 +380,7 @@ extern "C" int lpbox_policy_forward_dev(lpbox_policy *p, void *stream, const flo
         __nv_bfloat16 *h = p->h, *h2 = p->h2;
         for (auto &L : p->layers) {
             int rc = launch_gemm(st, h, L.Wqkv, p->qkv, Mt, 384, 128, Epi{nullptr, nullptr, nullptr, nullptr, 0}); if (rc) return rc;
-            attention_kernel<<<(unsigned)R, 256, 0, st>>>(p->qkv, T, h2);                                  // heads -> h2
+            attention_kernel<<<(unsigned)R, ((8 * T + 31) / 32) * 32, 0, st>>>(p->qkv, T, h2);                                  // heads -> h2
             rc = launch_gemm(st, h2, L.Wo, p->qkv /*reuse as [Mt][128] scratch*/, Mt, 128, 128, Epi{nullptr, h, L.s1, L.t1, 0}); if (rc) return rc;
             // NOTE: the out-proj result (h + MHA(h), BatchNorm folded) lives in the first Mt*128 elements of qkv
             __nv_bfloat16 *hn = p->qkv;

@@ -15,7 +15,11 @@ b = lpbox.LPBatch(probs); b.init()
 t = time.time(); plain = b.solve(20000); torch.cuda.synchronize(); t_plain = time.time() - t
 b.close()
 net = load_policy(os.path.join(ROOT, "accelerated-lpbox-admm_b200", "lpbox", "weights", os.environ.get("LPBOX_POLICY", "lp_mha_policy.pt")))
-if dtype == "bf16":
+if dtype == "kernel":
+    from lpbox.policy_kernel import PolicyKernel
+    pk = PolicyKernel(net, chunk_rows=32768)
+    score = pk
+elif dtype == "bf16":
     def score(x):
         with torch.autocast("cuda", dtype=torch.bfloat16):
             return net(x)[1]
