@@ -82,7 +82,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     uint64_t *acc_full = empty + STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;   // N-tiles of one M-tile are adjacent in launch order: A is read from HBM once
     const int nk = K / BK;
 
     if (threadIdx.x == 0) {
@@ -154,13 +154,35 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 __nv_bfloat16 *crow = C + (size_t)m * ldc + nb;
                 const __nv_bfloat16 *rrow = ep.resid ? ep.resid + (size_t)m * ldc + nb : nullptr;
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    float v0 = __uint_as_float(r[j]), v1 = __uint_as_float(r[j + 1]);
-                    if (ep.bias) { v0 += ep.bias[nb + j]; v1 += ep.bias[nb + j + 1]; }
-                    if (rrow) { const __nv_bfloat162 rr = *reinterpret_cast<const __nv_bfloat162 *>(rrow + j); v0 += __low2float(rr); v1 += __high2float(rr); }
-                    if (ep.relu) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
-                    if (ep.scale) { v0 = v0 * ep.scale[nb + j] + ep.shift[nb + j]; v1 = v1 * ep.scale[nb + j + 1] + ep.shift[nb + j + 1]; }
-                    *reinterpret_cast<__nv_bfloat162 *>(crow + j) = __floats2bfloat162_rn(v0, v1);
+                for (int g = 0; g < 4; ++g) {                      // 8 columns = one 16-byte store per group
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+                    if (ep.bias) {
+                        const float4 b0 = *reinterpret_cast<const float4 *>(ep.bias + nb + g * 8), b1 = *reinterpret_cast<const float4 *>(ep.bias + nb + g * 8 + 4);
+                        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                    }
+                    if (rrow) {
+                        const uint4 rr = *reinterpret_cast<const uint4 *>(rrow + g * 8);
+                        const __nv_bfloat162 *rp2 = reinterpret_cast<const __nv_bfloat162 *>(&rr);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(rp2[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+                    }
+                    if (ep.relu) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
+                    }
+                    if (ep.scale) {
+                        const float4 s0 = *reinterpret_cast<const float4 *>(ep.scale + nb + g * 8), s1 = *reinterpret_cast<const float4 *>(ep.scale + nb + g * 8 + 4);
+                        const float4 t0 = *reinterpret_cast<const float4 *>(ep.shift + nb + g * 8), t1 = *reinterpret_cast<const float4 *>(ep.shift + nb + g * 8 + 4);
+                        v[0] = v[0] * s0.x + t0.x; v[1] = v[1] * s0.y + t0.y; v[2] = v[2] * s0.z + t0.z; v[3] = v[3] * s0.w + t0.w;
+                        v[4] = v[4] * s1.x + t1.x; v[5] = v[5] * s1.y + t1.y; v[6] = v[6] * s1.z + t1.z; v[7] = v[7] * s1.w + t1.w;
+                    }
+                    uint4 o;
+                    __nv_bfloat162 *op = reinterpret_cast<__nv_bfloat162 *>(&o);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) op[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                    *reinterpret_cast<uint4 *>(crow + g * 8) = o;
                 }
             }
         }
@@ -275,7 +297,7 @@ int launch_gemm(cudaStream_t st, const __nv_bfloat16 *A, const __nv_bfloat16 *W,
     if (!make_map(&ma, A, (uint64_t)M, (uint64_t)K, BM) || !make_map(&mb, W, (uint64_t)N, (uint64_t)K, BN)) { lpbox_set_error("cuTensorMapEncodeTiled failed"); return LPBOX_E_CUDA; }
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(gemm_bf16_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM); attr = true; }
-    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)(N / BN));
+    dim3 grid((unsigned)(N / BN), (unsigned)((M + BM - 1) / BM));
     gemm_bf16_tcgen05<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ma, mb, C, (int)M, N, K, N, ep);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { lpbox_set_error(std::string("policy GEMM launch: ") + cudaGetErrorString(e)); return LPBOX_E_CUDA; }
