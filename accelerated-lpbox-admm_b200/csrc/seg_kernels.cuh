@@ -61,8 +61,8 @@ struct SegLaunch {
     int *counter;
 };
 
-constexpr int SEG_T = 512;
-constexpr int SEG_CH = 512;     // products staged per reduction per chunk
+constexpr int SEG_T = 256;
+constexpr int SEG_CH = 256;     // products staged per reduction per chunk
 constexpr int SEG_RMAX = 7;
 
 // y_i = ((0 + m_i1 v_j1) + m_i2 v_j2) + ...  row i of (DIAG ? 2A with the diagonal replaced by md : A)
@@ -141,7 +141,7 @@ __device__ __forceinline__ void seg_block_redux(F prod, int n, double *buf, doub
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(SEG_T, 2)
+__global__ void __launch_bounds__(SEG_T, 4)
 seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *buf = reinterpret_cast<double *>(smem_raw);                 // [2][SEG_RMAX][SEG_CH]
