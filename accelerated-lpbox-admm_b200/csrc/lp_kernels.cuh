@@ -395,7 +395,9 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                 double v = warp_redux_eigen1(S.a1, 1, n);
                 if (lane == 0) S.sc[0] = v;
             }
-            seq_spmv_ell<T, CE>(rlen, rsptr, rperm, ridx, S.ev_r, 0.0, S.gv, m, S.t1);
+            // E x of this iteration's x was already formed for the z4 update of the previous iteration (same operands, same
+            // order -> same bits) and is still in t1; only the first iteration of a window has to compute it
+            if (iter == la.iter_start) seq_spmv_ell<T, CE>(rlen, rsptr, rperm, ridx, S.ev_r, 0.0, S.gv, m, S.t1);
             __syncthreads();
             {
                 const double nrm = sqrt(S.sc[0]);
