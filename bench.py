@@ -158,7 +158,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--l2f-batch", type=int, default=2000, help="instances of the batch also solved with learned early fixing (0 = skip)")
+    ap.add_argument("--l2f-batch", type=int, default=10000, help="instances of the batch also solved with learned early fixing (0 = skip)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

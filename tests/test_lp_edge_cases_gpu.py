@@ -1,0 +1,117 @@
+"""GPU edge cases of the LP path vs the oracle (bit-exact): tiny and odd sizes (every residue of Eigen's reduction
+tail), empty rows / columns, m > n, fixing that leaves < 4 variables or none, fix-count validation, a larger random batch
+spot-checked against the oracle, and re-solving (determinism)."""
+import numpy as np
+import pytest
+
+from conftest import synth_auction
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle(g):
+    import oracle as orc
+    o = orc.OracleLP()
+    o.set_problem_csc(g["m"], g["n"], g["colptr"], g["rowidx"], np.ones(len(g["rowidx"])), g["b"], g["f"])
+    return o
+
+
+def _tuple(g):
+    return (g["m"], g["n"], g["colptr"], g["rowidx"], None, g["b"], g["f"])
+
+
+def _rand_problem(seed, m, n, density, empty_rows=(), empty_cols=()):
+    rng = np.random.default_rng(seed)
+    cols = []
+    for j in range(n):
+        if j in empty_cols:
+            cols.append(np.zeros(0, dtype=np.int32)); continue
+        rows = np.array([i for i in range(m) if i not in empty_rows and rng.random() < density], dtype=np.int32)
+        if len(rows) == 0:
+            rows = np.array([next(i for i in range(m) if i not in empty_rows)], dtype=np.int32)
+        cols.append(rows)
+    colptr = np.zeros(n + 1, dtype=np.int32); colptr[1:] = np.cumsum([len(c) for c in cols])
+    rowidx = np.concatenate(cols).astype(np.int32) if colptr[-1] else np.zeros(0, dtype=np.int32)
+    return dict(m=m, n=n, colptr=colptr, rowidx=rowidx, b=-rng.uniform(1, 50, n), f=np.ones(m))
+
+
+@pytest.mark.parametrize("m,n", [(1, 1), (2, 2), (2, 3), (3, 4), (3, 5), (4, 6), (5, 7), (3, 9), (6, 10), (7, 11), (9, 13)])
+def test_tiny_sizes_all_reduction_tails(m, n):
+    import lpbox
+    g = _rand_problem(100 * m + n, m, n, 0.5)
+    o = _oracle(g); o.solve_init(); ro = o.solve_iter(0, 400)
+    b = lpbox.LPBatch([_tuple(g)]); b.init(); rg = int(b.iters(0, 400)[0])
+    assert ro == rg and o.get_iter() == b.get_iter(0)
+    so, sg = o.state(), b.state(0)
+    for k in so:
+        assert np.array_equal(so[k], sg[k]), k
+
+
+def test_empty_rows_empty_columns_and_m_greater_than_n():
+    import lpbox
+    gs = [_rand_problem(1, 12, 30, 0.2, empty_rows=(0, 5, 11), empty_cols=(3, 29)), _rand_problem(2, 40, 17, 0.15), _rand_problem(3, 64, 64, 0.05)]
+    b = lpbox.LPBatch([_tuple(g) for g in gs]); b.init()
+    log = b.solve(3000)
+    for i, g in enumerate(gs):
+        o = _oracle(g); o.solve_init(); o.solve_iter(0, 3000)
+        assert log["iters"][i] == o.admm_iters() and log["cg_iters"][i] == o.cg_iters()
+        assert np.array_equal(b.state(i)["x"], o.state()["x"])
+        assert log["obj"][i] == o.cal_Obj()
+
+
+def test_fix_down_to_few_and_to_none():
+    import lpbox
+    g = synth_auction(9, 20, 40)
+    o = _oracle(g); o.solve_init()
+    s = lpbox.PyLPboxADMMsolver(0); s.set_problem(*[g[k] for k in ("m", "n", "colptr", "rowidx")], None, g["b"], g["f"]); s.solve_init()
+    assert o.solve_iter_l2f(0, 50, np.zeros(1), 0) == s.solve_iter_l2f(0, 50, np.zeros(1), 0)
+    x = o.state()["x"]
+    vec = (x >= 0.5) * 1.0
+    vec[:3] = -1.0                                   # leave 3 variables (< one Eigen packet pair)
+    assert o.solve_iter_l2f(50, 100, vec, 37) == s.solve_iter_l2f(50, 100, vec, 37)
+    assert o.get_n() == s.get_n() == 3
+    assert np.array_equal(o.state()["x"], s.get_final_x_sol(3).ravel())
+    assert np.array_equal(o.get_x_iters_2d(50), s.get_x_iters_2d(50))
+    x3 = o.state()["x"]
+    vec3 = (x3 >= 0.5) * 1.0                          # fix everything that is left (LP.cpp:1212-1217)
+    ro, rg = o.solve_iter_l2f(100, 150, vec3, 3), s.solve_iter_l2f(100, 150, vec3, 3)
+    assert ro == rg == 1 and o.get_n() == s.get_n() == 0
+    assert o.cal_Obj() == s.cal_Obj()
+    assert np.array_equal(o.get_x_sol(40), s.get_x_sol(40))
+    assert o.check_infeasible_l2f() == s.check_infeasible_l2f()
+
+
+def test_fix_count_is_validated():
+    import lpbox
+    g = synth_auction(4, 10, 24)
+    s = lpbox.PyLPboxADMMsolver(0); s.set_problem(*[g[k] for k in ("m", "n", "colptr", "rowidx")], None, g["b"], g["f"]); s.solve_init()
+    s.solve_iter_l2f(0, 10, np.zeros(1), 0)
+    vec = -np.ones(24); vec[:12] = 1.0
+    with pytest.raises(RuntimeError, match="does not match"):
+        s.solve_iter_l2f(10, 20, vec, 11)
+
+
+def test_unsupported_sizes_fail_loudly():
+    import lpbox
+    n = 2100
+    colptr = np.arange(n + 1, dtype=np.int32); rowidx = np.zeros(n, dtype=np.int32)
+    with pytest.raises(RuntimeError, match="on-chip kernel"):
+        lpbox.LPBatch([(1, n, colptr, rowidx, None, -np.ones(n), None)])
+
+
+def test_large_batch_spot_checked_and_deterministic():
+    """1500 generated auctions (j=100, k=500) solved in one launch; 4 random instances bit-compared with the oracle;
+    solving the same batch again gives identical log rows (determinism of the atomic work queue)."""
+    import lpbox
+    probs = lpbox.gen_auctions(99, 1500, 100, 500)
+    b = lpbox.LPBatch(probs); b.init(); log1 = b.solve(20000).copy()
+    b.init(); log2 = b.solve(20000)
+    assert np.array_equal(log1, log2)
+    assert (log1["status"] > 0).all() and (log1["iters"] > 100).all()
+    assert (log1["infeasible"] == 0).mean() > 0.95
+    rng = np.random.default_rng(0)
+    for i in rng.choice(1500, 4, replace=False):
+        m, n, cp, ri, _, bb, _ = probs[i]
+        o = _oracle(dict(m=m, n=n, colptr=cp, rowidx=ri, b=bb, f=np.ones(m))); o.solve_init(); o.solve_iter(0, 20000)
+        assert log1["iters"][i] == o.admm_iters() and log1["cg_iters"][i] == o.cg_iters() and log1["obj"][i] == o.cal_Obj()
+        assert np.array_equal(b.state(int(i))["x"], o.state()["x"])
