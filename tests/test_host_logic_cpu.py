@@ -1,0 +1,79 @@
+"""CPU tests of host-side logic that needs no GPU: native auction generator, host graph builder (C ABI) against the golden
+vectors from the reference binary, policy weight packing (numpy re-evaluation of the packed layout vs the torch module)."""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from conftest import GOLDEN, load_golden
+from policy_weights import fill_deterministic
+
+
+def test_generator_is_deterministic_and_reference_shaped():
+    import lpbox
+    a = lpbox.gen_auctions(5, 40, 100, 500, threads=3)
+    b = lpbox.gen_auctions(5, 40, 100, 500, threads=1)
+    for pa, pb in zip(a, b):
+        assert pa[0] == pb[0] and np.array_equal(pa[2], pb[2]) and np.array_equal(pa[3], pb[3]) and np.array_equal(pa[5], pb[5])
+    ms = np.array([p[0] for p in a]); nnz = np.array([len(p[3]) for p in a])
+    refs = [load_golden(f"auction_100_500_seed{s}.npz") for s in (0, 1, 2)]
+    # same shape statistics as the reference generator's instances (m ~ 186-196, nnz ~ 2.7-3.0k at j=100, k=500)
+    assert 175 <= ms.mean() <= 210 and 2300 <= nnz.mean() <= 3300
+    assert min(r["m"] for r in refs) - 25 <= ms.min() and ms.max() <= max(r["m"] for r in refs) + 25
+    for m, n, cp, ri, _, bb, _ in a[:5]:
+        assert n == 500 and cp[0] == 0 and cp[-1] == len(ri) and (bb < 0).all()
+        for j in range(n):
+            col = ri[cp[j]:cp[j + 1]]
+            assert len(col) >= 1 and (np.diff(col) > 0).all() and col.max() < m
+
+
+def test_host_graph_builder_equals_reference_binary():
+    import lpbox
+    z = np.load(os.path.join(GOLDEN, "seg_golden.npz"))
+    rp, ci, va, b, c = lpbox.build_graph(z["img"])
+    assert np.array_equal(rp, z["rowptr"]) and np.array_equal(ci, z["colidx"])
+    assert np.array_equal(va, z["val"]) and np.array_equal(b, z["b"]) and c == float(z["c"])
+    # every row stores its diagonal and at most 7 entries (SEG.cpp:213-219)
+    n = len(b)
+    assert (np.diff(rp) <= 7).all() and all(i in ci[rp[i]:rp[i + 1]] for i in range(0, n, 97))
+
+
+def test_policy_pack_layout_reproduces_the_module():
+    """Evaluate the network in numpy straight from the packed buffer (the layout lpbox_policy_create documents)."""
+    from lpbox.policy import GraphAttentionEncoder
+    from lpbox.policy_kernel import pack_policy
+    T = 5
+    net = GraphAttentionEncoder(tokens=T).eval()
+    fill_deterministic(net)
+    packed, L = pack_policy(net)
+    assert L == 2
+    w = packed.astype(np.float64)
+    o = 0
+
+    def take(*shape):
+        nonlocal o
+        k = int(np.prod(shape)); v = w[o:o + k].reshape(shape); o += k
+        return v
+    ew, eb, pe = take(128, 10), take(128), take(T, 5)
+    x = torch.rand(7, T, 5, generator=torch.Generator().manual_seed(3))
+    xin = np.concatenate([x.numpy().astype(np.float64), np.broadcast_to(pe, (7, T, 5))], -1)
+    h = xin @ ew.T + eb
+    for _ in range(L):
+        Wqkv, Wo, s1, t1, W1, b1, W2, b2, s2, t2 = take(384, 128), take(128, 128), take(128), take(128), take(512, 128), take(512), take(128, 512), take(128), take(128), take(128)
+        qkv = h @ Wqkv.T
+        q, k, v = (qkv[..., i * 128:(i + 1) * 128].reshape(7, T, 8, 16) for i in range(3))
+        att = np.einsum("bihk,bjhk->bhij", q, k) / 4.0
+        att = np.exp(att - att.max(-1, keepdims=True)); att /= att.sum(-1, keepdims=True)
+        heads = np.einsum("bhij,bjhk->bihk", att, v).reshape(7, T, 128)
+        h = (h + heads @ Wo.T) * s1 + t1
+        h = (h + np.maximum(h @ W1.T + b1, 0) @ W2.T + b2) * s2 + t2
+    fc1w, fc1b, fc2w, fc2b, fc3w, fc3b, fc4w, fc4b = take(256, T * 128), take(256), take(128, 256), take(128), take(16, 128), take(16), take(16), take(1)
+    assert o == len(w)
+    a = np.maximum(h.reshape(7, -1) @ fc1w.T + fc1b, 0)
+    a = np.maximum(a @ fc2w.T + fc2b, 0)
+    a = np.maximum(a @ fc3w.T + fc3b, 0)
+    sig = 1 / (1 + np.exp(-(a @ fc4w + fc4b)))
+    with torch.no_grad():
+        ref = net(x)[1].reshape(-1).numpy()
+    assert np.abs(sig - ref).max() < 1e-5
