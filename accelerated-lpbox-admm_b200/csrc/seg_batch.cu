@@ -240,7 +240,7 @@ extern "C" lpbox_seg_batch *lpbox_seg_create_csr(int device, int B, const int32_
     for (int k = 0; k < 2; ++k) { v.b[k] = h->d_b[k].p; v.rowptr[k] = h->d_rp[k].p; v.colidx[k] = h->d_ci[k].p; v.val[k] = h->d_val[k].p; }
     v.kidx = h->d_kidx.p; v.cnt = h->d_cnt.p; v.pow_tab = h->d_powtab.p;
     v.st = h->d_st.p; v.hist = h->d_hist.p; v.left_idx = h->d_left.p; v.ret_idx = h->d_ret_idx.p; v.ret_val = h->d_ret_val.p; v.powv = h->d_powv.p;
-    h->smem = sizeof(double) * (2 * SEG_RMAX * SEG_CH + 8 + 16);
+    h->smem = sizeof(double) * (SEG_BUF_DOUBLES + 8 + 16);
     int sms = 0, occ = 1;
     if (cudaFuncSetAttribute(seg_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess ||
         cudaFuncSetAttribute(seg_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess ||

@@ -64,6 +64,7 @@ struct SegLaunch {
 constexpr int SEG_T = 256;
 constexpr int SEG_CH = 256;     // products staged per reduction per chunk
 constexpr int SEG_RMAX = 7;
+constexpr int SEG_BUF_DOUBLES = (2 * 7 * 256 > 2 * 5 * 448) ? 2 * 7 * 256 : 2 * 5 * 448;   // max(block_redux ring, fused-pass ring)
 
 // y_i = ((0 + m_i1 v_j1) + m_i2 v_j2) + ...  row i of (DIAG ? 2A with the diagonal replaced by md : A)
 template <bool DIAG>
@@ -141,11 +142,80 @@ __device__ __forceinline__ void seg_block_redux(F prod, int n, double *buf, doub
     __syncthreads();
 }
 
+// Fused streaming pass + Eigen-order reductions.  body(i, v) is called EXACTLY ONCE for every i < n (in chunk order) by the
+// staging warps: it performs the element's work (global loads / stores) and returns the R products of element i.  The
+// products go to a double-buffered shared-memory ring; the reduction warp walks the four chains of each reduction one
+// chunk behind the producers, so the streaming work and the sequential chains overlap.  Results in sc[0..R).
+constexpr int SEG_FCH = 448;            // elements per chunk = 2 per staging thread (multiple of 4)
+constexpr int SEG_FR = 5;               // max reductions per fused pass
+template <int R, typename Body>
+__device__ __forceinline__ void seg_fused_pass(Body body, int n, double *buf, double *sc) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int RW = SEG_T / 32 - 1;
+    const int a2 = n & ~3, a1 = n & ~1;
+    const int q = lane >> 2, k = lane & 3;
+    const int nch = (n + SEG_FCH - 1) / SEG_FCH;
+    auto stage = [&](int c) {
+        double *dst = buf + (size_t)(c & 1) * R * SEG_FCH;
+        const int base = c * SEG_FCH;
+        const int lim = min(SEG_FCH, n - base);
+#pragma unroll 2
+        for (int idx = tid; idx < lim; idx += SEG_T - 32) {
+            double v[R];
+            body(base + idx, v);
+#pragma unroll
+            for (int r = 0; r < R; ++r) dst[r * SEG_FCH + idx] = v[r];
+        }
+    };
+    double acc = 0.0;
+    __syncthreads();   // previous readers of sc[] are done; operands written by other threads are visible
+    if (warp != RW) stage(0);
+    __syncthreads();
+    for (int c = 0; c < nch; ++c) {
+        if (warp != RW) { if (c + 1 < nch) stage(c + 1); }
+        else if (q < R && a1 > 2) {
+            const double *src = buf + (size_t)(c & 1) * R * SEG_FCH + q * SEG_FCH;
+            const int lim = min(SEG_FCH, a2 - c * SEG_FCH);     // chain part only (elements < a2)
+            int i = k;
+            if (c == 0) { acc = src[k]; i = 4 + k; }
+            for (; i + 28 < lim; i += 32) {
+                double t0 = src[i], t1 = src[i + 4], t2 = src[i + 8], t3 = src[i + 12], t4 = src[i + 16], t5 = src[i + 20],
+                       t6 = src[i + 24], t7 = src[i + 28];
+                acc = dA(acc, t0); acc = dA(acc, t1); acc = dA(acc, t2); acc = dA(acc, t3);
+                acc = dA(acc, t4); acc = dA(acc, t5); acc = dA(acc, t6); acc = dA(acc, t7);
+            }
+            for (; i < lim; i += 4) acc = dA(acc, src[i]);
+        }
+        __syncthreads();
+    }
+    if (warp == RW) {
+        // products of the tail elements (index >= a2) sit in the ring slot of the chunk that contains them
+        const int qq = q < R ? q : 0;
+        auto at = [&](int i) { const int c = i / SEG_FCH; return buf[(size_t)(c & 1) * R * SEG_FCH + qq * SEG_FCH + (i - c * SEG_FCH)]; };
+        // only the last two chunks are still resident: all indices >= a2 - and, for n < 4, indices 0..n-1 - are in them
+        double res;
+        if (a1 > 2) {
+            double hi = __shfl_down_sync(0xffffffffu, acc, 2);
+            double l = dA(acc, hi);
+            if (a1 > a2 && k < 2) l = dA(l, at(a2 + k));
+            double l1 = __shfl_down_sync(0xffffffffu, l, 1);
+            res = dA(l, l1);
+        } else if (a1 == 2) {
+            res = dA(at(0), at(1));
+        } else {
+            res = (n > 0) ? at(0) : 0.0;
+        }
+        if ((n & 1) && n > 1) res = dA(res, at(n - 1));
+        if (k == 0 && q < R) sc[q] = res;
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(SEG_T, 4)
 seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *buf = reinterpret_cast<double *>(smem_raw);                 // [2][SEG_RMAX][SEG_CH]
-    double *sc = buf + 2 * SEG_RMAX * SEG_CH;                           // [8]
+    double *sc = buf + SEG_BUF_DOUBLES;                                 // [8]
     double *ring = sc + 8;                                              // [16]
     __shared__ int s_work;
     const int tid = threadIdx.x;
@@ -176,19 +246,20 @@ seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
 
         int status = RUNNING, iter = la.iter_start, cc = 0;
         for (; iter < la.iter_end; ++iter) {
-            // ---- y1, y2 pre-image (SEG.cpp:1223-1234) ------------------------------------------------------------
-            for (int i = tid; i < n; i += SEG_T) {
+            // ---- pass 1: y1, y2 pre-image (SEG.cpp:1223-1234) + ||y||^2 ---------------------------------------------
+            seg_fused_pass<1>([&](int i, double (&v)[1]) {
                 const double xi = x[i];
                 double tt = dA(xi, dD(z1[i], rho1));
                 y1[i] = (tt > 1.0) ? 1.0 : ((tt < 0.0) ? 0.0 : tt);
-                y2[i] = dS(dA(xi, dD(z2[i], rho2)), 0.5);
-            }
-            __syncthreads();
-            seg_block_redux<1>([&](int, int i) { const double v = y2[i]; return dM(v, v); }, n, buf, sc);
+                const double sh = dS(dA(xi, dD(z2[i], rho2)), 0.5);
+                y2[i] = sh;
+                v[0] = dM(sh, sh);
+            }, n, buf, sc);
             const double den = dM(2.0, sqrt(sc[0]));
-            // ---- diagonal patch (:1240-1243), preconditioner (:1252-1255), y2 (:427 of LP.cpp), rhs (:1246), x = y1 ----
+            // ---- pass 2 (no reduction): diagonal patch (:1240-1243), preconditioner (:1252-1255), y2, rhs (:1246), x = y1 ----
             const bool patch = (iter != 0 && rhoUpdated);
             const double dpatch = dM(dA(prho1, prho2), ratio);
+#pragma unroll 4
             for (int i = tid; i < n; i += SEG_T) {
                 if (patch) md[i] = dA(md[i], dpatch);
                 if (rhoUpdated) { const double d = md[i]; invd[i] = (d != 0.0) ? dD(1.0, d) : 1.0; }
@@ -199,17 +270,14 @@ seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
                 x[i] = y1i;
             }
             rhoUpdated = 0;
-            __syncthreads();
-            // ---- PCG (SEG.cpp:272-342) ---------------------------------------------------------------------------
-            for (int i = tid; i < n; i += SEG_T) {
-                const double rr = dS(w[i], seg_row_dot<true>(rp, ci, av, md, x, i));
-                r[i] = rr; p[i] = dM(invd[i], rr);
-            }
-            __syncthreads();
-            seg_block_redux<3>([&](int q, int i) {
-                const double a = (q == 0) ? w[i] : r[i];
-                const double c = (q == 0) ? a : ((q == 1) ? a : p[i]);
-                return dM(a, c); }, n, buf, sc);
+            // ---- PCG (SEG.cpp:272-342).  pass 3: r = rhs - M x, p = invd r; rhs.rhs, r.r, r.p ---------------------------
+            seg_fused_pass<3>([&](int i, double (&v)[3]) {
+                const double rhs = w[i];
+                const double rr = dS(rhs, seg_row_dot<true>(rp, ci, av, md, x, i));
+                const double pp = dM(invd[i], rr);
+                r[i] = rr; p[i] = pp;
+                v[0] = dM(rhs, rhs); v[1] = dM(rr, rr); v[2] = dM(rr, pp);
+            }, n, buf, sc);
             const double rhsNorm2 = sc[0];
             int cg_it = 0;
             if (rhsNorm2 == 0.0) {
@@ -220,67 +288,61 @@ seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
                 double r2 = sc[1], absNew = sc[2];
                 if (!(r2 < threshold)) {
                     while (cg_it < pr.pcg_maxiters) {
-                        for (int i = tid; i < n; i += SEG_T) t[i] = seg_row_dot<true>(rp, ci, av, md, p, i);
-                        __syncthreads();
-                        seg_block_redux<1>([&](int, int i) { return dM(p[i], t[i]); }, n, buf, sc);
+                        // tmp = M p fused with p.dot(tmp)
+                        seg_fused_pass<1>([&](int i, double (&v)[1]) {
+                            const double ti = seg_row_dot<true>(rp, ci, av, md, p, i);
+                            t[i] = ti;
+                            v[0] = dM(p[i], ti);
+                        }, n, buf, sc);
                         const double alpha = dD(absNew, sc[0]);
-                        for (int i = tid; i < n; i += SEG_T) {
-                            const double pi = p[i];
-                            x[i] = dA(x[i], dM(alpha, pi));
+                        // x += alpha p; r -= alpha tmp; z = invd r fused with r.r and r.z
+                        seg_fused_pass<2>([&](int i, double (&v)[2]) {
+                            x[i] = dA(x[i], dM(alpha, p[i]));
                             const double rr = dS(r[i], dM(alpha, t[i]));
-                            r[i] = rr;
-                            t[i] = dM(invd[i], rr);                      // z
-                        }
-                        __syncthreads();
-                        seg_block_redux<2>([&](int q, int i) { const double a = r[i]; return dM(a, q == 0 ? a : t[i]); }, n, buf, sc);
+                            const double zz = dM(invd[i], rr);
+                            r[i] = rr; t[i] = zz;
+                            v[0] = dM(rr, rr); v[1] = dM(rr, zz);
+                        }, n, buf, sc);
                         r2 = sc[0];
                         if (r2 < threshold) { cg_it++; break; }
                         const double absOld = absNew;
                         absNew = sc[1];
                         const double beta = dD(absNew, absOld);
+#pragma unroll 4
                         for (int i = tid; i < n; i += SEG_T) p[i] = dA(t[i], dM(beta, p[i]));
                         cg_it++;
-                        __syncthreads();
                     }
                 }
             }
             cg_total += cg_it; admm_total += 1;
-            __syncthreads();
-            // ---- history (SEG.cpp:1131-1134), duals (:1280-1281), indicator ----------------------------------------
+            // ---- pass: history (SEG.cpp:1131-1134), duals (:1280-1281), indicator, A x; x.x, (x-y1)^2, (x-y2)^2, x.Ax, b.x ----
             double *h = nullptr;
             if (la.l2f && sv.hist_cap > 0) { if (cc < sv.hist_cap) h = sv.hist + sv.off_hist[inst] + (long long)cc * st->n0; cc++; }
             {
                 const double g1 = dM(gamma, rho1), g2 = dM(gamma, rho2);
-                for (int i = tid; i < n; i += SEG_T) {
+                seg_fused_pass<5>([&](int i, double (&v)[5]) {
                     const double xi = x[i];
                     if (h) h[i] = xi;
-                    z1[i] = dA(z1[i], dM(g1, dS(xi, y1[i])));
-                    z2[i] = dA(z2[i], dM(g2, dS(xi, y2[i])));
+                    const double d1 = dS(xi, y1[i]), d2 = dS(xi, y2[i]);
+                    z1[i] = dA(z1[i], dM(g1, d1));
+                    z2[i] = dA(z2[i], dM(g2, d2));
                     w[i] = (xi >= 0.5) ? 1.0 : 0.0;
-                }
+                    const double ax = seg_row_dot<false>(rp, ci, av, md, x, i);
+                    v[0] = dM(xi, xi); v[1] = dM(d1, d1); v[2] = dM(d2, d2); v[3] = dM(xi, ax); v[4] = dM(b[i], xi);
+                }, n, buf, sc);
             }
-            __syncthreads();
-            for (int i = tid; i < n; i += SEG_T) {
-                t[i] = seg_row_dot<false>(rp, ci, av, md, x, i);        // A x
-                r[i] = seg_row_dot<false>(rp, ci, av, md, w, i);        // A 1[x >= 0.5]
-            }
-            __syncthreads();
-            // x.x, (x-y1)^2, (x-y2)^2, x.Ax, b.x, idx.A idx, b.idx   (SEG.cpp:1285-1287, :568-572)
-            seg_block_redux<7>([&](int q, int i) {
-                const double xi = x[i];
-                switch (q) {
-                    case 0: return dM(xi, xi);
-                    case 1: { const double d = dS(xi, y1[i]); return dM(d, d); }
-                    case 2: { const double d = dS(xi, y2[i]); return dM(d, d); }
-                    case 3: return dM(xi, t[i]);
-                    case 4: return dM(b[i], xi);
-                    case 5: return dM(w[i], r[i]);
-                    default: return dM(b[i], w[i]);
-                } }, n, buf, sc);
+            const double nx2 = sc[0], d12 = sc[1], d22 = sc[2], obj_val = dA(sc[3], sc[4]);   // compute_cost: val + val2
+            // ---- pass: A 1[x >= 0.5]; idx.A idx, b.idx  (SEG.cpp:1323-1326) -------------------------------------------
+            seg_fused_pass<2>([&](int i, double (&v)[2]) {
+                const double wi = w[i];
+                v[0] = dM(wi, seg_row_dot<false>(rp, ci, av, md, w, i));
+                v[1] = dM(b[i], wi);
+            }, n, buf, sc);
+            const double bin_val = dA(sc[0], sc[1]);
             {
-                double temp0 = sqrt(sc[0]);
+                double temp0 = sqrt(nx2);
                 if (!(temp0 > 2.2204e-16)) temp0 = 2.2204e-16;
-                const double c1 = dD(sqrt(sc[1]), temp0), c2 = dD(sqrt(sc[2]), temp0);
+                const double c1 = dD(sqrt(d12), temp0), c2 = dD(sqrt(d22), temp0);
                 if (c1 <= pr.stop_threshold && c2 <= pr.stop_threshold) { status = STOP_Y; break; }   // SEG.cpp:1288-1292
             }
             if ((iter + 1) % pr.rho_change_step == 0) {                  // :1295-1303
@@ -292,7 +354,7 @@ seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
                 ratio = dS(pr.learning_fact, 1.0);
             }
             {
-                const double obj = dA(sc[3], sc[4]);                     // compute_cost: val + val2
+                const double obj = obj_val;
                 double so = std_obj;
                 if (obj_len + 1 >= (long long)pr.history_size) so = std_obj_after_push(ring, obj_len, obj, pr.history_size);
                 __syncthreads();
@@ -302,7 +364,7 @@ seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
                 __syncthreads();
                 if (std_obj <= pr.std_threshold) { status = STOP_STD; break; }   // :1313-1319
             }
-            cur_obj = dA(sc[5], sc[6]);                                  // :1323-1326
+            cur_obj = bin_val;                                           // :1323-1326
             if (best_bin_obj >= cur_obj) best_bin_obj = cur_obj;
         }
         __syncthreads();
@@ -335,7 +397,7 @@ __global__ void __launch_bounds__(SEG_T)
 seg_setup_kernel(SegView sv, Params pr, int use_x0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *buf = reinterpret_cast<double *>(smem_raw);
-    double *sc = buf + 2 * SEG_RMAX * SEG_CH;
+    double *sc = buf + SEG_BUF_DOUBLES;
     const int inst = blockIdx.x, tid = threadIdx.x;
     SegInst *st = sv.st + inst;
     const int n = st->n, cur = st->cur;

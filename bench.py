@@ -287,7 +287,7 @@ def main():
                        "parallelism": f"instances sharded over {world} GPU(s), no data-path collective"},
             "admm_iters_per_sec": tot_admm / (ms_per_step / 1e3), "cg_iters_per_sec": tot_cg / (ms_per_step / 1e3),
             "wall_ms_per_step": wall_ms / args.steps,
-            "e2e": {"value": tot_B / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "e2e": ({"value": tot_B / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)} if e2e_ms > 0 else None),
             "gpu_launches": int(tot_launch),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
