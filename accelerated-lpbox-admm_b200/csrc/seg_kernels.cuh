@@ -211,7 +211,7 @@ __device__ __forceinline__ void seg_fused_pass(Body body, int n, double *buf, do
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(SEG_T, 4)
+__global__ void __launch_bounds__(SEG_T, 5)
 seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *buf = reinterpret_cast<double *>(smem_raw);                 // [2][SEG_RMAX][SEG_CH]
