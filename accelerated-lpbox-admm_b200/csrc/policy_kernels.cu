@@ -192,61 +192,302 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
 }
 
+// ---- fused feed-forward sublayer -------------------------------------------------------------------------------------------
+// out = BN( X + W2 relu(W1 X + b1) + b2 )  (LP.mha:140-160: SkipConnection(Linear 128->512, ReLU, Linear 512->128) + Normalization)
+// in ONE persistent kernel: the [rows][512] hidden activation never leaves the SM.  A CTA owns a PAIR of 128-row tiles (so
+// every weight chunk fetched from L2 feeds 256 rows) and walks the hidden dimension in 4 chunks of 128:
+//     acc1[t] (TMEM) = X[t] . W1[c]^T            (tcgen05.mma, K = 128)
+//     H[t]    (smem) = bf16(relu(acc1[t] + b1))  (chunk-epilogue warps: tcgen05.ld -> registers -> 128B-swizzled K-major smem)
+//     acc2[t] (TMEM) += H[t] . W2[:, c]^T        (tcgen05.mma, K = 128)
+// and after the 4th chunk the drain warps read acc2[t], add bias + residual, apply the folded BatchNorm and store bf16.
+// TMEM: acc1[2] + acc2[2] = 512 columns.  smem: X[2] + H[2] + W1 chunk + W2 chunk = 6 x 32 KB.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2..9 = chunk epilogue (4 per tile), 10..13 = drain (both tiles in turn).
+constexpr int FF_THREADS = 32 * 14;
+constexpr uint32_t FF_TILE = 128 * 128 * 2;      // one [128][128] bf16 operand tile = two [128][64] swizzled boxes
+constexpr size_t FF_SMEM = 6 * (size_t)FF_TILE + 1024 /*align*/ + (512 + 3 * 128) * 4 + 256 /*barriers*/;
+
+__device__ __forceinline__ void mma_tile_k128(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool fresh) {
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint64_t da = make_desc(a_addr + kb * (FF_TILE / 2) + k * 32), db = make_desc(b_addr + kb * (FF_TILE / 2) + k * 32);
+            const uint32_t accum = (fresh && kb == 0 && k == 0) ? 0u : 1u;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "setp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+        }
+    }
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s2u(bar)) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(bar)) : "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(FF_THREADS, 1)
+ff_fused_tcgen05(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW1, const __grid_constant__ CUtensorMap mapW2,
+                 const __nv_bfloat16 *__restrict__ X, __nv_bfloat16 *__restrict__ out, int M, const float *__restrict__ b1,
+                 const float *__restrict__ b2, const float *__restrict__ s2, const float *__restrict__ t2) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char *sX = smem, *sH = smem + 2 * FF_TILE, *sW1 = smem + 4 * FF_TILE, *sW2 = smem + 5 * FF_TILE;
+    float *sb1 = reinterpret_cast<float *>(smem + 6 * FF_TILE), *sb2 = sb1 + 512, *ss2 = sb2 + 128, *st2 = ss2 + 128;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(st2 + 128);
+    uint64_t *x_full = bars, *x_empty = bars + 2, *w1_full = bars + 4, *w1_empty = bars + 5, *w2_full = bars + 6, *w2_empty = bars + 7,
+             *acc1_full = bars + 8, *h_full = bars + 10, *acc2_full = bars + 12, *acc2_empty = bars + 14;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_pairs = (M + 255) / 256;
+
+    for (int i = threadIdx.x; i < 512; i += FF_THREADS) sb1[i] = b1[i];
+    for (int i = threadIdx.x; i < 128; i += FF_THREADS) { sb2[i] = b2[i]; ss2[i] = s2[i]; st2[i] = t2[i]; }
+    if (threadIdx.x == 0) {
+        for (int t = 0; t < 2; ++t) {
+            mb_init(&x_full[t], 1); mb_init(&x_empty[t], 1); mb_init(&acc1_full[t], 1); mb_init(&h_full[t], 128);
+            mb_init(&acc2_full[t], 1); mb_init(&acc2_empty[t], 128);
+        }
+        mb_init(w1_full, 1); mb_init(w1_empty, 1); mb_init(w2_full, 1); mb_init(w2_empty, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_slot)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---- TMA producer ----
+            uint32_t it = 0, pc = 0;
+            for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pc) {
+                for (int t = 0; t < 2; ++t) {
+                    if (pc > 0) mb_wait(&x_empty[t], (pc - 1) & 1);
+                    mb_expect(&x_full[t], FF_TILE);
+                    tma_2d(sX + t * FF_TILE, &mapX, 0, pair * 256 + t * 128, &x_full[t]);
+                    tma_2d(sX + t * FF_TILE + FF_TILE / 2, &mapX, 64, pair * 256 + t * 128, &x_full[t]);
+                }
+                for (int c = 0; c < 4; ++c, ++it) {
+                    if (it > 0) mb_wait(w1_empty, (it - 1) & 1);
+                    mb_expect(w1_full, FF_TILE);
+                    tma_2d(sW1, &mapW1, 0, c * 128, w1_full);
+                    tma_2d(sW1 + FF_TILE / 2, &mapW1, 64, c * 128, w1_full);
+                    if (it > 0) mb_wait(w2_empty, (it - 1) & 1);
+                    mb_expect(w2_full, FF_TILE);
+                    tma_2d(sW2, &mapW2, c * 128, 0, w2_full);
+                    tma_2d(sW2 + FF_TILE / 2, &mapW2, c * 128 + 64, 0, w2_full);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---- MMA issuer ----
+            const uint32_t idesc = make_idesc();
+            uint32_t it = 0, pc = 0;
+            for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pc) {
+                for (int c = 0; c < 4; ++c, ++it) {
+                    mb_wait(w1_full, it & 1);
+                    for (int t = 0; t < 2; ++t) {
+                        if (c == 0) mb_wait(&x_full[t], pc & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        // acc1[t] was drained by the chunk epilogue of the previous chunk (h_full[t] waited below before MMA2)
+                        mma_tile_k128(tmem + t * 128, s2u(sX + t * FF_TILE), s2u(sW1), idesc, true);
+                        umma_commit(&acc1_full[t]);
+                        if (c == 3) umma_commit(&x_empty[t]);
+                    }
+                    umma_commit(w1_empty);
+                    mb_wait(w2_full, it & 1);
+                    for (int t = 0; t < 2; ++t) {
+                        mb_wait(&h_full[t], it & 1);
+                        if (c == 0 && pc > 0) mb_wait(&acc2_empty[t], (pc - 1) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        mma_tile_k128(tmem + 256 + t * 128, s2u(sH + t * FF_TILE), s2u(sW2), idesc, c == 0);
+                        if (c == 3) umma_commit(&acc2_full[t]);
+                    }
+                    umma_commit(w2_empty);
+                }
+            }
+        }
+    } else if (warp < 10) {
+        // ---- chunk epilogue: acc1[t] -> relu(+b1) -> bf16 -> H[t] (K-major, 128-byte swizzle: 16-byte chunk j of row r at j ^ (r & 7)) ----
+        const int t = (warp - 2) >> 2, q = warp & 3, row = q * 32 + lane;
+        unsigned char *hrow = sH + t * FF_TILE + row * 128;
+        uint32_t it = 0;
+        for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+            for (int c = 0; c < 4; ++c, ++it) {
+                mb_wait(&acc1_full[t], it & 1);   // also: MMA2 of the previous chunk (which read H[t]) has completed
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+                for (int g = 0; g < 4; ++g) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 128 + g * 32), r);
+                    const float *bb = sb1 + c * 128 + g * 32;
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        uint4 o;
+                        __nv_bfloat162 *op = reinterpret_cast<__nv_bfloat162 *>(&o);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float v0 = fmaxf(__uint_as_float(r[j8 * 8 + 2 * j]) + bb[j8 * 8 + 2 * j], 0.0f);
+                            const float v1 = fmaxf(__uint_as_float(r[j8 * 8 + 2 * j + 1]) + bb[j8 * 8 + 2 * j + 1], 0.0f);
+                            op[j] = __floats2bfloat162_rn(v0, v1);
+                        }
+                        const int ch = g * 4 + j8;                               // 16-byte chunk index inside the 256-byte row: box = ch / 8
+                        *reinterpret_cast<uint4 *>(hrow + (ch >> 3) * (FF_TILE / 2) + (((ch & 7) ^ (row & 7)) << 4)) = o;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> visible to the tensor core
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mb_arrive(&h_full[t]);
+            }
+        }
+    } else {
+        // ---- drain: acc2[t] + b2 + residual -> folded BatchNorm -> bf16 -> global ----
+        const int q = warp & 3, row = q * 32 + lane;
+        uint32_t pc = 0;
+        for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pc) {
+#pragma unroll 1
+            for (int t = 0; t < 2; ++t) {
+                const long long m = (long long)pair * 256 + t * 128 + row;
+                mb_wait(&acc2_full[t], pc & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+                for (int g = 0; g < 4; ++g) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(256 + t * 128 + g * 32), r);
+                    if (m < M) {
+#pragma unroll
+                        for (int j8 = 0; j8 < 4; ++j8) {
+                            const int n = g * 32 + j8 * 8;
+                            const uint4 rr = *reinterpret_cast<const uint4 *>(X + m * 128 + n);
+                            const __nv_bfloat162 *rp2 = reinterpret_cast<const __nv_bfloat162 *>(&rr);
+                            uint4 o;
+                            __nv_bfloat162 *op = reinterpret_cast<__nv_bfloat162 *>(&o);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 f = __bfloat1622float2(rp2[j]);
+                                const int nn = n + 2 * j;
+                                const float v0 = (__uint_as_float(r[j8 * 8 + 2 * j]) + sb2[nn] + f.x) * ss2[nn] + st2[nn];
+                                const float v1 = (__uint_as_float(r[j8 * 8 + 2 * j + 1]) + sb2[nn + 1] + f.y) * ss2[nn + 1] + st2[nn + 1];
+                                op[j] = __floats2bfloat162_rn(v0, v1);
+                            }
+                            *reinterpret_cast<uint4 *>(out + m * 128 + n) = o;
+                        }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mb_arrive(&acc2_empty[t]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+}
+
 // ---- small CUDA-core kernels ----------------------------------------------------------------------------------------------
 // embedding: h0[m][j] = sum_f We[j][f] x[m][f] + c[t][j],  c[t] = We[:,5:10] pe[t] + b  (LP.mha:229-235)
-__global__ void embed_kernel(const float *__restrict__ x, long long Mtok, int T, const float *__restrict__ We5 /*[128][5]*/,
-                             const float *__restrict__ cpos /*[T][128]*/, __nv_bfloat16 *__restrict__ h) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= Mtok * 128) return;
-    const long long m = idx >> 7;
-    const int j = (int)(idx & 127), t = (int)(m % T);
+// one thread = one token x 8 consecutive outputs (one 16-byte store)
+__global__ void __launch_bounds__(256) embed_kernel(const float *__restrict__ x, long long Mtok, int T, const float *__restrict__ We5 /*[128][5]*/,
+                                                    const float *__restrict__ cpos /*[T][128]*/, __nv_bfloat16 *__restrict__ h) {
+    __shared__ float sW[128 * 5];
+    for (int i = threadIdx.x; i < 640; i += 256) sW[i] = We5[i];
+    __syncthreads();
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;      // (token, group of 8 outputs)
+    if (idx >= Mtok * 16) return;
+    const long long m = idx >> 4;
+    const int j0 = (int)(idx & 15) * 8, t = (int)(m % T);
     const float *xm = x + m * 5;
-    float acc = cpos[t * 128 + j];
+    const float x0 = xm[0], x1 = xm[1], x2 = xm[2], x3 = xm[3], x4 = xm[4];
+    const float4 c0 = *reinterpret_cast<const float4 *>(cpos + t * 128 + j0), c1 = *reinterpret_cast<const float4 *>(cpos + t * 128 + j0 + 4);
+    float v[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
-    for (int f = 0; f < 5; ++f) acc += We5[j * 5 + f] * xm[f];
-    h[idx] = __float2bfloat16(acc);
+    for (int j = 0; j < 8; ++j) {
+        const float *wj = sW + (j0 + j) * 5;
+        v[j] += wj[0] * x0 + wj[1] * x1 + wj[2] * x2 + wj[3] * x3 + wj[4] * x4;
+    }
+    uint4 o;
+    __nv_bfloat162 *op = reinterpret_cast<__nv_bfloat162 *>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) op[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    *reinterpret_cast<uint4 *>(h + m * 128 + j0) = o;
 }
 
 // attention for one variable per CTA: qkv [T][384] (q | k | v, head-major inside each third) -> heads [T][128]
-// softmax(q k' / sqrt(16)) v per head (LP.mha:83-104).  Thread t < 8*T handles (head, query) = (t / T, t % T).
-__global__ void __launch_bounds__(256) attention_kernel(const __nv_bfloat16 *__restrict__ qkv, int T, __nv_bfloat16 *__restrict__ heads) {
-    __shared__ __align__(16) __nv_bfloat16 s[32 * 384];
+// softmax(q k' / sqrt(16)) v per head (LP.mha:83-104).  q, k, v are converted to fp32 ONCE while staging (shared memory
+// [T][388] floats, +4 padding against bank conflicts); thread t < 8*T handles (head, query) = (t / T, t % T) with
+// 128-bit shared loads.
+constexpr int ATT_LD = 388;
+template <int TT>   // TT > 0: compile-time token count (score array stays in registers); TT == 0: runtime T <= 32
+__global__ void __launch_bounds__(256) attention_kernel(const __nv_bfloat16 *__restrict__ qkv, int Trt, __nv_bfloat16 *__restrict__ heads) {
+    const int T = TT > 0 ? TT : Trt;
+    extern __shared__ __align__(16) float sf[];                                    // [T][ATT_LD]
     const long long var = blockIdx.x;
-    const uint4 *src = reinterpret_cast<const uint4 *>(qkv + var * T * 384);      // T*384*2 bytes, 16-byte aligned (384*2 = 768)
-    for (int i = threadIdx.x; i < T * 48; i += blockDim.x) reinterpret_cast<uint4 *>(s)[i] = src[i];
+    const uint4 *src = reinterpret_cast<const uint4 *>(qkv + var * T * 384);      // 48 x 16 bytes per token
+    for (int i = threadIdx.x; i < T * 48; i += blockDim.x) {
+        const uint4 u = src[i];
+        const __nv_bfloat162 *p2 = reinterpret_cast<const __nv_bfloat162 *>(&u);
+        const int tok = i / 48, c = (i - tok * 48) * 8;
+        float *d = sf + tok * ATT_LD + c;
+        const float2 f0 = __bfloat1622float2(p2[0]), f1 = __bfloat1622float2(p2[1]), f2 = __bfloat1622float2(p2[2]), f3 = __bfloat1622float2(p2[3]);
+        *reinterpret_cast<float4 *>(d) = make_float4(f0.x, f0.y, f1.x, f1.y);
+        *reinterpret_cast<float4 *>(d + 4) = make_float4(f2.x, f2.y, f3.x, f3.y);
+    }
     __syncthreads();
     if (threadIdx.x >= 8 * T) return;
     const int hd = threadIdx.x / T, i = threadIdx.x - hd * T;
-    float q[16];
-    {
-        const __nv_bfloat162 *qp = reinterpret_cast<const __nv_bfloat162 *>(s + i * 384 + hd * 16);
+    float4 q[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { const float2 f = __bfloat1622float2(qp[e]); q[2 * e] = f.x * 0.25f; q[2 * e + 1] = f.y * 0.25f; }
+    for (int e = 0; e < 4; ++e) {
+        q[e] = *reinterpret_cast<const float4 *>(sf + i * ATT_LD + hd * 16 + 4 * e);
+        q[e].x *= 0.25f; q[e].y *= 0.25f; q[e].z *= 0.25f; q[e].w *= 0.25f;
     }
-    float sc[32], mx = -INFINITY;
+    float sc[TT > 0 ? TT : 32], mx = -INFINITY;
+#pragma unroll
     for (int j = 0; j < T; ++j) {
-        const __nv_bfloat162 *kp = reinterpret_cast<const __nv_bfloat162 *>(s + j * 384 + 128 + hd * 16);
+        const float4 *kp = reinterpret_cast<const float4 *>(sf + j * ATT_LD + 128 + hd * 16);
         float d = 0.0f;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { const float2 f = __bfloat1622float2(kp[e]); d += q[2 * e] * f.x + q[2 * e + 1] * f.y; }
+        for (int e = 0; e < 4; ++e) { const float4 k4 = kp[e]; d += q[e].x * k4.x + q[e].y * k4.y + q[e].z * k4.z + q[e].w * k4.w; }
         sc[j] = d;
         mx = fmaxf(mx, d);
     }
     float den = 0.0f;
+#pragma unroll
     for (int j = 0; j < T; ++j) { sc[j] = __expf(sc[j] - mx); den += sc[j]; }
     const float inv = 1.0f / den;
-    float o[16];
+    float4 o[4];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) o[e] = 0.0f;
+    for (int e = 0; e < 4; ++e) o[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
     for (int j = 0; j < T; ++j) {
-        const __nv_bfloat162 *vp = reinterpret_cast<const __nv_bfloat162 *>(s + j * 384 + 256 + hd * 16);
+        const float4 *vp = reinterpret_cast<const float4 *>(sf + j * ATT_LD + 256 + hd * 16);
         const float p = sc[j] * inv;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { const float2 f = __bfloat1622float2(vp[e]); o[2 * e] += p * f.x; o[2 * e + 1] += p * f.y; }
+        for (int e = 0; e < 4; ++e) { const float4 v4 = vp[e]; o[e].x += p * v4.x; o[e].y += p * v4.y; o[e].z += p * v4.z; o[e].w += p * v4.w; }
     }
-    __nv_bfloat162 *dst = reinterpret_cast<__nv_bfloat162 *>(heads + (var * T + i) * 128 + hd * 16);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) dst[e] = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
+    uint4 w0, w1;
+    __nv_bfloat162 *a0 = reinterpret_cast<__nv_bfloat162 *>(&w0), *a1 = reinterpret_cast<__nv_bfloat162 *>(&w1);
+    a0[0] = __floats2bfloat162_rn(o[0].x, o[0].y); a0[1] = __floats2bfloat162_rn(o[0].z, o[0].w);
+    a0[2] = __floats2bfloat162_rn(o[1].x, o[1].y); a0[3] = __floats2bfloat162_rn(o[1].z, o[1].w);
+    a1[0] = __floats2bfloat162_rn(o[2].x, o[2].y); a1[1] = __floats2bfloat162_rn(o[2].z, o[2].w);
+    a1[2] = __floats2bfloat162_rn(o[3].x, o[3].y); a1[3] = __floats2bfloat162_rn(o[3].z, o[3].w);
+    uint4 *dst = reinterpret_cast<uint4 *>(heads + (var * T + i) * 128 + hd * 16);
+    dst[0] = w0; dst[1] = w1;
 }
 
 // head: a2 [R][128] (after fc2 + ReLU) -> fc3 (16) ReLU -> fc4 (1) -> sigmoid  (LP.mha:185-199)
@@ -301,6 +542,26 @@ int launch_gemm(cudaStream_t st, const __nv_bfloat16 *A, const __nv_bfloat16 *W,
     gemm_bf16_tcgen05<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ma, mb, C, (int)M, N, K, N, ep);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { lpbox_set_error(std::string("policy GEMM launch: ") + cudaGetErrorString(e)); return LPBOX_E_CUDA; }
+    return 0;
+}
+
+
+int g_sm_count = 0;
+int launch_ff_fused(cudaStream_t st, const __nv_bfloat16 *X, const __nv_bfloat16 *W1, const float *b1, const __nv_bfloat16 *W2, const float *b2,
+                    const float *s2, const float *t2, __nv_bfloat16 *out, long long M) {
+    if (M <= 0) return 0;
+    if (!b1 || !b2 || !s2 || !t2) { lpbox_set_error("fused FF: bias / scale / shift vectors are required"); return LPBOX_E_INVALID; }
+    CUtensorMap mx, m1, m2;
+    if (!make_map(&mx, X, (uint64_t)M, 128, 128) || !make_map(&m1, W1, 512, 128, 128) || !make_map(&m2, W2, 128, 512, 128)) {
+        lpbox_set_error("cuTensorMapEncodeTiled failed"); return LPBOX_E_CUDA;
+    }
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(ff_fused_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM); attr = true; }
+    if (!g_sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev); if (g_sm_count <= 0) g_sm_count = 148; }
+    const long long n_pairs = (M + 255) / 256;
+    ff_fused_tcgen05<<<(unsigned)std::min<long long>(n_pairs, g_sm_count), FF_THREADS, FF_SMEM, st>>>(mx, m1, m2, X, out, (int)M, b1, b2, s2, t2);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { lpbox_set_error(std::string("fused FF launch: ") + cudaGetErrorString(e)); return LPBOX_E_CUDA; }
     return 0;
 }
 
@@ -397,19 +658,25 @@ extern "C" int lpbox_policy_forward_dev(lpbox_policy *p, void *stream, const flo
     const int T = p->T;
     for (int64_t r0 = 0; r0 < rows; r0 += p->chunk) {
         const long long R = std::min<long long>(p->chunk, rows - r0), Mt = R * T;
-        embed_kernel<<<(unsigned)((Mt * 128 + 255) / 256), 256, 0, st>>>(input_dev + r0 * T * 5, Mt, T, p->We5, p->cpos, p->h);
+        embed_kernel<<<(unsigned)((Mt * 16 + 255) / 256), 256, 0, st>>>(input_dev + r0 * T * 5, Mt, T, p->We5, p->cpos, p->h);
         p->launches++;
         __nv_bfloat16 *h = p->h, *h2 = p->h2;
         for (auto &L : p->layers) {
             int rc = launch_gemm(st, h, L.Wqkv, p->qkv, Mt, 384, 128, Epi{nullptr, nullptr, nullptr, nullptr, 0}); if (rc) return rc;
-            attention_kernel<<<(unsigned)R, ((8 * T + 31) / 32) * 32, 0, st>>>(p->qkv, T, h2);                                  // heads -> h2
+            {
+                const unsigned at = ((8 * T + 31) / 32) * 32;
+                const size_t asm_ = sizeof(float) * (size_t)T * ATT_LD;
+                if (T == 20) attention_kernel<20><<<(unsigned)R, at, asm_, st>>>(p->qkv, T, h2);
+                else if (T == 10) attention_kernel<10><<<(unsigned)R, at, asm_, st>>>(p->qkv, T, h2);
+                else if (T == 5) attention_kernel<5><<<(unsigned)R, at, asm_, st>>>(p->qkv, T, h2);
+                else attention_kernel<0><<<(unsigned)R, at, asm_, st>>>(p->qkv, T, h2);
+            }                                  // heads -> h2
             rc = launch_gemm(st, h2, L.Wo, p->qkv /*reuse as [Mt][128] scratch*/, Mt, 128, 128, Epi{nullptr, h, L.s1, L.t1, 0}); if (rc) return rc;
             // NOTE: the out-proj result (h + MHA(h), BatchNorm folded) lives in the first Mt*128 elements of qkv
             __nv_bfloat16 *hn = p->qkv;
-            rc = launch_gemm(st, hn, L.W1, p->ff, Mt, 512, 128, Epi{L.b1, nullptr, nullptr, nullptr, 1}); if (rc) return rc;
-            rc = launch_gemm(st, p->ff, L.W2, h2, Mt, 128, 512, Epi{L.b2, hn, L.s2, L.t2, 0}); if (rc) return rc;
+            rc = launch_ff_fused(st, hn, L.W1, L.b1, L.W2, L.b2, L.s2, L.t2, h2, Mt); if (rc) return rc;
             std::swap(h, h2);
-            p->launches += 5;
+            p->launches += 4;
         }
         int rc = launch_gemm(st, h, p->Wfc1, p->a1, R, 256, T * 128, Epi{p->bfc1, nullptr, nullptr, nullptr, 1}); if (rc) return rc;
         rc = launch_gemm(st, p->a1, p->Wfc2, p->a2, R, 128, 256, Epi{p->bfc2, nullptr, nullptr, nullptr, 1}); if (rc) return rc;
@@ -428,4 +695,13 @@ extern "C" int lpbox_gemm_bf16_dev(void *stream, const void *A, const void *W, v
     if (!get_encode()) { lpbox_set_error("cuTensorMapEncodeTiled not available"); return LPBOX_E_CUDA; }
     return launch_gemm((cudaStream_t)stream, (const __nv_bfloat16 *)A, (const __nv_bfloat16 *)W, (__nv_bfloat16 *)C, M, N, K,
                        Epi{bias, nullptr, nullptr, nullptr, relu});
+}
+
+// the fused feed-forward sublayer alone (tests): out = ((X + W2 relu(W1 X + b1) + b2) * scale + shift), X/out bf16 [M][128],
+// W1 bf16 [512][128], W2 bf16 [128][512]
+extern "C" int lpbox_ff_fused_dev(void *stream, const void *X, const void *W1, const float *b1, const void *W2, const float *b2, const float *scale,
+                                  const float *shift, void *out, int64_t M) {
+    if (!get_encode()) { lpbox_set_error("cuTensorMapEncodeTiled not available"); return LPBOX_E_CUDA; }
+    return launch_ff_fused((cudaStream_t)stream, (const __nv_bfloat16 *)X, (const __nv_bfloat16 *)W1, b1, (const __nv_bfloat16 *)W2, b2, scale, shift,
+                           (__nv_bfloat16 *)out, M);
 }

@@ -242,6 +242,10 @@ int lpbox_policy_forward_dev(lpbox_policy *p, void *stream, const float *input_d
 int64_t lpbox_policy_launch_count(const lpbox_policy *p);
 /* the tcgen05 GEMM alone (tests): C[M][N] = A[M][K] . W[N][K]^T (+ bias[n]) (ReLU); bf16 DEVICE row-major; N % 128 == 0, K % 64 == 0 */
 int lpbox_gemm_bf16_dev(void *stream, const void *A, const void *W, void *C, int64_t M, int N, int K, const float *bias, int relu);
+/* the fused feed-forward sublayer alone (tests): out = (X + W2 relu(W1 X + b1) + b2) * scale + shift  (LP.mha:140-160 with the
+ * eval-mode BatchNorm folded into scale / shift); X, out: bf16 DEVICE [M][128]; W1: bf16 [512][128]; W2: bf16 [128][512] */
+int lpbox_ff_fused_dev(void *stream, const void *X, const void *W1, const float *b1, const void *W2, const float *b2,
+                       const float *scale, const float *shift, void *out, int64_t M);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * File format of the reference: data/instance/<k>_<j>/instance_<i>_{C,b}.txt under `root`

@@ -29,6 +29,30 @@ def test_tcgen05_gemm_matches_torch(M, N, K):
     assert err <= 0.02 * max(1.0, ref.abs().max().item()), err
 
 
+@pytest.mark.parametrize("M", [128, 256, 300, 5000, 100000])
+def test_fused_feed_forward_matches_torch(M):
+    import lpbox
+    L = lpbox._capi.lib()
+    g = torch.Generator(device="cuda").manual_seed(M)
+    X = (torch.randn(M, 128, device="cuda", generator=g) * 0.5).bfloat16()
+    W1 = (torch.randn(512, 128, device="cuda", generator=g) * 0.1).bfloat16()
+    W2 = (torch.randn(128, 512, device="cuda", generator=g) * 0.1).bfloat16()
+    b1 = torch.randn(512, device="cuda", generator=g) * 0.2
+    b2 = torch.randn(128, device="cuda", generator=g) * 0.2
+    sc = torch.rand(128, device="cuda", generator=g) + 0.5
+    sh = torch.randn(128, device="cuda", generator=g) * 0.1
+    out = torch.zeros(M, 128, device="cuda", dtype=torch.bfloat16)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    rc = L.lpbox_ff_fused_dev(st, vp(X), vp(W1), vp(b1), vp(W2), vp(b2), vp(sc), vp(sh), vp(out), M)
+    assert rc == 0, lpbox._capi.last_error()
+    torch.cuda.synchronize()
+    H = torch.relu(X.float() @ W1.float().t() + b1).bfloat16().float()      # the hidden activation is rounded to bf16 on chip
+    ref = (X.float() + H @ W2.float().t() + b2) * sc + sh
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 0.02 * max(1.0, ref.abs().max().item()), err
+
+
 @pytest.mark.parametrize("kind,T", [("GraphAttentionEncoder", 20), ("MLPEncoder", 20), ("GraphAttentionEncoder", 5), ("GraphAttentionEncoder", 10)])
 def test_policy_kernel_matches_torch_module(kind, T):
     from lpbox import policy
