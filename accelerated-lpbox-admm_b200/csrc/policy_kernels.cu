@@ -43,6 +43,12 @@ __device__ __forceinline__ void mb_wait(uint64_t *b, uint32_t parity) {
         "bra LW;\n\t"
         "LD:\n\t}" ::"r"(s2u(b)), "r"(parity) : "memory");
 }
+// one lane of a converged warp (the branch around it must be warp-uniform so that descriptors stay in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tma_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(s2u(dst)),
                  "l"(map), "r"(c0), "r"(c1), "r"(s2u(bar)) : "memory");
@@ -51,18 +57,26 @@ __device__ __forceinline__ void tma_2d(void *dst, const CUtensorMap *map, int c0
 // start address >> 4 in [0,14), LBO (16-byte units) in [16,30) = 1, SBO in [32,46) = 8 rows * 128 B = 1024 B,
 // version = 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    const uint32_t lo = ((smem_addr >> 4) & 0x3FFF) | (1u << 16);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
     return d;
 }
 // instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): D = fp32 (c_format 1, bits [4,6)), A = B = bf16
 // (format 1, bits [7,10) and [10,13)), both K-major (bits 15, 16 = 0), N >> 3 in [17,23), M >> 4 in [24,29)
 __device__ __forceinline__ uint32_t make_idesc() {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s2u(bar)) : "memory");
 }
 
 struct Epi {
@@ -81,7 +95,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     uint64_t *empty = full + STAGES;
     uint64_t *acc_full = empty + STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role index
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;   // N-tiles of one M-tile are adjacent in launch order: A is read from HBM once
     const int nk = K / BK;
 
@@ -97,19 +111,23 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-    if (warp == 0 && lane == 0) {
+    // Producer and MMA warps run their loops with all 32 lanes (warp-uniform control flow keeps the descriptors in uniform
+    // registers); one elected lane issues the TMA / tcgen05 instructions.
+    if (warp == 0) {
         // ---- TMA producer ----
         for (int kb = 0; kb < nk; ++kb) {
             const int s = kb % STAGES;
             if (kb >= STAGES) mb_wait(&empty[s], ((kb / STAGES) - 1) & 1);
             unsigned char *a = smem + (size_t)s * STAGE_BYTES, *b = a + (size_t)BM * BK * 2;
-            mb_expect(&full[s], (uint32_t)STAGE_BYTES);
-            tma_2d(a, &mapA, kb * BK, m0, &full[s]);
-            tma_2d(b, &mapB, kb * BK, n0, &full[s]);
+            if (elect_one()) {
+                mb_expect(&full[s], (uint32_t)STAGE_BYTES);
+                tma_2d(a, &mapA, kb * BK, m0, &full[s]);
+                tma_2d(b, &mapB, kb * BK, n0, &full[s]);
+            }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         // ---- MMA issuer ----
         const uint32_t idesc = make_idesc();
         for (int kb = 0; kb < nk; ++kb) {
@@ -117,19 +135,14 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             mb_wait(&full[s], (kb / STAGES) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a_addr = s2u(smem + (size_t)s * STAGE_BYTES), b_addr = a_addr + BM * BK * 2;
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {     // UMMA_K = 16 for bf16: advance 32 bytes inside the swizzled row
-                const uint64_t da = make_desc(a_addr + k * 32), db = make_desc(b_addr + k * 32);
-                const uint32_t accum = (kb | k) ? 1u : 0u;
-                asm volatile(
-                    "{\n\t.reg .pred p;\n\t"
-                    "setp.ne.b32 p, %4, 0;\n\t"
-                    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+                for (int k = 0; k < BK / 16; ++k)      // UMMA_K = 16 for bf16: advance 32 bytes inside the swizzled row
+                    umma_f16(tmem, make_desc(a_addr + k * 32), make_desc(b_addr + k * 32), idesc, (kb | k) ? 1u : 0u);
+                umma_commit(&empty[s]);   // frees the smem stage once the MMAs that read it have completed (implies fence::before_thread_sync)
+                if (kb == nk - 1) umma_commit(acc_full);
             }
-            // frees the smem stage once the MMAs that read it have completed (implies fence::before_thread_sync)
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s2u(&empty[s])) : "memory");
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s2u(acc_full)) : "memory");
     } else if (warp >= 2) {
         // ---- epilogue: warp w may touch TMEM lanes [32 (w % 4), +32) ----
         mb_wait(acc_full, 0);
@@ -195,36 +208,27 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 // ---- fused feed-forward sublayer -------------------------------------------------------------------------------------------
 // out = BN( X + W2 relu(W1 X + b1) + b2 )  (LP.mha:140-160: SkipConnection(Linear 128->512, ReLU, Linear 512->128) + Normalization)
 // in ONE persistent kernel: the [rows][512] hidden activation never leaves the SM.  A CTA owns a PAIR of 128-row tiles (so
-// every weight chunk fetched from L2 feeds 256 rows) and walks the hidden dimension in 4 chunks of 128:
-//     acc1[t] (TMEM) = X[t] . W1[c]^T            (tcgen05.mma, K = 128)
-//     H[t]    (smem) = bf16(relu(acc1[t] + b1))  (chunk-epilogue warps: tcgen05.ld -> registers -> 128B-swizzled K-major smem)
-//     acc2[t] (TMEM) += H[t] . W2[:, c]^T        (tcgen05.mma, K = 128)
-// and after the 4th chunk the drain warps read acc2[t], add bias + residual, apply the folded BatchNorm and store bf16.
-// TMEM: acc1[2] + acc2[2] = 512 columns.  smem: X[2] + H[2] + W1 chunk + W2 chunk = 6 x 32 KB.
+// every weight chunk fetched from L2 feeds 256 rows) and walks the hidden dimension in 8 chunks of 64:
+//     acc1[t][b] (TMEM, 64 cols)  = X[t] . W1[chunk]^T             tcgen05.mma M128 N64, K = 128
+//     H[t][b]    (smem, 16 KB)    = bf16(relu(acc1[t][b] + b1))    chunk-epilogue warps: tcgen05.ld -> cvt.relu -> 128B-swizzled K-major smem
+//     acc2[t]    (TMEM, 128 cols) += H[t][b] . W2[:, chunk]^T      tcgen05.mma M128 N128, K = 64
+// with b = chunk & 1, so the tensor core runs GEMM-1 of chunk c+1 while the epilogue warps convert chunk c.  After the 8th chunk
+// the drain warps read acc2[t], add the bias, apply the folded BatchNorm and store bf16.  The residual never touches a CUDA core:
+// acc2[t] is initialised by the tensor core as X[t] . I (exact in fp32), so X is read from HBM exactly once.
+// TMEM: 2 tiles x (2 x 64 + 128) = 512 columns.  smem: X[2] 64 KB + H[2][2] 64 KB + W1[2] 32 KB + W2[2] 32 KB.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2..9 = chunk epilogue (4 per tile), 10..13 = drain (both tiles in turn).
 constexpr int FF_THREADS = 32 * 14;
-constexpr uint32_t FF_TILE = 128 * 128 * 2;      // one [128][128] bf16 operand tile = two [128][64] swizzled boxes
-constexpr size_t FF_SMEM = 6 * (size_t)FF_TILE + 1024 /*align*/ + (512 + 3 * 128) * 4 + 256 /*barriers*/;
+constexpr int FF_NC = 8;                         // hidden chunks of 64
+constexpr uint32_t FF_TILE = 128 * 128 * 2;      // X tile: [128][128] bf16 = two [128][64] swizzled boxes
+constexpr uint32_t FF_BOX = 128 * 64 * 2;        // one [128][64] swizzled box (H chunk, W2 chunk); the W1 chunk is two [64][64] boxes
+constexpr uint32_t FF_IDN = 64 * 64 * 2;          // 64 x 64 identity (bf16, swizzled): the residual is added by the tensor core, acc2 += X . I
+constexpr size_t FF_SMEM = 2 * (size_t)FF_TILE + 8 * (size_t)FF_BOX + FF_IDN + 1024 /*align*/ + (512 + 3 * 128) * 4 + 256 /*barriers*/;
 
-__device__ __forceinline__ void mma_tile_k128(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool fresh) {
-#pragma unroll
-    for (int kb = 0; kb < 2; ++kb) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint64_t da = make_desc(a_addr + kb * (FF_TILE / 2) + k * 32), db = make_desc(b_addr + kb * (FF_TILE / 2) + k * 32);
-            const uint32_t accum = (fresh && kb == 0 && k == 0) ? 0u : 1u;
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "setp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
-        }
-    }
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s2u(bar)) : "memory");
+__device__ __forceinline__ uint32_t make_idesc_n(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 __device__ __forceinline__ void mb_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(bar)) : "memory"); }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t *r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
         "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -233,7 +237,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
           "=r"(r[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// bf16x2 {lo = relu(a), hi = relu(b)} in one instruction
+__device__ __forceinline__ uint32_t cvt_relu_bf16x2(float a, float b) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    return d;
 }
 
 __global__ void __launch_bounds__(FF_THREADS, 1)
@@ -242,23 +252,32 @@ ff_fused_tcgen05(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                  const float *__restrict__ b2, const float *__restrict__ s2, const float *__restrict__ t2) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    unsigned char *sX = smem, *sH = smem + 2 * FF_TILE, *sW1 = smem + 4 * FF_TILE, *sW2 = smem + 5 * FF_TILE;
-    float *sb1 = reinterpret_cast<float *>(smem + 6 * FF_TILE), *sb2 = sb1 + 512, *ss2 = sb2 + 128, *st2 = ss2 + 128;
+    unsigned char *sX = smem;                             // [tile][FF_TILE]
+    unsigned char *sH = smem + 2 * FF_TILE;               // [tile][buf][FF_BOX]
+    unsigned char *sW1 = sH + 4 * FF_BOX;                 // [buf][FF_BOX]: two [64 rows][64 k] boxes
+    unsigned char *sW2 = sW1 + 2 * FF_BOX;                // [buf][FF_BOX]: one [128 rows][64 k] box
+    unsigned char *sI = sW2 + 2 * FF_BOX;                 // [64 n][64 k] identity, K-major, 128-byte swizzle
+    float *sb1 = reinterpret_cast<float *>(sI + FF_IDN), *sb2 = sb1 + 512, *ss2 = sb2 + 128, *st2 = ss2 + 128;
     uint64_t *bars = reinterpret_cast<uint64_t *>(st2 + 128);
-    uint64_t *x_full = bars, *x_empty = bars + 2, *w1_full = bars + 4, *w1_empty = bars + 5, *w2_full = bars + 6, *w2_empty = bars + 7,
-             *acc1_full = bars + 8, *h_full = bars + 10, *acc2_full = bars + 12, *acc2_empty = bars + 14;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t *x_full = bars, *x_empty = bars + 2, *w1_full = bars + 4, *w1_empty = bars + 6, *w2_full = bars + 8, *w2_empty = bars + 10,
+             *acc1_full = bars + 12 /*[t*2+buf]*/, *h_full = bars + 16 /*[t*2+buf]*/, *acc2_full = bars + 20, *acc2_empty = bars + 22;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 24);
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role index
     const int n_pairs = (M + 255) / 256;
 
     for (int i = threadIdx.x; i < 512; i += FF_THREADS) sb1[i] = b1[i];
     for (int i = threadIdx.x; i < 128; i += FF_THREADS) { sb2[i] = b2[i]; ss2[i] = s2[i]; st2[i] = t2[i]; }
+    for (int i = threadIdx.x; i < (int)FF_IDN / 2; i += FF_THREADS) {     // element (n, k) lives in 16-byte chunk (k / 8) ^ (n & 7) of row n
+        const int n = i >> 6, ch = (i >> 3) & 7, e = i & 7, k = ((ch ^ (n & 7)) << 3) + e;
+        reinterpret_cast<unsigned short *>(sI)[i] = (k == n) ? (unsigned short)0x3F80 : (unsigned short)0;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (threadIdx.x == 0) {
         for (int t = 0; t < 2; ++t) {
-            mb_init(&x_full[t], 1); mb_init(&x_empty[t], 1); mb_init(&acc1_full[t], 1); mb_init(&h_full[t], 128);
-            mb_init(&acc2_full[t], 1); mb_init(&acc2_empty[t], 128);
+            mb_init(&x_full[t], 1); mb_init(&x_empty[t], 1); mb_init(&w1_full[t], 1); mb_init(&w1_empty[t], 1); mb_init(&w2_full[t], 1);
+            mb_init(&w2_empty[t], 1); mb_init(&acc2_full[t], 1); mb_init(&acc2_empty[t], 128);
         }
-        mb_init(w1_full, 1); mb_init(w1_empty, 1); mb_init(w2_full, 1); mb_init(w2_empty, 1);
+        for (int i = 0; i < 4; ++i) { mb_init(&acc1_full[i], 1); mb_init(&h_full[i], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -268,98 +287,132 @@ ff_fused_tcgen05(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    const int my_pairs = blockIdx.x < n_pairs ? (n_pairs - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const uint32_t n_it = (uint32_t)my_pairs * FF_NC;           // chunk steps of this CTA
 
+    // Producer and MMA warps run their loops with all 32 lanes (warp-uniform control flow keeps descriptors in uniform
+    // registers); one elected lane issues the TMA / tcgen05 instructions.
     if (warp == 0) {
-        if (lane == 0) {
-            // ---- TMA producer ----
-            uint32_t it = 0, pc = 0;
-            for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pc) {
-                for (int t = 0; t < 2; ++t) {
-                    if (pc > 0) mb_wait(&x_empty[t], (pc - 1) & 1);
-                    mb_expect(&x_full[t], FF_TILE);
-                    tma_2d(sX + t * FF_TILE, &mapX, 0, pair * 256 + t * 128, &x_full[t]);
-                    tma_2d(sX + t * FF_TILE + FF_TILE / 2, &mapX, 64, pair * 256 + t * 128, &x_full[t]);
+        {
+            // ---- TMA producer: chunk step `it` uses weight buffers it & 1 (phase (it >> 1) & 1) ----
+            for (uint32_t it = 0; it < n_it; ++it) {
+                const int c = it % FF_NC, buf = it & 1;
+                const uint32_t pc = it / FF_NC;
+                const int pair = blockIdx.x + (int)pc * gridDim.x;
+                if (c == 0) {
+                    for (int t = 0; t < 2; ++t) {
+                        if (pc > 0) mb_wait(&x_empty[t], (pc - 1) & 1);
+                        if (elect_one()) {
+                            mb_expect(&x_full[t], FF_TILE);
+                            tma_2d(sX + t * FF_TILE, &mapX, 0, pair * 256 + t * 128, &x_full[t]);
+                            tma_2d(sX + t * FF_TILE + FF_BOX, &mapX, 64, pair * 256 + t * 128, &x_full[t]);
+                        }
+                    }
                 }
-                for (int c = 0; c < 4; ++c, ++it) {
-                    if (it > 0) mb_wait(w1_empty, (it - 1) & 1);
-                    mb_expect(w1_full, FF_TILE);
-                    tma_2d(sW1, &mapW1, 0, c * 128, w1_full);
-                    tma_2d(sW1 + FF_TILE / 2, &mapW1, 64, c * 128, w1_full);
-                    if (it > 0) mb_wait(w2_empty, (it - 1) & 1);
-                    mb_expect(w2_full, FF_TILE);
-                    tma_2d(sW2, &mapW2, c * 128, 0, w2_full);
-                    tma_2d(sW2 + FF_TILE / 2, &mapW2, c * 128 + 64, 0, w2_full);
+                if (it >= 2) mb_wait(&w1_empty[buf], ((it >> 1) - 1) & 1);
+                if (elect_one()) {
+                    mb_expect(&w1_full[buf], FF_BOX);
+                    tma_2d(sW1 + buf * FF_BOX, &mapW1, 0, c * 64, &w1_full[buf]);
+                    tma_2d(sW1 + buf * FF_BOX + FF_BOX / 2, &mapW1, 64, c * 64, &w1_full[buf]);
+                }
+                if (it >= 2) mb_wait(&w2_empty[buf], ((it >> 1) - 1) & 1);
+                if (elect_one()) {
+                    mb_expect(&w2_full[buf], FF_BOX);
+                    tma_2d(sW2 + buf * FF_BOX, &mapW2, c * 64, 0, &w2_full[buf]);
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ---- MMA issuer ----
-            const uint32_t idesc = make_idesc();
-            uint32_t it = 0, pc = 0;
-            for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pc) {
-                for (int c = 0; c < 4; ++c, ++it) {
-                    mb_wait(w1_full, it & 1);
-                    for (int t = 0; t < 2; ++t) {
-                        if (c == 0) mb_wait(&x_full[t], pc & 1);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        // acc1[t] was drained by the chunk epilogue of the previous chunk (h_full[t] waited below before MMA2)
-                        mma_tile_k128(tmem + t * 128, s2u(sX + t * FF_TILE), s2u(sW1), idesc, true);
-                        umma_commit(&acc1_full[t]);
-                        if (c == 3) umma_commit(&x_empty[t]);
+        {
+            // ---- MMA issuer: GEMM-1 of step `it` is issued BEFORE GEMM-2 of step it-1, so the tensor core works while the
+            // epilogue warps convert step it-1 (at a pair boundary the order flips: the next X tile is still in flight) ----
+            const uint32_t idesc1 = make_idesc_n(64), idesc2 = make_idesc_n(128);
+            auto gemm1 = [&](uint32_t it) {
+                const int c = it % FF_NC, buf = it & 1;
+                const uint32_t pc = it / FF_NC;
+                mb_wait(&w1_full[buf], (it >> 1) & 1);
+                for (int t = 0; t < 2; ++t) {
+                    if (c == 0) mb_wait(&x_full[t], pc & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    // acc1[t][buf] was drained by the chunk epilogue of step it-2 (h_full waited before GEMM-2 of that step)
+                    const uint32_t a = s2u(sX + t * FF_TILE), b = s2u(sW1 + buf * FF_BOX), d = tmem + t * 128 + buf * 64;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_f16(d, make_desc(a + kb * FF_BOX + k * 32), make_desc(b + kb * (FF_BOX / 2) + k * 32), idesc1, (kb | k) ? 1u : 0u);
+                        umma_commit(&acc1_full[t * 2 + buf]);
+                        if (c == FF_NC - 1) umma_commit(&x_empty[t]);
+                        if (t == 1) umma_commit(&w1_empty[buf]);
                     }
-                    umma_commit(w1_empty);
-                    mb_wait(w2_full, it & 1);
-                    for (int t = 0; t < 2; ++t) {
-                        mb_wait(&h_full[t], it & 1);
-                        if (c == 0 && pc > 0) mb_wait(&acc2_empty[t], (pc - 1) & 1);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        mma_tile_k128(tmem + 256 + t * 128, s2u(sH + t * FF_TILE), s2u(sW2), idesc, c == 0);
-                        if (c == 3) umma_commit(&acc2_full[t]);
-                    }
-                    umma_commit(w2_empty);
                 }
+            };
+            auto gemm2 = [&](uint32_t it) {
+                const int c = it % FF_NC, buf = it & 1;
+                const uint32_t pc = it / FF_NC;
+                mb_wait(&w2_full[buf], (it >> 1) & 1);
+                for (int t = 0; t < 2; ++t) {
+                    mb_wait(&h_full[t * 2 + buf], (it >> 1) & 1);
+                    if (c == 0 && pc > 0) mb_wait(&acc2_empty[t], (pc - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a = s2u(sH + (t * 2 + buf) * FF_BOX), b = s2u(sW2 + buf * FF_BOX), d = tmem + 256 + t * 128;
+                    const uint32_t xa = s2u(sX + t * FF_TILE), ia = s2u(sI);
+                    if (elect_one()) {
+                        if (c == 0) {       // residual: acc2[t][:, kb*64 .. +64) = X[t][:, kb*64 .. +64) . I
+#pragma unroll
+                            for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) umma_f16(d + kb * 64, make_desc(xa + kb * FF_BOX + k * 32), make_desc(ia + k * 32), idesc1, k ? 1u : 0u);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_f16(d, make_desc(a + k * 32), make_desc(b + k * 32), idesc2, 1u);
+                        if (c == FF_NC - 1) umma_commit(&acc2_full[t]);
+                        if (t == 1) umma_commit(&w2_empty[buf]);
+                    }
+                }
+            };
+            for (uint32_t it = 0; it < n_it; ++it) {
+                if (it % FF_NC == 0) { if (it > 0) gemm2(it - 1); gemm1(it); }
+                else { gemm1(it); gemm2(it - 1); }
             }
+            if (n_it > 0) gemm2(n_it - 1);
         }
     } else if (warp < 10) {
-        // ---- chunk epilogue: acc1[t] -> relu(+b1) -> bf16 -> H[t] (K-major, 128-byte swizzle: 16-byte chunk j of row r at j ^ (r & 7)) ----
+        // ---- chunk epilogue: acc1[t][buf] -> relu(+b1) -> bf16 -> H[t][buf] (K-major, 128-byte swizzle: 16-byte chunk j of row r at j ^ (r & 7)) ----
         const int t = (warp - 2) >> 2, q = warp & 3, row = q * 32 + lane;
-        unsigned char *hrow = sH + t * FF_TILE + row * 128;
-        uint32_t it = 0;
-        for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-            for (int c = 0; c < 4; ++c, ++it) {
-                mb_wait(&acc1_full[t], it & 1);   // also: MMA2 of the previous chunk (which read H[t]) has completed
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-                for (int g = 0; g < 4; ++g) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 128 + g * 32), r);
-                    const float *bb = sb1 + c * 128 + g * 32;
+        for (uint32_t it = 0; it < n_it; ++it) {
+            const int c = it % FF_NC, buf = it & 1;
+            // acc1_full also tells that GEMM-2 of step it-2 (the last reader of H[t][buf]) has completed: it was issued earlier
+            mb_wait(&acc1_full[t * 2 + buf], (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t r[64];
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 128 + buf * 64);
+            tmem_ld32_nowait(taddr, r);
+            tmem_ld32_nowait(taddr + 32, r + 32);
+            tmem_ld_wait();
+            unsigned char *hrow = sH + (t * 2 + buf) * FF_BOX + row * 128;
+            const float4 *bb = reinterpret_cast<const float4 *>(sb1 + c * 64);
 #pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8) {
-                        uint4 o;
-                        __nv_bfloat162 *op = reinterpret_cast<__nv_bfloat162 *>(&o);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float v0 = fmaxf(__uint_as_float(r[j8 * 8 + 2 * j]) + bb[j8 * 8 + 2 * j], 0.0f);
-                            const float v1 = fmaxf(__uint_as_float(r[j8 * 8 + 2 * j + 1]) + bb[j8 * 8 + 2 * j + 1], 0.0f);
-                            op[j] = __floats2bfloat162_rn(v0, v1);
-                        }
-                        const int ch = g * 4 + j8;                               // 16-byte chunk index inside the 256-byte row: box = ch / 8
-                        *reinterpret_cast<uint4 *>(hrow + (ch >> 3) * (FF_TILE / 2) + (((ch & 7) ^ (row & 7)) << 4)) = o;
-                    }
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> visible to the tensor core
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                mb_arrive(&h_full[t]);
+            for (int j = 0; j < 8; ++j) {
+                const float4 c0 = bb[2 * j], c1 = bb[2 * j + 1];
+                uint4 o;
+                o.x = cvt_relu_bf16x2(__uint_as_float(r[8 * j]) + c0.x, __uint_as_float(r[8 * j + 1]) + c0.y);
+                o.y = cvt_relu_bf16x2(__uint_as_float(r[8 * j + 2]) + c0.z, __uint_as_float(r[8 * j + 3]) + c0.w);
+                o.z = cvt_relu_bf16x2(__uint_as_float(r[8 * j + 4]) + c1.x, __uint_as_float(r[8 * j + 5]) + c1.y);
+                o.w = cvt_relu_bf16x2(__uint_as_float(r[8 * j + 6]) + c1.z, __uint_as_float(r[8 * j + 7]) + c1.w);
+                *reinterpret_cast<uint4 *>(hrow + ((j ^ (row & 7)) << 4)) = o;
             }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> visible to the tensor core
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mb_arrive(&h_full[t * 2 + buf]);
         }
     } else {
-        // ---- drain: acc2[t] + b2 + residual -> folded BatchNorm -> bf16 -> global ----
+        // ---- drain: acc2[t] (= residual + FF) + b2 -> folded BatchNorm -> bf16 -> global ----
         const int q = warp & 3, row = q * 32 + lane;
-        uint32_t pc = 0;
-        for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pc) {
+        for (int pc = 0; pc < my_pairs; ++pc) {
+            const int pair = blockIdx.x + pc * gridDim.x;
 #pragma unroll 1
             for (int t = 0; t < 2; ++t) {
                 const long long m = (long long)pair * 256 + t * 128 + row;
@@ -368,21 +421,19 @@ ff_fused_tcgen05(const __grid_constant__ CUtensorMap mapX, const __grid_constant
 #pragma unroll 1
                 for (int g = 0; g < 4; ++g) {
                     uint32_t r[32];
-                    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(256 + t * 128 + g * 32), r);
+                    tmem_ld32_nowait(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(256 + t * 128 + g * 32), r);
+                    tmem_ld_wait();
                     if (m < M) {
 #pragma unroll
                         for (int j8 = 0; j8 < 4; ++j8) {
                             const int n = g * 32 + j8 * 8;
-                            const uint4 rr = *reinterpret_cast<const uint4 *>(X + m * 128 + n);
-                            const __nv_bfloat162 *rp2 = reinterpret_cast<const __nv_bfloat162 *>(&rr);
                             uint4 o;
                             __nv_bfloat162 *op = reinterpret_cast<__nv_bfloat162 *>(&o);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const float2 f = __bfloat1622float2(rp2[j]);
                                 const int nn = n + 2 * j;
-                                const float v0 = (__uint_as_float(r[j8 * 8 + 2 * j]) + sb2[nn] + f.x) * ss2[nn] + st2[nn];
-                                const float v1 = (__uint_as_float(r[j8 * 8 + 2 * j + 1]) + sb2[nn + 1] + f.y) * ss2[nn + 1] + st2[nn + 1];
+                                const float v0 = (__uint_as_float(r[j8 * 8 + 2 * j]) + sb2[nn]) * ss2[nn] + st2[nn];
+                                const float v1 = (__uint_as_float(r[j8 * 8 + 2 * j + 1]) + sb2[nn + 1]) * ss2[nn + 1] + st2[nn + 1];
                                 op[j] = __floats2bfloat162_rn(v0, v1);
                             }
                             *reinterpret_cast<uint4 *>(out + m * 128 + n) = o;
@@ -552,7 +603,7 @@ int launch_ff_fused(cudaStream_t st, const __nv_bfloat16 *X, const __nv_bfloat16
     if (M <= 0) return 0;
     if (!b1 || !b2 || !s2 || !t2) { lpbox_set_error("fused FF: bias / scale / shift vectors are required"); return LPBOX_E_INVALID; }
     CUtensorMap mx, m1, m2;
-    if (!make_map(&mx, X, (uint64_t)M, 128, 128) || !make_map(&m1, W1, 512, 128, 128) || !make_map(&m2, W2, 128, 512, 128)) {
+    if (!make_map(&mx, X, (uint64_t)M, 128, 128) || !make_map(&m1, W1, 512, 128, 64) || !make_map(&m2, W2, 128, 512, 128)) {
         lpbox_set_error("cuTensorMapEncodeTiled failed"); return LPBOX_E_CUDA;
     }
     static bool attr = false;
