@@ -27,6 +27,7 @@ constexpr int BM = 128, BN = 128, BK = 64, STAGES = 2;   // K is 128..2560: 2 st
 constexpr int GEMM_THREADS = 192;          // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..5: epilogue
 constexpr uint32_t TMEM_COLS = 128;        // 128 lanes x 128 fp32 columns = one 128 x 128 accumulator tile
 constexpr size_t STAGE_BYTES = (size_t)(BM + BN) * BK * 2;
+static_assert(STAGES * STAGE_BYTES >= (size_t)BM * BN * 4, "the epilogue stages a fp32 tile in the operand ring");
 constexpr size_t GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ uint32_t s2u(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -78,6 +79,18 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s2u(bar)) : "memory");
 }
+
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct Epi {
     const float *bias;            // [N] or NULL
@@ -145,60 +158,62 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         }
     } else if (warp >= 2) {
         // ---- epilogue: warp w may touch TMEM lanes [32 (w % 4), +32) ----
+        // Phase 1: accumulator rows -> fp32 staging tile in the (now idle) operand ring, 16-byte chunks XOR-swizzled by row.
+        // Phase 2: the same warp walks its 32 rows; one instruction covers one whole row, so bias / residual / scale / shift
+        // are per-lane constants and every global access is a full 128-byte line.
+        const int q = warp & 3, r = q * 32 + lane;
+        const int n = n0 + 4 * lane;
+        uint2 rv[2][8];                                                        // residual rows in groups of 8, one group in flight ahead
+        auto load_resid = [&](uint2 (&dst)[8], int g) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int m = m0 + q * 32 + g * 8 + i;
+                dst[i] = m < M ? *reinterpret_cast<const uint2 *>(ep.resid + (size_t)m * ldc + n) : make_uint2(0u, 0u);
+            }
+        };
+        if (ep.resid) load_resid(rv[0], 0);
         mb_wait(acc_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int q = warp & 3;
-        const int m = m0 + q * 32 + lane;
+        float *stage = reinterpret_cast<float *>(smem);                       // [128][128] fp32 = 64 KB = STAGES * STAGE_BYTES
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
-                "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                  "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-                  "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-                  "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (m < M) {
-                const int nb = n0 + c0;
-                __nv_bfloat16 *crow = C + (size_t)m * ldc + nb;
-                const __nv_bfloat16 *rrow = ep.resid ? ep.resid + (size_t)m * ldc + nb : nullptr;
+            uint32_t v[32];
+            tmem_ld32_nowait(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld_wait();
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {                      // 8 columns = one 16-byte store per group
-                    float v[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-                    if (ep.bias) {
-                        const float4 b0 = *reinterpret_cast<const float4 *>(ep.bias + nb + g * 8), b1 = *reinterpret_cast<const float4 *>(ep.bias + nb + g * 8 + 4);
-                        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                    }
-                    if (rrow) {
-                        const uint4 rr = *reinterpret_cast<const uint4 *>(rrow + g * 8);
-                        const __nv_bfloat162 *rp2 = reinterpret_cast<const __nv_bfloat162 *>(&rr);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(rp2[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
-                    }
-                    if (ep.relu) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
-                    }
-                    if (ep.scale) {
-                        const float4 s0 = *reinterpret_cast<const float4 *>(ep.scale + nb + g * 8), s1 = *reinterpret_cast<const float4 *>(ep.scale + nb + g * 8 + 4);
-                        const float4 t0 = *reinterpret_cast<const float4 *>(ep.shift + nb + g * 8), t1 = *reinterpret_cast<const float4 *>(ep.shift + nb + g * 8 + 4);
-                        v[0] = v[0] * s0.x + t0.x; v[1] = v[1] * s0.y + t0.y; v[2] = v[2] * s0.z + t0.z; v[3] = v[3] * s0.w + t0.w;
-                        v[4] = v[4] * s1.x + t1.x; v[5] = v[5] * s1.y + t1.y; v[6] = v[6] * s1.z + t1.z; v[7] = v[7] * s1.w + t1.w;
-                    }
-                    uint4 o;
-                    __nv_bfloat162 *op = reinterpret_cast<__nv_bfloat162 *>(&o);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) op[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                    *reinterpret_cast<uint4 *>(crow + g * 8) = o;
-                }
-            }
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<uint4 *>(stage + r * BN + ((((c0 >> 2) + j) ^ (r & 7)) << 2)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
+        __syncwarp();
+        float4 bi = make_float4(0.f, 0.f, 0.f, 0.f), sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ep.bias) bi = *reinterpret_cast<const float4 *>(ep.bias + n);
+        if (ep.scale) { sc = *reinterpret_cast<const float4 *>(ep.scale + n); sh = *reinterpret_cast<const float4 *>(ep.shift + n); }
+        auto finish_rows = [&](const uint2 (&res)[8], int g) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = q * 32 + g * 8 + i, m = m0 + rr;
+                if (m >= M) continue;
+                float4 a = *reinterpret_cast<const float4 *>(stage + rr * BN + ((lane ^ (rr & 7)) << 2));
+                a.x += bi.x; a.y += bi.y; a.z += bi.z; a.w += bi.w;
+                if (ep.resid) {
+                    const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&res[i].x)), f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&res[i].y));
+                    a.x += f0.x; a.y += f0.y; a.z += f1.x; a.w += f1.y;
+                }
+                if (ep.relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+                a.x = a.x * sc.x + sh.x; a.y = a.y * sc.y + sh.y; a.z = a.z * sc.z + sh.z; a.w = a.w * sc.w + sh.w;
+                uint2 o;
+                *reinterpret_cast<__nv_bfloat162 *>(&o.x) = __floats2bfloat162_rn(a.x, a.y);
+                *reinterpret_cast<__nv_bfloat162 *>(&o.y) = __floats2bfloat162_rn(a.z, a.w);
+                *reinterpret_cast<uint2 *>(C + (size_t)m * ldc + n) = o;
+            }
+        };
+        if (ep.resid) load_resid(rv[1], 1);
+        finish_rows(rv[0], 0);
+        if (ep.resid) load_resid(rv[0], 2);
+        finish_rows(rv[1], 1);
+        if (ep.resid) load_resid(rv[1], 3);
+        finish_rows(rv[0], 2);
+        finish_rows(rv[1], 3);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -216,8 +231,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 // the drain warps read acc2[t], add the bias, apply the folded BatchNorm and store bf16.  The residual never touches a CUDA core:
 // acc2[t] is initialised by the tensor core as X[t] . I (exact in fp32), so X is read from HBM exactly once.
 // TMEM: 2 tiles x (2 x 64 + 128) = 512 columns.  smem: X[2] 64 KB + H[2][2] 64 KB + W1[2] 32 KB + W2[2] 32 KB.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2..9 = chunk epilogue (4 per tile), 10..13 = drain (both tiles in turn).
-constexpr int FF_THREADS = 32 * 14;
+// Warp roles: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2..9 = chunk epilogue (4 per tile), 10..17 = drain (4 per tile).
+constexpr int FF_THREADS = 32 * 18;
 constexpr int FF_NC = 8;                         // hidden chunks of 64
 constexpr uint32_t FF_TILE = 128 * 128 * 2;      // X tile: [128][128] bf16 = two [128][64] swizzled boxes
 constexpr uint32_t FF_BOX = 128 * 64 * 2;        // one [128][64] swizzled box (H chunk, W2 chunk); the W1 chunk is two [64][64] boxes
@@ -228,17 +243,6 @@ __device__ __forceinline__ uint32_t make_idesc_n(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 __device__ __forceinline__ void mb_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(bar)) : "memory"); }
-__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t *r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
-        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
-          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
-          "=r"(r[31])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // bf16x2 {lo = relu(a), hi = relu(b)} in one instruction
 __device__ __forceinline__ uint32_t cvt_relu_bf16x2(float a, float b) {
     uint32_t d;
@@ -266,7 +270,7 @@ ff_fused_tcgen05(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     const int n_pairs = (M + 255) / 256;
 
     for (int i = threadIdx.x; i < 512; i += FF_THREADS) sb1[i] = b1[i];
-    for (int i = threadIdx.x; i < 128; i += FF_THREADS) { sb2[i] = b2[i]; ss2[i] = s2[i]; st2[i] = t2[i]; }
+    for (int i = threadIdx.x; i < 128; i += FF_THREADS) { sb2[i] = b2[i]; ss2[i] = s2[i]; st2[i] = b2[i] * s2[i] + t2[i]; }   // (acc + b2) s2 + t2 = acc s2 + st2
     for (int i = threadIdx.x; i < (int)FF_IDN / 2; i += FF_THREADS) {     // element (n, k) lives in 16-byte chunk (k / 8) ^ (n & 7) of row n
         const int n = i >> 6, ch = (i >> 3) & 7, e = i & 7, k = ((ch ^ (n & 7)) << 3) + e;
         reinterpret_cast<unsigned short *>(sI)[i] = (k == n) ? (unsigned short)0x3F80 : (unsigned short)0;
@@ -409,40 +413,35 @@ ff_fused_tcgen05(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             mb_arrive(&h_full[t * 2 + buf]);
         }
     } else {
-        // ---- drain: acc2[t] (= residual + FF) + b2 -> folded BatchNorm -> bf16 -> global ----
-        const int q = warp & 3, row = q * 32 + lane;
+        // ---- drain: acc2[t] (= residual + FF) -> (+ b2, folded BatchNorm) -> bf16 -> global ----
+        const int t = (warp - 10) >> 2, q = warp & 3, row = q * 32 + lane;
         for (int pc = 0; pc < my_pairs; ++pc) {
             const int pair = blockIdx.x + pc * gridDim.x;
+            const long long m = (long long)pair * 256 + t * 128 + row;
+            mb_wait(&acc2_full[t], pc & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-            for (int t = 0; t < 2; ++t) {
-                const long long m = (long long)pair * 256 + t * 128 + row;
-                mb_wait(&acc2_full[t], pc & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-                for (int g = 0; g < 4; ++g) {
-                    uint32_t r[32];
-                    tmem_ld32_nowait(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(256 + t * 128 + g * 32), r);
-                    tmem_ld_wait();
-                    if (m < M) {
+            for (int g = 0; g < 4; ++g) {
+                uint32_t r[32];
+                tmem_ld32_nowait(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(256 + t * 128 + g * 32), r);
+                tmem_ld_wait();
+                if (m < M) {
+                    const float4 *sc4 = reinterpret_cast<const float4 *>(ss2 + g * 32), *sh4 = reinterpret_cast<const float4 *>(st2 + g * 32);
 #pragma unroll
-                        for (int j8 = 0; j8 < 4; ++j8) {
-                            const int n = g * 32 + j8 * 8;
-                            uint4 o;
-                            __nv_bfloat162 *op = reinterpret_cast<__nv_bfloat162 *>(&o);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int nn = n + 2 * j;
-                                const float v0 = (__uint_as_float(r[j8 * 8 + 2 * j]) + sb2[nn]) * ss2[nn] + st2[nn];
-                                const float v1 = (__uint_as_float(r[j8 * 8 + 2 * j + 1]) + sb2[nn + 1]) * ss2[nn + 1] + st2[nn + 1];
-                                op[j] = __floats2bfloat162_rn(v0, v1);
-                            }
-                            *reinterpret_cast<uint4 *>(out + m * 128 + n) = o;
-                        }
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        const float4 a0 = sc4[2 * j8], a1 = sc4[2 * j8 + 1], c0 = sh4[2 * j8], c1 = sh4[2 * j8 + 1];
+                        uint4 o;
+                        __nv_bfloat162 *op = reinterpret_cast<__nv_bfloat162 *>(&o);
+                        op[0] = __floats2bfloat162_rn(__uint_as_float(r[j8 * 8 + 0]) * a0.x + c0.x, __uint_as_float(r[j8 * 8 + 1]) * a0.y + c0.y);
+                        op[1] = __floats2bfloat162_rn(__uint_as_float(r[j8 * 8 + 2]) * a0.z + c0.z, __uint_as_float(r[j8 * 8 + 3]) * a0.w + c0.w);
+                        op[2] = __floats2bfloat162_rn(__uint_as_float(r[j8 * 8 + 4]) * a1.x + c1.x, __uint_as_float(r[j8 * 8 + 5]) * a1.y + c1.y);
+                        op[3] = __floats2bfloat162_rn(__uint_as_float(r[j8 * 8 + 6]) * a1.z + c1.z, __uint_as_float(r[j8 * 8 + 7]) * a1.w + c1.w);
+                        *reinterpret_cast<uint4 *>(out + m * 128 + g * 32 + j8 * 8) = o;
                     }
                 }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                mb_arrive(&acc2_empty[t]);
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mb_arrive(&acc2_empty[t]);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -452,30 +451,35 @@ ff_fused_tcgen05(const __grid_constant__ CUtensorMap mapX, const __grid_constant
 
 // ---- small CUDA-core kernels ----------------------------------------------------------------------------------------------
 // embedding: h0[m][j] = sum_f We[j][f] x[m][f] + c[t][j],  c[t] = We[:,5:10] pe[t] + b  (LP.mha:229-235)
-// one thread = one token x 8 consecutive outputs (one 16-byte store)
+// a thread owns 8 consecutive outputs (its 40 weights live in registers) and walks tokens with stride 16 * gridDim.x;
+// the 16 threads of a token write one 256-byte row.
+constexpr int EMB_TOK = 64;   // tokens per thread
 __global__ void __launch_bounds__(256) embed_kernel(const float *__restrict__ x, long long Mtok, int T, const float *__restrict__ We5 /*[128][5]*/,
                                                     const float *__restrict__ cpos /*[T][128]*/, __nv_bfloat16 *__restrict__ h) {
-    __shared__ float sW[128 * 5];
-    for (int i = threadIdx.x; i < 640; i += 256) sW[i] = We5[i];
-    __syncthreads();
-    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;      // (token, group of 8 outputs)
-    if (idx >= Mtok * 16) return;
-    const long long m = idx >> 4;
-    const int j0 = (int)(idx & 15) * 8, t = (int)(m % T);
-    const float *xm = x + m * 5;
-    const float x0 = xm[0], x1 = xm[1], x2 = xm[2], x3 = xm[3], x4 = xm[4];
-    const float4 c0 = *reinterpret_cast<const float4 *>(cpos + t * 128 + j0), c1 = *reinterpret_cast<const float4 *>(cpos + t * 128 + j0 + 4);
-    float v[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    const int j0 = (threadIdx.x & 15) * 8, sub = threadIdx.x >> 4;          // 16 tokens in flight per block
+    float w[8][5];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float *wj = sW + (j0 + j) * 5;
-        v[j] += wj[0] * x0 + wj[1] * x1 + wj[2] * x2 + wj[3] * x3 + wj[4] * x4;
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int f = 0; f < 5; ++f) w[j][f] = We5[(j0 + j) * 5 + f];
+    const long long base = (long long)blockIdx.x * (16 * EMB_TOK);
+#pragma unroll 2
+    for (int i = 0; i < EMB_TOK; ++i) {
+        const long long m = base + i * 16 + sub;
+        if (m >= Mtok) break;
+        const int t = (int)(m % T);
+        const float *xm = x + m * 5;
+        const float x0 = xm[0], x1 = xm[1], x2 = xm[2], x3 = xm[3], x4 = xm[4];
+        const float4 c0 = *reinterpret_cast<const float4 *>(cpos + t * 128 + j0), c1 = *reinterpret_cast<const float4 *>(cpos + t * 128 + j0 + 4);
+        float v[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += w[j][0] * x0 + w[j][1] * x1 + w[j][2] * x2 + w[j][3] * x3 + w[j][4] * x4;
+        uint4 o;
+        __nv_bfloat162 *op = reinterpret_cast<__nv_bfloat162 *>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) op[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        *reinterpret_cast<uint4 *>(h + m * 128 + j0) = o;
     }
-    uint4 o;
-    __nv_bfloat162 *op = reinterpret_cast<__nv_bfloat162 *>(&o);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) op[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-    *reinterpret_cast<uint4 *>(h + m * 128 + j0) = o;
 }
 
 // attention for one variable per CTA: qkv [T][384] (q | k | v, head-major inside each third) -> heads [T][128]
@@ -709,7 +713,7 @@ extern "C" int lpbox_policy_forward_dev(lpbox_policy *p, void *stream, const flo
     const int T = p->T;
     for (int64_t r0 = 0; r0 < rows; r0 += p->chunk) {
         const long long R = std::min<long long>(p->chunk, rows - r0), Mt = R * T;
-        embed_kernel<<<(unsigned)((Mt * 16 + 255) / 256), 256, 0, st>>>(input_dev + r0 * T * 5, Mt, T, p->We5, p->cpos, p->h);
+        embed_kernel<<<(unsigned)((Mt + 16 * EMB_TOK - 1) / (16 * EMB_TOK)), 256, 0, st>>>(input_dev + r0 * T * 5, Mt, T, p->We5, p->cpos, p->h);
         p->launches++;
         __nv_bfloat16 *h = p->h, *h2 = p->h2;
         for (auto &L : p->layers) {
