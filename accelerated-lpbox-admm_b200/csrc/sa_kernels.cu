@@ -90,6 +90,7 @@ struct SaPost {
     float *G, *z1, *z2, *z3, *z4;
     const float *y1, *y2, *y3, *grad_in, *images, *eps, *nw, *stdv;
     float lambda1, rho1, rho2, rho3, rho4, step, minpix, maxpix;
+    const float *lambda1_img;   // per-image lambda1 (the batched lambda1 search), or NULL -> the scalar
     double rho4_d, k;
     float *hist;            // [n_img][n_elem] slot of this iteration, or NULL
 };
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(SA_T) sa_post_kernel(SaPost a) {
     const float gsum = block_sum(s, s_red);                                      // G.sum().item()  (:700)
     const float c4 = (float)(a.rho4_d * ((double)gsum - a.k));                   // cur_rho4*(G.sum().item() - k), a python float
     const float z4 = a.z4[img];
+    const float lambda1 = a.lambda1_img ? a.lambda1_img[img] : a.lambda1;
     float s2 = 0.0f;
     for (int i = tid; i < a.n_elem; i += SA_T) {
         const float g = a.G[o + i], e = a.eps[o + i], w = a.nw[o + i];
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(SA_T) sa_post_kernel(SaPost a) {
         cg = fM(cg, e);
         // grad_G (:697-700), left to right
         float gr = fM(fM(fM(fM(fM(2.0f, g), e), e), w), w);
-        gr = fA(gr, fM(a.lambda1, cg));
+        gr = fA(gr, fM(lambda1, cg));
         gr = fA(gr, a.z1[o + i]); gr = fA(gr, a.z2[o + i]); gr = fA(gr, a.z3[o + i]);
         gr = fA(gr, z4);
         gr = fA(gr, fM(a.rho1, fS(g, a.y1[o + i])));
@@ -144,6 +146,80 @@ __global__ void sa_apply_policy_kernel(long long n, const float *__restrict__ sc
     G[i] = g;
 }
 
+
+// ---- the perturbation step either side of update_G: update_epsilon, main_ori.py:310-354 ----------------
+// classifier input: (clamp(images + eps*G, minpix, maxpix) - mean) / std   (:317-319)
+__global__ void __launch_bounds__(SA_T) sa_eps_pre_kernel(int n_elem, int chan_elems, const float *__restrict__ images, const float *__restrict__ eps,
+                                                          const float *__restrict__ G, const float *__restrict__ mean, const float *__restrict__ stdv,
+                                                          float minpix, float maxpix, float *__restrict__ image_s) {
+    const size_t o = (size_t)blockIdx.x * n_elem;
+    for (int i = threadIdx.x; i < n_elem; i += SA_T) {
+        const int c = i / chan_elems;
+        float im = fA(images[o + i], fM(eps[o + i], G[o + i]));
+        im = fminf(fmaxf(im, minpix), maxpix);
+        image_s[o + i] = fD(fS(im, mean[c]), stdv[c]);
+    }
+}
+// eps <- eps - step * (2*eps*G*G*w*w + lambda1 * dLoss/deps)   (:341-343), dLoss/deps by the chain rule through
+// Normalization -> clamp -> mul
+__global__ void __launch_bounds__(SA_T) sa_eps_post_kernel(int n_elem, int chan_elems, float *__restrict__ eps, const float *__restrict__ G,
+                                                           const float *__restrict__ grad_in, const float *__restrict__ images,
+                                                           const float *__restrict__ nw, const float *__restrict__ stdv, float lambda1,
+                                                           const float *__restrict__ lambda1_img, float step, float minpix, float maxpix) {
+    const int img = blockIdx.x;
+    const size_t o = (size_t)img * n_elem;
+    const float lam = lambda1_img ? lambda1_img[img] : lambda1;
+    for (int i = threadIdx.x; i < n_elem; i += SA_T) {
+        const float e = eps[o + i], g = G[o + i], w = nw[o + i];
+        const float pre = fA(images[o + i], fM(e, g));
+        float cg = fD(grad_in[o + i], stdv[i / chan_elems]);
+        cg = (pre >= minpix && pre <= maxpix) ? cg : 0.0f;
+        cg = fM(cg, g);
+        float gr = fM(fM(fM(fM(fM(2.0f, e), g), g), w), w);
+        gr = fA(gr, fM(lam, cg));
+        eps[o + i] = fS(e, fM(step, gr));
+    }
+}
+
+__device__ __forceinline__ float block_max(float v, float *s_red) {
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    float t = (lane < SA_T / 32) ? s_red[lane] : 0.0f;
+    for (int o = 4; o > 0; o >>= 1) t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, o));
+    return __shfl_sync(0xffffffffu, t, 0);
+}
+// compute_statistics (utils.py:77-96) per image: out[img] = {G_sum, L0, L1, L2, Li, WL1, WL2, WLi} of
+// noise = clamp(images + eps*G) - images and noise * Weight; plus ||G*eps*w||_2^2 (the l2 term of compute_loss, utils.py:27)
+__global__ void __launch_bounds__(SA_T) sa_stats_kernel(int n_elem, const float *__restrict__ images, const float *__restrict__ eps,
+                                                        const float *__restrict__ G, const float *__restrict__ nw, float minpix, float maxpix,
+                                                        float *__restrict__ out) {
+    __shared__ float s_red[SA_T / 32];
+    const int img = blockIdx.x;
+    const size_t o = (size_t)img * n_elem;
+    float gs = 0.f, l0 = 0.f, l1 = 0.f, l2 = 0.f, li = 0.f, w1 = 0.f, w2 = 0.f, wi = 0.f, q = 0.f;
+    for (int i = threadIdx.x; i < n_elem; i += SA_T) {
+        const float g = G[o + i], e = eps[o + i], w = nw[o + i], im = images[o + i];
+        const float eg = fM(e, g);
+        const float noise = fS(fminf(fmaxf(fA(im, eg), minpix), maxpix), im);
+        const float wn = fM(noise, w);
+        gs = fA(gs, g);
+        l0 = fA(l0, g > 0.5f ? 1.0f : 0.0f);
+        l1 = fA(l1, fabsf(noise)); l2 = fA(l2, fM(noise, noise)); li = fmaxf(li, fabsf(noise));
+        w1 = fA(w1, fabsf(wn)); w2 = fA(w2, fM(wn, wn)); wi = fmaxf(wi, fabsf(wn));
+        const float t = fM(fM(g, e), w);
+        q = fA(q, fM(t, t));
+    }
+    gs = block_sum(gs, s_red); l0 = block_sum(l0, s_red); l1 = block_sum(l1, s_red); l2 = block_sum(l2, s_red); li = block_max(li, s_red);
+    w1 = block_sum(w1, s_red); w2 = block_sum(w2, s_red); wi = block_max(wi, s_red); q = block_sum(q, s_red);
+    if (threadIdx.x == 0) {
+        float *r = out + (size_t)img * 9;
+        r[0] = gs; r[1] = l0; r[2] = l1; r[3] = sqrtf(l2); r[4] = li; r[5] = w1; r[6] = sqrtf(w2); r[7] = wi; r[8] = q;
+    }
+}
+
 }  // namespace
 
 #define SACK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { lpbox_set_error(std::string(#call) + ": " + cudaGetErrorString(e_)); return LPBOX_E_CUDA; } } while (0)
@@ -169,12 +245,12 @@ extern "C" int lpbox_sa_pre_dev(void *stream, int n_img, int n_elem, int n_chan,
 
 extern "C" int lpbox_sa_post_dev(void *stream, int n_img, int n_elem, int n_chan, float *G, float *z1, float *z2, float *z3, float *z4,
                                  const float *y1, const float *y2, const float *y3, const float *grad_in, const float *images, const float *eps,
-                                 const float *nw, const float *stdv, double lambda1, double rho1, double rho2, double rho3, double rho4,
-                                 double step, double k, double minpix, double maxpix, float *hist_slot) {
+                                 const float *nw, const float *stdv, double lambda1, const float *lambda1_img, double rho1, double rho2,
+                                 double rho3, double rho4, double step, double k, double minpix, double maxpix, float *hist_slot) {
     if (n_img <= 0 || n_elem <= 0 || n_chan <= 0 || n_elem % n_chan) return LPBOX_E_INVALID;
     SaPost a;
     a.n_elem = n_elem; a.chan_elems = n_elem / n_chan; a.G = G; a.z1 = z1; a.z2 = z2; a.z3 = z3; a.z4 = z4; a.y1 = y1; a.y2 = y2; a.y3 = y3;
-    a.grad_in = grad_in; a.images = images; a.eps = eps; a.nw = nw; a.stdv = stdv; a.lambda1 = (float)lambda1; a.rho1 = (float)rho1;
+    a.grad_in = grad_in; a.images = images; a.eps = eps; a.nw = nw; a.stdv = stdv; a.lambda1 = (float)lambda1; a.lambda1_img = lambda1_img; a.rho1 = (float)rho1;
     a.rho2 = (float)rho2; a.rho3 = (float)rho3; a.rho4 = (float)rho4; a.step = (float)step; a.minpix = (float)minpix; a.maxpix = (float)maxpix;
     a.rho4_d = rho4; a.k = k; a.hist = hist_slot;
     sa_post_kernel<<<n_img, SA_T, 0, (cudaStream_t)stream>>>(a);
@@ -187,6 +263,32 @@ extern "C" int lpbox_sa_apply_policy_dev(void *stream, int64_t n, const float *s
     if (n <= 0) return LPBOX_E_INVALID;
     SACK(cudaMemsetAsync(counts2, 0, 2 * sizeof(int32_t), (cudaStream_t)stream));
     sa_apply_policy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, scores, last, (float)hi, (float)lo, G, counts2);
+    SACK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lpbox_sa_eps_pre_dev(void *stream, int n_img, int n_elem, int n_chan, const float *images, const float *eps, const float *G,
+                                    const float *mean, const float *stdv, double minpix, double maxpix, float *image_s) {
+    if (n_img <= 0 || n_elem <= 0 || n_chan <= 0 || n_elem % n_chan) return LPBOX_E_INVALID;
+    sa_eps_pre_kernel<<<n_img, SA_T, 0, (cudaStream_t)stream>>>(n_elem, n_elem / n_chan, images, eps, G, mean, stdv, (float)minpix, (float)maxpix, image_s);
+    SACK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lpbox_sa_eps_post_dev(void *stream, int n_img, int n_elem, int n_chan, float *eps, const float *G, const float *grad_in,
+                                     const float *images, const float *nw, const float *stdv, double lambda1, const float *lambda1_img,
+                                     double step, double minpix, double maxpix) {
+    if (n_img <= 0 || n_elem <= 0 || n_chan <= 0 || n_elem % n_chan) return LPBOX_E_INVALID;
+    sa_eps_post_kernel<<<n_img, SA_T, 0, (cudaStream_t)stream>>>(n_elem, n_elem / n_chan, eps, G, grad_in, images, nw, stdv, (float)lambda1, lambda1_img,
+                                                                 (float)step, (float)minpix, (float)maxpix);
+    SACK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lpbox_sa_stats_dev(void *stream, int n_img, int n_elem, const float *images, const float *eps, const float *G, const float *nw,
+                                  double minpix, double maxpix, float *out9) {
+    if (n_img <= 0 || n_elem <= 0) return LPBOX_E_INVALID;
+    sa_stats_kernel<<<n_img, SA_T, 0, (cudaStream_t)stream>>>(n_elem, images, eps, G, nw, (float)minpix, (float)maxpix, out9);
     SACK(cudaGetLastError());
     return 0;
 }

@@ -97,7 +97,10 @@ SIGNATURES = {
     "lpbox_seg_h2d_bytes": (C.c_int64, [_vp]),
     "lpbox_seg_d2h_bytes": (C.c_int64, [_vp]),
     "lpbox_sa_pre_dev": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int] + [_vp] * 11 + [C.c_double] * 6 + [_vp] * 4),
-    "lpbox_sa_post_dev": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int] + [_vp] * 13 + [C.c_double] * 9 + [_vp]),
+    "lpbox_sa_post_dev": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int] + [_vp] * 13 + [C.c_double, _vp] + [C.c_double] * 8 + [_vp]),
+    "lpbox_sa_eps_pre_dev": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int] + [_vp] * 5 + [C.c_double] * 2 + [_vp]),
+    "lpbox_sa_eps_post_dev": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int] + [_vp] * 6 + [C.c_double, _vp] + [C.c_double] * 3),
+    "lpbox_sa_stats_dev": (C.c_int, [_vp, C.c_int, C.c_int] + [_vp] * 4 + [C.c_double] * 2 + [_vp]),
     "lpbox_sa_apply_policy_dev": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_double, C.c_double, _vp, _vp]),
     "lpbox_policy_create": (_vp, [C.c_int, C.c_int, C.c_int, _vp, C.c_int64, C.c_int64]),
     "lpbox_policy_destroy": (None, [_vp]),

@@ -221,8 +221,19 @@ int lpbox_sa_pre_dev(void *stream, int n_img, int n_elem, int n_chan, int nseg, 
  * step, z1..z4 updates; writes the new G into hist_slot as well when it is not NULL (G_iters, main_ori.py:586) */
 int lpbox_sa_post_dev(void *stream, int n_img, int n_elem, int n_chan, float *G, float *z1, float *z2, float *z3, float *z4,
                       const float *y1, const float *y2, const float *y3, const float *grad_in, const float *images, const float *eps,
-                      const float *nw, const float *stdv, double lambda1, double rho1, double rho2, double rho3, double rho4,
-                      double step, double k, double minpix, double maxpix, float *hist_slot);
+                      const float *nw, const float *stdv, double lambda1, const float *lambda1_img /* [n_img] or NULL */, double rho1,
+                      double rho2, double rho3, double rho4, double step, double k, double minpix, double maxpix, float *hist_slot);
+/* The perturbation step either side of update_G (update_epsilon, main_ori.py:310-354):
+ * image_s = (clamp(images + eps*G, minpix, maxpix) - mean) / std  (:317-319) */
+int lpbox_sa_eps_pre_dev(void *stream, int n_img, int n_elem, int n_chan, const float *images, const float *eps, const float *G,
+                         const float *mean, const float *stdv, double minpix, double maxpix, float *image_s);
+/* eps <- eps - step * (2*eps*G*G*w*w + lambda1 * dLoss/d eps) (:341-343) given grad_in = dLoss/d image_s */
+int lpbox_sa_eps_post_dev(void *stream, int n_img, int n_elem, int n_chan, float *eps, const float *G, const float *grad_in,
+                          const float *images, const float *nw, const float *stdv, double lambda1, const float *lambda1_img,
+                          double step, double minpix, double maxpix);
+/* compute_statistics (utils.py:77-96) per image: out9[img] = {G_sum, L0, L1, L2, Li, WL1, WL2, WLi, ||G*eps*w||_2^2} */
+int lpbox_sa_stats_dev(void *stream, int n_img, int n_elem, const float *images, const float *eps, const float *G, const float *nw,
+                       double minpix, double maxpix, float *out9);
 /* update_G_l2f's rewrite of G from policy scores (main_ori.py:476-485): p > hi -> 1, p < lo -> 0, else `last`;
  * counts2[0], counts2[1] receive the number of ones / zeros fixed */
 int lpbox_sa_apply_policy_dev(void *stream, int64_t n, const float *scores, const float *last, double hi, double lo, float *G,

@@ -104,3 +104,124 @@ def loop(model, images, target_label, epsilon, G, st, B, noise_Weight, start_ite
         G_iters[cur_iter % 50] = G
         schedule(st, cur_iter, a)
     return G, G_iters.permute(1, 2, 3, 0)
+
+
+# ---- the outer loop either side of update_G ---------------------------------------------------------------
+OUTER_DEFAULTS = dict(lr_e=0.1, lr_g=0.1, rho1=5e-3, rho2=5e-3, rho3=5e-3, rho4=1e-4, maxIter_e=2000, maxIter_g=2000, maxIter_mm=1,
+                      init_lambda1=1e-3, lambda1_upper_bound=1e2, lambda1_lower_bound=0.0, lambda1_search_times=6)   # flags.py:83-131
+
+
+def _mean_std(mean, std):
+    mean = torch.full((1, 3, 1, 1), 0.5) if mean is None else mean
+    std = torch.ones((1, 3, 1, 1)) if std is None else std
+    return mean, std
+
+
+def _attack_loss(prediction, target_label, a):
+    if a["loss"] == "ce":
+        return torch.nn.functional.cross_entropy(prediction, target_label)
+    return cw_loss(prediction, target_label, a)
+
+
+def update_epsilon(model, images, target_label, epsilon, G, init_lr, noise_Weight, finetune, args=None, mean=None, std=None):
+    """main_ori.py:310-354: gradient descent on the perturbation with the mask fixed; maxIter_e steps (half when fine-tuning)."""
+    a = dict(DEFAULTS); a.update(OUTER_DEFAULTS); a.update(args or {})
+    mean, std = _mean_std(mean, std)
+    cur_step = init_lr
+    train_epochs = int(a["maxIter_e"] / 2.0) if finetune else a["maxIter_e"]
+    for cur_iter in range(1, train_epochs + 1):
+        epsilon = epsilon.detach().requires_grad_(True)
+        images_s = images + torch.mul(epsilon, G)
+        images_s = torch.clamp(images_s, a["min_pix_value"], a["max_pix_value"])
+        images_s = (images_s - mean) / std
+        loss = _attack_loss(model(images_s), target_label, a)
+        loss.backward()
+        epsilon_cnn_grad = epsilon.grad
+        e = epsilon.detach()
+        epsilon_grad = 2 * e * G * G * noise_Weight * noise_Weight + a["lambda1"] * epsilon_cnn_grad           # :341
+        epsilon = (e - cur_step * epsilon_grad).detach()
+        if cur_iter % a["lr_decay_step"] == 0:
+            cur_step = max(cur_step * a["lr_decay_factor"], a["lr_min"])
+    return epsilon, cur_step
+
+
+def compute_statistics(images, epsilon, G, noise_Weight, a):
+    """utils.py:77-96."""
+    noise = torch.clamp(images + torch.mul(epsilon, G), a["min_pix_value"], a["max_pix_value"]) - images
+    w_noise = noise * noise_Weight
+    return {"G_sum": float(torch.sum(G).item()), "L0": int(torch.sum((G > 0.5).float()).item()), "L1": float(torch.norm(noise, 1).item()),
+            "L2": float(torch.norm(noise, 2).item()), "Li": float(torch.max(torch.abs(noise)).item()),
+            "WL1": float(torch.norm(w_noise, 1).item()), "WL2": float(torch.norm(w_noise, 2).item()),
+            "WLi": float(torch.max(torch.abs(w_noise)).item())}
+
+
+def compute_loss(model, images, target_label, epsilon, G, B, noise_Weight, a, mean, std):
+    """utils.py:24-75."""
+    l2_loss = (torch.norm(G * epsilon * noise_Weight, 2).item()) ** 2
+    image_s = (torch.clamp(images + torch.mul(G, epsilon), a["min_pix_value"], a["max_pix_value"]) - mean) / std
+    with torch.no_grad():
+        cnn_loss = _attack_loss(model(image_s), target_label, a).item()
+    BG = B * G
+    group_loss = torch.sum(torch.norm(BG.reshape(BG.shape[0], -1), p=2, dim=1)).item()
+    return {"loss": float(l2_loss + a["lambda1"] * cnn_loss + a["lambda2"] * group_loss), "l2_loss": float(l2_loss),
+            "cnn_loss": float(cnn_loss), "group_loss": float(group_loss)}
+
+
+def compute_predictions_labels(model, images, epsilon, G, a, mean, std):
+    """utils.py:106-116: adv_image is the clamped, un-normalised image."""
+    adv_image = torch.clamp(images + torch.mul(G, epsilon), a["min_pix_value"], a["max_pix_value"])
+    with torch.no_grad():
+        labels = torch.argmax(model((adv_image - mean) / std), dim=1)
+    return labels.detach(), adv_image.detach()
+
+
+def train_sgd_atom(model, images, target_label, B, noise_Weight, args=None, mean=None, std=None):
+    """main_ori.py:252-307 for one image and one lambda1 (args['lambda1'])."""
+    a = dict(DEFAULTS); a.update(OUTER_DEFAULTS); a.update(args or {})
+    mean, std = _mean_std(mean, std)
+    G = torch.ones_like(images)
+    epsilon = torch.zeros_like(images)
+    ori_prediction, _ = compute_predictions_labels(model, images, epsilon, G, a, mean, std)
+    cur_lr_e = a["lr_e"]
+    cur_lr_g = {"cur_step_g": a["lr_g"], "cur_rho1": a["rho1"], "cur_rho2": a["rho2"], "cur_rho3": a["rho3"], "cur_rho4": a["rho4"]}
+    for _ in range(1, a["maxIter_mm"] + 1):
+        epsilon, cur_lr_e = update_epsilon(model, images, target_label, epsilon, G, cur_lr_e, noise_Weight, False, a, mean, std)
+        G, cur_lr_g, _ = update_G(model, images, target_label, epsilon, G, cur_lr_g, B, noise_Weight, a["maxIter_g"], a, mean, std)
+    G = (G > 0.5).float()
+    epsilon, cur_lr_e = update_epsilon(model, images, target_label, epsilon, G, cur_lr_e, noise_Weight, True, a, mean, std)
+    loss = compute_loss(model, images, target_label, epsilon, G, B, noise_Weight, a, mean, std)
+    stats = compute_statistics(images, epsilon, G, noise_Weight, a)
+    noise_label, adv_image = compute_predictions_labels(model, images, epsilon, G, a, mean, std)
+    res = {"status": bool(noise_label[0] == target_label[0]), "noise_label": noise_label.tolist(), "ori_prediction": ori_prediction.tolist(),
+           "G": G, "epsilon": epsilon, "adv_image": adv_image}
+    res.update(loss); res.update(stats)
+    return res
+
+
+def train_adaptive(model, images, target_label, B, noise_Weight, args=None, mean=None, std=None):
+    """main_ori.py:207-249 (`train_adptive`): lambda1 search -- x10 until the first success, bisection afterwards; six rounds."""
+    a = dict(DEFAULTS); a.update(OUTER_DEFAULTS); a.update(args or {})
+    lam = a["init_lambda1"]
+    upper, lower = a["lambda1_upper_bound"], a["lambda1_lower_bound"]
+    successes, results = [], None
+    times = 6                                                        # :212 overrides the flag
+    for search_time in range(1, times + 1):
+        a["lambda1"] = lam
+        results = train_sgd_atom(model, images, target_label, B, noise_Weight, a, mean, std)
+        results["lambda1"] = lam
+        if results["status"]:
+            successes.append(results)
+        if search_time < times:
+            if results["status"]:
+                if lam < 0.01 * a["init_lambda1"]:
+                    break
+                upper = min(upper, lam)
+                if upper < a["lambda1_upper_bound"]:
+                    lam = (upper + lower) / 2
+            else:
+                lower = max(lower, lam)
+                if upper < a["lambda1_upper_bound"]:
+                    lam = (upper + lower) / 2
+                else:
+                    lam *= 10
+    return successes[-1] if successes else results

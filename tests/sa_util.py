@@ -53,3 +53,21 @@ def make_problem(seed=3, n_images=1, device="cpu"):
     seg_id = torch.from_numpy(np.broadcast_to(seg, (3, 32, 32)).copy()).reshape(-1).to(torch.int32)
     model = model.to(device)
     return model, images.to(device), target.to(device), eps.to(device), G0.to(device), B.to(device), nw.to(device), seg_id.to(device)
+
+
+OUTER_CFG = dict(maxIter_e=30, maxIter_g=30, maxIter_mm=1, init_lambda1=0.1, k=1500)
+
+
+def make_outer_problem(seed=3, n_images=1, device="cpu"):
+    """Problem for the outer loop (lambda1 search): a seeded LINEAR 10-class classifier, sensitive enough that
+    the six-round search of `train_adptive` takes the x10 branch, succeeds, and bisects within 30 + 30 + 15 iterations per round
+    (a random-init CifarNet never flips its label at these iteration counts)."""
+    _, images, _, _, _, B, nw, seg_id = make_problem(seed=seed, n_images=n_images)
+    g = torch.Generator().manual_seed(seed + 2)
+    model = nn.Sequential(nn.Flatten(), nn.Linear(3072, 10))
+    with torch.no_grad():
+        model[1].weight.copy_(torch.randn(10, 3072, generator=g) * 0.05)
+        model[1].bias.zero_()
+        target = (model(images - 0.5).argmax(1) + 1) % 10
+    model = model.eval().to(device)
+    return model, images.to(device), target.to(device), B.to(device), nw.to(device), seg_id.to(device)

@@ -53,3 +53,62 @@ def test_loop_and_l2f_window_driver():
     Gl, ipl = sa.update_G_l2f(model, images, target, eps, G0.clone(), sa.init_params(), B, nw, score, windows=2, ws=50)
     assert Gl.shape == G0.shape and torch.isfinite(Gl).all()
     assert set(ipl) == {"cur_step_g", "cur_rho1", "cur_rho2", "cur_rho3", "cur_rho4"}
+
+
+# ---- outer loop: update_epsilon, statistics, lambda1 search ----------------------------------------------
+_MS = dict(mean=None, std=None)
+
+
+def _ms():
+    return dict(mean=torch.full((1, 3, 1, 1), 0.5, device="cuda"), std=torch.ones((1, 3, 1, 1), device="cuda"))
+
+
+@pytest.mark.parametrize("K,tol", [(1, 1e-6), (5, 1e-5), (20, 1e-4)])
+def test_update_epsilon_matches_oracle(K, tol):
+    import sa_oracle
+    from lpbox import sparse_attack as sa
+    model, images, target, eps, G0, B, nw, _ = make_problem(seed=3, n_images=1, device="cuda")
+    G = (torch.rand(G0.shape, generator=torch.Generator().manual_seed(11)) > 0.3).float().cuda()
+    eo, so = sa_oracle.update_epsilon(model, images, target, eps.clone(), G, 0.1, nw, False, dict(maxIter_e=K, lambda1=1e-3), **_ms())
+    eg, sg = sa.update_epsilon(model, images, target, eps.clone(), G, 0.1, B, nw, 1, False, args=dict(maxIter_e=K, lambda1=1e-3))
+    assert _rel(eg, eo) <= tol
+    assert sg == so
+
+
+def test_statistics_match_oracle():
+    import sa_oracle
+    from lpbox import sparse_attack as sa
+    model, images, target, eps, G0, B, nw, _ = make_problem(seed=7, n_images=4, device="cuda")
+    G = (torch.rand(G0.shape, generator=torch.Generator().manual_seed(2)) > 0.6).float().cuda()
+    nw = nw * (0.5 + torch.rand(nw.shape, generator=torch.Generator().manual_seed(3)).cuda())
+    eps = eps * 3                                  # make the clamp bite
+    got = sa.compute_statistics(images, eps, G, None, B, nw)
+    a = dict(sa_oracle.DEFAULTS)
+    for i in range(4):
+        ref = sa_oracle.compute_statistics(images[i:i + 1], eps[i:i + 1], G[i:i + 1], nw[i:i + 1], a)
+        for k, v in ref.items():
+            assert abs(float(got[k][i]) - v) <= 1e-5 * max(1.0, abs(v)), (k, i)
+
+
+def test_lambda1_search_matches_oracle_per_image():
+    """Batched train_adaptive == the oracle's single-image search for every image of the batch: same lambda1 path, same final
+    lambda1 / status / binary mask; perturbation and statistics to fp32 tolerance."""
+    import sa_oracle
+    from lpbox import sparse_attack as sa
+    from sa_util import OUTER_CFG, make_outer_problem
+    model, images, target, B, nw, _ = make_outer_problem(seed=3, n_images=4, device="cuda")
+    got = sa.train_adaptive(model, images, target, B, nw, dict(OUTER_CFG))
+    lams = set()
+    for i in range(4):
+        ref = sa_oracle.train_adaptive(model, images[i:i + 1], target[i:i + 1], B, nw[i:i + 1], dict(OUTER_CFG), **_ms())
+        assert bool(got["status"][i]) == ref["status"], i
+        assert float(got["lambda1"][i]) == ref["lambda1"], i
+        assert int(got["noise_label"][i]) == ref["noise_label"][0]
+        assert torch.equal(got["G"][i], ref["G"][0]), i
+        assert _rel(got["epsilon"][i], ref["epsilon"][0]) <= 1e-4
+        for k in ("L0", "L1", "L2", "Li"):
+            assert abs(float(got[k][i]) - ref[k]) <= 1e-4 * max(1.0, abs(ref[k])), (k, i)
+        for k in ("loss", "l2_loss", "cnn_loss", "group_loss"):
+            assert abs(float(got[k][i]) - ref[k]) <= 1e-3 * max(1.0, abs(ref[k])), (k, i)
+        lams.add(ref["lambda1"])
+    assert len(lams) > 1            # the images really took different search paths
