@@ -144,58 +144,29 @@ extern "C" void lpbox_seg_destroy(lpbox_seg_batch *h) {
     delete h;
 }
 
-extern "C" lpbox_seg_batch *lpbox_seg_create_csr(int device, int B, const int32_t *n, const int32_t *rowptr_all, const int32_t *colidx_all,
-                                                const double *val_all, const double *b_all, const double *c, int hist_cap) {
-    if (B <= 0 || !n || !rowptr_all || !colidx_all || !val_all || !b_all || hist_cap < 0) { lpbox_set_error("invalid argument"); return nullptr; }
+// allocation + kernel configuration shared by both constructors; CSR / b are filled afterwards (H2D or the device graph builder)
+static lpbox_seg_batch *seg_new(int device, int B, const int32_t *n, const int *nnz, const double *c, int hist_cap) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { lpbox_set_error("no CUDA device (there is no CPU fallback)"); return nullptr; }
     if (device < 0 || device >= ndev || cudaSetDevice(device) != cudaSuccess) { lpbox_set_error("bad device"); return nullptr; }
     lpbox_seg_batch *h = new lpbox_seg_batch();
     h->device = device; h->B = B; h->hist_cap = hist_cap;
-    h->n0.assign(n, n + B); h->nnz0.resize(B); h->cconst.assign(B, 0.0);
+    h->n0.assign(n, n + B); h->nnz0.assign(nnz, nnz + B); h->cconst.assign(B, 0.0);
     h->off_n.assign(B + 1, 0); h->off_nnz.assign(B + 1, 0); h->off_hist.assign(B + 1, 0);
-    long long rpo = 0;
-    std::vector<long long> rp_off(B + 1, 0);
+    std::vector<double> powv(B);
+    std::vector<SegInst> st(B);
     for (int i = 0; i < B; ++i) {
-        if (n[i] <= 0) { lpbox_set_error("n <= 0"); delete h; return nullptr; }
-        const int32_t *rp = rowptr_all + rpo;
-        h->nnz0[i] = rp[n[i]];
-        rp_off[i] = rpo; rpo += n[i] + 1;
         h->off_n[i + 1] = h->off_n[i] + ((n[i] + 3) & ~3);
         h->off_nnz[i + 1] = h->off_nnz[i] + ((h->nnz0[i] + 3) & ~3);
         h->off_hist[i + 1] = h->off_hist[i] + (long long)hist_cap * n[i];
         if (c) h->cconst[i] = c[i];
         h->max_n = std::max(h->max_n, n[i]);
-    }
-    rp_off[B] = rpo;
-    const size_t NN = (size_t)h->off_n[B], ZZ = (size_t)h->off_nnz[B];
-    std::vector<int> rp_pack(NN + 4 * (size_t)B, 0), ci_pack(ZZ, 0);
-    std::vector<double> va_pack(ZZ, 0.0), b_pack(NN, 0.0), powv(B);
-    std::vector<SegInst> st(B);
-    long long zo = 0, bo = 0;
-    for (int i = 0; i < B; ++i) {
-        const int ni = n[i], nz = h->nnz0[i];
-        const int32_t *rp = rowptr_all + rp_off[i];
-        for (int r = 0; r < ni; ++r) {
-            bool diag = false;
-            if (rp[r] > rp[r + 1]) { lpbox_set_error("bad rowptr"); delete h; return nullptr; }
-            for (int k = rp[r]; k < rp[r + 1]; ++k) {
-                const int cc = colidx_all[zo + k];
-                if (cc < 0 || cc >= ni || (k > rp[r] && cc <= colidx_all[zo + k - 1])) { lpbox_set_error("column indices must be in range and strictly ascending within each row"); delete h; return nullptr; }
-                if (cc == r) diag = true;
-            }
-            if (!diag) { lpbox_set_error("every row of A must store its diagonal entry (explicit zero allowed), as the reference's graph builder does"); delete h; return nullptr; }
-        }
-        memcpy(rp_pack.data() + h->off_n[i] + 4 * (size_t)i, rp, sizeof(int) * ((size_t)ni + 1));
-        memcpy(ci_pack.data() + h->off_nnz[i], colidx_all + zo, sizeof(int) * (size_t)nz);
-        memcpy(va_pack.data() + h->off_nnz[i], val_all + zo, sizeof(double) * (size_t)nz);
-        memcpy(b_pack.data() + h->off_n[i], b_all + bo, sizeof(double) * (size_t)ni);
-        zo += nz; bo += ni;
-        powv[i] = pow((double)ni, 1.0 / 2);
+        powv[i] = pow((double)n[i], 1.0 / 2);
         SegInst &s = st[i];
         memset(&s, 0, sizeof(s));
-        s.n0 = s.n = ni; s.nnz0 = s.nnz = nz; s.std_obj = 1.0; s.rhoUpdated = 1; s.cconst = h->cconst[i];
+        s.n0 = s.n = n[i]; s.nnz0 = s.nnz = h->nnz0[i]; s.std_obj = 1.0; s.rhoUpdated = 1; s.cconst = h->cconst[i];
     }
+    const size_t NN = (size_t)h->off_n[B], ZZ = (size_t)h->off_nnz[B];
     h->h_st = st;
     lpbox_params sp; lpbox_params_seg(&sp);
     h->pr.stop_threshold = sp.stop_threshold; h->pr.std_threshold = sp.std_threshold; h->pr.max_iters = sp.max_iters;
@@ -218,18 +189,10 @@ extern "C" lpbox_seg_batch *lpbox_seg_create_csr(int device, int B, const int32_
     H2D(h->d_off_n.p, h->off_n.data(), sizeof(long long) * (B + 1));
     H2D(h->d_off_nnz.p, h->off_nnz.data(), sizeof(long long) * (B + 1));
     H2D(h->d_off_hist.p, h->off_hist.data(), sizeof(long long) * (B + 1));
-    H2D(h->d_rp[0].p, rp_pack.data(), sizeof(int) * rp_pack.size());
-    H2D(h->d_ci[0].p, ci_pack.data(), sizeof(int) * ZZ);
-    H2D(h->d_val[0].p, va_pack.data(), sizeof(double) * ZZ);
-    H2D(h->d_b[0].p, b_pack.data(), sizeof(double) * NN);
     H2D(h->d_powv.p, powv.data(), sizeof(double) * (size_t)B);
     std::vector<double> powtab((size_t)h->max_n + 1);
     for (int k = 0; k <= h->max_n; ++k) powtab[k] = pow((double)k, 1.0 / 2);     // std::pow(n, 1.0/p) from the host libm
     H2D(h->d_powtab.p, powtab.data(), sizeof(double) * powtab.size());
-    H2D(h->d_rp_org.p, rp_pack.data(), sizeof(int) * rp_pack.size());
-    H2D(h->d_ci_org.p, ci_pack.data(), sizeof(int) * ZZ);
-    H2D(h->d_val_org.p, va_pack.data(), sizeof(double) * ZZ);
-    H2D(h->d_b_org.p, b_pack.data(), sizeof(double) * NN);
     H2D(h->d_st.p, st.data(), sizeof(SegInst) * (size_t)B);
     A(cudaStreamSynchronize(h->stream));
     if (!ok) { lpbox_seg_destroy(h); return nullptr; }
@@ -252,37 +215,229 @@ extern "C" lpbox_seg_batch *lpbox_seg_create_csr(int device, int B, const int32_
     return h;
 }
 
+extern "C" lpbox_seg_batch *lpbox_seg_create_csr(int device, int B, const int32_t *n, const int32_t *rowptr_all, const int32_t *colidx_all,
+                                                const double *val_all, const double *b_all, const double *c, int hist_cap) {
+    if (B <= 0 || !n || !rowptr_all || !colidx_all || !val_all || !b_all || hist_cap < 0) { lpbox_set_error("invalid argument"); return nullptr; }
+    std::vector<int> nnz(B);
+    std::vector<long long> rp_off(B + 1, 0);
+    long long zo = 0;
+    for (int i = 0; i < B; ++i) {
+        if (n[i] <= 0) { lpbox_set_error("n <= 0"); return nullptr; }
+        const int32_t *rp = rowptr_all + rp_off[i];
+        nnz[i] = rp[n[i]];
+        rp_off[i + 1] = rp_off[i] + n[i] + 1;
+        for (int r = 0; r < n[i]; ++r) {
+            bool diag = false;
+            if (rp[r] > rp[r + 1]) { lpbox_set_error("bad rowptr"); return nullptr; }
+            for (int k = rp[r]; k < rp[r + 1]; ++k) {
+                const int cc = colidx_all[zo + k];
+                if (cc < 0 || cc >= n[i] || (k > rp[r] && cc <= colidx_all[zo + k - 1])) { lpbox_set_error("column indices must be in range and strictly ascending within each row"); return nullptr; }
+                if (cc == r) diag = true;
+            }
+            if (!diag) { lpbox_set_error("every row of A must store its diagonal entry (explicit zero allowed), as the reference's graph builder does"); return nullptr; }
+        }
+        zo += nnz[i];
+    }
+    lpbox_seg_batch *h = seg_new(device, B, n, nnz.data(), c, hist_cap);
+    if (!h) return nullptr;
+    const size_t NN = (size_t)h->off_n[B], ZZ = (size_t)h->off_nnz[B];
+    std::vector<int> rp_pack(NN + 4 * (size_t)B, 0), ci_pack(ZZ, 0);
+    std::vector<double> va_pack(ZZ, 0.0), b_pack(NN, 0.0);
+    long long bo = 0;
+    zo = 0;
+    for (int i = 0; i < B; ++i) {
+        const int ni = n[i], nz = nnz[i];
+        memcpy(rp_pack.data() + h->off_n[i] + 4 * (size_t)i, rowptr_all + rp_off[i], sizeof(int) * ((size_t)ni + 1));
+        memcpy(ci_pack.data() + h->off_nnz[i], colidx_all + zo, sizeof(int) * (size_t)nz);
+        memcpy(va_pack.data() + h->off_nnz[i], val_all + zo, sizeof(double) * (size_t)nz);
+        memcpy(b_pack.data() + h->off_n[i], b_all + bo, sizeof(double) * (size_t)ni);
+        zo += nz; bo += ni;
+    }
+    bool ok = true;
+    auto H2D = [&](void *d, const void *s, size_t bytes) {
+        if (bytes) { if (cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) ok = false; h->h2d_bytes += (int64_t)bytes; }
+    };
+    H2D(h->d_rp[0].p, rp_pack.data(), sizeof(int) * rp_pack.size());
+    H2D(h->d_ci[0].p, ci_pack.data(), sizeof(int) * ZZ);
+    H2D(h->d_val[0].p, va_pack.data(), sizeof(double) * ZZ);
+    H2D(h->d_b[0].p, b_pack.data(), sizeof(double) * NN);
+    H2D(h->d_rp_org.p, rp_pack.data(), sizeof(int) * rp_pack.size());
+    H2D(h->d_ci_org.p, ci_pack.data(), sizeof(int) * ZZ);
+    H2D(h->d_val_org.p, va_pack.data(), sizeof(double) * ZZ);
+    H2D(h->d_b_org.p, b_pack.data(), sizeof(double) * NN);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) ok = false;
+    if (!ok) { lpbox_set_error("upload of the CSR arrays failed"); lpbox_seg_destroy(h); return nullptr; }
+    return h;
+}
+
+// ---- device graph builder: the same construction as lpbox_seg_build_graph, one CTA per image ------------------
+// All outputs are integer-valued (rounded costs / weights and their sums), so they do not depend on summation order; the
+// image mean / standard deviation, which feed exp(), are nevertheless summed in the host builder's (Eigen's) order by 4 lanes.
+struct SegBuildArgs {
+    const uint8_t *pixels; const long long *pix_off; const int *nr, *nc;
+    const long long *off_n, *off_nnz;
+    int *rowptr; int *colidx; double *val, *b, *scr_v, *scr_t;
+    SegInst *st;
+    double cst, den, log2v, bg, f1, f2;
+};
+
+__device__ double seg_build_eigen_sum4(const double *v, long n, double *s_part /*[4]*/) {   // called by all threads; result valid in thread 0
+    const long a2 = (n / 4) * 4, a1 = (n / 2) * 2;
+    if (threadIdx.x < 4 && a2 >= 4) {
+        double acc = v[threadIdx.x];
+        for (long i = 4 + threadIdx.x; i < a2; i += 4) acc = acc + v[i];
+        s_part[threadIdx.x] = acc;
+    }
+    __syncthreads();
+    double res = 0.0;
+    if (threadIdx.x == 0) {
+        if (!a1) res = n ? v[0] : 0.0;
+        else {
+            double p00, p01;
+            if (a2 >= 4) { p00 = s_part[0] + s_part[2]; p01 = s_part[1] + s_part[3]; if (a1 > a2) { p00 += v[a2]; p01 += v[a2 + 1]; } }
+            else { p00 = v[0]; p01 = v[1]; }
+            res = p00 + p01;
+            for (long i = a1; i < n; ++i) res += v[i];
+        }
+    }
+    __syncthreads();
+    return res;
+}
+
+__global__ void __launch_bounds__(256) seg_build_graph_kernel(SegBuildArgs a) {
+    __shared__ double s_part[4], s_bc[2], s_red[8];
+    const int img = blockIdx.x, tid = threadIdx.x;
+    const int nr = a.nr[img], nc = a.nc[img], n = nr * nc;
+    const uint8_t *pix = a.pixels + a.pix_off[img];
+    double *v = a.scr_v + a.off_n[img], *t = a.scr_t + a.off_n[img], *b = a.b + a.off_n[img];
+    int *rp = a.rowptr + a.off_n[img] + 4 * (long long)img, *ci = a.colidx + a.off_nnz[img];
+    double *va = a.val + a.off_nnz[img];
+    // unary costs in the column-major flattening (SEG.cpp:46-61, :727-743)
+    double c_part = 0.0;
+    for (int k = tid; k < n; k += 256) {
+        const int c = k / nr, r = k - c * nr;
+        const double x = (double)pix[(size_t)r * nc + c] / 263.0;
+        v[k] = x;
+        const double d0 = x - a.bg, d1 = x - a.f1, d2 = x - a.f2;
+        const double ab = (d0 * d0) / a.den + a.cst;
+        const double aa = exp(-(d1 * d1) / a.den) + exp(-(d2 * d2) / a.den);
+        const double af = -log(aa + 2.220446049250313e-16) + a.cst + a.log2v;
+        const double U1 = round(ab), U2 = round(af);
+        b[k] = U2 - U1;
+        c_part += U1;                                   // integers: exact in any order
+    }
+    for (int o = 16; o > 0; o >>= 1) c_part += __shfl_xor_sync(0xffffffffu, c_part, o);
+    if ((tid & 31) == 0) s_red[tid >> 5] = c_part;
+    __syncthreads();
+    if (tid == 0) { double cs = 0.0; for (int w = 0; w < 8; ++w) cs += s_red[w]; a.st[img].cconst = cs; }
+    __syncthreads();
+    // image statistics (SEG.cpp:181-186): mean and sample standard deviation
+    const double sum = seg_build_eigen_sum4(v, n, s_part);
+    if (tid == 0) s_bc[0] = sum / (double)n;
+    __syncthreads();
+    const double mean = s_bc[0];
+    for (int k = tid; k < n; k += 256) { const double d = v[k] - mean; t[k] = d * d; }
+    __syncthreads();
+    const double ss = seg_build_eigen_sum4(t, n, s_part);
+    if (tid == 0) s_bc[1] = sqrt(ss / (double)(n - 1));
+    __syncthreads();
+    const double sig = s_bc[1];
+    // pairwise weights, row-major p; offsets in ascending column order; explicit diagonal (SEG.cpp:144-248)
+    const int oa[7] = {-1, -1, 0, 0, 0, 1, 1}, ob[7] = {0, 1, -1, 0, 1, -1, 0};
+    for (int p = tid; p < n; p += 256) {
+        const int i = p / nc, j = p - i * nc;
+        const int up = i > 0, dn = i < nr - 1;
+        // entries stored before row i, and before column j inside row i (closed form of the stencil's validity pattern)
+        const long long rows_before = (long long)i * (3 * nc - 2) + (long long)(2 * nc - 1) * ((i > 0 ? i - 1 : 0) + (i < nr - 1 ? i : nr - 1));
+        const int jm = j < nc - 1 ? j : nc - 1, jl = j > 0 ? j - 1 : 0;
+        const int in_row = j + up * j + up * jm + jl + jm + dn * jl + dn * j;
+        int q = (int)(rows_before + in_row);
+        rp[p] = q;
+        if (p == n - 1) rp[n] = q + 1 + up + (up && j < nc - 1) + (j > 0) + (j < nc - 1) + (dn && j > 0) + dn;
+        const double i1 = (double)pix[(size_t)(p % nr) * nc + (p / nr)] / 263.0;           // the reference's index mismatch (:192-193)
+        int dq = -1;
+        double wsum = 0.0;
+#pragma unroll
+        for (int e = 0; e < 7; ++e) {
+            const int ao = oa[e], bo = ob[e];
+            if (ao == 0 && bo == 0) { dq = q; ci[q] = p; q++; continue; }
+            if (i + ao < 0 || i + ao >= nr || j + bo < 0 || j + bo >= nc) continue;
+            const int p2 = (i + ao) * nc + (j + bo);
+            const double i2 = (double)pix[(size_t)(p2 % nr) * nc + (p2 / nr)] / 263.0;
+            const double d = i1 - i2;
+            const double wgt = round(3 * exp(-((d * d) / sig)));
+            ci[q] = p2; va[q] = -wgt; q++;
+            wsum += wgt;                                // integers: exact in any order
+        }
+        va[dq] = wsum;
+    }
+}
+
 extern "C" lpbox_seg_batch *lpbox_seg_create_images(int device, int B, const uint8_t *pixels_all, const int32_t *nr, const int32_t *nc,
                                                    int hist_cap) {
-    if (B <= 0 || !pixels_all || !nr || !nc) { lpbox_set_error("invalid argument"); return nullptr; }
-    std::vector<long long> po(B + 1, 0), ro(B + 1, 0), zo(B + 1, 0), no(B + 1, 0);
+    if (B <= 0 || !pixels_all || !nr || !nc || hist_cap < 0) { lpbox_set_error("invalid argument"); return nullptr; }
+    std::vector<long long> po(B + 1, 0);
+    std::vector<int> ns(B), nnz(B);
     for (int i = 0; i < B; ++i) {
-        const long long n = (long long)nr[i] * nc[i];
-        po[i + 1] = po[i] + n; ro[i + 1] = ro[i] + n + 1; zo[i + 1] = zo[i] + 7 * n; no[i + 1] = no[i] + n;
+        if (nr[i] <= 0 || nc[i] <= 0 || (long long)nr[i] * nc[i] > (1 << 28)) { lpbox_set_error("bad image size"); return nullptr; }
+        const long long r = nr[i], c = nc[i];
+        ns[i] = (int)(r * c);
+        po[i + 1] = po[i] + r * c;
+        // stored entries: diagonal + the valid ones of the 6 offsets (-1,0) (-1,1) (0,-1) (0,1) (1,-1) (1,0)
+        nnz[i] = (int)(r * c + 2 * (r - 1) * c + 2 * r * (c - 1) + 2 * (r - 1) * (c - 1));
     }
-    std::vector<int32_t> rp((size_t)ro[B]), ci((size_t)zo[B]), ns(B);
-    std::vector<double> va((size_t)zo[B]), b((size_t)no[B]), c(B);
-    std::vector<int> nnz(B);
-    std::atomic<int> next(0);
-    int nt = std::max(1, std::min((int)std::thread::hardware_concurrency(), B));
-    std::vector<std::thread> pool;
-    for (int t = 0; t < nt; ++t)
-        pool.emplace_back([&]() {
-            for (int i; (i = next.fetch_add(1)) < B;) {
-                nnz[i] = lpbox_seg_build_graph(pixels_all + po[i], nr[i], nc[i], rp.data() + ro[i], ci.data() + zo[i], va.data() + zo[i], b.data() + no[i], &c[i]);
-                ns[i] = nr[i] * nc[i];
-            }
-        });
-    for (auto &th : pool) th.join();
-    // compact colidx / val to the layout lpbox_seg_create_csr takes (concatenated by actual nnz)
-    size_t w = 0;
-    for (int i = 0; i < B; ++i) {
-        if (nnz[i] < 0) { lpbox_set_error("graph builder failed"); return nullptr; }
-        memmove(ci.data() + w, ci.data() + zo[i], sizeof(int32_t) * (size_t)nnz[i]);
-        memmove(va.data() + w, va.data() + zo[i], sizeof(double) * (size_t)nnz[i]);
-        w += (size_t)nnz[i];
+    lpbox_seg_batch *h = seg_new(device, B, ns.data(), nnz.data(), nullptr, hist_cap);
+    if (!h) return nullptr;
+    const size_t NN = (size_t)h->off_n[B], ZZ = (size_t)h->off_nnz[B];
+    SBuf<uint8_t> d_pix; SBuf<long long> d_po; SBuf<int> d_nr, d_nc;
+    bool ok = d_pix.alloc((size_t)po[B]) == cudaSuccess && d_po.alloc(B + 1) == cudaSuccess && d_nr.alloc(B) == cudaSuccess && d_nc.alloc(B) == cudaSuccess;
+    auto C_ = [&](cudaError_t e) { if (e != cudaSuccess) { if (ok) lpbox_set_error(std::string("seg graph builder: ") + cudaGetErrorString(e)); ok = false; } };
+    if (ok) {
+        C_(cudaMemcpyAsync(d_pix.p, pixels_all, (size_t)po[B], cudaMemcpyHostToDevice, h->stream));
+        C_(cudaMemcpyAsync(d_po.p, po.data(), sizeof(long long) * (B + 1), cudaMemcpyHostToDevice, h->stream));
+        C_(cudaMemcpyAsync(d_nr.p, nr, sizeof(int) * (size_t)B, cudaMemcpyHostToDevice, h->stream));
+        C_(cudaMemcpyAsync(d_nc.p, nc, sizeof(int) * (size_t)B, cudaMemcpyHostToDevice, h->stream));
+        h->h2d_bytes += (int64_t)po[B] + (int64_t)sizeof(long long) * (B + 1) + 2 * (int64_t)sizeof(int) * B;
+        C_(cudaMemsetAsync(h->d_rp[0].p, 0, sizeof(int) * (NN + 4 * (size_t)B), h->stream));
+        C_(cudaMemsetAsync(h->d_ci[0].p, 0, sizeof(int) * ZZ, h->stream));
+        C_(cudaMemsetAsync(h->d_val[0].p, 0, sizeof(double) * ZZ, h->stream));
+        C_(cudaMemsetAsync(h->d_b[0].p, 0, sizeof(double) * NN, h->stream));
+        SegBuildArgs a;
+        a.pixels = d_pix.p; a.pix_off = d_po.p; a.nr = d_nr.p; a.nc = d_nc.p; a.off_n = h->d_off_n.p; a.off_nnz = h->d_off_nnz.p;
+        a.rowptr = h->d_rp[0].p; a.colidx = h->d_ci[0].p; a.val = h->d_val[0].p; a.b = h->d_b[0].p;
+        a.scr_v = h->vecs[7].p; a.scr_t = h->vecs[8].p; a.st = h->d_st.p;
+        const double sigma = 0.1;                                                               // SEG.cpp:734-737
+        a.cst = log(2.0 * 3.14159265358979323846) / 2.0 + log(sigma); a.den = 2 * sigma * sigma; a.log2v = log(2.0);
+        a.bg = 0.6; a.f1 = 0.2; a.f2 = 0.2;
+        seg_build_graph_kernel<<<B, 256, 0, h->stream>>>(a);
+        C_(cudaGetLastError());
+        h->launches++;
+        C_(cudaMemcpyAsync(h->d_rp_org.p, h->d_rp[0].p, sizeof(int) * (NN + 4 * (size_t)B), cudaMemcpyDeviceToDevice, h->stream));
+        C_(cudaMemcpyAsync(h->d_ci_org.p, h->d_ci[0].p, sizeof(int) * ZZ, cudaMemcpyDeviceToDevice, h->stream));
+        C_(cudaMemcpyAsync(h->d_val_org.p, h->d_val[0].p, sizeof(double) * ZZ, cudaMemcpyDeviceToDevice, h->stream));
+        C_(cudaMemcpyAsync(h->d_b_org.p, h->d_b[0].p, sizeof(double) * NN, cudaMemcpyDeviceToDevice, h->stream));
+        C_(cudaMemcpyAsync(h->h_st.data(), h->d_st.p, sizeof(SegInst) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+        C_(cudaStreamSynchronize(h->stream));
+        for (int i = 0; i < B && ok; ++i) h->cconst[i] = h->h_st[i].cconst;
+    } else {
+        lpbox_set_error("seg graph builder: out of device memory");
     }
-    return lpbox_seg_create_csr(device, B, ns.data(), rp.data(), ci.data(), va.data(), b.data(), c.data(), hist_cap);
+    d_pix.free_(); d_po.free_(); d_nr.free_(); d_nc.free_();
+    if (!ok) { lpbox_seg_destroy(h); return nullptr; }
+    return h;
+}
+
+// the graph the device builder produced for image i (tests / inspection): arrays sized n+1, nnz, nnz, n
+extern "C" int lpbox_seg_get_graph(lpbox_seg_batch *h, int i, int32_t *rowptr, int32_t *colidx, double *val, double *b, double *c) {
+    if (!h || i < 0 || i >= h->B) return LPBOX_E_INVALID;
+    if (cudaSetDevice(h->device) != cudaSuccess) return LPBOX_E_CUDA;
+    const int n = h->n0[i], nz = h->nnz0[i];
+    SCK(cudaMemcpy(rowptr, h->d_rp_org.p + h->off_n[i] + 4 * (size_t)i, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToHost));
+    SCK(cudaMemcpy(colidx, h->d_ci_org.p + h->off_nnz[i], sizeof(int) * (size_t)nz, cudaMemcpyDeviceToHost));
+    SCK(cudaMemcpy(val, h->d_val_org.p + h->off_nnz[i], sizeof(double) * (size_t)nz, cudaMemcpyDeviceToHost));
+    SCK(cudaMemcpy(b, h->d_b_org.p + h->off_n[i], sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+    if (c) *c = h->cconst[i];
+    return nz;
 }
 
 extern "C" int lpbox_seg_set_params(lpbox_seg_batch *h, const lpbox_params *p) {

@@ -79,6 +79,7 @@ SIGNATURES = {
     "lpbox_seg_create_images": (_vp, [C.c_int, C.c_int, _vp, _vp, _vp, C.c_int]),
     "lpbox_seg_destroy": (None, [_vp]),
     "lpbox_seg_build_graph": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "lpbox_seg_get_graph": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "lpbox_seg_set_params": (C.c_int, [_vp, C.POINTER(Params)]),
     "lpbox_seg_init": (C.c_int, [_vp, _vp]),
     "lpbox_seg_solve": (C.c_int, [_vp, _vp]),

@@ -57,6 +57,13 @@ class SegBatch:
             raise RuntimeError("lpbox_seg_create failed: " + _capi.last_error())
         self.h = C.c_void_p(h)
 
+    def graph(self, i):
+        """(rowptr, colidx, val, b, c) of problem i as held on the device (for images: what the device graph builder produced)."""
+        n = int(self.org_n[i])
+        rp = np.zeros(n + 1, dtype=np.int32); ci = np.zeros(7 * n, dtype=np.int32); va = np.zeros(7 * n); b = np.zeros(n); c = np.zeros(1)
+        nnz = check(self.L.lpbox_seg_get_graph(self.h, int(i), ptr(rp), ptr(ci), ptr(va), ptr(b), ptr(c)), "get_graph")
+        return rp, ci[:nnz].copy(), va[:nnz].copy(), b, float(c[0])
+
     def close(self):
         if getattr(self, "h", None):
             self.L.lpbox_seg_destroy(self.h)

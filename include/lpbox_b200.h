@@ -171,13 +171,18 @@ typedef struct lpbox_seg_batch lpbox_seg_batch;
  * constant c (`_c`, SEG.cpp:238).  rowptr_all: the B rowptr arrays back to back (n[i]+1 entries each, starting at 0). */
 lpbox_seg_batch *lpbox_seg_create_csr(int device, int B, const int32_t *n, const int32_t *rowptr_all, const int32_t *colidx_all,
                                       const double *val_all, const double *b_all, const double *c, int hist_cap);
-/* B grey images (row-major uint8, nr[i] x nc[i], already scaled to the node budget): runs the reference's graph
- * builder (get_unary_cost / get_binary_cost / get_A_b_from_cost, SEG.cpp:55-81,144-248,727-758) on the host cores and
- * uploads.  Replaces the image front-end of ADMM_bqp_unconstrained_init (SEG.cpp:705-758) minus imread/resize. */
+/* B grey images (row-major uint8, nr[i] x nc[i], already scaled to the node budget): uploads the PIXELS only and runs the
+ * reference's graph construction (get_unary_cost / get_binary_cost / get_A_b_from_cost, SEG.cpp:55-81,144-248,727-758) on
+ * the device, one CTA per image, straight into the solver's CSR buffers.  Replaces the image front-end
+ * of ADMM_bqp_unconstrained_init (SEG.cpp:705-758) minus imread/resize. */
 lpbox_seg_batch *lpbox_seg_create_images(int device, int B, const uint8_t *pixels_all, const int32_t *nr, const int32_t *nc,
                                          int hist_cap);
 void lpbox_seg_destroy(lpbox_seg_batch *h);
-/* the graph builder alone: outputs rowptr[n+1], colidx/val[<= 7n], b[n], *c; returns nnz */
+/* the graph the batch holds for image / problem i (what the device builder produced): rowptr[n+1], colidx/val[nnz], b[n], *c;
+ * returns nnz */
+int lpbox_seg_get_graph(lpbox_seg_batch *h, int i, int32_t *rowptr, int32_t *colidx, double *val, double *b, double *c);
+/* the HOST graph builder alone (single image; the literal restatement the device builder is tested against): outputs
+ * rowptr[n+1], colidx/val[<= 7n], b[n], *c; returns nnz */
 int lpbox_seg_build_graph(const uint8_t *pixels, int nr, int nc, int32_t *rowptr, int32_t *colidx, double *val, double *b,
                           double *c_out);
 int lpbox_seg_set_params(lpbox_seg_batch *h, const lpbox_params *p);        /* default: lpbox_params_seg() */

@@ -23,6 +23,26 @@ def test_graph_builder_matches_reference(gold):
     assert np.array_equal(va, gold["val"]) and np.array_equal(b, gold["b"]) and c == float(gold["c"])
 
 
+def test_device_graph_builder_equals_host_builder_and_reference(gold):
+    """N3: the device graph builder (one CTA per image, pixels in -> CSR in the solver's buffers) == the host restatement ==
+    the reference binary's builder, entry for entry (rowptr, colidx, weights, b, c) -- incl. ragged shapes and 1-pixel-wide images."""
+    import lpbox
+    shapes = [(24, 30), (37, 41), (1, 17), (19, 1), (2, 2), (1, 1), (64, 48), (75, 100)]
+    imgs = [gold["img"]] + [synth_image(s, nr, nc) for s, (nr, nc) in enumerate(shapes)]
+    imgs.append(np.random.default_rng(5).integers(0, 256, (40, 55)).astype(np.uint8))       # white noise: every weight class
+    imgs.append(np.full((9, 13), 200, dtype=np.uint8))                                      # constant image: sigma = 0 -> exp(-0/0)
+    batch = lpbox.SegBatch(imgs)
+    for i, img in enumerate(imgs):
+        dev = batch.graph(i)
+        host = lpbox.build_graph(img)
+        for k, (d, h) in enumerate(zip(dev[:4], host[:4])):
+            assert np.array_equal(d, h, equal_nan=True), (i, k)
+        assert dev[4] == host[4], i
+    d0 = batch.graph(0)
+    assert np.array_equal(d0[0], gold["rowptr"]) and np.array_equal(d0[1], gold["colidx"]) and np.array_equal(d0[2], gold["val"])
+    assert np.array_equal(d0[3], gold["b"]) and d0[4] == float(gold["c"])
+
+
 @pytest.mark.parametrize("K", [1, 5, 20, 100, 10000])
 def test_iterates_match_reference_binary(gold, K):
     import lpbox
