@@ -281,7 +281,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"configs[1]: {B} synthetic combinatorial-auction instances per GPU (j={N_ITEMS}, k={N_BIDS}), "
                                    "plain Lp-Box ADMM to convergence (ADMM_lp_iters_init + ADMM_lp_iters(0,2e4)), parity mode "
-                                   "(bit-identical to the reference); learned early fixing not in the timed path yet",
+                                   "(bit-identical to the reference); the same batch with MHA early fixing is timed separately in the "
+                                   "`l2f` object (approximate solutions, so it is not the headline)",
                        "instances_per_gpu": B, "n_items": N_ITEMS, "n_bids": N_BIDS,
                        "l2": f"inputs larger than L2 ({state_bytes / 1e6:.0f} MB of instance state per GPU vs 126 MB L2)",
                        "parallelism": f"instances sharded over {world} GPU(s), no data-path collective"},
