@@ -275,6 +275,15 @@ def main():
         peak, peak_src = measured_peak()
         # roofline of the dominant kernel (lp_admm_window_kernel) on ONE GPU: algorithmic bytes of one launch / its duration
         ach = (abytes / 1e9) / (kern_ms / 1e3)
+        traffic = None                      # dram bytes per launch, from the committed ncu capture of the same launch (10,000 instances)
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_window_kernel_traffic.json")) as fh:
+                tj = json.load(fh)
+            if B == 10000:
+                traffic = int(tj["dram_bytes_read"]) + int(tj["dram_bytes_write"])
+        except (OSError, ValueError, KeyError):
+            traffic = None
+        alg_bytes_launch = int(abytes)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -291,10 +300,12 @@ def main():
             "e2e": ({"value": tot_B / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)} if e2e_ms > 0 else None),
             "gpu_launches": int(tot_launch),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                          "kernel": "lp_admm_window_kernel", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes_launch,
                          "note": "achieved = algorithmic bytes (SURVEY.md 8d streaming model) / kernel duration; the kernel keeps the "
-                                 "iteration on chip, so physical DRAM traffic is far below the algorithmic bytes (see profiles/)"},
+                                 "iteration on chip, so physical DRAM traffic (`traffic`, bytes per launch from the ncu capture of this "
+                                 "launch configuration, profiles/r01_window_kernel_traffic.json) is far below the algorithmic bytes"},
         }
         if l2f is not None:
             line["l2f"] = l2f
