@@ -545,6 +545,128 @@ __global__ void __launch_bounds__(256) attention_kernel(const __nv_bfloat16 *__r
     dst[0] = w0; dst[1] = w1;
 }
 
+// ---- attention on the tensor cores (warp-level mma.sync; the tiles are too small for tcgen05) ------------------------------------
+// One CTA per variable, one warp per head: S = Q K^T (m16n8k16 bf16 -> fp32), softmax on the accumulator fragments, P (bf16) V.
+// qkv of the variable is staged once in shared memory ([32 tokens][392] bf16, pad rows zeroed); fragments come from ldmatrix.
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t &r0, uint32_t &r1) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t addr, uint32_t &r0, uint32_t &r1) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&v);
+}
+
+constexpr int ATM_LD = 392;    // bf16 per staged row: 784 bytes = 49 x 16 -> ldmatrix rows land in distinct banks
+template <int TT>
+__global__ void __launch_bounds__(256) attention_mma_kernel(const __nv_bfloat16 *__restrict__ qkv, __nv_bfloat16 *__restrict__ heads) {
+    constexpr int MT = (TT + 15) / 16, NT = (TT + 7) / 8, KS = (TT + 15) / 16, ROWS = 16 * MT;
+    __shared__ __align__(16) __nv_bfloat16 sq[ROWS * ATM_LD];
+    const long long var = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    {   // stage [TT][384] (48 x 16-byte chunks per token), zero the pad rows
+        const uint4 *src = reinterpret_cast<const uint4 *>(qkv + var * TT * 384);
+        for (int i = threadIdx.x; i < ROWS * 48; i += 256) {
+            const int tok = i / 48, c = i - tok * 48;
+            *reinterpret_cast<uint4 *>(sq + tok * ATM_LD + c * 8) = tok < TT ? src[i] : make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+    __syncthreads();
+    const int hd = warp;                                   // 8 warps = 8 heads
+    const uint32_t base = s2u(sq);
+    // ---- S = Q K^T ----
+    float S[MT][NT][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        uint32_t a[4];
+        ldsm_x4(base + (uint32_t)(((mt * 16 + (lane & 15)) * ATM_LD + hd * 16 + (lane >> 4) * 8) * 2), a[0], a[1], a[2], a[3]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            uint32_t b0, b1;
+            ldsm_x2(base + (uint32_t)(((nt * 8 + (lane & 7)) * ATM_LD + 128 + hd * 16 + ((lane >> 3) & 1) * 8) * 2), b0, b1);
+            S[mt][nt][0] = S[mt][nt][1] = S[mt][nt][2] = S[mt][nt][3] = 0.0f;
+            mma_bf16_16816(S[mt][nt], a, b0, b1);
+        }
+    }
+    // ---- softmax over the TT valid columns of each row (rows lane/4 and lane/4 + 8 of every m-tile) ----
+    uint32_t P[MT][2 * KS][2];                              // bf16x2 A-fragments of P: [m-tile][n-tile (zero beyond NT)][row half]
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int col = nt * 8 + (lane & 3) * 2 + j;
+                    float v = S[mt][nt][hf * 2 + j] * 0.25f;
+                    v = col < TT ? v : -INFINITY;
+                    S[mt][nt][hf * 2 + j] = v;
+                    mx = fmaxf(mx, v);
+                }
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            float den = 0.0f;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) { const float e = __expf(S[mt][nt][hf * 2 + j] - mx); S[mt][nt][hf * 2 + j] = e; den += e; }
+            den += __shfl_xor_sync(0xffffffffu, den, 1);
+            den += __shfl_xor_sync(0xffffffffu, den, 2);
+            const float inv = 1.0f / den;
+#pragma unroll
+            for (int nt = 0; nt < 2 * KS; ++nt)
+                P[mt][nt][hf] = nt < NT ? pack_bf16x2(S[mt][nt][hf * 2] * inv, S[mt][nt][hf * 2 + 1] * inv) : 0u;
+        }
+    }
+    // ---- O = P V ----
+    float O[MT][2][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int dt = 0; dt < 2; ++dt) O[mt][dt][0] = O[mt][dt][1] = O[mt][dt][2] = O[mt][dt][3] = 0.0f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+        for (int dt = 0; dt < 2; ++dt) {
+            uint32_t b0, b1;
+            ldsm_x2_trans(base + (uint32_t)(((ks * 16 + (lane & 15)) * ATM_LD + 256 + hd * 16 + dt * 8) * 2), b0, b1);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const uint32_t a[4] = {P[mt][2 * ks][0], P[mt][2 * ks][1], P[mt][2 * ks + 1][0], P[mt][2 * ks + 1][1]};
+                mma_bf16_16816(O[mt][dt], a, b0, b1);
+            }
+        }
+    }
+    // ---- O -> bf16 into this head's (dead) Q columns, then whole rows go out with 16-byte stores ----
+    __syncwarp();
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int dt = 0; dt < 2; ++dt)
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                const int row = mt * 16 + hf * 8 + (lane >> 2);
+                *reinterpret_cast<uint32_t *>(sq + row * ATM_LD + hd * 16 + dt * 8 + (lane & 3) * 2) = pack_bf16x2(O[mt][dt][hf * 2], O[mt][dt][hf * 2 + 1]);
+            }
+    __syncthreads();
+    uint4 *dst = reinterpret_cast<uint4 *>(heads + var * TT * 128);
+    for (int i = threadIdx.x; i < TT * 16; i += 256) {
+        const int tok = i >> 4, c = i & 15;
+        dst[i] = *reinterpret_cast<const uint4 *>(sq + tok * ATM_LD + c * 8);
+    }
+}
+
 // head: a2 [R][128] (after fc2 + ReLU) -> fc3 (16) ReLU -> fc4 (1) -> sigmoid  (LP.mha:185-199)
 __global__ void head_kernel(const __nv_bfloat16 *__restrict__ a2, long long R, const float *__restrict__ w3 /*[16][128]*/, const float *__restrict__ b3,
                             const float *__restrict__ w4 /*[16]*/, float b4, float *__restrict__ scores) {
@@ -721,10 +843,10 @@ extern "C" int lpbox_policy_forward_dev(lpbox_policy *p, void *stream, const flo
             {
                 const unsigned at = ((8 * T + 31) / 32) * 32;
                 const size_t asm_ = sizeof(float) * (size_t)T * ATT_LD;
-                if (T == 20) attention_kernel<20><<<(unsigned)R, at, asm_, st>>>(p->qkv, T, h2);
-                else if (T == 10) attention_kernel<10><<<(unsigned)R, at, asm_, st>>>(p->qkv, T, h2);
-                else if (T == 5) attention_kernel<5><<<(unsigned)R, at, asm_, st>>>(p->qkv, T, h2);
-                else attention_kernel<0><<<(unsigned)R, at, asm_, st>>>(p->qkv, T, h2);
+                if (T == 20) attention_mma_kernel<20><<<(unsigned)R, 256, 0, st>>>(p->qkv, h2);
+                else if (T == 10) attention_mma_kernel<10><<<(unsigned)R, 256, 0, st>>>(p->qkv, h2);
+                else if (T == 5) attention_mma_kernel<5><<<(unsigned)R, 256, 0, st>>>(p->qkv, h2);
+                else attention_kernel<0><<<(unsigned)R, at, asm_, st>>>(p->qkv, T, h2);   // CUDA-core version for other token counts
             }                                  // heads -> h2
             rc = launch_gemm(st, h2, L.Wo, p->qkv /*reuse as [Mt][128] scratch*/, Mt, 128, 128, Epi{nullptr, h, L.s1, L.t1, 0}); if (rc) return rc;
             // NOTE: the out-proj result (h + MHA(h), BatchNorm folded) lives in the first Mt*128 elements of qkv
