@@ -667,6 +667,284 @@ __global__ void __launch_bounds__(256) attention_mma_kernel(const __nv_bfloat16 
     }
 }
 
+// ---- fused multi-head-attention sublayer ---------------------------------------------------------------------------------------
+// out = BN( X + Wo . MHA(X) )  (LP.mha:58-122 + SkipConnection + Normalization) in ONE persistent kernel: the [rows][384] q|k|v
+// activation and the [rows][128] head outputs never leave the SM.  A tile is VPT = 128 / T whole variables (T tokens each):
+//     acc_qkv (TMEM, 384 cols) = X . Wqkv^T                      tcgen05.mma, 3 chunks of N = 128, K = 128
+//     acc_o   (TMEM, 128 cols) = X . I                           the residual, added by the tensor core
+//     sQ (smem)  = bf16(acc_qkv) of 4 heads at a time            worker warps: tcgen05.ld -> shared memory
+//     sHd (smem) = softmax(q k'/4) v per (variable, head)        worker warps: mma.sync + ldmatrix, written as the swizzled A operand
+//     acc_o += sHd . Wo^T                                        tcgen05.mma
+//     out = bf16(acc_o * scale + shift)                          worker warps
+// Warp roles: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2..9 = workers.  The QKV GEMM of tile t+1 is issued as soon as the
+// workers have read acc_qkv of tile t, so it overlaps attention / out-projection / drain of tile t.
+constexpr int MH_THREADS = 320;
+constexpr int MH_QLD = 200;              // bf16 per staged row (Q | K | V of 4 heads = 192, + 8: 400 bytes = 25 x 16 -> conflict-free ldmatrix)
+constexpr int MH_QROWS = 136;            // 128 tile rows + the rows a padded m-tile of the last variable can touch
+constexpr size_t MH_SMEM = 5 * (size_t)FF_TILE + FF_IDN + (size_t)MH_QROWS * MH_QLD * 2 + 2 * 128 * 4 + 256 + 1024;
+
+template <int TT>
+__global__ void __launch_bounds__(MH_THREADS, 1)
+mha_fused_tcgen05(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapWqkv, const __grid_constant__ CUtensorMap mapWo,
+                  __nv_bfloat16 *__restrict__ out, int M, const float *__restrict__ scale, const float *__restrict__ shift) {
+    constexpr int VPT = 128 / TT, TR = VPT * TT;
+    constexpr int MT = (TT + 15) / 16, NT = (TT + 7) / 8, KS = (TT + 15) / 16;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char *sX = smem, *sW = sX + FF_TILE /*[2]*/, *sWo = sW + 2 * FF_TILE, *sHd = sWo + FF_TILE, *sI = sHd + FF_TILE;
+    __nv_bfloat16 *sQ = reinterpret_cast<__nv_bfloat16 *>(sI + FF_IDN);
+    float *ssc = reinterpret_cast<float *>(sQ + MH_QROWS * MH_QLD), *ssh = ssc + 128;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ssh + 128);
+    uint64_t *x_full = bars, *x_empty = bars + 1, *w_full = bars + 2 /*[2]*/, *w_empty = bars + 4 /*[2]*/, *wo_full = bars + 6, *qkv_full = bars + 7,
+             *qkv_empty = bars + 8, *hd_full = bars + 9, *o_full = bars + 10, *acc_o_empty = bars + 11;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12);
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    const int n_tiles = (M + TR - 1) / TR;
+    const int my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+
+    for (int i = threadIdx.x; i < 128; i += MH_THREADS) { ssc[i] = scale[i]; ssh[i] = shift[i]; }
+    for (int i = threadIdx.x; i < (int)FF_IDN / 2; i += MH_THREADS) {
+        const int n = i >> 6, ch = (i >> 3) & 7, e = i & 7, k = ((ch ^ (n & 7)) << 3) + e;
+        reinterpret_cast<unsigned short *>(sI)[i] = (k == n) ? (unsigned short)0x3F80 : (unsigned short)0;
+    }
+    for (int i = threadIdx.x; i < MH_QROWS * MH_QLD / 2; i += MH_THREADS) reinterpret_cast<uint32_t *>(sQ)[i] = 0u;   // pad rows must stay finite
+    for (int i = threadIdx.x; i < (int)FF_TILE / 4; i += MH_THREADS) reinterpret_cast<uint32_t *>(sHd)[i] = 0u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (threadIdx.x == 0) {
+        mb_init(x_full, 1); mb_init(x_empty, 1); mb_init(&w_full[0], 1); mb_init(&w_full[1], 1); mb_init(&w_empty[0], 1); mb_init(&w_empty[1], 1);
+        mb_init(wo_full, 1); mb_init(qkv_full, 1); mb_init(qkv_empty, 256); mb_init(hd_full, 256); mb_init(o_full, 1); mb_init(acc_o_empty, 256);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_slot)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    if (warp == 0) {
+        // ---- TMA producer ----
+        if (my_tiles > 0 && elect_one()) {
+            mb_expect(wo_full, FF_TILE);
+            tma_2d(sWo, &mapWo, 0, 0, wo_full);
+            tma_2d(sWo + FF_BOX, &mapWo, 64, 0, wo_full);
+        }
+        for (int i = 0; i < my_tiles; ++i) {
+            const int row0 = (blockIdx.x + i * gridDim.x) * TR;
+            if (i > 0) mb_wait(x_empty, (i - 1) & 1);
+            if (elect_one()) {
+                mb_expect(x_full, FF_TILE);
+                tma_2d(sX, &mapX, 0, row0, x_full);
+                tma_2d(sX + FF_BOX, &mapX, 64, row0, x_full);
+            }
+            for (int c = 0; c < 3; ++c) {
+                const uint32_t cc = (uint32_t)i * 3 + c, buf = cc & 1;
+                if (cc >= 2) mb_wait(&w_empty[buf], ((cc >> 1) - 1) & 1);
+                if (elect_one()) {
+                    mb_expect(&w_full[buf], FF_TILE);
+                    tma_2d(sW + buf * FF_TILE, &mapWqkv, 0, c * 128, &w_full[buf]);
+                    tma_2d(sW + buf * FF_TILE + FF_BOX, &mapWqkv, 64, c * 128, &w_full[buf]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer ----
+        const uint32_t idesc128 = make_idesc_n(128), idesc64 = make_idesc_n(64);
+        auto qkv_gemm = [&](int i) {
+            mb_wait(x_full, i & 1);
+            for (int c = 0; c < 3; ++c) {
+                const uint32_t cc = (uint32_t)i * 3 + c, buf = cc & 1;
+                mb_wait(&w_full[buf], (cc >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a = s2u(sX), b = s2u(sW + buf * FF_TILE), d = tmem + c * 128;
+                if (elect_one()) {
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_f16(d, make_desc(a + kb * FF_BOX + k * 32), make_desc(b + kb * FF_BOX + k * 32), idesc128, (kb | k) ? 1u : 0u);
+                    umma_commit(&w_empty[buf]);
+                }
+            }
+        };
+        auto residual = [&]() {       // acc_o[:, kb*64 .. +64) = X[:, kb*64 .. +64) . I ; then the tile's X and acc_qkv hand-offs
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a = s2u(sX), b = s2u(sI), d = tmem + 384;
+            if (elect_one()) {
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16(d + kb * 64, make_desc(a + kb * FF_BOX + k * 32), make_desc(b + k * 32), idesc64, k ? 1u : 0u);
+                umma_commit(qkv_full);
+                umma_commit(x_empty);
+            }
+        };
+        if (my_tiles > 0) { qkv_gemm(0); residual(); }
+        for (int i = 0; i < my_tiles; ++i) {
+            if (i + 1 < my_tiles) { mb_wait(qkv_empty, i & 1); qkv_gemm(i + 1); }
+            if (i == 0) mb_wait(wo_full, 0);
+            mb_wait(hd_full, i & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            {
+                const uint32_t a = s2u(sHd), b = s2u(sWo), d = tmem + 384;
+                if (elect_one()) {
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_f16(d, make_desc(a + kb * FF_BOX + k * 32), make_desc(b + kb * FF_BOX + k * 32), idesc128, 1u);
+                    umma_commit(o_full);
+                }
+            }
+            if (i + 1 < my_tiles) { mb_wait(acc_o_empty, i & 1); residual(); }
+        }
+    } else {
+        // ---- workers ----
+        const int w8 = warp - 2, q = warp & 3, wsub = w8 >> 2, row = q * 32 + lane;
+        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+        const uint32_t sq_base = s2u(sQ);
+        for (int i = 0; i < my_tiles; ++i) {
+            const long long row0 = (long long)(blockIdx.x + i * gridDim.x) * TR;
+            mb_wait(qkv_full, i & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int hf = 0; hf < 2; ++hf) {
+                // acc_qkv -> sQ: q | k | v of heads 4 hf .. 4 hf + 3; this warp copies 32 columns of each part for its 32 rows
+#pragma unroll 1
+                for (int part = 0; part < 3; ++part) {
+                    uint32_t r[32];
+                    tmem_ld32_nowait(lane_base + (uint32_t)(part * 128 + hf * 64 + wsub * 32), r);
+                    tmem_ld_wait();
+                    __nv_bfloat16 *dst = sQ + row * MH_QLD + part * 64 + wsub * 32;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4 *>(dst + 8 * j) =
+                            make_uint4(pack_bf16x2(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1])), pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])),
+                                       pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])), pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])));
+                }
+                if (hf == 1) {                                  // every read of acc_qkv is done: the next tile's QKV GEMM may overwrite it
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mb_arrive(qkv_empty);
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                // attention tasks (variable v of the tile, head 4 hf + hh)
+#pragma unroll 1
+                for (int tsk = w8; tsk < VPT * 4; tsk += 8) {
+                    const int v = tsk >> 2, hh = tsk & 3, r0 = v * TT;
+                    float S[MT][NT][4];
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        uint32_t a[4];
+                        ldsm_x4(sq_base + (uint32_t)(((r0 + mt * 16 + (lane & 15)) * MH_QLD + hh * 16 + (lane >> 4) * 8) * 2), a[0], a[1], a[2], a[3]);
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) {
+                            uint32_t b0, b1;
+                            ldsm_x2(sq_base + (uint32_t)(((r0 + nt * 8 + (lane & 7)) * MH_QLD + 64 + hh * 16 + ((lane >> 3) & 1) * 8) * 2), b0, b1);
+                            S[mt][nt][0] = S[mt][nt][1] = S[mt][nt][2] = S[mt][nt][3] = 0.0f;
+                            mma_bf16_16816(S[mt][nt], a, b0, b1);
+                        }
+                    }
+                    uint32_t P[MT][2 * KS][2];
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                        for (int hr = 0; hr < 2; ++hr) {
+                            float mx = -INFINITY;
+#pragma unroll
+                            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                                for (int j = 0; j < 2; ++j) {
+                                    const int col = nt * 8 + (lane & 3) * 2 + j;
+                                    float x = S[mt][nt][hr * 2 + j] * 0.25f;
+                                    x = col < TT ? x : -INFINITY;
+                                    S[mt][nt][hr * 2 + j] = x;
+                                    mx = fmaxf(mx, x);
+                                }
+                            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                            float den = 0.0f;
+#pragma unroll
+                            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                                for (int j = 0; j < 2; ++j) { const float e = __expf(S[mt][nt][hr * 2 + j] - mx); S[mt][nt][hr * 2 + j] = e; den += e; }
+                            den += __shfl_xor_sync(0xffffffffu, den, 1);
+                            den += __shfl_xor_sync(0xffffffffu, den, 2);
+                            const float inv = 1.0f / den;
+#pragma unroll
+                            for (int nt = 0; nt < 2 * KS; ++nt)
+                                P[mt][nt][hr] = nt < NT ? pack_bf16x2(S[mt][nt][hr * 2] * inv, S[mt][nt][hr * 2 + 1] * inv) : 0u;
+                        }
+                    }
+                    float O[MT][2][4];
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                        for (int dt = 0; dt < 2; ++dt) O[mt][dt][0] = O[mt][dt][1] = O[mt][dt][2] = O[mt][dt][3] = 0.0f;
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                        for (int dt = 0; dt < 2; ++dt) {
+                            uint32_t b0, b1;
+                            ldsm_x2_trans(sq_base + (uint32_t)(((r0 + ks * 16 + (lane & 15)) * MH_QLD + 128 + hh * 16 + dt * 8) * 2), b0, b1);
+#pragma unroll
+                            for (int mt = 0; mt < MT; ++mt) {
+                                const uint32_t a[4] = {P[mt][2 * ks][0], P[mt][2 * ks][1], P[mt][2 * ks + 1][0], P[mt][2 * ks + 1][1]};
+                                mma_bf16_16816(O[mt][dt], a, b0, b1);
+                            }
+                        }
+                    // head output -> A operand of the out-projection (K-major, 128-byte swizzle; k = (4 hf + hh) * 16 + d lives in box hf)
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                        for (int hr = 0; hr < 2; ++hr) {
+                            const int ti = mt * 16 + hr * 8 + (lane >> 2);
+                            if (ti < TT) {
+                                const int rr = r0 + ti;
+#pragma unroll
+                                for (int dt = 0; dt < 2; ++dt)
+                                    *reinterpret_cast<uint32_t *>(sHd + hf * FF_BOX + rr * 128 + (((hh * 2 + dt) ^ (rr & 7)) << 4) + (lane & 3) * 4) =
+                                        pack_bf16x2(O[mt][dt][hr * 2], O[mt][dt][hr * 2 + 1]);
+                            }
+                        }
+                }
+                if (hf == 0) asm volatile("bar.sync 1, 256;" ::: "memory");      // sQ is restaged for the second half
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mb_arrive(hd_full);
+            // ---- drain: acc_o (= X + Wo heads) -> folded BatchNorm -> bf16 -> global; this warp: 64 columns of its 32 rows ----
+            mb_wait(o_full, i & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const long long m = row0 + row;
+#pragma unroll 1
+            for (int g = 0; g < 2; ++g) {
+                uint32_t r[32];
+                const int c0 = wsub * 64 + g * 32;
+                tmem_ld32_nowait(lane_base + (uint32_t)(384 + c0), r);
+                tmem_ld_wait();
+                if (row < TR && m < M) {
+                    const float4 *sc4 = reinterpret_cast<const float4 *>(ssc + c0), *sh4 = reinterpret_cast<const float4 *>(ssh + c0);
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        const float4 a0 = sc4[2 * j8], a1 = sc4[2 * j8 + 1], b0 = sh4[2 * j8], b1 = sh4[2 * j8 + 1];
+                        uint4 o;
+                        o.x = pack_bf16x2(__uint_as_float(r[j8 * 8 + 0]) * a0.x + b0.x, __uint_as_float(r[j8 * 8 + 1]) * a0.y + b0.y);
+                        o.y = pack_bf16x2(__uint_as_float(r[j8 * 8 + 2]) * a0.z + b0.z, __uint_as_float(r[j8 * 8 + 3]) * a0.w + b0.w);
+                        o.z = pack_bf16x2(__uint_as_float(r[j8 * 8 + 4]) * a1.x + b1.x, __uint_as_float(r[j8 * 8 + 5]) * a1.y + b1.y);
+                        o.w = pack_bf16x2(__uint_as_float(r[j8 * 8 + 6]) * a1.z + b1.z, __uint_as_float(r[j8 * 8 + 7]) * a1.w + b1.w);
+                        *reinterpret_cast<uint4 *>(out + m * 128 + c0 + j8 * 8) = o;
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mb_arrive(acc_o_empty);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+}
+
 // head: a2 [R][128] (after fc2 + ReLU) -> fc3 (16) ReLU -> fc4 (1) -> sigmoid  (LP.mha:185-199)
 __global__ void head_kernel(const __nv_bfloat16 *__restrict__ a2, long long R, const float *__restrict__ w3 /*[16][128]*/, const float *__restrict__ b3,
                             const float *__restrict__ w4 /*[16]*/, float b4, float *__restrict__ scores) {
@@ -742,6 +1020,34 @@ int launch_ff_fused(cudaStream_t st, const __nv_bfloat16 *X, const __nv_bfloat16
     return 0;
 }
 
+template <int TT>
+int launch_mha_fused_t(cudaStream_t st, const CUtensorMap &mx, const CUtensorMap &mq, const CUtensorMap &mo, __nv_bfloat16 *out, long long M,
+                       const float *scale, const float *shift) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(mha_fused_tcgen05<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MH_SMEM); attr = true; }
+    constexpr int TR = (128 / TT) * TT;
+    const long long n_tiles = (M + TR - 1) / TR;
+    mha_fused_tcgen05<TT><<<(unsigned)std::min<long long>(n_tiles, g_sm_count), MH_THREADS, MH_SMEM, st>>>(mx, mq, mo, out, (int)M, scale, shift);
+    return 0;
+}
+// out = (X + Wo . MHA(X)) * scale + shift for rows grouped in variables of T tokens (T = 20, 10 or 5)
+int launch_mha_fused(cudaStream_t st, const __nv_bfloat16 *X, const __nv_bfloat16 *Wqkv, const __nv_bfloat16 *Wo, const float *scale,
+                     const float *shift, __nv_bfloat16 *out, long long M, int T) {
+    if (M <= 0) return 0;
+    if (!scale || !shift || (T != 20 && T != 10 && T != 5) || M % T) { lpbox_set_error("fused MHA: T must be 20, 10 or 5 and rows a multiple of T"); return LPBOX_E_INVALID; }
+    CUtensorMap mx, mq, mo;
+    if (!make_map(&mx, X, (uint64_t)M, 128, 128) || !make_map(&mq, Wqkv, 384, 128, 128) || !make_map(&mo, Wo, 128, 128, 128)) {
+        lpbox_set_error("cuTensorMapEncodeTiled failed"); return LPBOX_E_CUDA;
+    }
+    if (!g_sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev); if (g_sm_count <= 0) g_sm_count = 148; }
+    if (T == 20) launch_mha_fused_t<20>(st, mx, mq, mo, out, M, scale, shift);
+    else if (T == 10) launch_mha_fused_t<10>(st, mx, mq, mo, out, M, scale, shift);
+    else launch_mha_fused_t<5>(st, mx, mq, mo, out, M, scale, shift);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { lpbox_set_error(std::string("fused MHA launch: ") + cudaGetErrorString(e)); return LPBOX_E_CUDA; }
+    return 0;
+}
+
 template <typename Tp>
 Tp *dalloc(size_t n) { Tp *p = nullptr; return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(Tp)) == cudaSuccess ? p : nullptr; }
 
@@ -759,6 +1065,7 @@ struct lpbox_policy {
     float *bfc1 = nullptr, *bfc2 = nullptr;
     __nv_bfloat16 *h = nullptr, *h2 = nullptr, *qkv = nullptr, *ff = nullptr, *a1 = nullptr, *a2 = nullptr;
     int64_t launches = 0;
+    bool fused_mha = true;      // LPBOX_POLICY_UNFUSED_MHA=1 selects the three-kernel path (tests compare the two)
 };
 
 static __nv_bfloat16 *upload_bf16(lpbox_policy *p, const float *src, size_t n) {
@@ -788,6 +1095,7 @@ extern "C" lpbox_policy *lpbox_policy_create(int device, int tokens, int n_layer
     if (!get_encode()) { lpbox_set_error("cuTensorMapEncodeTiled not available"); return nullptr; }
     lpbox_policy *p = new lpbox_policy();
     p->device = device; p->T = tokens; p->L = n_layers; p->chunk = chunk_rows > 0 ? chunk_rows : 16384;
+    p->fused_mha = getenv("LPBOX_POLICY_UNFUSED_MHA") == nullptr;
     const float *w = packed;
     const float *ew = w; w += 128 * 10;
     const float *eb = w; w += 128;
@@ -839,18 +1147,21 @@ extern "C" int lpbox_policy_forward_dev(lpbox_policy *p, void *stream, const flo
         p->launches++;
         __nv_bfloat16 *h = p->h, *h2 = p->h2;
         for (auto &L : p->layers) {
-            int rc = launch_gemm(st, h, L.Wqkv, p->qkv, Mt, 384, 128, Epi{nullptr, nullptr, nullptr, nullptr, 0}); if (rc) return rc;
-            {
+            int rc;
+            __nv_bfloat16 *hn = p->qkv;       // the sublayer output (h + MHA(h), BatchNorm folded) lives in the first Mt*128 elements of qkv
+            if (p->fused_mha && (T == 20 || T == 10 || T == 5)) {
+                rc = launch_mha_fused(st, h, L.Wqkv, L.Wo, L.s1, L.t1, hn, Mt, T); if (rc) return rc;
+                p->launches -= 2;
+            } else {
+                rc = launch_gemm(st, h, L.Wqkv, p->qkv, Mt, 384, 128, Epi{nullptr, nullptr, nullptr, nullptr, 0}); if (rc) return rc;
                 const unsigned at = ((8 * T + 31) / 32) * 32;
                 const size_t asm_ = sizeof(float) * (size_t)T * ATT_LD;
                 if (T == 20) attention_mma_kernel<20><<<(unsigned)R, 256, 0, st>>>(p->qkv, h2);
                 else if (T == 10) attention_mma_kernel<10><<<(unsigned)R, 256, 0, st>>>(p->qkv, h2);
                 else if (T == 5) attention_mma_kernel<5><<<(unsigned)R, 256, 0, st>>>(p->qkv, h2);
                 else attention_kernel<0><<<(unsigned)R, at, asm_, st>>>(p->qkv, T, h2);   // CUDA-core version for other token counts
-            }                                  // heads -> h2
-            rc = launch_gemm(st, h2, L.Wo, p->qkv /*reuse as [Mt][128] scratch*/, Mt, 128, 128, Epi{nullptr, h, L.s1, L.t1, 0}); if (rc) return rc;
-            // NOTE: the out-proj result (h + MHA(h), BatchNorm folded) lives in the first Mt*128 elements of qkv
-            __nv_bfloat16 *hn = p->qkv;
+                rc = launch_gemm(st, h2, L.Wo, hn /*reuse as [Mt][128] scratch*/, Mt, 128, 128, Epi{nullptr, h, L.s1, L.t1, 0}); if (rc) return rc;
+            }
             rc = launch_ff_fused(st, hn, L.W1, L.b1, L.W2, L.b2, L.s2, L.t2, h2, Mt); if (rc) return rc;
             std::swap(h, h2);
             p->launches += 4;
@@ -881,4 +1192,13 @@ extern "C" int lpbox_ff_fused_dev(void *stream, const void *X, const void *W1, c
     if (!get_encode()) { lpbox_set_error("cuTensorMapEncodeTiled not available"); return LPBOX_E_CUDA; }
     return launch_ff_fused((cudaStream_t)stream, (const __nv_bfloat16 *)X, (const __nv_bfloat16 *)W1, b1, (const __nv_bfloat16 *)W2, b2, scale, shift,
                            (__nv_bfloat16 *)out, M);
+}
+
+// the fused multi-head-attention sublayer alone (tests): out = (X + Wo MHA(X)) * scale + shift; X/out bf16 [M][128], M = variables * T,
+// Wqkv bf16 [384][128] (q | k | v, head-major inside each third), Wo bf16 [128][128]; T = 20, 10 or 5
+extern "C" int lpbox_mha_fused_dev(void *stream, const void *X, const void *Wqkv, const void *Wo, const float *scale, const float *shift, void *out,
+                                   int64_t M, int T) {
+    if (!get_encode()) { lpbox_set_error("cuTensorMapEncodeTiled not available"); return LPBOX_E_CUDA; }
+    return launch_mha_fused((cudaStream_t)stream, (const __nv_bfloat16 *)X, (const __nv_bfloat16 *)Wqkv, (const __nv_bfloat16 *)Wo, scale, shift,
+                            (__nv_bfloat16 *)out, M, T);
 }

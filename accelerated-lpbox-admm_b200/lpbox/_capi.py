@@ -109,6 +109,7 @@ SIGNATURES = {
     "lpbox_policy_launch_count": (C.c_int64, [_vp]),
     "lpbox_gemm_bf16_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, C.c_int]),
     "lpbox_ff_fused_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64]),
+    "lpbox_mha_fused_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int]),
     "lpbox_read_instance": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, _ip, _ip, C.POINTER(_ip), C.POINTER(_ip),
                                       C.POINTER(_dp), C.POINTER(_dp)]),
     "lpbox_free": (None, [_vp]),

@@ -258,6 +258,11 @@ int lpbox_policy_forward_dev(lpbox_policy *p, void *stream, const float *input_d
 int64_t lpbox_policy_launch_count(const lpbox_policy *p);
 /* the tcgen05 GEMM alone (tests): C[M][N] = A[M][K] . W[N][K]^T (+ bias[n]) (ReLU); bf16 DEVICE row-major; N % 128 == 0, K % 64 == 0 */
 int lpbox_gemm_bf16_dev(void *stream, const void *A, const void *W, void *C, int64_t M, int N, int K, const float *bias, int relu);
+/* the fused multi-head-attention sublayer alone (tests): out = (X + Wo MHA(X)) * scale + shift (LP.mha:58-122 + skip + eval-mode
+ * BatchNorm); X, out: bf16 DEVICE [M][128] with M = variables * T rows, T = 20, 10 or 5 tokens per variable; Wqkv: bf16 [384][128]
+ * (q | k | v, head-major inside each third); Wo: bf16 [128][128] */
+int lpbox_mha_fused_dev(void *stream, const void *X, const void *Wqkv, const void *Wo, const float *scale, const float *shift,
+                        void *out, int64_t M, int T);
 /* the fused feed-forward sublayer alone (tests): out = (X + W2 relu(W1 X + b1) + b2) * scale + shift  (LP.mha:140-160 with the
  * eval-mode BatchNorm folded into scale / shift); X, out: bf16 DEVICE [M][128]; W1: bf16 [512][128]; W2: bf16 [128][512] */
 int lpbox_ff_fused_dev(void *stream, const void *X, const void *W1, const float *b1, const void *W2, const float *b2,

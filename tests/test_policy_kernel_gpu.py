@@ -53,6 +53,34 @@ def test_fused_feed_forward_matches_torch(M):
     assert err <= 0.02 * max(1.0, ref.abs().max().item()), err
 
 
+@pytest.mark.parametrize("T,R", [(20, 6), (20, 7), (20, 1000), (10, 12), (10, 501), (5, 25), (5, 1003), (20, 40000)])
+def test_fused_mha_sublayer_matches_torch(T, R):
+    """out = (X + Wo MHA(X)) * scale + shift for R variables of T tokens vs an fp32 PyTorch restatement (q, k, v and the head
+    outputs are rounded to bf16 on chip, like the unfused kernels)."""
+    import lpbox
+    L = lpbox._capi.lib()
+    g = torch.Generator(device="cuda").manual_seed(T * 1000 + R)
+    M = R * T
+    X = (torch.randn(M, 128, device="cuda", generator=g) * 0.7).bfloat16()
+    Wqkv = (torch.randn(384, 128, device="cuda", generator=g) * 0.12).bfloat16()
+    Wo = (torch.randn(128, 128, device="cuda", generator=g) * 0.1).bfloat16()
+    sc = torch.rand(128, device="cuda", generator=g) + 0.5
+    sh = torch.randn(128, device="cuda", generator=g) * 0.1
+    out = torch.zeros(M, 128, device="cuda", dtype=torch.bfloat16)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    rc = L.lpbox_mha_fused_dev(st, vp(X), vp(Wqkv), vp(Wo), vp(sc), vp(sh), vp(out), M, T)
+    assert rc == 0, lpbox._capi.last_error()
+    torch.cuda.synchronize()
+    qkv = (X.float() @ Wqkv.float().t()).bfloat16().float().view(R, T, 3, 8, 16)
+    q, k, v = qkv[:, :, 0].transpose(1, 2), qkv[:, :, 1].transpose(1, 2), qkv[:, :, 2].transpose(1, 2)      # (R, 8, T, 16)
+    p = torch.softmax(q @ k.transpose(-1, -2) * 0.25, dim=-1).bfloat16().float()
+    heads = (p @ v).transpose(1, 2).reshape(M, 128).bfloat16().float()
+    ref = (X.float() + heads @ Wo.float().t()) * sc + sh
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 0.03 * max(1.0, ref.abs().max().item()), err
+
+
 @pytest.mark.parametrize("kind,T", [("GraphAttentionEncoder", 20), ("MLPEncoder", 20), ("GraphAttentionEncoder", 5), ("GraphAttentionEncoder", 10)])
 def test_policy_kernel_matches_torch_module(kind, T):
     from lpbox import policy
