@@ -90,6 +90,13 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t *r) {
           "=r"(r[31])
         : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct Epi {
@@ -558,7 +565,7 @@ __device__ __forceinline__ void ldsm_x2_trans(uint32_t addr, uint32_t &r0, uint3
     asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
 }
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"   // register-only: free to be scheduled
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -676,12 +683,112 @@ __global__ void __launch_bounds__(256) attention_mma_kernel(const __nv_bfloat16 
 //     sHd (smem) = softmax(q k'/4) v per (variable, head)        worker warps: mma.sync + ldmatrix, written as the swizzled A operand
 //     acc_o += sHd . Wo^T                                        tcgen05.mma
 //     out = bf16(acc_o * scale + shift)                          worker warps
-// Warp roles: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2..9 = workers.  The QKV GEMM of tile t+1 is issued as soon as the
+// Warp roles: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2..13 = workers.  The QKV GEMM of tile t+1 is issued as soon as the
 // workers have read acc_qkv of tile t, so it overlaps attention / out-projection / drain of tile t.
-constexpr int MH_THREADS = 320;
+constexpr int MH_WORKERS = 12;           // worker warps: 3 per TMEM lane quarter (= per SM sub-partition)
+constexpr int MH_THREADS = 32 * (2 + MH_WORKERS);
 constexpr int MH_QLD = 200;              // bf16 per staged row (Q | K | V of 4 heads = 192, + 8: 400 bytes = 25 x 16 -> conflict-free ldmatrix)
 constexpr int MH_QROWS = 136;            // 128 tile rows + the rows a padded m-tile of the last variable can touch
 constexpr size_t MH_SMEM = 5 * (size_t)FF_TILE + FF_IDN + (size_t)MH_QROWS * MH_QLD * 2 + 2 * 128 * 4 + 256 + 1024;
+
+// Two attention tasks (variable v = tsk >> 2 of the tile, head hh = tsk & 3 of the staged half) interleaved in one warp:
+// S = q k' (mma.sync), softmax on the fragments, O = P v, O -> the swizzled A operand of the out-projection (box `hd_box`).
+template <int TT>
+__device__ __forceinline__ void mha_attention_pair(uint32_t sq_base, unsigned char *hd_box, int tsk0, int tsk1, bool valid1, int lane) {
+    constexpr int MT = (TT + 15) / 16, NT = (TT + 7) / 8, KS = (TT + 15) / 16;
+    const int r0[2] = {(tsk0 >> 2) * TT, (tsk1 >> 2) * TT}, hh[2] = {tsk0 & 3, tsk1 & 3};
+    float S[2][MT][NT][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            uint32_t a[4];
+            ldsm_x4(sq_base + (uint32_t)(((r0[u] + mt * 16 + (lane & 15)) * MH_QLD + hh[u] * 16 + (lane >> 4) * 8) * 2), a[0], a[1], a[2], a[3]);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                uint32_t b0, b1;
+                ldsm_x2(sq_base + (uint32_t)(((r0[u] + nt * 8 + (lane & 7)) * MH_QLD + 64 + hh[u] * 16 + ((lane >> 3) & 1) * 8) * 2), b0, b1);
+                S[u][mt][nt][0] = S[u][mt][nt][1] = S[u][mt][nt][2] = S[u][mt][nt][3] = 0.0f;
+                mma_bf16_16816(S[u][mt][nt], a, b0, b1);
+            }
+        }
+    uint32_t P[2][MT][2 * KS][2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int hr = 0; hr < 2; ++hr) {
+                if (mt * 16 + hr * 8 >= TT) {                 // these 8 rows are all padding: no softmax, P = 0
+#pragma unroll
+                    for (int nt = 0; nt < 2 * KS; ++nt) P[u][mt][nt][hr] = 0u;
+                    continue;
+                }
+                float mx = -INFINITY;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int col = nt * 8 + (lane & 3) * 2 + j;
+                        float x = S[u][mt][nt][hr * 2 + j] * 0.25f;
+                        x = col < TT ? x : -INFINITY;
+                        S[u][mt][nt][hr * 2 + j] = x;
+                        mx = fmaxf(mx, x);
+                    }
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                float den = 0.0f;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) { const float e = __expf(S[u][mt][nt][hr * 2 + j] - mx); S[u][mt][nt][hr * 2 + j] = e; den += e; }
+                den += __shfl_xor_sync(0xffffffffu, den, 1);
+                den += __shfl_xor_sync(0xffffffffu, den, 2);
+                const float inv = 1.0f / den;
+#pragma unroll
+                for (int nt = 0; nt < 2 * KS; ++nt)
+                    P[u][mt][nt][hr] = nt < NT ? pack_bf16x2(S[u][mt][nt][hr * 2] * inv, S[u][mt][nt][hr * 2 + 1] * inv) : 0u;
+            }
+    float O[2][MT][2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int dt = 0; dt < 2; ++dt) O[u][mt][dt][0] = O[u][mt][dt][1] = O[u][mt][dt][2] = O[u][mt][dt][3] = 0.0f;
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+            for (int dt = 0; dt < 2; ++dt) {
+                uint32_t b0, b1;
+                ldsm_x2_trans(sq_base + (uint32_t)(((r0[u] + ks * 16 + (lane & 15)) * MH_QLD + 128 + hh[u] * 16 + dt * 8) * 2), b0, b1);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const uint32_t a[4] = {P[u][mt][2 * ks][0], P[u][mt][2 * ks][1], P[u][mt][2 * ks + 1][0], P[u][mt][2 * ks + 1][1]};
+                    mma_bf16_16816(O[u][mt][dt], a, b0, b1);
+                }
+            }
+    // head output -> A operand of the out-projection (K-major, 128-byte swizzle; k = (4 hf + hh) * 16 + d lives in box hf)
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !valid1) break;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int hr = 0; hr < 2; ++hr) {
+                const int ti = mt * 16 + hr * 8 + (lane >> 2);
+                if (ti < TT) {
+                    const int rr = r0[u] + ti;
+#pragma unroll
+                    for (int dt = 0; dt < 2; ++dt)
+                        *reinterpret_cast<uint32_t *>(hd_box + rr * 128 + (((hh[u] * 2 + dt) ^ (rr & 7)) << 4) + (lane & 3) * 4) =
+                            pack_bf16x2(O[u][mt][dt][hr * 2], O[u][mt][dt][hr * 2 + 1]);
+                }
+            }
+    }
+}
 
 template <int TT>
 __global__ void __launch_bounds__(MH_THREADS, 1)
@@ -712,7 +819,7 @@ mha_fused_tcgen05(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (threadIdx.x == 0) {
         mb_init(x_full, 1); mb_init(x_empty, 1); mb_init(&w_full[0], 1); mb_init(&w_full[1], 1); mb_init(&w_empty[0], 1); mb_init(&w_empty[1], 1);
-        mb_init(wo_full, 1); mb_init(qkv_full, 1); mb_init(qkv_empty, 256); mb_init(hd_full, 256); mb_init(o_full, 1); mb_init(acc_o_empty, 256);
+        mb_init(wo_full, 1); mb_init(qkv_full, 1); mb_init(qkv_empty, 32 * MH_WORKERS); mb_init(hd_full, 32 * MH_WORKERS); mb_init(o_full, 1); mb_init(acc_o_empty, 32 * MH_WORKERS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -765,10 +872,11 @@ mha_fused_tcgen05(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 #pragma unroll
                         for (int k = 0; k < 4; ++k) umma_f16(d, make_desc(a + kb * FF_BOX + k * 32), make_desc(b + kb * FF_BOX + k * 32), idesc128, (kb | k) ? 1u : 0u);
                     umma_commit(&w_empty[buf]);
+                    if (c == 2) umma_commit(qkv_full);
                 }
             }
         };
-        auto residual = [&]() {       // acc_o[:, kb*64 .. +64) = X[:, kb*64 .. +64) . I ; then the tile's X and acc_qkv hand-offs
+        auto residual = [&]() {       // acc_o[:, kb*64 .. +64) = X[:, kb*64 .. +64) . I ; afterwards the X buffer is free
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a = s2u(sX), b = s2u(sI), d = tmem + 384;
             if (elect_one()) {
@@ -776,7 +884,6 @@ mha_fused_tcgen05(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                 for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
                     for (int k = 0; k < 4; ++k) umma_f16(d + kb * 64, make_desc(a + kb * FF_BOX + k * 32), make_desc(b + k * 32), idesc64, k ? 1u : 0u);
-                umma_commit(qkv_full);
                 umma_commit(x_empty);
             }
         };
@@ -800,132 +907,70 @@ mha_fused_tcgen05(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         }
     } else {
         // ---- workers ----
-        const int w8 = warp - 2, q = warp & 3, wsub = w8 >> 2, row = q * 32 + lane;
+        const int w8 = warp - 2, q = warp & 3, wsub = w8 >> 2, row = q * 32 + lane;      // wsub = 0..2: the q / k / v part this warp stages
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
         const uint32_t sq_base = s2u(sQ);
+        // acc_qkv -> sQ: q | k | v of heads 4 hf .. 4 hf + 3; this warp copies the 64 columns of part `wsub` for its 32 rows
+        auto stage = [&](int hf) {
+#pragma unroll 1
+            for (int g = 0; g < 2; ++g) {
+                uint32_t r[32];
+                tmem_ld32_nowait(lane_base + (uint32_t)(wsub * 128 + hf * 64 + g * 32), r);
+                tmem_ld_wait();
+                __nv_bfloat16 *dst = sQ + row * MH_QLD + wsub * 64 + g * 32;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4 *>(dst + 8 * j) =
+                        make_uint4(pack_bf16x2(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1])), pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])),
+                                   pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])), pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])));
+            }
+        };
+        auto worker_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(32 * MH_WORKERS) : "memory"); };
+        if (my_tiles > 0) {
+            mb_wait(qkv_full, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            stage(0);
+        }
         for (int i = 0; i < my_tiles; ++i) {
             const long long row0 = (long long)(blockIdx.x + i * gridDim.x) * TR;
-            mb_wait(qkv_full, i & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
             for (int hf = 0; hf < 2; ++hf) {
-                // acc_qkv -> sQ: q | k | v of heads 4 hf .. 4 hf + 3; this warp copies 32 columns of each part for its 32 rows
+                if (hf == 1) {
+                    stage(1);
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");      // every read of acc_qkv is done: the next tile's
+                    mb_arrive(qkv_empty);                                                 // QKV GEMM may overwrite it
+                }
+                worker_bar();
+                // attention tasks (variable v of the tile, head 4 hf + hh), two at a time per warp for instruction-level parallelism
 #pragma unroll 1
-                for (int part = 0; part < 3; ++part) {
-                    uint32_t r[32];
-                    tmem_ld32_nowait(lane_base + (uint32_t)(part * 128 + hf * 64 + wsub * 32), r);
-                    tmem_ld_wait();
-                    __nv_bfloat16 *dst = sQ + row * MH_QLD + part * 64 + wsub * 32;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        *reinterpret_cast<uint4 *>(dst + 8 * j) =
-                            make_uint4(pack_bf16x2(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1])), pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])),
-                                       pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])), pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])));
+                for (int tsk = w8; tsk < VPT * 4; tsk += 2 * MH_WORKERS) {
+                    const int tsk1 = tsk + MH_WORKERS;
+                    mha_attention_pair<TT>(sq_base, sHd + hf * FF_BOX, tsk, tsk1 < VPT * 4 ? tsk1 : tsk, tsk1 < VPT * 4, lane);
                 }
-                if (hf == 1) {                                  // every read of acc_qkv is done: the next tile's QKV GEMM may overwrite it
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    mb_arrive(qkv_empty);
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                // attention tasks (variable v of the tile, head 4 hf + hh)
-#pragma unroll 1
-                for (int tsk = w8; tsk < VPT * 4; tsk += 8) {
-                    const int v = tsk >> 2, hh = tsk & 3, r0 = v * TT;
-                    float S[MT][NT][4];
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
-                        uint32_t a[4];
-                        ldsm_x4(sq_base + (uint32_t)(((r0 + mt * 16 + (lane & 15)) * MH_QLD + hh * 16 + (lane >> 4) * 8) * 2), a[0], a[1], a[2], a[3]);
-#pragma unroll
-                        for (int nt = 0; nt < NT; ++nt) {
-                            uint32_t b0, b1;
-                            ldsm_x2(sq_base + (uint32_t)(((r0 + nt * 8 + (lane & 7)) * MH_QLD + 64 + hh * 16 + ((lane >> 3) & 1) * 8) * 2), b0, b1);
-                            S[mt][nt][0] = S[mt][nt][1] = S[mt][nt][2] = S[mt][nt][3] = 0.0f;
-                            mma_bf16_16816(S[mt][nt], a, b0, b1);
-                        }
-                    }
-                    uint32_t P[MT][2 * KS][2];
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
-#pragma unroll
-                        for (int hr = 0; hr < 2; ++hr) {
-                            float mx = -INFINITY;
-#pragma unroll
-                            for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                                for (int j = 0; j < 2; ++j) {
-                                    const int col = nt * 8 + (lane & 3) * 2 + j;
-                                    float x = S[mt][nt][hr * 2 + j] * 0.25f;
-                                    x = col < TT ? x : -INFINITY;
-                                    S[mt][nt][hr * 2 + j] = x;
-                                    mx = fmaxf(mx, x);
-                                }
-                            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-                            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-                            float den = 0.0f;
-#pragma unroll
-                            for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                                for (int j = 0; j < 2; ++j) { const float e = __expf(S[mt][nt][hr * 2 + j] - mx); S[mt][nt][hr * 2 + j] = e; den += e; }
-                            den += __shfl_xor_sync(0xffffffffu, den, 1);
-                            den += __shfl_xor_sync(0xffffffffu, den, 2);
-                            const float inv = 1.0f / den;
-#pragma unroll
-                            for (int nt = 0; nt < 2 * KS; ++nt)
-                                P[mt][nt][hr] = nt < NT ? pack_bf16x2(S[mt][nt][hr * 2] * inv, S[mt][nt][hr * 2 + 1] * inv) : 0u;
-                        }
-                    }
-                    float O[MT][2][4];
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                        for (int dt = 0; dt < 2; ++dt) O[mt][dt][0] = O[mt][dt][1] = O[mt][dt][2] = O[mt][dt][3] = 0.0f;
-#pragma unroll
-                    for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-                        for (int dt = 0; dt < 2; ++dt) {
-                            uint32_t b0, b1;
-                            ldsm_x2_trans(sq_base + (uint32_t)(((r0 + ks * 16 + (lane & 15)) * MH_QLD + 128 + hh * 16 + dt * 8) * 2), b0, b1);
-#pragma unroll
-                            for (int mt = 0; mt < MT; ++mt) {
-                                const uint32_t a[4] = {P[mt][2 * ks][0], P[mt][2 * ks][1], P[mt][2 * ks + 1][0], P[mt][2 * ks + 1][1]};
-                                mma_bf16_16816(O[mt][dt], a, b0, b1);
-                            }
-                        }
-                    // head output -> A operand of the out-projection (K-major, 128-byte swizzle; k = (4 hf + hh) * 16 + d lives in box hf)
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                        for (int hr = 0; hr < 2; ++hr) {
-                            const int ti = mt * 16 + hr * 8 + (lane >> 2);
-                            if (ti < TT) {
-                                const int rr = r0 + ti;
-#pragma unroll
-                                for (int dt = 0; dt < 2; ++dt)
-                                    *reinterpret_cast<uint32_t *>(sHd + hf * FF_BOX + rr * 128 + (((hh * 2 + dt) ^ (rr & 7)) << 4) + (lane & 3) * 4) =
-                                        pack_bf16x2(O[mt][dt][hr * 2], O[mt][dt][hr * 2 + 1]);
-                            }
-                        }
-                }
-                if (hf == 0) asm volatile("bar.sync 1, 256;" ::: "memory");      // sQ is restaged for the second half
+                worker_bar();                                                            // sQ is restaged next
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mb_arrive(hd_full);
-            // ---- drain: acc_o (= X + Wo heads) -> folded BatchNorm -> bf16 -> global; this warp: 64 columns of its 32 rows ----
+            if (i + 1 < my_tiles) {                   // stage the first half of the next tile while the out-projection of this one runs
+                mb_wait(qkv_full, (i + 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                stage(0);
+            }
+            // ---- drain: acc_o (= X + Wo heads) -> folded BatchNorm -> bf16 -> global; 8 groups of 16 columns over the 3 warps of a quarter ----
             mb_wait(o_full, i & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const long long m = row0 + row;
 #pragma unroll 1
-            for (int g = 0; g < 2; ++g) {
-                uint32_t r[32];
-                const int c0 = wsub * 64 + g * 32;
-                tmem_ld32_nowait(lane_base + (uint32_t)(384 + c0), r);
+            for (int g = wsub * 3; g < (wsub == 2 ? 8 : wsub * 3 + 3); ++g) {
+                uint32_t r[16];
+                const int c0 = g * 16;
+                tmem_ld16_nowait(lane_base + (uint32_t)(384 + c0), r);
                 tmem_ld_wait();
                 if (row < TR && m < M) {
                     const float4 *sc4 = reinterpret_cast<const float4 *>(ssc + c0), *sh4 = reinterpret_cast<const float4 *>(ssh + c0);
 #pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8) {
+                    for (int j8 = 0; j8 < 2; ++j8) {
                         const float4 a0 = sc4[2 * j8], a1 = sc4[2 * j8 + 1], b0 = sh4[2 * j8], b1 = sh4[2 * j8 + 1];
                         uint4 o;
                         o.x = pack_bf16x2(__uint_as_float(r[j8 * 8 + 0]) * a0.x + b0.x, __uint_as_float(r[j8 * 8 + 1]) * a0.y + b0.y);
