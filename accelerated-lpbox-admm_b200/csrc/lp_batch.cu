@@ -94,6 +94,9 @@ struct lpbox_batch {
     std::vector<int> h_active;
     std::vector<long long> h_row_off;
     bool dev_fix_pending = false;
+    std::vector<int> pat_bytes_i, pat_head_i;   // sliced-ELL image size of every instance, and its size without the column index array
+    int pat_smem = 0;                           // bytes of shared memory reserved for the image (< max_pat: the largest images keep their column indices in L2)
+    DevBuf<int> d_work;                         // launch order when pat_smem < max_pat (instances with a spilled image first)
 };
 
 template <int T, int EPT, bool UNIT>
@@ -124,15 +127,52 @@ static int configure(lpbox_batch *h) {
     if ((int)h->smem > dev_smem || (int)h->fix_smem > dev_smem) {
         set_err("instance does not fit in shared memory"); return LPBOX_E_UNSUPPORTED;
     }
-    int occ = 1;
     bool u = h->all_unit;
-    cudaError_t e;
-    switch (h->tcfg) {
-        case 0: e = u ? prep_kernel<128, 4, true>(h->smem, &occ) : prep_kernel<128, 4, false>(h->smem, &occ); break;
-        case 1: e = u ? prep_kernel<256, 4, true>(h->smem, &occ) : prep_kernel<256, 4, false>(h->smem, &occ); break;
-        default: e = u ? prep_kernel<512, 4, true>(h->smem, &occ) : prep_kernel<512, 4, false>(h->smem, &occ); break;
+    auto occ_at = [&](size_t smem, int *occ) -> cudaError_t {
+        switch (h->tcfg) {
+            case 0: return u ? prep_kernel<128, 4, true>(smem, occ) : prep_kernel<128, 4, false>(smem, occ);
+            case 1: return u ? prep_kernel<256, 4, true>(smem, occ) : prep_kernel<256, 4, false>(smem, occ);
+            default: return u ? prep_kernel<512, 4, true>(smem, occ) : prep_kernel<512, 4, false>(smem, occ);
+        }
+    };
+    int occ = 1, occ_reg = 1;
+    CK(occ_at(1024, &occ_reg));          // what the registers allow
+    CK(occ_at(h->smem, &occ));
+    h->pat_smem = h->max_pat;
+    h->d_work.free_();
+    // Shared memory is sized for the LARGEST sliced-ELL image of the batch; a few instances with a wide pattern can cost the
+    // whole batch one resident CTA per SM.  When that happens the image budget is cut to what full occupancy allows and the
+    // (few) instances above it keep their last array -- the column index array -- in global memory (L2) instead.
+    const char *forced = getenv("LPBOX_IMAGE_BUDGET");      // tests: force a budget (bytes) to exercise the spilled-image path
+    if (u && (occ < occ_reg || forced) && (int)h->pat_bytes_i.size() == h->B) {
+        int budget = 0;
+        if (forced) {
+            budget = atoi(forced) & ~15;
+        } else {
+            size_t lo = 1024, hi = h->smem;                   // largest dynamic size that still reaches occ_reg
+            int o = 0;
+            while (hi - lo > 16) {
+                size_t mid = ((lo + hi) / 2) & ~(size_t)15;
+                CK(occ_at(mid, &o));
+                if (o >= occ_reg) lo = mid; else hi = mid;
+            }
+            const size_t fixed = smem_bytes(np, mp, 0, 0, 0);
+            budget = lo > fixed ? (int)((lo - fixed) & ~(size_t)15) : 0;
+        }
+        int fit = 0, head_max = 0;
+        for (int i = 0; i < h->B; ++i) { fit += h->pat_bytes_i[i] <= budget; head_max = std::max(head_max, h->pat_head_i[i]); }
+        if (head_max <= budget && budget < h->max_pat && (forced || fit >= (h->B * 9) / 10)) {
+            h->pat_smem = budget;
+            h->smem = smem_bytes(np, mp, budget, 0, 0);
+            std::vector<int> order;
+            for (int i = 0; i < h->B; ++i) if (h->pat_bytes_i[i] > budget) order.push_back(i);
+            for (int i = 0; i < h->B; ++i) if (h->pat_bytes_i[i] <= budget) order.push_back(i);
+            CK(h->d_work.alloc(order.size()));
+            CK(cudaMemcpy(h->d_work.p, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice));
+            if (getenv("LPBOX_DEBUG")) fprintf(stderr, "[lpbox] image budget %d B (largest %d B): %d of %d instances keep their column indices in L2\n", budget, h->max_pat, h->B - fit, h->B);
+        }
+        CK(occ_at(h->smem, &occ));
     }
-    CK(e);
     CK(cudaFuncSetAttribute(lp_fix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fix_smem));
     if (occ < 1) occ = 1;
     h->grid = std::max(1, std::min(h->B, sms * occ));
@@ -142,8 +182,8 @@ static int configure(lpbox_batch *h) {
 static int run_window(lpbox_batch *h, int iter_start, int iter_end, int l2f, int skip_done) {
     Launch la{};
     la.iter_start = iter_start; la.iter_end = iter_end; la.l2f = l2f; la.skip_done = skip_done;
-    la.n_work = h->B; la.work = nullptr; la.counter = h->d_counter.p;
-    la.mp = (h->max_m + 1) & ~1; la.np = std::max((h->max_n + 1) & ~1, la.mp); la.pat_bytes = h->max_pat;
+    la.n_work = h->B; la.work = h->d_work.p; la.counter = h->d_counter.p;
+    la.mp = (h->max_m + 1) & ~1; la.np = std::max((h->max_n + 1) & ~1, la.mp); la.pat_bytes = h->pat_smem;
     la.evr_elems = h->all_unit ? 0 : h->max_evr; la.evc_elems = h->all_unit ? 0 : h->max_evc;
     CK(cudaMemsetAsync(h->d_counter.p, 0, sizeof(int), h->stream));
     bool u = h->all_unit;
@@ -217,6 +257,7 @@ extern "C" lpbox_batch *lpbox_batch_create(int device, int B, const int32_t *m, 
         h->off_hist[i + 1] = h->off_hist[i] + (long long)hist_cap * n[i];
         h->max_n = std::max(h->max_n, n[i]); h->max_m = std::max(h->max_m, m[i]); h->max_nnz = std::max(h->max_nnz, h->nnz0[i]);
         h->max_pat = std::max(h->max_pat, EL.bytes);
+        h->pat_bytes_i.push_back(EL.bytes); h->pat_head_i.push_back(EL.o_cidx);
     }
     long long tot_nnz = h->h_nnz_off[B];
     h->h_colptr.assign(colptr_all, colptr_all + h->h_cp_off[B]);
@@ -351,7 +392,7 @@ extern "C" void lpbox_batch_destroy(lpbox_batch *h) {
     h->d_x.free_(); h->d_y1.free_(); h->d_y2.free_(); h->d_z1.free_(); h->d_z2.free_(); h->d_b.free_(); h->d_Pd.free_(); h->d_Esq.free_();
     h->d_y3.free_(); h->d_z4.free_(); h->d_f.free_(); h->d_val_r.free_(); h->d_val_c.free_(); h->d_r4v.free_(); h->d_hist.free_();
     h->d_ret_val.free_(); h->d_pow.free_(); h->d_vec.free_(); h->d_pat.free_(); h->d_st.free_(); h->d_left.free_(); h->d_ret_idx.free_();
-    h->d_counter.free_(); h->d_num.free_();
+    h->d_counter.free_(); h->d_num.free_(); h->d_work.free_();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);

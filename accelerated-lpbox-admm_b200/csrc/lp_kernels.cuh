@@ -249,7 +249,8 @@ struct Smem {
     uint64_t *bar;
 };
 __host__ __device__ inline size_t smem_bytes(int np, int mp, int pat_bytes, int evr_elems, int evc_elems) {
-    size_t d = (size_t)np * 3 + (size_t)mp * 2 + 8 + 16 + (size_t)evr_elems + 2 * (size_t)evc_elems;
+    // wb (a copy of z4, m entries) shares the n-sized a2 buffer with f - y3 (also m entries) whenever both fit: 2 mp <= np
+    size_t d = (size_t)np * 3 + (size_t)mp * (2 * mp <= np ? 1 : 2) + 8 + 16 + (size_t)evr_elems + 2 * (size_t)evc_elems;
     return d * sizeof(double) + (size_t)pat_bytes + 16;
 }
 __device__ __forceinline__ Smem carve(unsigned char *base, int np, int mp, int pat_bytes, int evr_elems, int evc_elems) {
@@ -259,7 +260,7 @@ __device__ __forceinline__ Smem carve(unsigned char *base, int np, int mp, int p
     s.a1 = d; d += np;
     s.a2 = d; d += np;
     s.t1 = d; d += mp;
-    s.wb = d; d += mp;
+    if (2 * mp <= np) s.wb = s.a2 + mp; else { s.wb = d; d += mp; }
     s.sc = d; d += 8;
     s.ring = d; d += 16;
     s.ev_r = d; d += evr_elems;
@@ -299,8 +300,11 @@ __device__ __forceinline__ double std_obj_after_push(const double *ring, long lo
 // The window kernel.  T threads, EPT elements (and rows) per thread: max(n, m) <= T*EPT.
 // UNIT: all stored values of E are 1.0 (pattern-only matrices; rho4*E^T is one scalar).
 // =====================================================================================================================
+#ifndef LPB_CTAS_128
+#define LPB_CTAS_128 7
+#endif
 template <int T, int EPT, bool UNIT>
-__global__ void __launch_bounds__(T, (T <= 128 ? 6 : (T <= 256 ? 3 : 1)))
+__global__ void __launch_bounds__(T, (T <= 128 ? LPB_CTAS_128 : (T <= 256 ? 3 : 1)))
 lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem S = carve(smem_raw, la.np, la.mp, la.pat_bytes, la.evr_elems, la.evc_elems);
@@ -329,10 +333,12 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
         // ---------------- stage the instance --------------------------------------------------------------------
         const int n = stp->n, m = stp->m;
         const EllLayout PL = ell_layout(stp->n0, stp->m0, stp->rcap, stp->ccap);
+        // an image larger than the shared-memory budget of this launch keeps its last array (the column indices) in global memory
+        const bool spill = PL.bytes > la.pat_bytes;
         if (tid == 0) {
             fence_proxy_async();  // order earlier generic-proxy reads of the previous instance's blob before the overwrite
-            mbar_expect_tx(S.bar, (uint32_t)PL.bytes);
-            tma_load_1d(S.pat, bv.pat + bv.off_pat[inst], (uint32_t)PL.bytes, S.bar);
+            mbar_expect_tx(S.bar, (uint32_t)(spill ? PL.o_cidx : PL.bytes));
+            tma_load_1d(S.pat, bv.pat + bv.off_pat[inst], (uint32_t)(spill ? PL.o_cidx : PL.bytes), S.bar);
         }
         const long long on = bv.off_n[inst], om = bv.off_m[inst];
         const double *__restrict__ gb = bv.b + on;    // read-only during a window
@@ -372,6 +378,12 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
         const u16 *csptr = reinterpret_cast<const u16 *>(S.pat + PL.o_csptr);
         const u16 *cperm = reinterpret_cast<const u16 *>(S.pat + PL.o_cperm);
         const u16 *cidx = reinterpret_cast<const u16 *>(S.pat + PL.o_cidx);
+        const u16 *gcidx = reinterpret_cast<const u16 *>(bv.pat + bv.off_pat[inst] + PL.o_cidx);   // used instead of cidx when the image is spilled
+#define LPB_COL_SPMV(COEF, VAL, SCALE, VIN, VOUT)                                                                     \
+    do {                                                                                                              \
+        if (spill) seq_spmv_ell<T, COEF>(clen, csptr, cperm, gcidx, VAL, SCALE, VIN, n, VOUT);                        \
+        else seq_spmv_ell<T, COEF>(clen, csptr, cperm, cidx, VAL, SCALE, VIN, n, VOUT);                               \
+    } while (0)
         const double pow_n = bv.pow_tab[n];               // std::pow(n, 1.0/p), p = 2 (LP.cpp:427)
         const int lane = tid & 31, rq = lane >> 2;        // reduction group of this lane (reduction warp only)
 
@@ -441,8 +453,8 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
             }
             __syncthreads();
             // ---- rhs (:872-878): R4ET (f - y3) -> a1, ET z4 -> gv ------------------------------------------------
-            seq_spmv_ell<T, CR>(clen, csptr, cperm, cidx, S.r4v, r4s, S.a2, n, S.a1);
-            seq_spmv_ell<T, CE>(clen, csptr, cperm, cidx, S.ev_c, 0.0, S.wb, n, S.gv);
+            LPB_COL_SPMV(CR, S.r4v, r4s, S.a2, S.a1);
+            LPB_COL_SPMV(CE, S.ev_c, 0.0, S.wb, S.gv);
             __syncthreads();
             // ---- PCG (:251-335), warm start x = y1 (:892) ------------------------------------------------------
             double rhs[EPT], xc[EPT];
@@ -464,7 +476,7 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
             seq_spmv_ell<T, CE>(rlen, rsptr, rperm, ridx, S.ev_r, 0.0, S.gv, m, S.t1);
             __syncthreads();
             const double rhsNorm2 = S.sc[0];
-            seq_spmv_ell<T, CR>(clen, csptr, cperm, cidx, S.r4v, r4s, S.t1, n, S.a2);
+            LPB_COL_SPMV(CR, S.r4v, r4s, S.t1, S.a2);
             __syncthreads();
             LPB_FOR_E {
                 int j = tid + e * T;
@@ -495,7 +507,7 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                     while (cg_it < pr.pcg_maxiters) {                        // gv holds p here
                         seq_spmv_ell<T, CE>(rlen, rsptr, rperm, ridx, S.ev_r, 0.0, S.gv, m, S.t1);
                         __syncthreads();
-                        seq_spmv_ell<T, CR>(clen, csptr, cperm, cidx, S.r4v, r4s, S.t1, n, S.a2);
+                        LPB_COL_SPMV(CR, S.r4v, r4s, S.t1, S.a2);
                         __syncthreads();
                         double tmp[EPT];
                         LPB_FOR_E {

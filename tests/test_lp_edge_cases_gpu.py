@@ -115,3 +115,48 @@ def test_large_batch_spot_checked_and_deterministic():
         o = _oracle(dict(m=m, n=n, colptr=cp, rowidx=ri, b=bb, f=np.ones(m))); o.solve_init(); o.solve_iter(0, 20000)
         assert log1["iters"][i] == o.admm_iters() and log1["cg_iters"][i] == o.cg_iters() and log1["obj"][i] == o.cal_Obj()
         assert np.array_equal(b.state(int(i))["x"], o.state()["x"])
+
+
+def test_spilled_pattern_image_is_bit_identical(monkeypatch):
+    """Instances whose sliced-ELL image exceeds the shared-memory budget of the launch keep their column index array in
+    global memory (the path that lets a batch with a few wide instances still run at full occupancy).  Forcing a small
+    budget makes about half of a batch take that path; log rows, iterates and the early-fix window loop must not change."""
+    import lpbox
+    probs = lpbox.gen_auctions(5, 64, 100, 500)
+    b = lpbox.LPBatch(probs); b.init(); ref = b.solve(20000).copy(); xs = [b.state(i)["x"].copy() for i in (0, 7, 63)]
+    smem_ref = b.config()["smem_bytes"]
+    b.close()
+    # median image size of this batch (bytes): half of the instances spill
+    def image_bytes(p):
+        m, n, cp, ri = p[0], p[1], np.asarray(p[2]), np.asarray(p[3])
+        a16 = lambda x: (x + 15) & ~15
+        rs = np.sort(np.bincount(ri, minlength=m))[::-1]; cs = np.sort(np.diff(cp))[::-1]
+        return (a16(2 * m) + a16(2 * ((m + 31) // 32 + 1)) + a16(2 * m) + a16(64 * int(rs[::32].sum())) + a16(2 * n)
+                + a16(2 * ((n + 31) // 32 + 1)) + a16(2 * n) + a16(64 * int(cs[::32].sum())))
+    sizes = sorted(image_bytes(p) for p in probs)
+    monkeypatch.setenv("LPBOX_IMAGE_BUDGET", str(sizes[len(sizes) // 2]))
+    b2 = lpbox.LPBatch(probs); b2.init()
+    assert b2.config()["smem_bytes"] < smem_ref           # the budget really applies
+    got = b2.solve(20000)
+    assert np.array_equal(got, ref)
+    for k, i in enumerate((0, 7, 63)):
+        assert np.array_equal(b2.state(i)["x"], xs[k])
+    b2.close()
+    # window loop with device-side fixing on the spilled layout vs the default layout
+    def windows():
+        bb = lpbox.LPBatch(probs[:16], hist_cap=100); bb.init()
+        bb.iters_l2f(0, 100)
+        vecs, nums = [], []
+        for i in range(16):
+            xi = bb.x_iters(i, 100)[:, -1]
+            v = np.where(xi > 0.97, 1.0, np.where(xi < 0.03, 0.0, -1.0)); vecs.append(v); nums.append(int((v >= 0).sum()))
+        bb.iters_l2f(100, 400, vecs, nums)
+        out = (bb.results()[0].copy(), [bb.state(i)["x"].copy() for i in range(16)])
+        bb.close()
+        return out
+    spilled = windows()
+    monkeypatch.delenv("LPBOX_IMAGE_BUDGET")
+    plain = windows()
+    assert np.array_equal(spilled[0], plain[0])
+    for a, c in zip(spilled[1], plain[1]):
+        assert np.array_equal(a, c)
