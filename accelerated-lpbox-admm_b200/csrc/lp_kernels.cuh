@@ -72,13 +72,12 @@ __device__ __forceinline__ double prod_at(const double *a, const double *c, bool
     if (ind) cv = (cv >= 0.5) ? 1.0 : 0.0;
     return dM(a[i], cv);
 }
-// mode 0: sum of v[i]   (operand = materialised products)      mode 1: sum of v[i]*v[i]   (squaredNorm)
-__device__ __forceinline__ double term_at(const double *v, int mode, int i) {
-    const double t = v[i];
-    return mode ? dM(t, t) : t;
-}
-// one-operand variant of warp_redux_eigen2: each lane group reduces its own array `v` in mode `mode` (see term_at)
-__device__ __forceinline__ double warp_redux_eigen1(const double *v, int mode, int n) {
+// one-operand variant of warp_redux_eigen2: each lane group sums its own array `v` of MATERIALISED terms (the owner threads
+// stage the products / squares -- the same __dmul_rn the reduction would issue -- so the single reduction warp, which is the
+// critical path of every CG iteration, only loads and adds)
+__device__ __forceinline__ double term_at(const double *v, int, int i) { return v[i]; }
+__device__ __forceinline__ double warp_redux_eigen1(const double *v, int n) {
+    constexpr int mode = 0;
     const int lane = threadIdx.x & 31;
     const int k = lane & 3;
     const int a2 = n & ~3, a1 = n & ~1;
@@ -399,12 +398,12 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                 double t = dA(x[e], dD(z1[e], rho1));
                 y1[e] = (t > 1.0) ? 1.0 : ((t < 0.0) ? 0.0 : t);
                 y2[e] = dS(dA(x[e], dD(z2[e], rho2)), 0.5);
-                if (j < n) { S.a1[j] = y2[e]; S.gv[j] = x[e]; }
+                if (j < n) { S.a1[j] = dM(y2[e], y2[e]); S.gv[j] = x[e]; }     // squares staged for ||y|| (:425)
             }
             __syncthreads();
             // ---- ||y|| (:425) on the reduction warp, E x (:825) on the row slots -------------------------------
             if (warp == RW) {
-                double v = warp_redux_eigen1(S.a1, 1, n);
+                double v = warp_redux_eigen1(S.a1, n);
                 if (lane == 0) S.sc[0] = v;
             }
             // E x of this iteration's x was already formed for the z4 update of the previous iteration (same operands, same
@@ -465,12 +464,12 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                     t = dA(t, S.a1[j]);
                     rhs[e] = dS(t, S.gv[j]);
                     xc[e] = y1[e];
-                    S.gv[j] = xc[e]; S.a1[j] = rhs[e];
+                    S.gv[j] = xc[e]; S.a1[j] = dM(rhs[e], rhs[e]);
                 } else { rhs[e] = 0.0; xc[e] = 0.0; }
             }
             __syncthreads();
             if (warp == RW) {
-                double v = warp_redux_eigen1(S.a1, 1, n);                  // rhs.squaredNorm() :277
+                double v = warp_redux_eigen1(S.a1, n);                     // rhs.squaredNorm() :277
                 if (lane == 0) S.sc[0] = v;
             }
             seq_spmv_ell<T, CE>(rlen, rsptr, rperm, ridx, S.ev_r, 0.0, S.gv, m, S.t1);
@@ -484,12 +483,12 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                     double mv = dA(dA(0.0, dM(D, xc[e])), S.a2[j]);          // D v (+) R4ET (E v)   :115-162
                     r[e] = dS(rhs[e], mv);                                   // :273
                     p[e] = dM(invd[e], r[e]);                                // :297
-                    S.a1[j] = r[e]; S.gv[j] = p[e]; S.a2[j] = dM(r[e], p[e]);
+                    S.a1[j] = dM(r[e], r[e]); S.gv[j] = p[e]; S.a2[j] = dM(r[e], p[e]);
                 }
             }
             __syncthreads();
             if (warp == RW) {
-                double v = warp_redux_eigen1(rq == 0 ? S.a1 : S.a2, rq == 0, n);       // r.r :288, r.p :300
+                double v = warp_redux_eigen1(rq == 0 ? S.a1 : S.a2, n);                // r.r :288, r.p :300
                 if (lane == 0) S.sc[1] = v;
                 if (lane == 4) S.sc[2] = v;
             }
@@ -519,7 +518,7 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                         }
                         __syncthreads();
                         if (warp == RW) {
-                            double v = warp_redux_eigen1(S.a2, 0, n);             // p.dot(tmp) :306
+                            double v = warp_redux_eigen1(S.a2, n);                // p.dot(tmp) :306
                             if (lane == 0) S.sc[0] = v;
                         }
                         __syncthreads();
@@ -531,11 +530,11 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                             xc[e] = dA(xc[e], dM(alpha, p[e]));               // :308
                             r[e] = dS(r[e], dM(alpha, tmp[e]));               // :310
                             zz[e] = dM(invd[e], r[e]);                        // :320
-                            if (j < n) { S.a1[j] = r[e]; S.gv[j] = dM(r[e], zz[e]); }
+                            if (j < n) { S.a1[j] = dM(r[e], r[e]); S.gv[j] = dM(r[e], zz[e]); }
                         }
                         __syncthreads();
                         if (warp == RW) {
-                            double v = warp_redux_eigen1(rq == 0 ? S.a1 : S.gv, rq == 0, n);       // r.r :311, r.z :323
+                            double v = warp_redux_eigen1(rq == 0 ? S.a1 : S.gv, n);                // r.r :311, r.z :323
                             if (lane == 0) S.sc[1] = v;
                             if (lane == 4) S.sc[2] = v;
                         }
