@@ -75,34 +75,42 @@ __device__ __forceinline__ double prod_at(const double *a, const double *c, bool
 // one-operand variant of warp_redux_eigen2: each lane group sums its own array `v` of MATERIALISED terms (the owner threads
 // stage the products / squares -- the same __dmul_rn the reduction would issue -- so the single reduction warp, which is the
 // critical path of every CG iteration, only loads and adds)
-__device__ __forceinline__ double term_at(const double *v, int, int i) { return v[i]; }
 __device__ __forceinline__ double warp_redux_eigen1(const double *v, int n) {
-    constexpr int mode = 0;
     const int lane = threadIdx.x & 31;
     const int k = lane & 3;
     const int a2 = n & ~3, a1 = n & ~1;
     double res;
     if (a1 > 2) {
-        double acc = term_at(v, mode, k);
-        int i = 4 + k;
-        for (; i + 28 < a2; i += 32) {
-            double t0 = term_at(v, mode, i), t1 = term_at(v, mode, i + 4), t2 = term_at(v, mode, i + 8), t3 = term_at(v, mode, i + 12),
-                   t4 = term_at(v, mode, i + 16), t5 = term_at(v, mode, i + 20), t6 = term_at(v, mode, i + 24), t7 = term_at(v, mode, i + 28);
+        // chain k adds v[k], v[k+4], ... in order.  The loads of the NEXT four terms are issued before the four dependent adds
+        // (loop-carried prefetch), otherwise ptxas, short of registers, serialises load -> add -> load on one register and
+        // every step pays the shared-memory latency on top of the fp64 add latency.
+        double acc = v[k];
+        const double *pv = v + 4 + k;
+        int left = a2 / 4 - 1;                         // terms still to add
+        if (left >= 4) {
+            double t0 = pv[0], t1 = pv[4], t2 = pv[8], t3 = pv[12];
+            pv += 16; left -= 4;
+#pragma unroll 1
+            while (left >= 4) {
+                const double u0 = pv[0], u1 = pv[4], u2 = pv[8], u3 = pv[12];
+                acc = dA(acc, t0); acc = dA(acc, t1); acc = dA(acc, t2); acc = dA(acc, t3);
+                t0 = u0; t1 = u1; t2 = u2; t3 = u3;
+                pv += 16; left -= 4;
+            }
             acc = dA(acc, t0); acc = dA(acc, t1); acc = dA(acc, t2); acc = dA(acc, t3);
-            acc = dA(acc, t4); acc = dA(acc, t5); acc = dA(acc, t6); acc = dA(acc, t7);
         }
-        for (; i < a2; i += 4) acc = dA(acc, term_at(v, mode, i));
+        for (; left > 0; --left, pv += 4) acc = dA(acc, pv[0]);
         double hi = __shfl_down_sync(0xffffffffu, acc, 2);
         double l = dA(acc, hi);
-        if (a1 > a2 && k < 2) l = dA(l, term_at(v, mode, a2 + k));
+        if (a1 > a2 && k < 2) l = dA(l, v[a2 + k]);
         double l1 = __shfl_down_sync(0xffffffffu, l, 1);
         res = dA(l, l1);
     } else if (a1 == 2) {
-        res = dA(term_at(v, mode, 0), term_at(v, mode, 1));
+        res = dA(v[0], v[1]);
     } else {
-        res = (n > 0) ? term_at(v, mode, 0) : 0.0;
+        res = (n > 0) ? v[0] : 0.0;
     }
-    if ((n & 1) && n > 1) res = dA(res, term_at(v, mode, n - 1));
+    if ((n & 1) && n > 1) res = dA(res, v[n - 1]);
     return __shfl_sync(0xffffffffu, res, lane & ~3);
 }
 __device__ __forceinline__ double warp_redux_eigen2(const double *__restrict__ a, const double *__restrict__ c, bool ind, int n) {
