@@ -81,6 +81,28 @@ __device__ __forceinline__ double seg_row_dot(const int *__restrict__ rp, const 
     return acc;
 }
 
+// Walks one Eigen chain: adds src[i], src[i+4], ... (indices < lim) to acc IN ORDER.  The next four terms are fetched into
+// loop-carried registers before the four dependent adds; otherwise ptxas, short of registers (5 CTAs/SM), serialises
+// load -> add -> load on one register and every step pays the shared-memory latency on top of the fp64 add latency.
+__device__ __forceinline__ double seg_chain(const double *src, int i, int lim, double acc) {
+    int left = lim > i ? (lim - i + 3) >> 2 : 0;
+    const double *pv = src + i;
+    if (left >= 4) {
+        double t0 = pv[0], t1 = pv[4], t2 = pv[8], t3 = pv[12];
+        pv += 16; left -= 4;
+#pragma unroll 1
+        while (left >= 4) {
+            const double u0 = pv[0], u1 = pv[4], u2 = pv[8], u3 = pv[12];
+            acc = dA(acc, t0); acc = dA(acc, t1); acc = dA(acc, t2); acc = dA(acc, t3);
+            t0 = u0; t1 = u1; t2 = u2; t3 = u3;
+            pv += 16; left -= 4;
+        }
+        acc = dA(acc, t0); acc = dA(acc, t1); acc = dA(acc, t2); acc = dA(acc, t3);
+    }
+    for (; left > 0; --left, pv += 4) acc = dA(acc, pv[0]);
+    return acc;
+}
+
 // Block-cooperative Eigen-order reduction of R product streams prod(q, i), i < n.  Results in sc[0..R).
 // buf: shared, 2 * R * SEG_CH doubles.  All SEG_T threads must call.
 template <int R, typename F>
@@ -111,13 +133,7 @@ __device__ __forceinline__ void seg_block_redux(F prod, int n, double *buf, doub
                 const int lim = min(SEG_CH, a2 - c * SEG_CH);
                 int i = k;
                 if (c == 0) { acc = src[k]; i = 4 + k; }
-                for (; i + 28 < lim; i += 32) {
-                    double t0 = src[i], t1 = src[i + 4], t2 = src[i + 8], t3 = src[i + 12], t4 = src[i + 16], t5 = src[i + 20],
-                           t6 = src[i + 24], t7 = src[i + 28];
-                    acc = dA(acc, t0); acc = dA(acc, t1); acc = dA(acc, t2); acc = dA(acc, t3);
-                    acc = dA(acc, t4); acc = dA(acc, t5); acc = dA(acc, t6); acc = dA(acc, t7);
-                }
-                for (; i < lim; i += 4) acc = dA(acc, src[i]);
+                acc = seg_chain(src, i, lim, acc);
             }
             __syncthreads();
         }
@@ -178,13 +194,7 @@ __device__ __forceinline__ void seg_fused_pass(Body body, int n, double *buf, do
             const int lim = min(SEG_FCH, a2 - c * SEG_FCH);     // chain part only (elements < a2)
             int i = k;
             if (c == 0) { acc = src[k]; i = 4 + k; }
-            for (; i + 28 < lim; i += 32) {
-                double t0 = src[i], t1 = src[i + 4], t2 = src[i + 8], t3 = src[i + 12], t4 = src[i + 16], t5 = src[i + 20],
-                       t6 = src[i + 24], t7 = src[i + 28];
-                acc = dA(acc, t0); acc = dA(acc, t1); acc = dA(acc, t2); acc = dA(acc, t3);
-                acc = dA(acc, t4); acc = dA(acc, t5); acc = dA(acc, t6); acc = dA(acc, t7);
-            }
-            for (; i < lim; i += 4) acc = dA(acc, src[i]);
+            acc = seg_chain(src, i, lim, acc);
         }
         __syncthreads();
     }
