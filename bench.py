@@ -144,7 +144,7 @@ def reference_arm(args, rank):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs, "kind": kind,
                              "sample": f"{sample} instances per step, one process per core, logging off"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ---- GPU arm ---------------------------------------------------------------------------------------------------------
@@ -317,12 +317,21 @@ def main():
             line["cpu_baseline"] = {"value": sample / wall, "unit": UNIT, "cores": procs, "kind": kind,
                                     "sample": f"first {sample} instances of the same batch, one process per core, logging off; "
                                               f"{sum(per) / len(per):.2f} s per instance per core"}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     batch.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def _emit(line):
+    """The ONE JSON line of the contract goes to the real stdout; everything else this process (or a library such as NCCL,
+    which prints its version banner to stdout) writes to fd 1 has been redirected to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 if __name__ == "__main__":
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     main()
