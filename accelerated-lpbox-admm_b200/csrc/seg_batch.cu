@@ -34,6 +34,7 @@ struct SBuf {
 
 struct lpbox_seg_batch {
     int device = 0, B = 0, hist_cap = 0;
+    bool compact = false;        // A stored as (int16 column distance, int8 value): see SegFmt in seg_kernels.cuh
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<int> n0, nnz0;
@@ -145,12 +146,12 @@ extern "C" void lpbox_seg_destroy(lpbox_seg_batch *h) {
 }
 
 // allocation + kernel configuration shared by both constructors; CSR / b are filled afterwards (H2D or the device graph builder)
-static lpbox_seg_batch *seg_new(int device, int B, const int32_t *n, const int *nnz, const double *c, int hist_cap) {
+static lpbox_seg_batch *seg_new(int device, int B, const int32_t *n, const int *nnz, const double *c, int hist_cap, bool compact) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { lpbox_set_error("no CUDA device (there is no CPU fallback)"); return nullptr; }
     if (device < 0 || device >= ndev || cudaSetDevice(device) != cudaSuccess) { lpbox_set_error("bad device"); return nullptr; }
     lpbox_seg_batch *h = new lpbox_seg_batch();
-    h->device = device; h->B = B; h->hist_cap = hist_cap;
+    h->device = device; h->B = B; h->hist_cap = hist_cap; h->compact = compact;
     h->n0.assign(n, n + B); h->nnz0.assign(nnz, nnz + B); h->cconst.assign(B, 0.0);
     h->off_n.assign(B + 1, 0); h->off_nnz.assign(B + 1, 0); h->off_hist.assign(B + 1, 0);
     std::vector<double> powv(B);
@@ -179,11 +180,13 @@ static lpbox_seg_batch *seg_new(int device, int B, const int32_t *n, const int *
     A(cudaEventCreate(&h->ev0)); A(cudaEventCreate(&h->ev1));
     A(h->d_off_n.alloc(B + 1)); A(h->d_off_nnz.alloc(B + 1)); A(h->d_off_hist.alloc(B + 1));
     for (auto &v : h->vecs) A(v.alloc(NN));
-    for (int k = 0; k < 2; ++k) { A(h->d_b[k].alloc(NN)); A(h->d_val[k].alloc(ZZ)); A(h->d_rp[k].alloc(NN + 4 * (size_t)B)); A(h->d_ci[k].alloc(ZZ)); }
+    // element counts of the typed buffers that hold colidx / val: 2 + 1 bytes per entry in the compact format, 4 + 8 otherwise
+    const size_t ZCI = compact ? (ZZ + 1) / 2 : ZZ, ZVA = compact ? (ZZ + 7) / 8 : ZZ;
+    for (int k = 0; k < 2; ++k) { A(h->d_b[k].alloc(NN)); A(h->d_val[k].alloc(ZVA)); A(h->d_rp[k].alloc(NN + 4 * (size_t)B)); A(h->d_ci[k].alloc(ZCI)); }
     A(h->d_hist.alloc((size_t)h->off_hist[B])); A(h->d_ret_val.alloc(NN)); A(h->d_powv.alloc(B)); A(h->d_left.alloc(NN)); A(h->d_ret_idx.alloc(NN));
     A(h->d_counter.alloc(1)); A(h->d_st.alloc(B));
     A(h->d_kidx.alloc(NN)); A(h->d_cnt.alloc(NN)); A(h->d_num.alloc(B)); A(h->d_off_vec.alloc(B + 1)); A(h->d_vec.alloc(NN)); A(h->d_powtab.alloc((size_t)h->max_n + 1));
-    A(h->d_rp_org.alloc(NN + 4 * (size_t)B)); A(h->d_ci_org.alloc(ZZ)); A(h->d_val_org.alloc(ZZ)); A(h->d_b_org.alloc(NN));
+    A(h->d_rp_org.alloc(NN + 4 * (size_t)B)); A(h->d_ci_org.alloc(ZCI)); A(h->d_val_org.alloc(ZVA)); A(h->d_b_org.alloc(NN));
     if (!ok) { lpbox_seg_destroy(h); return nullptr; }
     auto H2D = [&](void *d, const void *s, size_t bytes) { if (bytes) { A(cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, h->stream)); h->h2d_bytes += (int64_t)bytes; } };
     H2D(h->d_off_n.p, h->off_n.data(), sizeof(long long) * (B + 1));
@@ -205,10 +208,13 @@ static lpbox_seg_batch *seg_new(int device, int B, const int32_t *n, const int *
     v.st = h->d_st.p; v.hist = h->d_hist.p; v.left_idx = h->d_left.p; v.ret_idx = h->d_ret_idx.p; v.ret_val = h->d_ret_val.p; v.powv = h->d_powv.p;
     h->smem = sizeof(double) * (SEG_BUF_DOUBLES + 8 + 16);
     int sms = 0, occ = 1;
-    if (cudaFuncSetAttribute(seg_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess ||
-        cudaFuncSetAttribute(seg_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess ||
+    if (cudaFuncSetAttribute(seg_admm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess ||
+        cudaFuncSetAttribute(seg_admm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess ||
+        cudaFuncSetAttribute(seg_setup_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess ||
+        cudaFuncSetAttribute(seg_setup_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess ||
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seg_admm_kernel, SEG_T, h->smem) != cudaSuccess) {
+        (compact ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seg_admm_kernel<true>, SEG_T, h->smem)
+                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seg_admm_kernel<false>, SEG_T, h->smem)) != cudaSuccess) {
         lpbox_set_error("seg kernel configuration failed"); lpbox_seg_destroy(h); return nullptr;
     }
     h->grid = std::max(1, std::min(B, sms * std::max(occ, 1)));
@@ -238,18 +244,44 @@ extern "C" lpbox_seg_batch *lpbox_seg_create_csr(int device, int B, const int32_
         }
         zo += nnz[i];
     }
-    lpbox_seg_batch *h = seg_new(device, B, n, nnz.data(), c, hist_cap);
+    // compact storage when every value is an integer in int8 range and every stored column is < 2^15 rows from its row
+    bool compact = true;
+    {
+        long long z = 0;
+        for (int i = 0; i < B && compact; ++i) {
+            const int32_t *rp = rowptr_all + rp_off[i];
+            for (int r = 0; r < n[i] && compact; ++r)
+                for (int k = rp[r]; k < rp[r + 1]; ++k) {
+                    const double a = val_all[z + k];
+                    const long long d = (long long)colidx_all[z + k] - r;
+                    if (!(a >= -128.0 && a <= 127.0) || a != (double)(signed char)a || d < -32768 || d > 32767) { compact = false; break; }
+                }
+            z += nnz[i];
+        }
+    }
+    lpbox_seg_batch *h = seg_new(device, B, n, nnz.data(), c, hist_cap, compact);
     if (!h) return nullptr;
     const size_t NN = (size_t)h->off_n[B], ZZ = (size_t)h->off_nnz[B];
-    std::vector<int> rp_pack(NN + 4 * (size_t)B, 0), ci_pack(ZZ, 0);
-    std::vector<double> va_pack(ZZ, 0.0), b_pack(NN, 0.0);
+    std::vector<int> rp_pack(NN + 4 * (size_t)B, 0), ci_pack(compact ? 0 : ZZ, 0);
+    std::vector<double> va_pack(compact ? 0 : ZZ, 0.0), b_pack(NN, 0.0);
+    std::vector<short> ci16(compact ? ZZ : 0, 0);
+    std::vector<signed char> va8(compact ? ZZ : 0, 0);
     long long bo = 0;
     zo = 0;
     for (int i = 0; i < B; ++i) {
         const int ni = n[i], nz = nnz[i];
         memcpy(rp_pack.data() + h->off_n[i] + 4 * (size_t)i, rowptr_all + rp_off[i], sizeof(int) * ((size_t)ni + 1));
-        memcpy(ci_pack.data() + h->off_nnz[i], colidx_all + zo, sizeof(int) * (size_t)nz);
-        memcpy(va_pack.data() + h->off_nnz[i], val_all + zo, sizeof(double) * (size_t)nz);
+        if (compact) {
+            const int32_t *rp = rowptr_all + rp_off[i];
+            for (int r = 0; r < ni; ++r)
+                for (int k = rp[r]; k < rp[r + 1]; ++k) {
+                    ci16[h->off_nnz[i] + k] = (short)(colidx_all[zo + k] - r);
+                    va8[h->off_nnz[i] + k] = (signed char)val_all[zo + k];
+                }
+        } else {
+            memcpy(ci_pack.data() + h->off_nnz[i], colidx_all + zo, sizeof(int) * (size_t)nz);
+            memcpy(va_pack.data() + h->off_nnz[i], val_all + zo, sizeof(double) * (size_t)nz);
+        }
         memcpy(b_pack.data() + h->off_n[i], b_all + bo, sizeof(double) * (size_t)ni);
         zo += nz; bo += ni;
     }
@@ -258,12 +290,15 @@ extern "C" lpbox_seg_batch *lpbox_seg_create_csr(int device, int B, const int32_
         if (bytes) { if (cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) ok = false; h->h2d_bytes += (int64_t)bytes; }
     };
     H2D(h->d_rp[0].p, rp_pack.data(), sizeof(int) * rp_pack.size());
-    H2D(h->d_ci[0].p, ci_pack.data(), sizeof(int) * ZZ);
-    H2D(h->d_val[0].p, va_pack.data(), sizeof(double) * ZZ);
+    const void *ci_src = compact ? (const void *)ci16.data() : (const void *)ci_pack.data();
+    const void *va_src = compact ? (const void *)va8.data() : (const void *)va_pack.data();
+    const size_t ci_bytes = (compact ? sizeof(short) : sizeof(int)) * ZZ, va_bytes = (compact ? sizeof(signed char) : sizeof(double)) * ZZ;
+    H2D(h->d_ci[0].p, ci_src, ci_bytes);
+    H2D(h->d_val[0].p, va_src, va_bytes);
     H2D(h->d_b[0].p, b_pack.data(), sizeof(double) * NN);
     H2D(h->d_rp_org.p, rp_pack.data(), sizeof(int) * rp_pack.size());
-    H2D(h->d_ci_org.p, ci_pack.data(), sizeof(int) * ZZ);
-    H2D(h->d_val_org.p, va_pack.data(), sizeof(double) * ZZ);
+    H2D(h->d_ci_org.p, ci_src, ci_bytes);
+    H2D(h->d_val_org.p, va_src, va_bytes);
     H2D(h->d_b_org.p, b_pack.data(), sizeof(double) * NN);
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) ok = false;
     if (!ok) { lpbox_set_error("upload of the CSR arrays failed"); lpbox_seg_destroy(h); return nullptr; }
@@ -276,8 +311,9 @@ extern "C" lpbox_seg_batch *lpbox_seg_create_csr(int device, int B, const int32_
 struct SegBuildArgs {
     const uint8_t *pixels; const long long *pix_off; const int *nr, *nc;
     const long long *off_n, *off_nnz;
-    int *rowptr; int *colidx; double *val, *b, *scr_v, *scr_t;
+    int *rowptr; void *colidx; void *val; double *b, *scr_v, *scr_t;      // colidx / val in the format of SegFmt<CMP>
     SegInst *st;
+    int *bad;          // set when a weight cannot be stored in the compact format (NaN weights of a constant image)
     double cst, den, log2v, bg, f1, f2;
 };
 
@@ -304,14 +340,18 @@ __device__ double seg_build_eigen_sum4(const double *v, long n, double *s_part /
     return res;
 }
 
+template <bool CMP>
 __global__ void __launch_bounds__(256) seg_build_graph_kernel(SegBuildArgs a) {
+    using CI = typename SegFmt<CMP>::CI;
+    using AV = typename SegFmt<CMP>::AV;
     __shared__ double s_part[4], s_bc[2], s_red[8];
     const int img = blockIdx.x, tid = threadIdx.x;
     const int nr = a.nr[img], nc = a.nc[img], n = nr * nc;
     const uint8_t *pix = a.pixels + a.pix_off[img];
     double *v = a.scr_v + a.off_n[img], *t = a.scr_t + a.off_n[img], *b = a.b + a.off_n[img];
-    int *rp = a.rowptr + a.off_n[img] + 4 * (long long)img, *ci = a.colidx + a.off_nnz[img];
-    double *va = a.val + a.off_nnz[img];
+    int *rp = a.rowptr + a.off_n[img] + 4 * (long long)img;
+    CI *ci = reinterpret_cast<CI *>(a.colidx) + a.off_nnz[img];
+    AV *va = reinterpret_cast<AV *>(a.val) + a.off_nnz[img];
     // unary costs in the column-major flattening (SEG.cpp:46-61, :727-743)
     double c_part = 0.0;
     for (int k = tid; k < n; k += 256) {
@@ -360,21 +400,22 @@ __global__ void __launch_bounds__(256) seg_build_graph_kernel(SegBuildArgs a) {
 #pragma unroll
         for (int e = 0; e < 7; ++e) {
             const int ao = oa[e], bo = ob[e];
-            if (ao == 0 && bo == 0) { dq = q; ci[q] = p; q++; continue; }
+            if (ao == 0 && bo == 0) { dq = q; ci[q] = (CI)(CMP ? 0 : p); q++; continue; }
             if (i + ao < 0 || i + ao >= nr || j + bo < 0 || j + bo >= nc) continue;
             const int p2 = (i + ao) * nc + (j + bo);
             const double i2 = (double)pix[(size_t)(p2 % nr) * nc + (p2 / nr)] / 263.0;
             const double d = i1 - i2;
             const double wgt = round(3 * exp(-((d * d) / sig)));
-            ci[q] = p2; va[q] = -wgt; q++;
+            if (CMP && !(wgt >= 0.0 && wgt <= 3.0)) *a.bad = 1;            // NaN (constant image): not representable as int8
+            ci[q] = (CI)(CMP ? p2 - p : p2); va[q] = (AV)(-wgt); q++;      // weights are 0..3: exact in int8
             wsum += wgt;                                // integers: exact in any order
         }
-        va[dq] = wsum;
+        va[dq] = (AV)wsum;                              // <= 18
     }
 }
 
-extern "C" lpbox_seg_batch *lpbox_seg_create_images(int device, int B, const uint8_t *pixels_all, const int32_t *nr, const int32_t *nc,
-                                                   int hist_cap) {
+static lpbox_seg_batch *seg_create_images_fmt(int device, int B, const uint8_t *pixels_all, const int32_t *nr, const int32_t *nc,
+                                              int hist_cap, bool compact, bool *unrepresentable) {
     if (B <= 0 || !pixels_all || !nr || !nc || hist_cap < 0) { lpbox_set_error("invalid argument"); return nullptr; }
     std::vector<long long> po(B + 1, 0);
     std::vector<int> ns(B), nnz(B);
@@ -386,11 +427,13 @@ extern "C" lpbox_seg_batch *lpbox_seg_create_images(int device, int B, const uin
         // stored entries: diagonal + the valid ones of the 6 offsets (-1,0) (-1,1) (0,-1) (0,1) (1,-1) (1,0)
         nnz[i] = (int)(r * c + 2 * (r - 1) * c + 2 * r * (c - 1) + 2 * (r - 1) * (c - 1));
     }
-    lpbox_seg_batch *h = seg_new(device, B, ns.data(), nnz.data(), nullptr, hist_cap);
+    lpbox_seg_batch *h = seg_new(device, B, ns.data(), nnz.data(), nullptr, hist_cap, compact);
     if (!h) return nullptr;
     const size_t NN = (size_t)h->off_n[B], ZZ = (size_t)h->off_nnz[B];
-    SBuf<uint8_t> d_pix; SBuf<long long> d_po; SBuf<int> d_nr, d_nc;
-    bool ok = d_pix.alloc((size_t)po[B]) == cudaSuccess && d_po.alloc(B + 1) == cudaSuccess && d_nr.alloc(B) == cudaSuccess && d_nc.alloc(B) == cudaSuccess;
+    SBuf<uint8_t> d_pix; SBuf<long long> d_po; SBuf<int> d_nr, d_nc, d_bad;
+    const size_t ci_sz = compact ? sizeof(short) : sizeof(int), va_sz = compact ? sizeof(signed char) : sizeof(double);
+    int bad = 0;
+    bool ok = d_bad.alloc(1) == cudaSuccess && d_pix.alloc((size_t)po[B]) == cudaSuccess && d_po.alloc(B + 1) == cudaSuccess && d_nr.alloc(B) == cudaSuccess && d_nc.alloc(B) == cudaSuccess;
     auto C_ = [&](cudaError_t e) { if (e != cudaSuccess) { if (ok) lpbox_set_error(std::string("seg graph builder: ") + cudaGetErrorString(e)); ok = false; } };
     if (ok) {
         C_(cudaMemcpyAsync(d_pix.p, pixels_all, (size_t)po[B], cudaMemcpyHostToDevice, h->stream));
@@ -399,22 +442,25 @@ extern "C" lpbox_seg_batch *lpbox_seg_create_images(int device, int B, const uin
         C_(cudaMemcpyAsync(d_nc.p, nc, sizeof(int) * (size_t)B, cudaMemcpyHostToDevice, h->stream));
         h->h2d_bytes += (int64_t)po[B] + (int64_t)sizeof(long long) * (B + 1) + 2 * (int64_t)sizeof(int) * B;
         C_(cudaMemsetAsync(h->d_rp[0].p, 0, sizeof(int) * (NN + 4 * (size_t)B), h->stream));
-        C_(cudaMemsetAsync(h->d_ci[0].p, 0, sizeof(int) * ZZ, h->stream));
-        C_(cudaMemsetAsync(h->d_val[0].p, 0, sizeof(double) * ZZ, h->stream));
+        C_(cudaMemsetAsync(h->d_ci[0].p, 0, ci_sz * ZZ, h->stream));
+        C_(cudaMemsetAsync(h->d_val[0].p, 0, va_sz * ZZ, h->stream));
+        C_(cudaMemsetAsync(d_bad.p, 0, sizeof(int), h->stream));
         C_(cudaMemsetAsync(h->d_b[0].p, 0, sizeof(double) * NN, h->stream));
         SegBuildArgs a;
         a.pixels = d_pix.p; a.pix_off = d_po.p; a.nr = d_nr.p; a.nc = d_nc.p; a.off_n = h->d_off_n.p; a.off_nnz = h->d_off_nnz.p;
-        a.rowptr = h->d_rp[0].p; a.colidx = h->d_ci[0].p; a.val = h->d_val[0].p; a.b = h->d_b[0].p;
+        a.rowptr = h->d_rp[0].p; a.colidx = h->d_ci[0].p; a.val = h->d_val[0].p; a.b = h->d_b[0].p; a.bad = d_bad.p;
         a.scr_v = h->vecs[7].p; a.scr_t = h->vecs[8].p; a.st = h->d_st.p;
         const double sigma = 0.1;                                                               // SEG.cpp:734-737
         a.cst = log(2.0 * 3.14159265358979323846) / 2.0 + log(sigma); a.den = 2 * sigma * sigma; a.log2v = log(2.0);
         a.bg = 0.6; a.f1 = 0.2; a.f2 = 0.2;
-        seg_build_graph_kernel<<<B, 256, 0, h->stream>>>(a);
+        if (compact) seg_build_graph_kernel<true><<<B, 256, 0, h->stream>>>(a);
+        else seg_build_graph_kernel<false><<<B, 256, 0, h->stream>>>(a);
         C_(cudaGetLastError());
         h->launches++;
         C_(cudaMemcpyAsync(h->d_rp_org.p, h->d_rp[0].p, sizeof(int) * (NN + 4 * (size_t)B), cudaMemcpyDeviceToDevice, h->stream));
-        C_(cudaMemcpyAsync(h->d_ci_org.p, h->d_ci[0].p, sizeof(int) * ZZ, cudaMemcpyDeviceToDevice, h->stream));
-        C_(cudaMemcpyAsync(h->d_val_org.p, h->d_val[0].p, sizeof(double) * ZZ, cudaMemcpyDeviceToDevice, h->stream));
+        C_(cudaMemcpyAsync(h->d_ci_org.p, h->d_ci[0].p, ci_sz * ZZ, cudaMemcpyDeviceToDevice, h->stream));
+        C_(cudaMemcpyAsync(h->d_val_org.p, h->d_val[0].p, va_sz * ZZ, cudaMemcpyDeviceToDevice, h->stream));
+        C_(cudaMemcpyAsync(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         C_(cudaMemcpyAsync(h->d_b_org.p, h->d_b[0].p, sizeof(double) * NN, cudaMemcpyDeviceToDevice, h->stream));
         C_(cudaMemcpyAsync(h->h_st.data(), h->d_st.p, sizeof(SegInst) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
         C_(cudaStreamSynchronize(h->stream));
@@ -422,19 +468,50 @@ extern "C" lpbox_seg_batch *lpbox_seg_create_images(int device, int B, const uin
     } else {
         lpbox_set_error("seg graph builder: out of device memory");
     }
-    d_pix.free_(); d_po.free_(); d_nr.free_(); d_nc.free_();
+    d_pix.free_(); d_po.free_(); d_nr.free_(); d_nc.free_(); d_bad.free_();
     if (!ok) { lpbox_seg_destroy(h); return nullptr; }
+    if (unrepresentable) *unrepresentable = bad != 0;
+    if (bad) { lpbox_seg_destroy(h); return nullptr; }
     return h;
 }
 
+extern "C" lpbox_seg_batch *lpbox_seg_create_images(int device, int B, const uint8_t *pixels_all, const int32_t *nr, const int32_t *nc,
+                                                   int hist_cap) {
+    if (B <= 0 || !pixels_all || !nr || !nc || hist_cap < 0) { lpbox_set_error("invalid argument"); return nullptr; }
+    bool compact = true, bad = false;
+    for (int i = 0; i < B; ++i) if (nc[i] + 1 > 32767) compact = false;       // the int16 column distance would overflow
+    if (compact) {
+        lpbox_seg_batch *h = seg_create_images_fmt(device, B, pixels_all, nr, nc, hist_cap, true, &bad);
+        if (h || !bad) return h;                                             // bad: a constant image (NaN weights) -> general format
+    }
+    return seg_create_images_fmt(device, B, pixels_all, nr, nc, hist_cap, false, nullptr);
+}
+
 // the graph the device builder produced for image i (tests / inspection): arrays sized n+1, nnz, nnz, n
+// colidx / val of problem i as int32 / fp64, from the buffers `ci_dev` / `va_dev` (either storage format)
+static int seg_fetch_matrix(lpbox_seg_batch *h, int i, const void *ci_dev, const void *va_dev, const int32_t *rowptr, int32_t *colidx, double *val) {
+    const int n = h->n0[i], nz = h->nnz0[i];
+    const size_t oz = (size_t)h->off_nnz[i];
+    if (!h->compact) {
+        SCK(cudaMemcpy(colidx, (const int *)ci_dev + oz, sizeof(int) * (size_t)nz, cudaMemcpyDeviceToHost));
+        SCK(cudaMemcpy(val, (const double *)va_dev + oz, sizeof(double) * (size_t)nz, cudaMemcpyDeviceToHost));
+        return 0;
+    }
+    std::vector<short> c16((size_t)nz);
+    std::vector<signed char> v8((size_t)nz);
+    SCK(cudaMemcpy(c16.data(), (const short *)ci_dev + oz, sizeof(short) * (size_t)nz, cudaMemcpyDeviceToHost));
+    SCK(cudaMemcpy(v8.data(), (const signed char *)va_dev + oz, (size_t)nz, cudaMemcpyDeviceToHost));
+    for (int r = 0; r < n; ++r)
+        for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) { colidx[k] = r + c16[k]; val[k] = (double)v8[k]; }
+    return 0;
+}
+
 extern "C" int lpbox_seg_get_graph(lpbox_seg_batch *h, int i, int32_t *rowptr, int32_t *colidx, double *val, double *b, double *c) {
     if (!h || i < 0 || i >= h->B) return LPBOX_E_INVALID;
     if (cudaSetDevice(h->device) != cudaSuccess) return LPBOX_E_CUDA;
     const int n = h->n0[i], nz = h->nnz0[i];
     SCK(cudaMemcpy(rowptr, h->d_rp_org.p + h->off_n[i] + 4 * (size_t)i, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToHost));
-    SCK(cudaMemcpy(colidx, h->d_ci_org.p + h->off_nnz[i], sizeof(int) * (size_t)nz, cudaMemcpyDeviceToHost));
-    SCK(cudaMemcpy(val, h->d_val_org.p + h->off_nnz[i], sizeof(double) * (size_t)nz, cudaMemcpyDeviceToHost));
+    if (int rc = seg_fetch_matrix(h, i, h->d_ci_org.p, h->d_val_org.p, rowptr, colidx, val)) return rc;
     SCK(cudaMemcpy(b, h->d_b_org.p + h->off_n[i], sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
     if (c) *c = h->cconst[i];
     return nz;
@@ -461,7 +538,8 @@ extern "C" int lpbox_seg_init(lpbox_seg_batch *h, const double *x0_all) {
         SCK(cudaStreamSynchronize(h->stream));
     }
     SCK(cudaEventRecord(h->ev0, h->stream));
-    seg_setup_kernel<<<h->B, SEG_T, h->smem, h->stream>>>(h->sv, h->pr, x0_all ? 1 : 0);
+    if (h->compact) seg_setup_kernel<true><<<h->B, SEG_T, h->smem, h->stream>>>(h->sv, h->pr, x0_all ? 1 : 0);
+    else seg_setup_kernel<false><<<h->B, SEG_T, h->smem, h->stream>>>(h->sv, h->pr, x0_all ? 1 : 0);
     SCK(cudaGetLastError());
     h->launches += 1;
     SCK(cudaEventRecord(h->ev1, h->stream));
@@ -476,7 +554,8 @@ static int seg_run(lpbox_seg_batch *h, int iter_start, int iter_end, int l2f, in
     la.iter_start = iter_start; la.iter_end = iter_end; la.l2f = l2f; la.skip_done = skip_done; la.n_work = h->B; la.counter = h->d_counter.p;
     SCK(cudaMemsetAsync(h->d_counter.p, 0, sizeof(int), h->stream));
     SCK(cudaEventRecord(h->ev0, h->stream));
-    seg_admm_kernel<<<h->grid, SEG_T, h->smem, h->stream>>>(h->sv, h->pr, la);
+    if (h->compact) seg_admm_kernel<true><<<h->grid, SEG_T, h->smem, h->stream>>>(h->sv, h->pr, la);
+    else seg_admm_kernel<false><<<h->grid, SEG_T, h->smem, h->stream>>>(h->sv, h->pr, la);
     SCK(cudaGetLastError());
     h->launches += 1;
     SCK(cudaEventRecord(h->ev1, h->stream));
@@ -520,7 +599,8 @@ extern "C" int lpbox_seg_iters_l2f(lpbox_seg_batch *h, int iter_start, int iter_
     } else {
         SCK(cudaMemsetAsync(h->d_num.p, 0, sizeof(int) * (size_t)h->B, h->stream));
     }
-    seg_fix_kernel<<<h->B, SEG_T, 0, h->stream>>>(h->sv, h->pr, h->d_vec.p, h->d_off_vec.p, h->d_num.p, skip_done);
+    if (h->compact) seg_fix_kernel<true><<<h->B, SEG_T, 0, h->stream>>>(h->sv, h->pr, h->d_vec.p, h->d_off_vec.p, h->d_num.p, skip_done);
+    else seg_fix_kernel<false><<<h->B, SEG_T, 0, h->stream>>>(h->sv, h->pr, h->d_vec.p, h->d_off_vec.p, h->d_num.p, skip_done);
     SCK(cudaGetLastError());
     h->launches += 1;
     int rc = seg_run(h, iter_start, iter_end, 1, skip_done);
@@ -593,8 +673,7 @@ extern "C" double lpbox_seg_get_final_obj(lpbox_seg_batch *h, int i) {
     std::vector<int> rp(s.n0 + 1), ci(s.nnz0);
     if (lpbox_seg_get_x_sol(h, i, xs.data()) < 0) return NAN;
     if (seg_d2h(h, rp.data(), h->d_rp_org.p + h->off_n[i] + 4 * (size_t)i, sizeof(int) * ((size_t)s.n0 + 1)) ||
-        seg_d2h(h, ci.data(), h->d_ci_org.p + h->off_nnz[i], sizeof(int) * (size_t)s.nnz0) ||
-        seg_d2h(h, va.data(), h->d_val_org.p + h->off_nnz[i], sizeof(double) * (size_t)s.nnz0) ||
+        seg_fetch_matrix(h, i, h->d_ci_org.p, h->d_val_org.p, rp.data(), ci.data(), va.data()) ||
         seg_d2h(h, b.data(), h->d_b_org.p + h->off_n[i], sizeof(double) * (size_t)s.n0)) return NAN;
     for (int r = 0; r < s.n0; ++r) { double acc = 0.0; for (int k = rp[r]; k < rp[r + 1]; ++k) acc = acc + va[k] * xs[ci[k]]; ax[r] = acc; }
     std::vector<double> pr1(s.n0), pr2(s.n0);

@@ -42,8 +42,8 @@ struct SegView {
     double *x, *y1, *y2, *z1, *z2, *md, *invd, *r, *p, *t, *w;   // n-vectors
     double *b[2];              // double-buffered (early fixing rewrites it)
     int *rowptr[2];            // (off_n + i) offset, n0 + 1 entries per instance (stride n0r + 4 keeps room)
-    int *colidx[2];
-    double *val[2];
+    void *colidx[2];           // general: int32 column index, fp64 value;  compact: int16 (column - row), int8 value --
+    void *val[2];              // see SegFmt (values of the graph builder are small integers, neighbours are < 2^15 rows away)
     SegInst *st;
     double *hist;              // [cc][n0]
     int *left_idx, *ret_idx;
@@ -66,15 +66,24 @@ constexpr int SEG_CH = 256;     // products staged per reduction per chunk
 constexpr int SEG_RMAX = 7;
 constexpr int SEG_BUF_DOUBLES = (2 * 7 * 256 > 2 * 5 * 448) ? 2 * 7 * 256 : 2 * 5 * 448;   // max(block_redux ring, fused-pass ring)
 
+// Storage format of A.  COMPACT = 3 bytes per stored entry instead of 12: the column index as int16 distance from the row and the
+// value as int8 (exact: both conversions are lossless for the graphs of the reference's builder and for any user matrix the host
+// has checked), so the streamed matrix traffic of every SpMV drops by 4x while the fp64 arithmetic sees the same numbers.
+template <bool CMP> struct SegFmt { using CI = int; using AV = double; };
+template <> struct SegFmt<true> { using CI = short; using AV = signed char; };
+template <bool CMP>
+__device__ __forceinline__ int seg_col(const typename SegFmt<CMP>::CI *__restrict__ ci, int k, int i) { return CMP ? i + (int)ci[k] : (int)ci[k]; }
+
 // y_i = ((0 + m_i1 v_j1) + m_i2 v_j2) + ...  row i of (DIAG ? 2A with the diagonal replaced by md : A)
-template <bool DIAG>
-__device__ __forceinline__ double seg_row_dot(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ av,
-                                              const double *__restrict__ md, const double *__restrict__ v, int i) {
+template <bool DIAG, bool CMP>
+__device__ __forceinline__ double seg_row_dot(const int *__restrict__ rp, const typename SegFmt<CMP>::CI *__restrict__ ci,
+                                              const typename SegFmt<CMP>::AV *__restrict__ av, const double *__restrict__ md,
+                                              const double *__restrict__ v, int i) {
     double acc = 0.0;
     const int e = rp[i + 1];
     for (int k = rp[i]; k < e; ++k) {
-        const int c = ci[k];
-        double m = av[k];
+        const int c = seg_col<CMP>(ci, k, i);
+        double m = (double)av[k];
         if (DIAG) m = (c == i) ? md[i] : dM(2.0, m);
         acc = dA(acc, dM(m, v[c]));
     }
@@ -221,8 +230,11 @@ __device__ __forceinline__ void seg_fused_pass(Body body, int n, double *buf, do
     __syncthreads();
 }
 
+template <bool CMP>
 __global__ void __launch_bounds__(SEG_T, 5)
 seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
+    using CI = typename SegFmt<CMP>::CI;
+    using AV = typename SegFmt<CMP>::AV;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *buf = reinterpret_cast<double *>(smem_raw);                 // [2][SEG_RMAX][SEG_CH]
     double *sc = buf + SEG_BUF_DOUBLES;                                 // [8]
@@ -244,8 +256,8 @@ seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
                *invd = sv.invd + on, *r = sv.r + on, *p = sv.p + on, *t = sv.t + on, *w = sv.w + on;
         const double *__restrict__ b = sv.b[cur] + on;
         const int *__restrict__ rp = sv.rowptr[cur] + on + 4 * inst;      // n0r + 4 ints reserved per instance
-        const int *__restrict__ ci = sv.colidx[cur] + oz;
-        const double *__restrict__ av = sv.val[cur] + oz;
+        const CI *__restrict__ ci = reinterpret_cast<const CI *>(sv.colidx[cur]) + oz;
+        const AV *__restrict__ av = reinterpret_cast<const AV *>(sv.val[cur]) + oz;
         double rho1 = st->rho1, rho2 = st->rho2, prho1 = st->prho1, prho2 = st->prho2, gamma = st->gamma, ratio = st->ratio,
                std_obj = st->std_obj, cur_obj = st->cur_obj, best_bin_obj = st->best_bin_obj;
         int rhoUpdated = st->rhoUpdated;
@@ -283,7 +295,7 @@ seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
             // ---- PCG (SEG.cpp:272-342).  pass 3: r = rhs - M x, p = invd r; rhs.rhs, r.r, r.p ---------------------------
             seg_fused_pass<3>([&](int i, double (&v)[3]) {
                 const double rhs = w[i];
-                const double rr = dS(rhs, seg_row_dot<true>(rp, ci, av, md, x, i));
+                const double rr = dS(rhs, seg_row_dot<true, CMP>(rp, ci, av, md, x, i));
                 const double pp = dM(invd[i], rr);
                 r[i] = rr; p[i] = pp;
                 v[0] = dM(rhs, rhs); v[1] = dM(rr, rr); v[2] = dM(rr, pp);
@@ -300,7 +312,7 @@ seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
                     while (cg_it < pr.pcg_maxiters) {
                         // tmp = M p fused with p.dot(tmp)
                         seg_fused_pass<1>([&](int i, double (&v)[1]) {
-                            const double ti = seg_row_dot<true>(rp, ci, av, md, p, i);
+                            const double ti = seg_row_dot<true, CMP>(rp, ci, av, md, p, i);
                             t[i] = ti;
                             v[0] = dM(p[i], ti);
                         }, n, buf, sc);
@@ -337,7 +349,7 @@ seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
                     z1[i] = dA(z1[i], dM(g1, d1));
                     z2[i] = dA(z2[i], dM(g2, d2));
                     w[i] = (xi >= 0.5) ? 1.0 : 0.0;
-                    const double ax = seg_row_dot<false>(rp, ci, av, md, x, i);
+                    const double ax = seg_row_dot<false, CMP>(rp, ci, av, md, x, i);
                     v[0] = dM(xi, xi); v[1] = dM(d1, d1); v[2] = dM(d2, d2); v[3] = dM(xi, ax); v[4] = dM(b[i], xi);
                 }, n, buf, sc);
             }
@@ -345,7 +357,7 @@ seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
             // ---- pass: A 1[x >= 0.5]; idx.A idx, b.idx  (SEG.cpp:1323-1326) -------------------------------------------
             seg_fused_pass<2>([&](int i, double (&v)[2]) {
                 const double wi = w[i];
-                v[0] = dM(wi, seg_row_dot<false>(rp, ci, av, md, w, i));
+                v[0] = dM(wi, seg_row_dot<false, CMP>(rp, ci, av, md, w, i));
                 v[1] = dM(b[i], wi);
             }, n, buf, sc);
             const double bin_val = dA(sc[0], sc[1]);
@@ -382,7 +394,7 @@ seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
             // legacy epilogue (SEG.cpp:1366-1367): cur_obj = compute_cost(1[x >= 0.5])
             for (int i = tid; i < n; i += SEG_T) w[i] = (x[i] >= 0.5) ? 1.0 : 0.0;
             __syncthreads();
-            for (int i = tid; i < n; i += SEG_T) r[i] = seg_row_dot<false>(rp, ci, av, md, w, i);
+            for (int i = tid; i < n; i += SEG_T) r[i] = seg_row_dot<false, CMP>(rp, ci, av, md, w, i);
             __syncthreads();
             seg_block_redux<2>([&](int q, int i) { return dM(q == 0 ? w[i] : b[i], q == 0 ? r[i] : w[i]); }, n, buf, sc);
             cur_obj = dA(sc[0], sc[1]);
@@ -403,8 +415,11 @@ seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
 
 // ADMM_bqp_unconstrained_init (SEG.cpp:747-810) for every image: x = x0 (zeros), y = x, z = 0, md = 2 a_ii + (rho1+rho2),
 // best_bin_obj = compute_cost(x0).  One CTA per image.
+template <bool CMP>
 __global__ void __launch_bounds__(SEG_T)
 seg_setup_kernel(SegView sv, Params pr, int use_x0) {
+    using CI = typename SegFmt<CMP>::CI;
+    using AV = typename SegFmt<CMP>::AV;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *buf = reinterpret_cast<double *>(smem_raw);
     double *sc = buf + SEG_BUF_DOUBLES;
@@ -413,8 +428,8 @@ seg_setup_kernel(SegView sv, Params pr, int use_x0) {
     const int n = st->n, cur = st->cur;
     const long long on = sv.off_n[inst], oz = sv.off_nnz[inst];
     const int *rp = sv.rowptr[cur] + on + 4 * inst;
-    const int *ci = sv.colidx[cur] + oz;
-    const double *av = sv.val[cur] + oz;
+    const CI *ci = reinterpret_cast<const CI *>(sv.colidx[cur]) + oz;
+    const AV *av = reinterpret_cast<const AV *>(sv.val[cur]) + oz;
     const double *b = sv.b[cur] + on;
     double *x = sv.x + on, *t = sv.t + on;
     const double rho = pr.initial_rho;
@@ -423,11 +438,11 @@ seg_setup_kernel(SegView sv, Params pr, int use_x0) {
         x[i] = x0; sv.y1[on + i] = x0; sv.y2[on + i] = x0; sv.z1[on + i] = 0.0; sv.z2[on + i] = 0.0;
         sv.left_idx[on + i] = i;
         double d = 0.0;
-        for (int k = rp[i]; k < rp[i + 1]; ++k) if (ci[k] == i) d = dM(2.0, av[k]);
+        for (int k = rp[i]; k < rp[i + 1]; ++k) if (seg_col<CMP>(ci, k, i) == i) d = dM(2.0, (double)av[k]);
         sv.md[on + i] = dA(d, dA(rho, rho));                             // temp_mat = 2A; diag += rho1 + rho2
     }
     __syncthreads();
-    for (int i = tid; i < n; i += SEG_T) t[i] = seg_row_dot<false>(rp, ci, av, nullptr, x, i);
+    for (int i = tid; i < n; i += SEG_T) t[i] = seg_row_dot<false, CMP>(rp, ci, av, nullptr, x, i);
     __syncthreads();
     seg_block_redux<2>([&](int q, int i) { return dM(q == 0 ? x[i] : b[i], q == 0 ? t[i] : x[i]); }, n, buf, sc);
     if (tid == 0) {
@@ -465,6 +480,7 @@ __device__ __forceinline__ int seg_block_exscan_global(int *data, int n, int *s_
     return carry;
 }
 
+template <bool CMP>
 __global__ void __launch_bounds__(SEG_T)
 seg_fix_kernel(SegView sv, Params pr, const double *__restrict__ vec, const long long *__restrict__ off_vec, const int *__restrict__ num,
                int skip_done) {
@@ -478,10 +494,16 @@ seg_fix_kernel(SegView sv, Params pr, const double *__restrict__ vec, const long
     const int cur = st->cur, nxt = cur ^ 1;
     const long long on = sv.off_n[inst], oz = sv.off_nnz[inst];
     const double *v = vec + off_vec[inst];
-    const int *rp = sv.rowptr[cur] + on + 4 * inst, *ci = sv.colidx[cur] + oz;
-    const double *av = sv.val[cur] + oz, *b = sv.b[cur] + on;
-    int *rp2 = sv.rowptr[nxt] + on + 4 * inst, *ci2 = sv.colidx[nxt] + oz;
-    double *av2 = sv.val[nxt] + oz, *b2 = sv.b[nxt] + on;
+    using CI = typename SegFmt<CMP>::CI;
+    using AV = typename SegFmt<CMP>::AV;
+    const int *rp = sv.rowptr[cur] + on + 4 * inst;
+    const CI *ci = reinterpret_cast<const CI *>(sv.colidx[cur]) + oz;
+    const AV *av = reinterpret_cast<const AV *>(sv.val[cur]) + oz;
+    const double *b = sv.b[cur] + on;
+    int *rp2 = sv.rowptr[nxt] + on + 4 * inst;
+    CI *ci2 = reinterpret_cast<CI *>(sv.colidx[nxt]) + oz;
+    AV *av2 = reinterpret_cast<AV *>(sv.val[nxt]) + oz;
+    double *b2 = sv.b[nxt] + on;
     int *kidx = sv.kidx + on, *cnt = sv.cnt + on;
     auto is_fixed = [&](int i) { const double t = v[i]; return t == 1.0 || t == 0.0; };
     for (int i = tid; i < n; i += SEG_T) kidx[i] = is_fixed(i) ? 0 : 1;
@@ -515,7 +537,7 @@ seg_fix_kernel(SegView sv, Params pr, const double *__restrict__ vec, const long
     for (int i = tid; i < n; i += SEG_T) {
         if (is_fixed(i)) continue;
         int c = 0;
-        for (int k = rp[i]; k < rp[i + 1]; ++k) c += is_fixed(ci[k]) ? 0 : 1;
+        for (int k = rp[i]; k < rp[i + 1]; ++k) c += is_fixed(seg_col<CMP>(ci, k, i)) ? 0 : 1;
         cnt[kidx[i]] = c;
     }
     __syncthreads();
@@ -528,10 +550,10 @@ seg_fix_kernel(SegView sv, Params pr, const double *__restrict__ vec, const long
         rp2[r] = q;
         double acc = 0.0, dg = 0.0;
         for (int k = rp[i]; k < rp[i + 1]; ++k) {
-            const int c = ci[k];
-            const double a = av[k];
+            const int c = seg_col<CMP>(ci, k, i);
+            const double a = (double)av[k];
             if (is_fixed(c)) acc = dA(acc, dM(a, v[c]));
-            else { ci2[q] = kidx[c]; av2[q] = a; q++; if (c == i) dg = dM(2.0, a); }
+            else { ci2[q] = (CI)(CMP ? kidx[c] - r : kidx[c]); av2[q] = av[k]; q++; if (c == i) dg = dM(2.0, a); }   // kept neighbours only move closer
         }
         b2[r] = dA(dM(2.0, acc), b[i]);
         sv.md[on + r] = dA(dg, rr);
