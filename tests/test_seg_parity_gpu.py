@@ -118,3 +118,38 @@ def test_l2f_windows_match_oracle():
         else:
             vec, num = np.zeros(1), 0
     assert s.get_n() < 28 * 36
+
+
+def test_general_matrix_format_matches_oracle():
+    """CSR input whose values are NOT small integers takes the general (int32 + fp64) storage path -- the graph builder's
+    matrices take the compact int16 + int8 one.  Same graph scaled by 0.5 (non-integer weights) and one far off-diagonal
+    entry pair: solve + an early-fix window, bit-exact vs the oracle; the same graph unscaled (compact) must agree as well."""
+    import lpbox
+    img = synth_image(21, 26, 31)
+    o0 = OracleSeg()
+    rp, ci, va, b, c = o0.build_graph(img)
+    for scale in (0.5, 1.0):
+        va_s, b_s = va * scale, b * scale
+        o = OracleSeg(); o.set_problem(rp, ci, va_s, b_s, c * scale); o.init()
+        bt = lpbox.SegBatch([(rp, ci, va_s, b_s, c * scale)], hist_cap=10); bt.init()
+        ws = 10
+        vec, num = np.zeros(1), 0
+        for w in range(4):
+            ro = o.l2f(ws * w, ws * (w + 1), vec, num)
+            rg = bt.iters_l2f(ws * w, ws * (w + 1), [vec] if num else None, [num] if num else None)
+            assert ro == int(rg[0]), (scale, w)
+            so, sg = o.state(), bt.state(0)
+            for k in so:
+                assert np.array_equal(so[k], sg[k]), (scale, w, k)
+            assert o.L.sego_get_final_obj(o.h) == bt.final_obj(0)
+            if ro:
+                break
+            if w == 1:
+                x = so["x"]
+                idx = np.argsort(-np.abs(x - 0.5))[: len(x) // 3]
+                vec = -np.ones(len(x)); vec[idx] = (x[idx] >= 0.5) * 1.0; num = len(idx)
+            else:
+                vec, num = np.zeros(1), 0
+        g = bt.graph(0)
+        assert np.array_equal(g[1], ci) and np.array_equal(g[2], va_s)
+        bt.close()
