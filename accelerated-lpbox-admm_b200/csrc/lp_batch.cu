@@ -8,6 +8,8 @@
 
 #include <algorithm>
 #include <string>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "../../include/lpbox_b200.h"
@@ -98,6 +100,22 @@ struct lpbox_batch {
     int pat_smem = 0;                           // bytes of shared memory reserved for the image (< max_pat: the largest images keep their column indices in L2)
     DevBuf<int> d_work;                         // launch order when pat_smem < max_pat (instances with a spilled image first)
 };
+
+// instance-parallel host loops of lpbox_batch_create (sorting, packing): blocks of 64 instances over the host cores
+template <typename F>
+static void host_parallel_for(int count, F f) {
+    int nt = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+    if (count < 512) nt = 1;
+    if (nt == 1) { for (int i = 0; i < count; ++i) f(i); return; }
+    std::atomic<int> next(0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt; ++t)
+        pool.emplace_back([&]() {
+            for (int i0; (i0 = next.fetch_add(64)) < count;)
+                for (int i = i0; i < std::min(i0 + 64, count); ++i) f(i);
+        });
+    for (auto &th : pool) th.join();
+}
 
 template <int T, int EPT, bool UNIT>
 static cudaError_t prep_kernel(size_t smem, int *occ) {
@@ -220,30 +238,44 @@ extern "C" lpbox_batch *lpbox_batch_create(int device, int B, const int32_t *m, 
     std::vector<int> rcap(B, 0), ccap(B, 0);
     std::vector<std::vector<uint16_t>> rperm_all(B), cperm_all(B);
     h->off_hist.assign(B + 1, 0); h->h_nnz_off.assign(B + 1, 0); h->h_cp_off.assign(B + 1, 0);
+    // (1) cheap serial pass: sizes and the offsets that depend on n, m, nnz only
+    std::vector<long long> b_in_off(B + 1, 0), f_in_off(B + 1, 0);
     for (int i = 0; i < B; ++i) {
         if (n[i] <= 0 || m[i] < 0) { set_err("instance with n <= 0"); delete h; return nullptr; }
         const int32_t *cp = colptr_all + h->h_cp_off[i];
         h->nnz0[i] = cp[n[i]];
+        if (h->nnz0[i] < 0) { set_err("bad colptr"); delete h; return nullptr; }
         h->h_cp_off[i + 1] = h->h_cp_off[i] + n[i] + 1;
         h->h_nnz_off[i + 1] = h->h_nnz_off[i] + h->nnz0[i];
         h->off_n[i + 1] = h->off_n[i] + ((n[i] + 1) & ~1);
         h->off_m[i + 1] = h->off_m[i] + ((m[i] + 1) & ~1);
-        {   // SpMV work assignment: slots sorted by descending stored length (stable); capacities of the sliced-ELL image
-            const int ni = n[i], mi = m[i];
-            const int32_t *ri = rowidx_all + h->h_nnz_off[i];
-            std::vector<int> rl(mi, 0), cl(ni), ord(mi);
-            for (int k = 0; k < h->nnz0[i]; ++k) { if (ri[k] < 0 || ri[k] >= mi) { set_err("row index out of range"); delete h; return nullptr; } rl[ri[k]]++; }
-            for (int j = 0; j < ni; ++j) cl[j] = cp[j + 1] - cp[j];
-            for (int r = 0; r < mi; ++r) ord[r] = r;
-            std::stable_sort(ord.begin(), ord.end(), [&](int a, int b2) { return rl[a] > rl[b2]; });
-            rperm_all[i].resize(mi);
-            for (int r = 0; r < mi; ++r) { rperm_all[i][r] = (uint16_t)ord[r]; if ((r & 31) == 0) rcap[i] += rl[ord[r]]; }
-            ord.resize(ni);
-            for (int j = 0; j < ni; ++j) ord[j] = j;
-            std::stable_sort(ord.begin(), ord.end(), [&](int a, int b2) { return cl[a] > cl[b2]; });
-            cperm_all[i].resize(ni);
-            for (int j = 0; j < ni; ++j) { cperm_all[i][j] = (uint16_t)ord[j]; if ((j & 31) == 0) ccap[i] += cl[ord[j]]; }
-        }
+        h->off_hist[i + 1] = h->off_hist[i] + (long long)hist_cap * n[i];
+        b_in_off[i + 1] = b_in_off[i] + n[i]; f_in_off[i + 1] = f_in_off[i] + m[i];
+        h->max_n = std::max(h->max_n, n[i]); h->max_m = std::max(h->max_m, m[i]); h->max_nnz = std::max(h->max_nnz, h->nnz0[i]);
+    }
+    // (2) per instance, in parallel on the host cores: SpMV work assignment -- slots sorted by descending stored length
+    //     (stable) -- and the capacities of the sliced-ELL image
+    std::atomic<int> err1(0);
+    host_parallel_for(B, [&](int i) {
+        const int ni = n[i], mi = m[i];
+        const int32_t *cp = colptr_all + h->h_cp_off[i];
+        const int32_t *ri = rowidx_all + h->h_nnz_off[i];
+        std::vector<int> rl(mi, 0), cl(ni), ord(mi);
+        for (int k = 0; k < h->nnz0[i]; ++k) { if (ri[k] < 0 || ri[k] >= mi) { err1.store(1); return; } rl[ri[k]]++; }
+        for (int j = 0; j < ni; ++j) cl[j] = cp[j + 1] - cp[j];
+        for (int r = 0; r < mi; ++r) ord[r] = r;
+        std::stable_sort(ord.begin(), ord.end(), [&](int a, int b2) { return rl[a] > rl[b2]; });
+        rperm_all[i].resize(mi);
+        for (int r = 0; r < mi; ++r) { rperm_all[i][r] = (uint16_t)ord[r]; if ((r & 31) == 0) rcap[i] += rl[ord[r]]; }
+        ord.resize(ni);
+        for (int j = 0; j < ni; ++j) ord[j] = j;
+        std::stable_sort(ord.begin(), ord.end(), [&](int a, int b2) { return cl[a] > cl[b2]; });
+        cperm_all[i].resize(ni);
+        for (int j = 0; j < ni; ++j) { cperm_all[i][j] = (uint16_t)ord[j]; if ((j & 31) == 0) ccap[i] += cl[ord[j]]; }
+    });
+    if (err1.load()) { set_err("row index out of range"); delete h; return nullptr; }
+    // (3) serial: offsets that depend on the layouts
+    for (int i = 0; i < B; ++i) {
         EllLayout EL = ell_layout(n[i], m[i], rcap[i], ccap[i]);
         CsrLayout PL = csr_layout(n[i], m[i], h->nnz0[i]);
         h->off_pat[i + 1] = h->off_pat[i] + EL.bytes;
@@ -254,8 +286,6 @@ extern "C" lpbox_batch *lpbox_batch_create(int device, int B, const int32_t *m, 
         h->max_csr = std::max(h->max_csr, PL.bytes);
         h->max_evr = std::max(h->max_evr, 32 * rcap[i]); h->max_evc = std::max(h->max_evc, 32 * ccap[i]);
         if (rcap[i] > 2047 || ccap[i] > 2047) { set_err("pattern too large for the on-chip kernel"); delete h; return nullptr; }
-        h->off_hist[i + 1] = h->off_hist[i] + (long long)hist_cap * n[i];
-        h->max_n = std::max(h->max_n, n[i]); h->max_m = std::max(h->max_m, m[i]); h->max_nnz = std::max(h->max_nnz, h->nnz0[i]);
         h->max_pat = std::max(h->max_pat, EL.bytes);
         h->pat_bytes_i.push_back(EL.bytes); h->pat_head_i.push_back(EL.o_cidx);
     }
@@ -273,9 +303,10 @@ extern "C" lpbox_batch *lpbox_batch_create(int device, int B, const int32_t *m, 
     if (!h->all_unit) { val_r.assign((size_t)h->off_val[B], 0.0); val_c.assign((size_t)h->off_val[B], 0.0); }
     std::vector<double> fvec((size_t)h->off_m[B], 1.0), bvec((size_t)h->off_n[B], 0.0);
     std::vector<InstState> st(B);
-    long long boff = 0, foff = 0;
-    for (int i = 0; i < B; ++i) {
+    std::atomic<int> err2(0);
+    host_parallel_for(B, [&](int i) {
         const int ni = n[i], mi = m[i], nz = h->nnz0[i];
+        const long long boff = b_in_off[i], foff = f_in_off[i];
         const int32_t *cp = colptr_all + h->h_cp_off[i];
         const int32_t *ri = rowidx_all + h->h_nnz_off[i];
         const double *va = val_all ? val_all + h->h_nnz_off[i] : nullptr;
@@ -291,11 +322,11 @@ extern "C" lpbox_batch *lpbox_batch_create(int device, int B, const int32_t *m, 
         uint16_t *colidx = (uint16_t *)(blob + PL.o_colidx), *rowidx = (uint16_t *)(blob + PL.o_rowidx);
         std::vector<int> rcount(mi + 1, 0);
         for (int j = 0; j < ni; ++j) {
-            if (cp[j] > cp[j + 1] || cp[0] != 0) { set_err("bad colptr"); delete h; return nullptr; }
+            if (cp[j] > cp[j + 1] || cp[0] != 0) { err2.store(1); return; }
             colptr[j] = (uint16_t)cp[j];
             for (int k = cp[j]; k < cp[j + 1]; ++k) {
                 if (ri[k] < 0 || ri[k] >= mi || (k > cp[j] && ri[k] <= ri[k - 1])) {
-                    set_err("row indices must be in range and strictly ascending within each column"); delete h; return nullptr;
+                    err2.store(2); return;
                 }
                 rowidx[k] = (uint16_t)ri[k];
                 rcount[ri[k] + 1]++;
@@ -313,11 +344,11 @@ extern "C" lpbox_batch *lpbox_batch_create(int device, int B, const int32_t *m, 
             }
         memcpy(bvec.data() + h->off_n[i], b_all + boff, sizeof(double) * (size_t)ni);
         if (f_all) memcpy(fvec.data() + h->off_m[i], f_all + foff, sizeof(double) * (size_t)mi);
-        boff += ni; foff += mi;
         InstState &s = st[i];
         memset(&s, 0, sizeof(s));
         s.n0 = s.n = ni; s.m0 = s.m = mi; s.nnz0 = s.nnz = nz; s.rcap = rcap[i]; s.ccap = ccap[i]; s.unit = h->all_unit ? 1 : 0; s.std_obj = 1.0; s.rhoUpdated = 1;
-    }
+    });
+    if (err2.load()) { set_err(err2.load() == 1 ? "bad colptr" : "row indices must be in range and strictly ascending within each column"); delete h; return nullptr; }
     h->h_st = st;
     lpbox_params lp; lpbox_params_lp(&lp);
     h->pr.stop_threshold = lp.stop_threshold; h->pr.std_threshold = lp.std_threshold; h->pr.max_iters = lp.max_iters;

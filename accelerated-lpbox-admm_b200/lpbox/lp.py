@@ -38,6 +38,13 @@ def read_instance(root, i, k, j):
     return m.value, n.value, colptr, rowidx, val, bb
 
 
+class ProblemList(list):
+    """A list of problem tuples that may also carry the same instances already concatenated (`packed`), as produced by
+    `gen_auctions`.  Slices and copies are plain lists, so `packed` can never describe a different set of problems --
+    unless the list is mutated in place, which LPBatch detects by the length."""
+    packed = None
+
+
 class LPBatch:
     """B independent instances `min b'x s.t. Ex<=f, x in {0,1}^n` resident on one GPU.
 
@@ -49,18 +56,22 @@ class LPBatch:
         L = _capi.lib()
         self.L = L
         self.B = len(problems)
-        ms = _i32([p[0] for p in problems])
-        ns = _i32([p[1] for p in problems])
-        colptr = _i32(np.concatenate([np.asarray(p[2]) for p in problems]))
-        rowidx = _i32(np.concatenate([np.asarray(p[3]) for p in problems]))
-        has_val = any(p[4] is not None for p in problems)
-        val = None
-        if has_val:
-            val = _f64(np.concatenate([np.ones(len(p[3])) if p[4] is None else np.asarray(p[4]) for p in problems]))
-        b = _f64(np.concatenate([np.asarray(p[5]) for p in problems]))
-        f = None
-        if any(len(p) > 6 and p[6] is not None for p in problems):
-            f = _f64(np.concatenate([np.ones(p[0]) if (len(p) <= 6 or p[6] is None) else np.asarray(p[6]) for p in problems]))
+        pk = getattr(problems, "packed", None)
+        if pk is not None and len(pk["ms"]) == self.B:
+            ms, ns, colptr, rowidx, b, val, f = pk["ms"], pk["ns"], pk["colptr"], pk["rowidx"], pk["b"], None, None
+        else:
+            ms = _i32([p[0] for p in problems])
+            ns = _i32([p[1] for p in problems])
+            colptr = _i32(np.concatenate([np.asarray(p[2]) for p in problems]))
+            rowidx = _i32(np.concatenate([np.asarray(p[3]) for p in problems]))
+            has_val = any(p[4] is not None for p in problems)
+            val = None
+            if has_val:
+                val = _f64(np.concatenate([np.ones(len(p[3])) if p[4] is None else np.asarray(p[4]) for p in problems]))
+            b = _f64(np.concatenate([np.asarray(p[5]) for p in problems]))
+            f = None
+            if any(len(p) > 6 and p[6] is not None for p in problems):
+                f = _f64(np.concatenate([np.ones(p[0]) if (len(p) <= 6 or p[6] is None) else np.asarray(p[6]) for p in problems]))
         self.org_n = ns.copy()
         self.h = L.lpbox_batch_create(int(device), self.B, ptr(ms), ptr(ns), ptr(colptr), ptr(rowidx), ptr(val), ptr(b),
                                       ptr(f), int(hist_cap))
@@ -300,9 +311,13 @@ def gen_auctions(seed, count, n_items=100, n_bids=500, add_item_prob=0.7, thread
     finally:
         for p in (m_p, cp_p, ri_p, pr_p):
             L.lpbox_free(C.cast(p, C.c_void_p))
-    out, o = [], 0
+    out, o = ProblemList(), 0
+    nb = -prs
     for i in range(count):
         nz = int(cps[i, -1])
-        out.append((int(ms[i]), n_bids, cps[i], ris[o:o + nz], None, -prs[i], None))
+        out.append((int(ms[i]), n_bids, cps[i], ris[o:o + nz], None, nb[i], None))
         o += nz
+    # the same data in the concatenated layout LPBatch hands to the C ABI (saves re-concatenating 10^4 small arrays)
+    out.packed = dict(ms=ms.astype(np.int32), ns=np.full(count, n_bids, dtype=np.int32), colptr=np.ascontiguousarray(cps.reshape(-1), dtype=np.int32),
+                      rowidx=np.ascontiguousarray(ris, dtype=np.int32), b=np.ascontiguousarray(nb.reshape(-1), dtype=np.float64))
     return out
