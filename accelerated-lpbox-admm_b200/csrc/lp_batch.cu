@@ -672,8 +672,8 @@ extern "C" int lpbox_batch_results(lpbox_batch *h, lpbox_log_row *log, uint8_t *
     std::vector<int> left(NN), ridx(NN);
     if (d2h(h, x.data(), h->d_x.p, sizeof(double) * NN) || d2h(h, rval.data(), h->d_ret_val.p, sizeof(double) * NN) ||
         d2h(h, left.data(), h->d_left.p, sizeof(int) * NN) || d2h(h, ridx.data(), h->d_ret_idx.p, sizeof(int) * NN)) return LPBOX_E_CUDA;
-    std::vector<double> xs, acc;
-    for (int i = 0; i < h->B; ++i) {
+    host_parallel_for(h->B, [&](int i) {
+        std::vector<double> xs, acc;
         const InstState &s = h->h_st[i];
         long long on = h->off_n[i];
         xs.assign(s.n0, 0.0);
@@ -697,7 +697,7 @@ extern "C" int lpbox_batch_results(lpbox_batch *h, lpbox_log_row *log, uint8_t *
             L.iters = (int32_t)s.admm_iters; L.status = s.status; L.cg_iters = s.cg_iters;
             L.obj = s.n != 0 ? s.sum_fix_obj + s.cur_obj : s.sum_fix_obj; L.cur_bin_obj = s.cur_obj; L.n_left = s.n; L.infeasible = inf;
         }
-    }
+    });
     return 0;
 }
 
