@@ -77,3 +77,16 @@ def test_policy_pack_layout_reproduces_the_module():
     with torch.no_grad():
         ref = net(x)[1].reshape(-1).numpy()
     assert np.abs(sig - ref).max() < 1e-5
+
+
+def test_generator_packed_layout_matches_the_tuples():
+    """`gen_auctions` returns problem tuples plus the same data concatenated (`packed`, what LPBatch hands to the C ABI);
+    slices are plain lists without it."""
+    import lpbox
+    p = lpbox.gen_auctions(3, 40, 20, 60)
+    pk = p.packed
+    assert np.array_equal(np.concatenate([np.asarray(t[2]) for t in p]), pk["colptr"])
+    assert np.array_equal(np.concatenate([np.asarray(t[3]) for t in p]), pk["rowidx"])
+    assert np.array_equal(np.concatenate([t[5] for t in p]), pk["b"])
+    assert np.array_equal([t[0] for t in p], pk["ms"]) and np.array_equal([t[1] for t in p], pk["ns"])
+    assert getattr(p[:10], "packed", None) is None and type(p[:10]) is list
