@@ -90,8 +90,16 @@ __device__ __forceinline__ double warp_redux_eigen1(const double *v, int n) {
         if (left >= 4) {
             double t0 = pv[0], t1 = pv[4], t2 = pv[8], t3 = pv[12];
             pv += 16; left -= 4;
+            // two batches per trip, ping-pong between the t and u registers (no register moves in the loop)
 #pragma unroll 1
-            while (left >= 4) {
+            while (left >= 8) {
+                const double u0 = pv[0], u1 = pv[4], u2 = pv[8], u3 = pv[12];
+                acc = dA(acc, t0); acc = dA(acc, t1); acc = dA(acc, t2); acc = dA(acc, t3);
+                t0 = pv[16]; t1 = pv[20]; t2 = pv[24]; t3 = pv[28];
+                acc = dA(acc, u0); acc = dA(acc, u1); acc = dA(acc, u2); acc = dA(acc, u3);
+                pv += 32; left -= 8;
+            }
+            if (left >= 4) {
                 const double u0 = pv[0], u1 = pv[4], u2 = pv[8], u3 = pv[12];
                 acc = dA(acc, t0); acc = dA(acc, t1); acc = dA(acc, t2); acc = dA(acc, t3);
                 t0 = u0; t1 = u1; t2 = u2; t3 = u3;
