@@ -96,6 +96,7 @@ struct lpbox_batch {
     std::vector<int> h_active;
     std::vector<long long> h_row_off;
     bool dev_fix_pending = false;
+    bool record_plain = false;          // lpbox_batch_set_record_history
     std::vector<int> pat_bytes_i, pat_head_i;   // sliced-ELL image size of every instance, and its size without the column index array
     int pat_smem = 0;                           // bytes of shared memory reserved for the image (< max_pat: the largest images keep their column indices in L2)
     DevBuf<int> d_work;                         // launch order when pat_smem < max_pat (instances with a spilled image first)
@@ -199,7 +200,7 @@ static int configure(lpbox_batch *h) {
 
 static int run_window(lpbox_batch *h, int iter_start, int iter_end, int l2f, int skip_done) {
     Launch la{};
-    la.iter_start = iter_start; la.iter_end = iter_end; la.l2f = l2f; la.skip_done = skip_done;
+    la.iter_start = iter_start; la.iter_end = iter_end; la.l2f = l2f; la.skip_done = skip_done; la.record = h->record_plain ? 1 : 0;
     la.n_work = h->B; la.work = h->d_work.p; la.counter = h->d_counter.p;
     la.mp = (h->max_m + 1) & ~1; la.np = std::max((h->max_n + 1) & ~1, la.mp); la.pat_bytes = h->pat_smem;
     la.evr_elems = h->all_unit ? 0 : h->max_evr; la.evc_elems = h->all_unit ? 0 : h->max_evc;
@@ -473,6 +474,15 @@ extern "C" int lpbox_batch_init(lpbox_batch *h, const double *x0_all) {
     { int rc = sync_states(h); if (rc) return rc; }
     h->inited = true;
     return 1;   // ADMM_lp_iters_init returns 1 (LP.cpp:762)
+}
+
+// the plain loop (lpbox_batch_iters / _solve) also writes every iterate into the history ring (hist_cap iterations per call),
+// readable with lpbox_batch_get_x_iters: what print_fix_info == 2 dumps to xiter/*.csv (LP.cpp:903-909)
+extern "C" int lpbox_batch_set_record_history(lpbox_batch *h, int on) {
+    if (!h) return LPBOX_E_INVALID;
+    if (on && h->hist_cap <= 0) { set_err("create the batch with hist_cap > 0 to record the history"); return LPBOX_E_INVALID; }
+    h->record_plain = on != 0;
+    return 0;
 }
 
 extern "C" int lpbox_batch_iters(lpbox_batch *h, int iter_start, int iter_end, int32_t *ret) {

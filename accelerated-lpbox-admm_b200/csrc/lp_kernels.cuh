@@ -578,7 +578,7 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
             LPB_FOR_E x[e] = xc[e];
             admm_total += 1;
             // ---- iterate history (:1472-1475) ----------------------------------------------------------------
-            if (la.l2f && bv.hist_cap > 0) {
+            if ((la.l2f || la.record) && bv.hist_cap > 0) {
                 if (cc < bv.hist_cap) {
                     double *h = bv.hist + bv.off_hist[inst] + (long long)cc * stp->n0;
                     LPB_FOR_E { int j = tid + e * T; if (j < n) h[j] = x[e]; }
@@ -678,7 +678,7 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
             stp->last_ret = ret;
             // the window driver stops calling once a call returned 1 (LP.trainer:521); the plain driver calls once
             stp->done = la.l2f ? ret : (status != RUNNING);
-            if (la.l2f) { stp->xit_cols = cc; }
+            if (la.l2f || la.record) { stp->xit_cols = cc; if (!la.l2f) stp->xit_rows = n; }
         }
         __syncthreads();
     }

@@ -127,6 +127,7 @@ struct BatchView {
 struct Launch {
     int iter_start, iter_end;
     int l2f;                 // 1: ADMM_lp_iters_l2f semantics (record history, ret=1 on either stop, CG bail-out returns)
+    int record;              // 1: also record the iterate history in the plain loop (print_fix_info == 2, LP.cpp:903-909)
     int skip_done;           // 1: skip instances whose previous call returned "stop" (batch drivers)
     int n_work;              // number of work items
     const int *work;         // instance ids (NULL: identity)

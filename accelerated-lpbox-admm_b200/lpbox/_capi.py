@@ -48,6 +48,7 @@ SIGNATURES = {
     "lpbox_batch_destroy": (None, [_vp]),
     "lpbox_batch_set_params": (C.c_int, [_vp, C.POINTER(Params), C.c_int]),
     "lpbox_batch_init": (C.c_int, [_vp, _vp]),
+    "lpbox_batch_set_record_history": (C.c_int, [_vp, C.c_int]),
     "lpbox_batch_iters": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "lpbox_batch_iters_l2f": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "lpbox_batch_solve": (C.c_int, [_vp, C.c_int, _vp]),

@@ -3,6 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import time
 
 import numpy as np
 
@@ -214,6 +215,7 @@ class PyLPboxADMMsolver:
         self._problem = None
         self._device = int(os.environ.get("LPBOX_DEVICE", "0"))
         self._hist_cap = 500    # x_iters = Zero(n, 500)  (LP.cpp:1113)
+        self._file_idx, self._allres_path, self._xiters_path = 0, None, None
 
     # -- problem in ------------------------------------------------------------------------------------------
     def read_File(self, i, k, j):
@@ -221,6 +223,11 @@ class PyLPboxADMMsolver:
         m, n, colptr, rowidx, val, b = read_instance(root, int(i), int(k), int(j))
         self._problem = (m, n, colptr, rowidx, val, b, np.ones(m))     # f = 1 (LP.cpp:2522)
         self._batch = None
+        # output files of the reference (readFile, LP.cpp:2490-2498): xiter/allres.csv and, with print_info == 2,
+        # xiter/<k>_<j>_xiters_<i>.csv
+        self._file_idx = int(i)
+        self._allres_path = os.path.join(root, "xiter", "allres.csv")
+        self._xiters_path = os.path.join(root, "xiter", "%d_%d_xiters_%d.csv" % (int(k), int(j), int(i)))
 
     def set_problem(self, m, n, colptr, rowidx, val, b, f=None):
         """In-memory alternative to read_File: E column-compressed, b as the solver sees it (negated bids)."""
@@ -243,7 +250,50 @@ class PyLPboxADMMsolver:
         return self._batch.init()
 
     def solve_iter(self, i, j):
-        return int(self._need().iters(int(i), int(j))[0])
+        """ADMM_lp_iters(i, j).  Like the reference it appends `file_idx,-cur_obj,iters,seconds` to xiter/allres.csv
+        (LP.cpp:1081) when the problem came from read_File, and with print_info == 2 it dumps every iterate as
+        `Iter<t>,x_1,...,x_n` (%lf) to xiter/<k>_<j>_xiters_<i>.csv (LP.cpp:903-909) -- the file trainer.py / get_iterations.py
+        read.  Missing directories are skipped silently (the reference would crash on the NULL FILE*)."""
+        b = self._need()
+        i, j = int(i), int(j)
+        t0 = time.time()
+        if self.print_info == 2 and self._xiters_path is not None:
+            ret = self._solve_dumping_iterates(b, i, j)
+        else:
+            ret = int(b.iters(i, j)[0])
+        if self._allres_path is not None:
+            try:
+                with open(self._allres_path, "a+") as fh:
+                    fh.write("%d,%f,%d,%f\n" % (self._file_idx, -b.cur_bin_obj(0), b.get_iter(0) + 1, int((time.time() - t0) * 1000) / 1000.0))     # `iter+1` of the loop variable
+            except OSError:
+                pass
+        return ret
+
+    def _solve_dumping_iterates(self, b, i, j):
+        check(b.L.lpbox_batch_set_record_history(b.h, 1), "set_record_history")
+        ret, fh = 0, None
+        try:
+            try:
+                fh = open(self._xiters_path, "w+")
+            except OSError:
+                fh = None
+            s = i
+            while s < j:
+                e = min(s + self._hist_cap, j)
+                ret = int(b.iters(s, e)[0])
+                done = b.get_iter(0) - s + 1 if ret else e - s       # iterates recorded in this window (the stopping one included)
+                if fh is not None and done > 0:
+                    xit = b.x_iters(0, done)                          # (n, done)
+                    for c in range(done):
+                        fh.write("Iter%d," % (s + c + 1) + ",".join("%f" % v for v in xit[:, c]) + "\n")
+                if ret:
+                    break
+                s = e
+        finally:
+            if fh is not None:
+                fh.close()
+            check(b.L.lpbox_batch_set_record_history(b.h, 0), "set_record_history")
+        return ret
 
     def solve_iter_l2f(self, i, j, vec, num):
         vec = _f64(vec)

@@ -91,6 +91,9 @@ int lpbox_batch_set_params(lpbox_batch *h, const lpbox_params *p, int variant);
 /* ADMM_lp_iters_init (LP.cpp:489-763) for every instance; x0_all == NULL means x = 1 (LP.cpp:583-586). */
 int lpbox_batch_init(lpbox_batch *h, const double *x0_all);
 
+/* print_fix_info == 2 (LP.cpp:903-909): the plain loop records every iterate too (at most hist_cap per call); read with
+ * lpbox_batch_get_x_iters */
+int lpbox_batch_set_record_history(lpbox_batch *h, int on);
 /* ADMM_lp_iters(iter_start, iter_end) (LP.cpp:766-1095) for every instance that has not stopped.
  * ret[i] (may be NULL) receives the reference's return value (1 only for the objective-std stop). */
 int lpbox_batch_iters(lpbox_batch *h, int iter_start, int iter_end, int32_t *ret);

@@ -156,3 +156,34 @@ def test_general_values_match_oracle():
     for k in so:
         assert _same(so[k], sg[k]), k
     assert o.cal_Obj() == b.cal_obj(0)
+
+
+def test_reference_output_files(tmp_path, monkeypatch):
+    """N1: with print_info == 2 the mirror class writes what the reference writes next to its data (LP.cpp:903-909, :1081):
+    xiter/<k>_<j>_xiters_<i>.csv (`Iter<t>,x_1..x_n`, %lf) and a row of xiter/allres.csv.  Input: the text files the reference's
+    own generator wrote for seed 0; the dumped iterates are the oracle's (6 decimals) and dumping does not change the solve."""
+    import lpbox
+    g = load_golden("auction_100_500_seed0.npz")
+    d = tmp_path / "instance" / "100_500"
+    d.mkdir(parents=True); (tmp_path / "xiter").mkdir()
+    (d / "instance_1_C.txt").write_bytes(g["c_txt"].tobytes())
+    (d / "instance_1_b.txt").write_bytes(g["b_txt"].tobytes())
+    monkeypatch.setenv("LPBOX_DATA_ROOT", str(tmp_path))
+    K = 620                                   # more than one history window (500)
+    s = lpbox.PyLPboxADMMsolver(2)
+    s.read_File(1, 100, 500); s.solve_init(); s.solve_iter(0, K)
+    rows = open(tmp_path / "xiter" / "100_500_xiters_1.csv").read().strip().split("\n")
+    assert len(rows) == K and rows[0].startswith("Iter1,") and rows[-1].startswith(f"Iter{K},")
+    assert all(len(r.split(",")) == 501 for r in rows[:3] + rows[-3:])
+    import oracle as orc
+    m, n = int(g["m"]), int(g["n"])
+    for it in (3, 501, K):                    # iterates across the window boundary
+        o = orc.OracleLP(); o.set_problem_csc(m, n, g["colptr"], g["rowidx"], np.ones(len(g["rowidx"])), g["b"], np.ones(m))
+        o.solve_init(); o.solve_iter(0, it)
+        got = np.array([float(v) for v in rows[it - 1].split(",")[1:]])
+        assert np.allclose(got, o.state()["x"], atol=5.1e-7, rtol=0), it
+    f = open(tmp_path / "xiter" / "allres.csv").read().strip().split("\n")[-1].split(",")
+    assert int(f[0]) == 1 and int(f[2]) == K + 1 and abs(float(f[1]) + s.get_curBinObj()) < 1e-5    # the loop variable + 1
+    t = lpbox.PyLPboxADMMsolver(0); t.read_File(1, 100, 500); t.solve_init(); t.solve_iter(0, K)
+    assert t.get_iter() == s.get_iter() and t.cal_Obj() == s.cal_Obj()
+    assert np.array_equal(t._batch.state(0)["x"], s._batch.state(0)["x"])
