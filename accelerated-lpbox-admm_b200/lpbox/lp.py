@@ -214,7 +214,9 @@ class PyLPboxADMMsolver:
         self._batch = None
         self._problem = None
         self._device = int(os.environ.get("LPBOX_DEVICE", "0"))
-        self._hist_cap = 500    # x_iters = Zero(n, 500)  (LP.cpp:1113)
+        # x_iters = Zero(n, 500) (LP.cpp:1113); print_info == 2 dumps EVERY iterate of a solve_iter call, which cannot be split
+        # into windows (iteration `iter_start` of ADMM_lp_iters is special, LP.cpp:920-934), so the whole history is kept
+        self._hist_cap = 10000 if self.print_info == 2 else 500
         self._file_idx, self._allres_path, self._xiters_path = 0, None, None
 
     # -- problem in ------------------------------------------------------------------------------------------
@@ -271,28 +273,19 @@ class PyLPboxADMMsolver:
 
     def _solve_dumping_iterates(self, b, i, j):
         check(b.L.lpbox_batch_set_record_history(b.h, 1), "set_record_history")
-        ret, fh = 0, None
         try:
-            try:
-                fh = open(self._xiters_path, "w+")
-            except OSError:
-                fh = None
-            s = i
-            while s < j:
-                e = min(s + self._hist_cap, j)
-                ret = int(b.iters(s, e)[0])
-                done = b.get_iter(0) - s + 1 if ret else e - s       # iterates recorded in this window (the stopping one included)
-                if fh is not None and done > 0:
-                    xit = b.x_iters(0, done)                          # (n, done)
-                    for c in range(done):
-                        fh.write("Iter%d," % (s + c + 1) + ",".join("%f" % v for v in xit[:, c]) + "\n")
-                if ret:
-                    break
-                s = e
+            ret = int(b.iters(i, j)[0])
         finally:
-            if fh is not None:
-                fh.close()
             check(b.L.lpbox_batch_set_record_history(b.h, 0), "set_record_history")
+        done = min((b.get_iter(0) - i + 1) if ret else (j - i), self._hist_cap)      # iterates recorded (the stopping one included)
+        try:
+            with open(self._xiters_path, "w+") as fh:
+                if done > 0:
+                    xit = b.x_iters(0, done)                                          # (n, done)
+                    for c in range(done):
+                        fh.write("Iter%d," % (i + c + 1) + ",".join("%f" % v for v in xit[:, c]) + "\n")
+        except OSError:
+            pass
         return ret
 
     def solve_iter_l2f(self, i, j, vec, num):

@@ -169,7 +169,7 @@ def test_reference_output_files(tmp_path, monkeypatch):
     (d / "instance_1_C.txt").write_bytes(g["c_txt"].tobytes())
     (d / "instance_1_b.txt").write_bytes(g["b_txt"].tobytes())
     monkeypatch.setenv("LPBOX_DATA_ROOT", str(tmp_path))
-    K = 620                                   # more than one history window (500)
+    K = 620
     s = lpbox.PyLPboxADMMsolver(2)
     s.read_File(1, 100, 500); s.solve_init(); s.solve_iter(0, K)
     rows = open(tmp_path / "xiter" / "100_500_xiters_1.csv").read().strip().split("\n")
@@ -177,7 +177,7 @@ def test_reference_output_files(tmp_path, monkeypatch):
     assert all(len(r.split(",")) == 501 for r in rows[:3] + rows[-3:])
     import oracle as orc
     m, n = int(g["m"]), int(g["n"])
-    for it in (3, 501, K):                    # iterates across the window boundary
+    for it in (3, 501, K):
         o = orc.OracleLP(); o.set_problem_csc(m, n, g["colptr"], g["rowidx"], np.ones(len(g["rowidx"])), g["b"], np.ones(m))
         o.solve_init(); o.solve_iter(0, it)
         got = np.array([float(v) for v in rows[it - 1].split(",")[1:]])
