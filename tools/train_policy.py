@@ -25,6 +25,7 @@ def main():
     epochs = int(sys.argv[2]) if len(sys.argv) > 2 else 8
     out = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "accelerated-lpbox-admm_b200", "lpbox", "weights", "lp_mha_policy.pt")
     ws, nwin = 100, 10
+    neg_w = float(os.environ.get("LPBOX_TRAIN_NEG_WEIGHT", "1"))   # > 1: false fix-to-one decisions (the cause of infeasible solutions) cost more
     torch.manual_seed(19260817)                      # cmd_args.py:11
     probs = lpbox.gen_auctions(777, n_inst, 100, 500)
     # labels: plain solve to convergence
@@ -56,6 +57,8 @@ def main():
             xb = X[:, a:e].reshape(nwin * n, 20, 5)
             yb = y[a:e].repeat(nwin).view(-1, 1)
             wb = torch.cat([torch.full((n, 1), 1.0 / (i + 1), device="cuda") for i in range(nwin)])
+            if neg_w != 1.0:
+                wb = wb * torch.where(yb > 0.5, torch.ones_like(yb), torch.full_like(yb, neg_w))
             logit, _ = net(xb)
             loss = torch.nn.functional.binary_cross_entropy_with_logits(logit, yb, weight=wb)
             opt.zero_grad(); loss.backward(); opt.step()
