@@ -100,7 +100,13 @@ struct lpbox_batch {
     std::vector<int> pat_bytes_i, pat_head_i;   // sliced-ELL image size of every instance, and its size without the column index array
     int pat_smem = 0;                           // bytes of shared memory reserved for the image (< max_pat: the largest images keep their column indices in L2)
     DevBuf<int> d_work;                         // launch order when pat_smem < max_pat (instances with a spilled image first)
+    DevBuf<double> d_park;                      // [grid][PK_COUNT][cap] per-CTA parking lot of the window kernel
+    DevBuf<int> d_err;                          // [2]: error flag of the window kernel, result of the shared-window probe
+    int cap = 0, nwarps = 0;                    // T * EPT and T / 32 of the window-kernel variant
+    int max_col_len = 0, tab_len = 0;           // longest column of the batch; entries of the shared 1/diag table (unit case)
+    bool fast = false;                          // lpbox_batch_set_mode: tree reductions + FMA (not bit-identical)
 };
+static const int SM_RANK_SLOTS = 1024;          // >= highest %smid + 1
 
 // instance-parallel host loops of lpbox_batch_create (sorting, packing): blocks of 64 instances over the host cores
 template <typename F>
@@ -120,13 +126,16 @@ static void host_parallel_for(int count, F f) {
 
 template <int T, int EPT, bool UNIT>
 static cudaError_t prep_kernel(size_t smem, int *occ) {
-    cudaError_t e = cudaFuncSetAttribute(lp_admm_window_kernel<T, EPT, UNIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(lp_admm_window_kernel<T, EPT, UNIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, lp_admm_window_kernel<T, EPT, UNIT>, T, smem);
+    e = cudaFuncSetAttribute(lp_admm_window_kernel<T, EPT, UNIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, lp_admm_window_kernel<T, EPT, UNIT, false>, T, smem);
 }
 template <int T, int EPT, bool UNIT>
 static void launch_window(lpbox_batch *h, const Launch &la, int grid) {
-    lp_admm_window_kernel<T, EPT, UNIT><<<grid, T, h->smem, h->stream>>>(h->bv, h->pr, la);
+    if (h->fast) lp_admm_window_kernel<T, EPT, UNIT, true><<<grid, T, h->smem, h->stream>>>(h->bv, h->pr, la);
+    else lp_admm_window_kernel<T, EPT, UNIT, false><<<grid, T, h->smem, h->stream>>>(h->bv, h->pr, la);
 }
 
 static int configure(lpbox_batch *h) {
@@ -138,7 +147,10 @@ static int configure(lpbox_batch *h) {
     if (h->max_nnz > 65535) { set_err("nnz > 65535 is not supported by the on-chip kernel"); return LPBOX_E_UNSUPPORTED; }
     int mp = (h->max_m + 1) & ~1, np = std::max((h->max_n + 1) & ~1, mp);   // m-vectors alias n-sized buffers
     int val_elems = h->all_unit ? 0 : ((h->max_nnz + 1) & ~1);
-    h->smem = smem_bytes(np, mp, h->max_pat, h->all_unit ? 0 : h->max_evr, h->all_unit ? 0 : h->max_evc);
+    const int T = h->tcfg == 0 ? 128 : (h->tcfg == 1 ? 256 : 512);
+    h->cap = T * 4; h->nwarps = T / 32; h->bv.cap = h->cap;
+    h->tab_len = h->all_unit ? h->max_col_len + 1 : 0;
+    h->smem = smem_bytes(h->cap, np, mp, h->max_pat, h->all_unit ? 0 : h->max_evr, h->all_unit ? 0 : h->max_evc, h->nwarps, h->tab_len);
     h->fix_smem = fix_smem_bytes((h->max_n + 1) & ~1, mp, h->max_csr, val_elems);
     int dev_smem = 0, sms = 0;
     CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
@@ -175,14 +187,14 @@ static int configure(lpbox_batch *h) {
                 CK(occ_at(mid, &o));
                 if (o >= occ_reg) lo = mid; else hi = mid;
             }
-            const size_t fixed = smem_bytes(np, mp, 0, 0, 0);
+            const size_t fixed = smem_bytes(h->cap, np, mp, 0, 0, 0, h->nwarps, h->tab_len);
             budget = lo > fixed ? (int)((lo - fixed) & ~(size_t)15) : 0;
         }
         int fit = 0, head_max = 0;
         for (int i = 0; i < h->B; ++i) { fit += h->pat_bytes_i[i] <= budget; head_max = std::max(head_max, h->pat_head_i[i]); }
         if (head_max <= budget && budget < h->max_pat && (forced || fit >= (h->B * 9) / 10)) {
             h->pat_smem = budget;
-            h->smem = smem_bytes(np, mp, budget, 0, 0);
+            h->smem = smem_bytes(h->cap, np, mp, budget, 0, 0, h->nwarps, h->tab_len);
             std::vector<int> order;
             for (int i = 0; i < h->B; ++i) if (h->pat_bytes_i[i] > budget) order.push_back(i);
             for (int i = 0; i < h->B; ++i) if (h->pat_bytes_i[i] <= budget) order.push_back(i);
@@ -195,6 +207,19 @@ static int configure(lpbox_batch *h) {
     CK(cudaFuncSetAttribute(lp_fix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fix_smem));
     if (occ < 1) occ = 1;
     h->grid = std::max(1, std::min(h->B, sms * occ));
+    h->d_park.free_();
+    CK(h->d_park.alloc((size_t)h->grid * PK_COUNT * (size_t)h->cap));
+    // the ELL image stores absolute shared-window addresses: ask where the dynamic shared memory of a kernel without static
+    // shared memory starts (the window kernel checks that its own base is the same)
+    if (!h->d_err.p) CK(h->d_err.alloc(2));
+    CK(cudaMemsetAsync(h->d_err.p, 0, 2 * sizeof(int), h->stream));
+    lp_probe_kernel<<<1, 1, 64, h->stream>>>(h->d_err.p + 1);
+    CK(cudaGetLastError());
+    int probe[2] = {0, 0};
+    CK(cudaMemcpyAsync(probe, h->d_err.p, sizeof(probe), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->bv.sbase = probe[1];
+    if (h->bv.sbase + gather_base(h->cap) + 8 * (h->cap + 2) > 65535) { set_err("shared-window addresses do not fit in 16 bits"); return LPBOX_E_UNSUPPORTED; }
     return 0;
 }
 
@@ -203,8 +228,10 @@ static int run_window(lpbox_batch *h, int iter_start, int iter_end, int l2f, int
     la.iter_start = iter_start; la.iter_end = iter_end; la.l2f = l2f; la.skip_done = skip_done; la.record = h->record_plain ? 1 : 0;
     la.n_work = h->B; la.work = h->d_work.p; la.counter = h->d_counter.p;
     la.mp = (h->max_m + 1) & ~1; la.np = std::max((h->max_n + 1) & ~1, la.mp); la.pat_bytes = h->pat_smem;
-    la.evr_elems = h->all_unit ? 0 : h->max_evr; la.evc_elems = h->all_unit ? 0 : h->max_evc;
-    CK(cudaMemsetAsync(h->d_counter.p, 0, sizeof(int), h->stream));
+    la.evr_elems = h->all_unit ? 0 : h->max_evr; la.evc_elems = h->all_unit ? 0 : h->max_evc; la.tab_len = h->tab_len;
+    static const bool no_rotate = getenv("LPBOX_NO_ROTATE") != nullptr;     // experiments: reduction warp fixed to the last warp
+    la.sm_rank = no_rotate ? nullptr : h->d_counter.p + 1; la.park = h->d_park.p; la.fast = h->fast ? 1 : 0; la.error = h->d_err.p;
+    CK(cudaMemsetAsync(h->d_counter.p, 0, sizeof(int) * (1 + SM_RANK_SLOTS), h->stream));
     bool u = h->all_unit;
     switch (h->tcfg) {
         case 0: u ? launch_window<128, 4, true>(h, la, h->grid) : launch_window<128, 4, false>(h, la, h->grid); break;
@@ -219,7 +246,10 @@ static int run_window(lpbox_batch *h, int iter_start, int iter_end, int l2f, int
 static int sync_states(lpbox_batch *h) {
     h->d2h_bytes += (int64_t)(sizeof(InstState) * (size_t)h->B);
     CK(cudaMemcpyAsync(h->h_st.data(), h->d_st.p, sizeof(InstState) * (size_t)h->B, cudaMemcpyDeviceToHost, h->stream));
+    int err = 0;
+    CK(cudaMemcpyAsync(&err, h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (err) { set_err("window kernel: unexpected shared-window base address (ELL image addresses are invalid)"); return LPBOX_E_CUDA; }
     return 0;
 }
 
@@ -236,7 +266,7 @@ extern "C" lpbox_batch *lpbox_batch_create(int device, int B, const int32_t *m, 
     h->n0.assign(n, n + B); h->m0.assign(m, m + B); h->nnz0.resize(B);
     h->off_n.assign(B + 1, 0); h->off_m.assign(B + 1, 0); h->off_pat.assign(B + 1, 0); h->off_val.assign(B + 1, 0);
     h->off_csr.assign(B + 1, 0); h->off_evr.assign(B + 1, 0); h->off_evc.assign(B + 1, 0);
-    std::vector<int> rcap(B, 0), ccap(B, 0);
+    std::vector<int> rcap(B, 0), ccap(B, 0), maxcl(B, 0);
     std::vector<std::vector<uint16_t>> rperm_all(B), cperm_all(B);
     h->off_hist.assign(B + 1, 0); h->h_nnz_off.assign(B + 1, 0); h->h_cp_off.assign(B + 1, 0);
     // (1) cheap serial pass: sizes and the offsets that depend on n, m, nnz only
@@ -273,6 +303,7 @@ extern "C" lpbox_batch *lpbox_batch_create(int device, int B, const int32_t *m, 
         std::stable_sort(ord.begin(), ord.end(), [&](int a, int b2) { return cl[a] > cl[b2]; });
         cperm_all[i].resize(ni);
         for (int j = 0; j < ni; ++j) { cperm_all[i][j] = (uint16_t)ord[j]; if ((j & 31) == 0) ccap[i] += cl[ord[j]]; }
+        maxcl[i] = cl[ord[0]];
     });
     if (err1.load()) { set_err("row index out of range"); delete h; return nullptr; }
     // (3) serial: offsets that depend on the layouts
@@ -287,16 +318,22 @@ extern "C" lpbox_batch *lpbox_batch_create(int device, int B, const int32_t *m, 
         h->max_csr = std::max(h->max_csr, PL.bytes);
         h->max_evr = std::max(h->max_evr, 32 * rcap[i]); h->max_evc = std::max(h->max_evc, 32 * ccap[i]);
         if (rcap[i] > 2047 || ccap[i] > 2047) { set_err("pattern too large for the on-chip kernel"); delete h; return nullptr; }
-        h->max_pat = std::max(h->max_pat, EL.bytes);
-        h->pat_bytes_i.push_back(EL.bytes); h->pat_head_i.push_back(EL.o_cidx);
+        h->max_pat = std::max(h->max_pat, EL.o_rperm);
+        h->max_col_len = std::max(h->max_col_len, maxcl[i]);
+        h->pat_bytes_i.push_back(EL.o_rperm); h->pat_head_i.push_back(EL.o_cidx);   // staged bytes with / without the column offsets
     }
     long long tot_nnz = h->h_nnz_off[B];
     h->h_colptr.assign(colptr_all, colptr_all + h->h_cp_off[B]);
     h->h_rowidx.assign(rowidx_all, rowidx_all + tot_nnz);
+    std::vector<double> ones;
     if (val_all) {
         h->h_val.assign(val_all, val_all + tot_nnz);
         h->all_unit = true;
         for (long long k = 0; k < tot_nnz; ++k) if (val_all[k] != 1.0) { h->all_unit = false; break; }
+    }
+    if (h->all_unit && h->max_col_len > 255) {   // the unit kernel indexes its 1/diag table with 8-bit column lengths: use the general path
+        h->all_unit = false;
+        if (!val_all) { ones.assign((size_t)tot_nnz, 1.0); val_all = ones.data(); h->h_val = ones; }
     }
     // build pattern blobs (+ values in both orders) on the host
     std::vector<unsigned char> pat((size_t)h->off_pat[B], 0), csr((size_t)h->off_csr[B], 0);
@@ -377,7 +414,7 @@ extern "C" lpbox_batch *lpbox_batch_create(int device, int B, const int32_t *m, 
                   A(cudaMemset(h->d_r4v.p, 0, sizeof(double) * std::max<size_t>(h->d_r4v.n, 1))); }
     }
     A(h->d_hist.alloc((size_t)h->off_hist[B]));
-    A(h->d_st.alloc(B)); A(h->d_counter.alloc(1)); A(h->d_num.alloc(B));
+    A(h->d_st.alloc(B)); A(h->d_counter.alloc(1 + SM_RANK_SLOTS)); A(h->d_num.alloc(B));
     A(h->d_pow.alloc((size_t)h->max_n + 1));
     if (!ok) { lpbox_batch_destroy(h); return nullptr; }
     std::vector<double> powtab((size_t)h->max_n + 1);
@@ -424,12 +461,20 @@ extern "C" void lpbox_batch_destroy(lpbox_batch *h) {
     h->d_x.free_(); h->d_y1.free_(); h->d_y2.free_(); h->d_z1.free_(); h->d_z2.free_(); h->d_b.free_(); h->d_Pd.free_(); h->d_Esq.free_();
     h->d_y3.free_(); h->d_z4.free_(); h->d_f.free_(); h->d_val_r.free_(); h->d_val_c.free_(); h->d_r4v.free_(); h->d_hist.free_();
     h->d_ret_val.free_(); h->d_pow.free_(); h->d_vec.free_(); h->d_pat.free_(); h->d_st.free_(); h->d_left.free_(); h->d_ret_idx.free_();
-    h->d_counter.free_(); h->d_num.free_(); h->d_work.free_();
+    h->d_counter.free_(); h->d_num.free_(); h->d_work.free_(); h->d_park.free_(); h->d_err.free_();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
     h->d_active.free_(); h->d_row_off.free_();
     delete h;
+}
+
+// mode 0: parity (default, bit-identical to the reference); mode 1: fast (tree reductions over all warps + FMA in the vector
+// updates; iterates agree to rounding level only -- never used for parity claims)
+extern "C" int lpbox_batch_set_mode(lpbox_batch *h, int mode) {
+    if (!h || (mode != 0 && mode != 1)) return LPBOX_E_INVALID;
+    h->fast = mode == 1;
+    return 0;
 }
 
 extern "C" int lpbox_batch_set_params(lpbox_batch *h, const lpbox_params *p, int variant) {

@@ -203,13 +203,9 @@ lp_fix_kernel(BatchView bv, Params pr, const double *__restrict__ vec, const lon
         for (int s2 = tid; s2 < n; s2 += FIX_T) { int c = pold[s2]; if (!is_fixed(c)) g_cperm[cnt[s2]] = (u16)kidx[c]; }
     }
     __syncthreads();
-    // sliced-ELL images of the compacted pattern (rows keep their slots; lengths only shrink)
-    build_ell(g_rowptr, g_colidx, unit ? nullptr : bv.val_r + ov, reinterpret_cast<const u16 *>(gell + EL.o_rperm), m,
-              reinterpret_cast<u16 *>(gell + EL.o_rlen), reinterpret_cast<u16 *>(gell + EL.o_rsptr),
-              reinterpret_cast<u16 *>(gell + EL.o_ridx), unit ? nullptr : bv.ev_r + bv.off_evr[inst], s_w);
-    build_ell(g_colptr, g_rowidx, unit ? nullptr : bv.val_c + ov, reinterpret_cast<const u16 *>(gell + EL.o_cperm), k_tot,
-              reinterpret_cast<u16 *>(gell + EL.o_clen), reinterpret_cast<u16 *>(gell + EL.o_csptr),
-              reinterpret_cast<u16 *>(gell + EL.o_cidx), unit ? nullptr : bv.ev_c + bv.off_evc[inst], s_w);
+    // padded sliced-ELL image of the compacted pattern (rows keep their slots; lengths only shrink); cnt / pold are free now
+    build_ell_image(bv, inst, st, k_tot, m, g_rowptr, g_colidx, g_colptr, g_rowidx, unit, ov, reinterpret_cast<u16 *>(cnt),
+                    reinterpret_cast<u16 *>(pold), s_w);
     // 9. update_expression with the current rho (:1329, :2289-2404) on the new column-compressed pattern
     const double rho1 = st->rho1, rho2 = st->rho2, rho4 = st->rho4;
     const double D = dA(0.0, dA(rho1, rho2));

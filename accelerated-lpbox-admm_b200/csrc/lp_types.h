@@ -59,19 +59,24 @@ struct InstState {
 // (1) CsrLayout -- both compressed orientations (rowptr/colidx, colptr/rowidx).  Lives in HBM only; used by the
 //     set-up / early-fix kernels and the host getters.
 // (2) EllLayout -- the image the window kernel stages into shared memory with one 1-D TMA bulk copy: both
-//     orientations in SLICED-ELL form.  "Slot" s (work item of thread s % T) holds row rperm[s] (column cperm[s]);
-//     slots are sorted by descending stored length, a slice = 32 consecutive slots, stored column-major:
-//     entry k of the slot with lane l of slice w sits at idx[(sptr[w] + k) * 32 + l].  The 32 lanes of a warp read 32
-//     consecutive uint16 (one conflict-free 64-byte wavefront) and the addresses do not depend on loaded data, so the
-//     next batch of indices can be prefetched.  Only WHO computes a row/column product changes -- the order of
-//     operations inside each product (ascending inner index) is the reference's.
+//     orientations in PADDED SLICED-ELL form.  "Slot" s is the work item AND the home of row rperm[s] (column
+//     cperm[s]): the thread that owns slot s keeps that row's / column's vector entries and computes its sparse
+//     product.  Slots are sorted by descending stored length; a slice = 32 consecutive slots, stored column-major and
+//     padded to the length of its longest slot: entry k of lane l of slice w sits at idx[(sptr[w] + k) * 32 + l].
+//     An entry is not an index but the SHARED-WINDOW ADDRESS of the operand it gathers (sbase = start of the window
+//     kernel's dynamic shared memory): sbase + 8 * (slot of that column) for the row image (operand vector G at offset
+//     0), sbase + gather_base(cap) + 8 * (slot of that row) for the column image (operand vector T1); padding entries
+//     point at one shared 0.0 (sbase + zero_off(cap)) -- adding +0.0 to a sum that started at +0.0 never changes it, so padding is value-neutral and
+//     every lane of a warp runs the same trip count.  Only WHO computes a row / column product and WHERE operands sit
+//     changes; the order of operations inside each product (ascending inner index) is the reference's.
+//     sptr / idx arrays are staged; the two slot -> index permutations stay in global memory (read once per window).
 struct CsrLayout {
     int o_rowptr, o_colptr, o_colidx, o_rowidx, bytes;
 };
 struct EllLayout {
-    int o_rlen, o_rsptr, o_rperm, o_ridx, o_clen, o_csptr, o_cperm, o_cidx, bytes;
+    int o_rsptr, o_csptr, o_ridx, o_cidx, o_rperm, o_cperm, bytes;   // [0, o_rperm) is staged; o_cidx.. may stay in L2
 };
-LPB_HD int a16(int x) { return (x + 15) & ~15; }
+LPB_HD constexpr int a16(int x) { return (x + 15) & ~15; }
 LPB_HD CsrLayout csr_layout(int n0, int m0, int nnz0) {
     CsrLayout L;
     L.o_rowptr = 0;
@@ -86,17 +91,26 @@ LPB_HD CsrLayout csr_layout(int n0, int m0, int nnz0) {
 LPB_HD EllLayout ell_layout(int n0, int m0, int rcap, int ccap) {
     EllLayout L;
     const int nsr = (m0 + 31) / 32, nsc = (n0 + 31) / 32;
-    L.o_rlen = 0;
-    L.o_rsptr = a16(2 * m0);
-    L.o_rperm = L.o_rsptr + a16(2 * (nsr + 1));
-    L.o_ridx = L.o_rperm + a16(2 * m0);
-    L.o_clen = L.o_ridx + a16(64 * rcap);
-    L.o_csptr = L.o_clen + a16(2 * n0);
-    L.o_cperm = L.o_csptr + a16(2 * (nsc + 1));
-    L.o_cidx = L.o_cperm + a16(2 * n0);
-    L.bytes = L.o_cidx + a16(64 * ccap);
+    L.o_rsptr = 0;
+    L.o_csptr = a16(2 * (nsr + 1));
+    L.o_ridx = L.o_csptr + a16(2 * (nsc + 1));
+    L.o_cidx = L.o_ridx + a16(64 * rcap);
+    L.o_rperm = L.o_cidx + a16(64 * ccap);
+    L.o_cperm = L.o_rperm + a16(2 * m0);
+    L.bytes = L.o_cperm + a16(2 * n0);
     return L;
 }
+// Chain-major reduction buffers: element j of an n-vector sits at (j & 3) * CH + (j >> 2) (Eigen's four interleaved
+// chains become four contiguous runs).  CH = 2 (mod 16) doubles: the four chains start 16 bytes apart modulo 128, and
+// two buffers laid out back to back start 64 bytes apart modulo 128 -> eight lanes reading 16 bytes each (two
+// reductions side by side) touch every bank exactly once.
+LPB_HD constexpr int chain_stride(int np) {
+    const int c = np / 4 + 3;                  // terms per chain, the slot of the tail elements, two never-written doubles
+    return 16 * ((c - 2 + 15) / 16) + 2;       // (the last two doubles of a buffer stay 0.0: padding operand of the z4 copy)
+}
+// shared-memory map of the window kernel that the image refers to; cap = T * EPT of the kernel variant in use
+LPB_HD constexpr int zero_off(int cap) { return 4 * chain_stride(cap) * 8; }     // the shared 0.0 (end of the G region)
+LPB_HD constexpr int gather_base(int cap) { return zero_off(cap) + 16; }         // T1 starts here
 
 // Device view of a batch.
 struct BatchView {
@@ -122,6 +136,8 @@ struct BatchView {
     int *ret_idx;                                  // [off_n] fixed original ids (ret_idx_prev)
     double *ret_val;                               // [off_n]
     const double *pow_tab;                         // pow_tab[k] = pow((double)k, 0.5) from the host libm
+    int cap;                                       // T * EPT of the window-kernel variant of this batch (offsets in the ELL image)
+    int sbase;                                     // shared-window address of the window kernel's dynamic shared memory (lp_probe_kernel)
 };
 
 struct Launch {
@@ -135,6 +151,11 @@ struct Launch {
     int np, mp;              // shared-memory vector strides (>= max n0, m0 of the batch; even)
     int pat_bytes;           // shared-memory bytes reserved for the sliced-ELL blob
     int evr_elems, evc_elems; // shared-memory doubles reserved for the ELL-order value arrays (0 when unit)
+    int tab_len;             // unit case: entries of the shared 1/diag table (longest column of the batch + 1)
+    int *sm_rank;            // [#SMs] zeroed per launch: arrival order of the CTAs of one SM (rotates the reduction warp)
+    double *park;            // [grid][8][cap] per-CTA parking lot (L2-resident) for vectors that are not touched inside PCG
+    int *error;              // device flag: set when the shared-window base differs from BatchView::sbase
+    int fast;                // 1: fast mode (tree reductions, FMA) -- NOT bit-identical to the reference
 };
 
 }  // namespace lpb

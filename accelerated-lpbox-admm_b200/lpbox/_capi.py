@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "liblpbox_b200.so")
+LIB_PATH = os.environ.get("LPBOX_LIB") or os.path.join(_PKG, "liblpbox_b200.so")   # LPBOX_LIB: developer builds (tools/)
 
 E_INVALID, E_CUDA, E_UNSUPPORTED, E_IO = -1, -2, -3, -4
 
@@ -47,6 +47,7 @@ SIGNATURES = {
     "lpbox_batch_create": (_vp, [C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
     "lpbox_batch_destroy": (None, [_vp]),
     "lpbox_batch_set_params": (C.c_int, [_vp, C.POINTER(Params), C.c_int]),
+    "lpbox_batch_set_mode": (C.c_int, [_vp, C.c_int]),
     "lpbox_batch_init": (C.c_int, [_vp, _vp]),
     "lpbox_batch_set_record_history": (C.c_int, [_vp, C.c_int]),
     "lpbox_batch_iters": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),

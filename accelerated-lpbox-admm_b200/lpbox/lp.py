@@ -100,6 +100,10 @@ class LPBatch:
             setattr(p, k, v)
         check(self.L.lpbox_batch_set_params(self.h, C.byref(p), int(variant)), "set_params")
 
+    def set_mode(self, mode="parity"):
+        """"parity" (default): bit-identical to the reference; "fast": tree reductions + FMA, NOT bit-identical (opt-in)."""
+        check(self.L.lpbox_batch_set_mode(self.h, {"parity": 0, "fast": 1}[mode]), "set_mode")
+
     def init(self, x0=None):
         x0 = None if x0 is None else _f64(np.concatenate([np.asarray(v) for v in x0]))
         return check(self.L.lpbox_batch_init(self.h, ptr(x0)), "init")

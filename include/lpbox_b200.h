@@ -105,10 +105,14 @@ int lpbox_batch_iters(lpbox_batch *h, int iter_start, int iter_end, int32_t *ret
 int lpbox_batch_iters_l2f(lpbox_batch *h, int iter_start, int iter_end, const double *vec_all, const int32_t *num,
                           int32_t *ret);
 
-/* Whole window loop on the device (LP.trainer:510-535) with fix vectors produced by thresholding caller-supplied
- * scores: after each window of `ws` iterations the callback-free variant below applies
- * deter_fix_2 (LP.trainer:101-135: p>0.9 -> 1, p<0.1 -> 0, else -1; fewer than 11 fixes -> none) to scores computed
- * by the built-in policy kernel (lpbox_batch_set_policy) -- see lpbox_batch_solve_l2f. */
+/* Arithmetic mode of the window kernel.  0 (default) = PARITY: every fp64 operation in the reference's order, iterates
+ * bit-identical to the reference's compiled Eigen code (LP.cpp:251-335, :766-1095).  1 = FAST: the same iteration with tree
+ * reductions over all warps and fused multiply-adds in the vector updates; iterates agree with the reference to rounding
+ * level per step only, so final solutions can differ -- opt-in, never used for parity claims. */
+int lpbox_batch_set_mode(lpbox_batch *h, int mode);
+
+/* Plain Lp-Box ADMM to convergence for every instance: update_expression + ADMM_lp_iters(0, max_iters) (LP.cpp:766-1095),
+ * one launch; log (B rows, may be NULL) as lpbox_batch_results fills it. */
 int lpbox_batch_solve(lpbox_batch *h, int max_iters, lpbox_log_row *log /* B rows, may be NULL */);
 
 /* ---- device-resident window loop: window -> policy -> threshold -> compact without host copies of the iterates ----
