@@ -83,7 +83,8 @@ struct lpbox_batch {
     DevBuf<int> d_left, d_ret_idx, d_counter, d_num;
     std::vector<InstState> h_st;
     bool inited = false;
-    int tcfg = 0;  // 0: <128,4>  1: <256,4>  2: <512,4>
+    int tcfg = 0;  // 0: <128,4>  1: <256,4>  2: <512,4>  3: <256,2> (n <= 512 with twice the threads)  4: <512,2> (n <= 1024)
+    int threads = 128, ept = 4;
     int grid = 0;
     size_t smem = 0, fix_smem = 0;
     double last_ms = 0;
@@ -140,15 +141,18 @@ static void launch_window(lpbox_batch *h, const Launch &la, int grid) {
 
 static int configure(lpbox_batch *h) {
     int dim = std::max(h->max_n, h->max_m);
-    if (dim <= 512) h->tcfg = 0;
-    else if (dim <= 1024) h->tcfg = 1;
+    const char *force = getenv("LPBOX_TCFG");     // developer override: "256x2" / "512x2" run small shapes with more threads per CTA
+    if (dim <= 512) h->tcfg = (force && !strcmp(force, "256x2")) ? 3 : 0;
+    else if (dim <= 1024) h->tcfg = (force && !strcmp(force, "512x2")) ? 4 : 1;
     else if (dim <= 2048) h->tcfg = 2;
     else { set_err("max(n, m) > 2048 is not supported by the on-chip kernel"); return LPBOX_E_UNSUPPORTED; }
     if (h->max_nnz > 65535) { set_err("nnz > 65535 is not supported by the on-chip kernel"); return LPBOX_E_UNSUPPORTED; }
     int mp = (h->max_m + 1) & ~1, np = std::max((h->max_n + 1) & ~1, mp);   // m-vectors alias n-sized buffers
     int val_elems = h->all_unit ? 0 : ((h->max_nnz + 1) & ~1);
-    const int T = h->tcfg == 0 ? 128 : (h->tcfg == 1 ? 256 : 512);
-    h->cap = T * 4; h->nwarps = T / 32; h->bv.cap = h->cap;
+    static const int cfgT[5] = {128, 256, 512, 256, 512}, cfgE[5] = {4, 4, 4, 2, 2};
+    const int T = cfgT[h->tcfg];
+    h->threads = T; h->ept = cfgE[h->tcfg];
+    h->cap = T * h->ept; h->nwarps = T / 32; h->bv.cap = h->cap;
     h->tab_len = h->all_unit ? h->max_col_len + 1 : 0;
     h->smem = smem_bytes(h->cap, np, mp, h->max_pat, h->all_unit ? 0 : h->max_evr, h->all_unit ? 0 : h->max_evc, h->nwarps, h->tab_len);
     h->fix_smem = fix_smem_bytes((h->max_n + 1) & ~1, mp, h->max_csr, val_elems);
@@ -163,6 +167,8 @@ static int configure(lpbox_batch *h) {
         switch (h->tcfg) {
             case 0: return u ? prep_kernel<128, 4, true>(smem, occ) : prep_kernel<128, 4, false>(smem, occ);
             case 1: return u ? prep_kernel<256, 4, true>(smem, occ) : prep_kernel<256, 4, false>(smem, occ);
+            case 3: return u ? prep_kernel<256, 2, true>(smem, occ) : prep_kernel<256, 2, false>(smem, occ);
+            case 4: return u ? prep_kernel<512, 2, true>(smem, occ) : prep_kernel<512, 2, false>(smem, occ);
             default: return u ? prep_kernel<512, 4, true>(smem, occ) : prep_kernel<512, 4, false>(smem, occ);
         }
     };
@@ -236,6 +242,8 @@ static int run_window(lpbox_batch *h, int iter_start, int iter_end, int l2f, int
     switch (h->tcfg) {
         case 0: u ? launch_window<128, 4, true>(h, la, h->grid) : launch_window<128, 4, false>(h, la, h->grid); break;
         case 1: u ? launch_window<256, 4, true>(h, la, h->grid) : launch_window<256, 4, false>(h, la, h->grid); break;
+        case 3: u ? launch_window<256, 2, true>(h, la, h->grid) : launch_window<256, 2, false>(h, la, h->grid); break;
+        case 4: u ? launch_window<512, 2, true>(h, la, h->grid) : launch_window<512, 2, false>(h, la, h->grid); break;
         default: u ? launch_window<512, 4, true>(h, la, h->grid) : launch_window<512, 4, false>(h, la, h->grid); break;
     }
     CK(cudaGetLastError());
@@ -836,7 +844,7 @@ extern "C" int lpbox_batch_iters_l2f_dev(lpbox_batch *h, int iter_start, int ite
 
 extern "C" int lpbox_batch_config(const lpbox_batch *h, int32_t *out4) {
     if (!h || !out4) return LPBOX_E_INVALID;
-    out4[0] = h->grid; out4[1] = (int32_t)h->smem; out4[2] = h->tcfg == 0 ? 128 : (h->tcfg == 1 ? 256 : 512); out4[3] = (int32_t)h->fix_smem;
+    out4[0] = h->grid; out4[1] = (int32_t)h->smem; out4[2] = h->threads; out4[3] = (int32_t)h->fix_smem;
     return 0;
 }
 extern "C" int64_t lpbox_batch_h2d_bytes(const lpbox_batch *h) { return h ? h->h2d_bytes : -1; }

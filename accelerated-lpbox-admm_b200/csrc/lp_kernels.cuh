@@ -75,6 +75,8 @@ __device__ __forceinline__ double2 lds128(uint32_t a) {
     double2 v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a)); return v;
 }
 __device__ __forceinline__ uint32_t lds16(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint2 lds_u32x2(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_u32x2(uint32_t a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory"); }
 __device__ __forceinline__ void sts64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 __device__ __forceinline__ unsigned smid() { unsigned v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
 
@@ -295,8 +297,14 @@ __device__ __forceinline__ double ell_dot(uint32_t ia, const u16 *__restrict__ g
             if (!more) break;
         }
     }
-#pragma unroll 1
-    for (; k < W; ++k, pos += 32) {
+    if (W & 2) {                                     // W is warp-uniform: straight-line tail
+        const uint32_t i0 = ld_idx<GIDX>(ia, gidx, pos), i1 = ld_idx<GIDX>(ia, gidx, pos + 32);
+        double t0 = lds64(i0 + add), t1 = lds64(i1 + add);
+        if (COEF == 2) { t0 = dM(val[pos], t0); t1 = dM(val[pos + 32], t1); }
+        acc = dA(acc, t0); acc = dA(acc, t1);
+        pos += 64;
+    }
+    if (W & 1) {
         double t = lds64(ld_idx<GIDX>(ia, gidx, pos) + add);
         if (COEF == 2) t = dM(val[pos], t);
         acc = dA(acc, t);
@@ -391,6 +399,7 @@ struct Smem {
     uint32_t T1;     // [mp+2]  operand of E^T w in row-slot order: E v (scaled by rho4 in the unit case) / rho4 (f - y3)
     uint32_t R0, R1; // [4*CH]  chain-major reduction operands; R1 also holds the copy of z4 gathered by E^T z4
     uint32_t tab;    // [tab_len] unit case: 1 / precond_diag as a function of the column length
+    uint32_t cst;    // [T] 8 bytes per thread: chain-major staging offsets (uint16, relative to R0) of the thread's columns
     double *sc;      // [16]    reduction results / broadcast scalars
     double *blk;     // [2][SB_COUNT] ADMM-level scalars (rho's, gamma, objective bookkeeping), double-buffered per iteration
     double *ring;    // [16]    tail of obj_list
@@ -401,8 +410,8 @@ struct Smem {
     uint64_t *bar;
 };
 __host__ __device__ inline size_t smem_bytes(int cap, int np, int mp, int pat_bytes, int evr_elems, int evc_elems, int nwarps, int tab_len) {
-    size_t d = (size_t)((mp + 3) & ~1) + 8 * (size_t)chain_stride(np) + (size_t)((tab_len + 1) & ~1) + 16 + 2 * SB_COUNT + 16 +
-               2 * 4 * (size_t)nwarps + 2 + (size_t)evr_elems + 2 * (size_t)evc_elems;
+    size_t d = (size_t)((mp + 3) & ~1) + 8 * (size_t)chain_stride(np) + (size_t)((tab_len + 1) & ~1) + 32 * (size_t)nwarps + 16 +
+               2 * SB_COUNT + 16 + 2 * 4 * (size_t)nwarps + 2 + (size_t)evr_elems + 2 * (size_t)evc_elems;
     return (size_t)gather_base(cap) + d * sizeof(double) + (size_t)pat_bytes + 16;
 }
 __device__ __forceinline__ Smem carve(unsigned char *base, int cap, int np, int mp, int pat_bytes, int evr_elems, int evc_elems, int nwarps,
@@ -417,6 +426,7 @@ __device__ __forceinline__ Smem carve(unsigned char *base, int cap, int np, int 
     s.R0 = s.T1 + (uint32_t)(d - d0) * 8u; d += 4 * CH;
     s.R1 = s.T1 + (uint32_t)(d - d0) * 8u; d += 4 * CH;
     s.tab = s.T1 + (uint32_t)(d - d0) * 8u; d += (tab_len + 1) & ~1;
+    s.cst = s.T1 + (uint32_t)(d - d0) * 8u; d += 32 * nwarps;
     s.sc = d; d += 16;
     s.blk = d; d += 2 * SB_COUNT;
     s.ring = d; d += 16;
@@ -582,13 +592,13 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
         // registers across the whole window: x, chain-major staging address (in R0) of the owned columns, and 1/diag (unit
         // case: the column lengths, packed, that index the shared 1/diag table)
         double x[EPT], invd[UNIT ? 1 : EPT];
-        uint32_t cst[EPT];
         uint32_t lens = 0;
+        uint32_t cpk[2] = {0u, 0u};                          // chain-major staging offsets (bytes from R0) of the owned columns, 16 bits each
         LPB_FOR_E {
             const int s = vt + e * T;
             const bool in = s < n;
             const int j = in ? (int)g_cperm[s] : 0;
-            cst[e] = S.R0 + (uint32_t)((j & 3) * CH + (j >> 2)) * 8u;
+            cpk[e >> 1] |= ((uint32_t)((j & 3) * CH + (j >> 2)) * 8u) << (16 * (e & 1));
             x[e] = in ? bv.x[on + j] : 0.0;
             const double pd = in ? bv.Pd[on + j] : 1.0;
             const double iv = (pd != 0.0) ? dD(1.0, pd) : 1.0;   // value in use when rhoUpdated == 0 (Eigen: zero diagonal -> 1)
@@ -607,6 +617,13 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                 park[PK_Y3 * CAP + e * T] = bv.y3[om + i]; park[PK_Z4 * CAP + e * T] = bv.z4[om + i]; park[PK_F * CAP + e * T] = bv.f[om + i];
             }
         }
+        sts_u32x2(S.cst + 8u * (uint32_t)tid, make_uint2(cpk[0], cpk[1]));   // read back (by this thread only) at every staging step
+        // staging addresses of this thread's columns in R0; kept in shared memory between uses (registers are scarce in PCG)
+#define LPB_CST_LOAD()                                                                                                \
+        uint32_t cst[EPT];                                                                                            \
+        if (!FAST) { const uint2 cw_ = lds_u32x2(S.cst + 8u * (uint32_t)tid);                                         \
+                     LPB_FOR_E cst[e] = S.R0 + (((((e) >> 1) ? cw_.y : cw_.x) >> (16 * ((e) & 1))) & 0xffffu); }      \
+        else { LPB_FOR_E cst[e] = 0u; }
 #define LPB_INVD(e) (UNIT ? lds64(S.tab + 8u * ((lens >> (8 * (e))) & 0xffu)) : invd[UNIT ? 0 : (e)])
         double D = stp->D, r4s = stp->r4s;
         int rhoUpdated = stp->rhoUpdated;
@@ -673,6 +690,7 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
         if (iter < la.iter_end) {
             double ysq[1] = {0.0};
             const double rho2 = S.blk[SB_RHO2];
+            LPB_CST_LOAD();
             LPB_FOR_E {
                 const int s = vt + e * T;
                 if (s < n) {
@@ -771,6 +789,7 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                 }
             }
             __syncthreads();                                                 // all reads of T1 / R1 (z4 copy) done
+            { LPB_CST_LOAD();
             LPB_FOR_E {
                 const int s = vt + e * T;
                 if (s < n) {
@@ -778,16 +797,24 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                     if (FAST) rn[0] = fma(rhs[e], rhs[e], rn[0]);
                     else sts64(cst[e], dM(rhs[e], rhs[e]));
                 }
-            }
+            } }
             __syncthreads();
             LPB_ROW_SPMV(UNIT);                                              // E x0
+            // PCG scalars (parity mode): the keeper -- lane 0 of the reduction warp -- forms threshold, alpha, beta and the stop
+            // decisions right after each reduction and publishes them; nobody else carries them in registers.
+            //   sc[0] alpha | sc[2] beta | sc[8] threshold | sc[9] absNew | ctl[3] 0 = iterate, 1 = rhs is zero, 2 = converged
             if (!FAST && is_rw) {
                 const double v = warp_redux_cm1(S.R0, n, CH, 1);                // rhs.squaredNorm() :277
-                if (lane == 0) S.sc[0] = v;
+                if (lane == 0) {
+                    double threshold = dM(dM(pr.pcg_tol, pr.pcg_tol), v);        // :287
+                    if (!(threshold > DBL_MIN)) threshold = DBL_MIN;
+                    S.sc[8] = threshold;
+                    S.ctl[3] = (v == 0.0) ? 1 : 0;                               // :279-284
+                }
             }
             if (FAST) LPB_BLOCK_SUM(1, rn); else __syncthreads();
-            const double rhsNorm2 = FAST ? rn[0] : S.sc[0];
             double rr[2] = {0.0, 0.0};
+            { LPB_CST_LOAD();
             LPB_FOR_E {
                 const int s = vt + e * T;
                 double acc;
@@ -800,93 +827,111 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                     if (FAST) { rr[0] = fma(r[e], r[e], rr[0]); rr[1] = fma(r[e], p[e], rr[1]); }
                     else { sts64(cst[e], dM(r[e], r[e])); sts64(cst[e] + r1_off, dM(r[e], p[e])); }
                 } else { r[e] = 0.0; p[e] = 0.0; }
-            }
-            if (FAST) LPB_BLOCK_SUM(2, rr);
-            else {
+            } }
+            int cg_code;
+            double threshold = 0.0, absNew = 0.0;                            // fast mode only (parity: shared scalars)
+            if (FAST) {
+                LPB_BLOCK_SUM(2, rr);
+                threshold = dM(dM(pr.pcg_tol, pr.pcg_tol), rn[0]);
+                if (!(threshold > DBL_MIN)) threshold = DBL_MIN;
+                absNew = rr[1];
+                cg_code = (rn[0] == 0.0) ? 1 : ((rr[0] < threshold) ? 2 : 0);
+            } else {
                 __syncthreads();
                 if (is_rw) {
                     const double v = warp_redux_cm1(rq == 0 ? S.R0 : S.R1, n, CH, 2);    // r.r :288, r.p :300
-                    if (lane == 0) S.sc[1] = v;
-                    if (lane == 4) S.sc[2] = v;
+                    const double v1 = __shfl_sync(0xffffffffu, v, 4);
+                    if (lane == 0) {
+                        S.sc[9] = v1;                                            // absNew :300
+                        S.ctl[3] = S.ctl[3] ? 1 : ((v < S.sc[8]) ? 2 : 0);       // :290-295
+                    }
                 }
                 __syncthreads();
+                cg_code = S.ctl[3];
             }
             int cg_it = 0;
             bool cg_fail = false;
-            if (rhsNorm2 == 0.0) {                                           // :279-284
+            if (cg_code == 1) {                                              // :279-284
                 LPB_FOR_E x[e] = 0.0;
-            } else {
-                double threshold = dM(dM(pr.pcg_tol, pr.pcg_tol), rhsNorm2); // :287
-                if (!(threshold > DBL_MIN)) threshold = DBL_MIN;
-                double r2 = FAST ? rr[0] : S.sc[1];
-                double absNew = FAST ? rr[1] : S.sc[2];
-                if (!(r2 < threshold)) {                                     // :290-295
-                    while (cg_it < pr.pcg_maxiters) {                        // G holds p here
-                        LPB_ROW_SPMV(UNIT);
+            } else if (cg_code == 0) {
+                while (cg_it < pr.pcg_maxiters) {                            // G holds p here
+                    LPB_ROW_SPMV(UNIT);
+                    __syncthreads();
+                    double tmp[EPT];
+                    double pq[1] = {0.0};
+                    { LPB_CST_LOAD();
+                    LPB_FOR_E {
+                        const int s = vt + e * T;
+                        double acc;
+                        LPB_COL_DOT(e, acc);
+                        if (s < n) {
+                            tmp[e] = dA(dA(0.0, dM(D, p[e])), acc);          // :304
+                            if (FAST) pq[0] = fma(p[e], tmp[e], pq[0]);
+                            else sts64(cst[e], dM(p[e], tmp[e]));
+                        } else tmp[e] = 0.0;
+                    } }
+                    double alpha;
+                    if (FAST) { LPB_BLOCK_SUM(1, pq); alpha = dD(absNew, pq[0]); }
+                    else {
                         __syncthreads();
-                        double tmp[EPT];
-                        double pq[1] = {0.0};
-                        LPB_FOR_E {
-                            const int s = vt + e * T;
-                            double acc;
-                            LPB_COL_DOT(e, acc);
-                            if (s < n) {
-                                tmp[e] = dA(dA(0.0, dM(D, p[e])), acc);      // :304
-                                if (FAST) pq[0] = fma(p[e], tmp[e], pq[0]);
-                                else sts64(cst[e], dM(p[e], tmp[e]));
-                            } else tmp[e] = 0.0;
+                        if (is_rw) {
+                            const double v = warp_redux_cm1(S.R0, n, CH, 1);    // p.dot(tmp) :306
+                            if (lane == 0) S.sc[0] = dD(S.sc[9], v);            // alpha = absNew / p.tmp
                         }
-                        if (FAST) LPB_BLOCK_SUM(1, pq);
-                        else {
-                            __syncthreads();
-                            if (is_rw) {
-                                const double v = warp_redux_cm1(S.R0, n, CH, 1);    // p.dot(tmp) :306
-                                if (lane == 0) S.sc[0] = v;
-                            }
-                            __syncthreads();
-                        }
-                        const double alpha = dD(absNew, FAST ? pq[0] : S.sc[0]);
-                        if (pr.alpha_bailout && alpha < 0.0) { cg_fail = true; break; }  // :307
-                        double zz[EPT];
-                        double rz[2] = {0.0, 0.0};
-                        LPB_FOR_E {
-                            const int s = vt + e * T;
-                            if (FAST) {
-                                x[e] = fma(alpha, p[e], x[e]);
-                                r[e] = fma(-alpha, tmp[e], r[e]);
-                            } else {
-                                x[e] = dA(x[e], dM(alpha, p[e]));             // :308
-                                r[e] = dS(r[e], dM(alpha, tmp[e]));           // :310
-                            }
-                            if (s < n) {
-                                zz[e] = dM(LPB_INVD(e), r[e]);                // :320
-                                if (FAST) { rz[0] = fma(r[e], r[e], rz[0]); rz[1] = fma(r[e], zz[e], rz[1]); }
-                                else { sts64(cst[e], dM(r[e], r[e])); sts64(cst[e] + r1_off, dM(r[e], zz[e])); }
-                            } else zz[e] = 0.0;
-                        }
-                        if (FAST) LPB_BLOCK_SUM(2, rz);
-                        else {
-                            __syncthreads();
-                            if (is_rw) {
-                                const double v = warp_redux_cm1(rq == 0 ? S.R0 : S.R1, n, CH, 2);   // r.r :311, r.z :323
-                                if (lane == 0) S.sc[1] = v;
-                                if (lane == 4) S.sc[2] = v;
-                            }
-                            __syncthreads();
-                        }
-                        r2 = FAST ? rz[0] : S.sc[1];
-                        if (r2 < threshold) { cg_it++; break; }              // :315-318
-                        const double absOld = absNew;
-                        absNew = FAST ? rz[1] : S.sc[2];
-                        const double beta = dD(absNew, absOld);              // :324
-                        LPB_FOR_E {
-                            const int s = vt + e * T;
-                            p[e] = FAST ? fma(beta, p[e], zz[e]) : dA(zz[e], dM(beta, p[e]));   // :325
-                            if (s < n) sts64(S.G + 8u * (uint32_t)s, p[e]);
-                        }
-                        cg_it++;
                         __syncthreads();
+                        alpha = S.sc[0];
                     }
+                    if (pr.alpha_bailout && alpha < 0.0) { cg_fail = true; break; }  // :307
+                    double rz[2] = {0.0, 0.0};
+                    { LPB_CST_LOAD();
+                    LPB_FOR_E {
+                        const int s = vt + e * T;
+                        if (FAST) {
+                            x[e] = fma(alpha, p[e], x[e]);
+                            r[e] = fma(-alpha, tmp[e], r[e]);
+                        } else {
+                            x[e] = dA(x[e], dM(alpha, p[e]));                 // :308
+                            r[e] = dS(r[e], dM(alpha, tmp[e]));               // :310
+                        }
+                        if (s < n) {
+                            const double zz = dM(LPB_INVD(e), r[e]);          // :320 (formed again after the reduction: same product)
+                            if (FAST) { rz[0] = fma(r[e], r[e], rz[0]); rz[1] = fma(r[e], zz, rz[1]); }
+                            else { sts64(cst[e], dM(r[e], r[e])); sts64(cst[e] + r1_off, dM(r[e], zz)); }
+                        }
+                    } }
+                    double beta;
+                    bool cg_done;
+                    if (FAST) {
+                        LPB_BLOCK_SUM(2, rz);
+                        cg_done = rz[0] < threshold;
+                        beta = dD(rz[1], absNew);
+                        absNew = rz[1];
+                    } else {
+                        __syncthreads();
+                        if (is_rw) {
+                            const double v = warp_redux_cm1(rq == 0 ? S.R0 : S.R1, n, CH, 2);   // r.r :311, r.z :323
+                            const double v1 = __shfl_sync(0xffffffffu, v, 4);
+                            if (lane == 0) {
+                                const int done = (v < S.sc[8]) ? 1 : 0;          // :315-318
+                                S.ctl[3] = done;
+                                if (!done) { S.sc[2] = dD(v1, S.sc[9]); S.sc[9] = v1; }   // beta = absNew / absOld :324
+                            }
+                        }
+                        __syncthreads();
+                        cg_done = S.ctl[3] != 0;
+                        beta = S.sc[2];
+                    }
+                    if (cg_done) { cg_it++; break; }                         // :315-318
+                    LPB_FOR_E {
+                        const int s = vt + e * T;
+                        if (s < n) {
+                            const double zz = dM(LPB_INVD(e), r[e]);          // :320
+                            p[e] = FAST ? fma(beta, p[e], zz) : dA(zz, dM(beta, p[e]));   // :325
+                            sts64(S.G + 8u * (uint32_t)s, p[e]);
+                        }
+                    }
+                    cg_it++;
+                    __syncthreads();
                 }
             }
             cg_total += cg_it;
@@ -910,6 +955,7 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
             {
                 const double gamma = blk[SB_GAMMA];
                 const double g1 = dM(gamma, blk[SB_RHO1]), g2 = dM(gamma, blk[SB_RHO2]);
+                LPB_CST_LOAD();
                 LPB_FOR_E {
                     const int s = vt + e * T;
                     if (s < n) {
@@ -947,6 +993,7 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                         park[PK_Z4 * CAP + e * T] = assign ? t : dA(park[PK_Z4 * CAP + e * T], t);
                     }
                 }
+                LPB_CST_LOAD();
                 LPB_FOR_E {
                     const int s = vt + e * T;
                     if (s < n) {
