@@ -261,9 +261,24 @@ static int sync_states(lpbox_batch *h) {
     return 0;
 }
 
+static lpbox_batch *batch_create_impl(int device, int B, const int32_t *m, const int32_t *n, const int32_t *colptr_all,
+                                      const int32_t *rowidx_all, const double *val_all, const double *b_all,
+                                      const double *f_all, int hist_cap);
 extern "C" lpbox_batch *lpbox_batch_create(int device, int B, const int32_t *m, const int32_t *n, const int32_t *colptr_all,
                                            const int32_t *rowidx_all, const double *val_all, const double *b_all,
                                            const double *f_all, int hist_cap) {
+    try {   // no C++ exception may cross the C boundary
+        return batch_create_impl(device, B, m, n, colptr_all, rowidx_all, val_all, b_all, f_all, hist_cap);
+    } catch (const std::exception &e) {
+        set_err(std::string("lpbox_batch_create: ") + e.what());
+    } catch (...) {
+        set_err("lpbox_batch_create: unknown exception");
+    }
+    return nullptr;
+}
+static lpbox_batch *batch_create_impl(int device, int B, const int32_t *m, const int32_t *n, const int32_t *colptr_all,
+                                      const int32_t *rowidx_all, const double *val_all, const double *b_all,
+                                      const double *f_all, int hist_cap) {
     if (B <= 0 || !m || !n || !colptr_all || !rowidx_all || !b_all || hist_cap < 0) { set_err("invalid argument"); return nullptr; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { set_err("no CUDA device (there is no CPU fallback)"); return nullptr; }
@@ -281,9 +296,14 @@ extern "C" lpbox_batch *lpbox_batch_create(int device, int B, const int32_t *m, 
     std::vector<long long> b_in_off(B + 1, 0), f_in_off(B + 1, 0);
     for (int i = 0; i < B; ++i) {
         if (n[i] <= 0 || m[i] < 0) { set_err("instance with n <= 0"); delete h; return nullptr; }
+        if (n[i] > 2048 || m[i] > 2048) { set_err("max(n, m) > 2048 is not supported by the on-chip kernel"); delete h; return nullptr; }
         const int32_t *cp = colptr_all + h->h_cp_off[i];
+        // validate the column pointers BEFORE anything is sized from them
+        bool ok_cp = cp[0] == 0;
+        for (int j = 0; ok_cp && j < n[i]; ++j) ok_cp = cp[j + 1] >= cp[j];
+        if (!ok_cp) { set_err("bad colptr (must start at 0 and be non-decreasing)"); delete h; return nullptr; }
         h->nnz0[i] = cp[n[i]];
-        if (h->nnz0[i] < 0) { set_err("bad colptr"); delete h; return nullptr; }
+        if (h->nnz0[i] > 65535) { set_err("nnz > 65535 is not supported by the on-chip kernel"); delete h; return nullptr; }
         h->h_cp_off[i + 1] = h->h_cp_off[i] + n[i] + 1;
         h->h_nnz_off[i + 1] = h->h_nnz_off[i] + h->nnz0[i];
         h->off_n[i + 1] = h->off_n[i] + ((n[i] + 1) & ~1);

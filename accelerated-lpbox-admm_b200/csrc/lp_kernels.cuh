@@ -522,7 +522,7 @@ static __device__ __noinline__ int admm_bookkeep(const Params &pr, const double 
 #define LPB_CTAS_256 4
 #endif
 #ifndef LPB_CTAS_512
-#define LPB_CTAS_512 1
+#define LPB_CTAS_512 2
 #endif
 enum ParkSlot : int { PK_Y1 = 0, PK_Y2, PK_Z1, PK_Z2, PK_B, PK_X, PK_Y3, PK_Z4, PK_F, PK_COUNT };
 constexpr int lpb_ctas(int T, int EPT) { return T <= 128 ? LPB_CTAS_128 : (T <= 256 ? (EPT <= 2 ? LPB_CTAS_256 : 3) : LPB_CTAS_512); }

@@ -1036,8 +1036,6 @@ int launch_gemm(cudaStream_t st, const __nv_bfloat16 *A, const __nv_bfloat16 *W,
     if (N % BN || K % BK) { lpbox_set_error("policy GEMM: N must be a multiple of 128 and K of 64"); return LPBOX_E_INVALID; }
     CUtensorMap ma, mb;
     if (!make_map(&ma, A, (uint64_t)M, (uint64_t)K, BM) || !make_map(&mb, W, (uint64_t)N, (uint64_t)K, BN)) { lpbox_set_error("cuTensorMapEncodeTiled failed"); return LPBOX_E_CUDA; }
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(gemm_bf16_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM); attr = true; }
     dim3 grid((unsigned)(N / BN), (unsigned)((M + BM - 1) / BM));
     gemm_bf16_tcgen05<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ma, mb, C, (int)M, N, K, N, ep);
     cudaError_t e = cudaGetLastError();
@@ -1046,7 +1044,27 @@ int launch_gemm(cudaStream_t st, const __nv_bfloat16 *A, const __nv_bfloat16 *W,
 }
 
 
-int g_sm_count = 0;
+// per-device state: the opt-in shared-memory sizes are function attributes of the CURRENT device's context, and devices may
+// differ in SM count -- both are set / read per device (lpbox_policy_create calls policy_prepare_device after cudaSetDevice)
+static int g_sm_counts[64] = {0};
+static bool g_attr_done[64] = {false};
+static int sm_count_current() {
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    if (!g_sm_counts[dev]) { int c = 0; cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev); g_sm_counts[dev] = c > 0 ? c : 148; }
+    return g_sm_counts[dev];
+}
+static bool policy_prepare_device() {
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && g_attr_done[dev]) return true;
+    bool ok = cudaFuncSetAttribute(gemm_bf16_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(ff_fused_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(mha_fused_tcgen05<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MH_SMEM) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(mha_fused_tcgen05<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MH_SMEM) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(mha_fused_tcgen05<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MH_SMEM) == cudaSuccess;
+    if (ok && dev >= 0 && dev < 64) g_attr_done[dev] = true;
+    return ok;
+}
 int launch_ff_fused(cudaStream_t st, const __nv_bfloat16 *X, const __nv_bfloat16 *W1, const float *b1, const __nv_bfloat16 *W2, const float *b2,
                     const float *s2, const float *t2, __nv_bfloat16 *out, long long M) {
     if (M <= 0) return 0;
@@ -1055,11 +1073,8 @@ int launch_ff_fused(cudaStream_t st, const __nv_bfloat16 *X, const __nv_bfloat16
     if (!make_map(&mx, X, (uint64_t)M, 128, 128) || !make_map(&m1, W1, 512, 128, 64) || !make_map(&m2, W2, 128, 512, 128)) {
         lpbox_set_error("cuTensorMapEncodeTiled failed"); return LPBOX_E_CUDA;
     }
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(ff_fused_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM); attr = true; }
-    if (!g_sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev); if (g_sm_count <= 0) g_sm_count = 148; }
     const long long n_pairs = (M + 255) / 256;
-    ff_fused_tcgen05<<<(unsigned)std::min<long long>(n_pairs, g_sm_count), FF_THREADS, FF_SMEM, st>>>(mx, m1, m2, X, out, (int)M, b1, b2, s2, t2);
+    ff_fused_tcgen05<<<(unsigned)std::min<long long>(n_pairs, sm_count_current()), FF_THREADS, FF_SMEM, st>>>(mx, m1, m2, X, out, (int)M, b1, b2, s2, t2);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { lpbox_set_error(std::string("fused FF launch: ") + cudaGetErrorString(e)); return LPBOX_E_CUDA; }
     return 0;
@@ -1068,11 +1083,9 @@ int launch_ff_fused(cudaStream_t st, const __nv_bfloat16 *X, const __nv_bfloat16
 template <int TT>
 int launch_mha_fused_t(cudaStream_t st, const CUtensorMap &mx, const CUtensorMap &mq, const CUtensorMap &mo, __nv_bfloat16 *out, long long M,
                        const float *scale, const float *shift) {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(mha_fused_tcgen05<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MH_SMEM); attr = true; }
     constexpr int TR = (128 / TT) * TT;
     const long long n_tiles = (M + TR - 1) / TR;
-    mha_fused_tcgen05<TT><<<(unsigned)std::min<long long>(n_tiles, g_sm_count), MH_THREADS, MH_SMEM, st>>>(mx, mq, mo, out, (int)M, scale, shift);
+    mha_fused_tcgen05<TT><<<(unsigned)std::min<long long>(n_tiles, sm_count_current()), MH_THREADS, MH_SMEM, st>>>(mx, mq, mo, out, (int)M, scale, shift);
     return 0;
 }
 // out = (X + Wo . MHA(X)) * scale + shift for rows grouped in variables of T tokens (T = 20, 10 or 5)
@@ -1084,7 +1097,6 @@ int launch_mha_fused(cudaStream_t st, const __nv_bfloat16 *X, const __nv_bfloat1
     if (!make_map(&mx, X, (uint64_t)M, 128, 128) || !make_map(&mq, Wqkv, 384, 128, 128) || !make_map(&mo, Wo, 128, 128, 128)) {
         lpbox_set_error("cuTensorMapEncodeTiled failed"); return LPBOX_E_CUDA;
     }
-    if (!g_sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev); if (g_sm_count <= 0) g_sm_count = 148; }
     if (T == 20) launch_mha_fused_t<20>(st, mx, mq, mo, out, M, scale, shift);
     else if (T == 10) launch_mha_fused_t<10>(st, mx, mq, mo, out, M, scale, shift);
     else launch_mha_fused_t<5>(st, mx, mq, mo, out, M, scale, shift);
@@ -1111,18 +1123,21 @@ struct lpbox_policy {
     __nv_bfloat16 *h = nullptr, *h2 = nullptr, *qkv = nullptr, *ff = nullptr, *a1 = nullptr, *a2 = nullptr;
     int64_t launches = 0;
     bool fused_mha = true;      // LPBOX_POLICY_UNFUSED_MHA=1 selects the three-kernel path (tests compare the two)
+    bool failed = false;        // an allocation or upload failed during create
 };
 
 static __nv_bfloat16 *upload_bf16(lpbox_policy *p, const float *src, size_t n) {
     std::vector<__nv_bfloat16> tmp(n);
     for (size_t i = 0; i < n; ++i) tmp[i] = __float2bfloat16(src[i]);
     __nv_bfloat16 *d = dalloc<__nv_bfloat16>(n);
-    if (d) { cudaMemcpy(d, tmp.data(), n * 2, cudaMemcpyHostToDevice); p->owned.push_back(d); }
+    if (d) { p->owned.push_back(d); if (cudaMemcpy(d, tmp.data(), n * 2, cudaMemcpyHostToDevice) != cudaSuccess) p->failed = true; }
+    else p->failed = true;
     return d;
 }
 static float *upload_f32(lpbox_policy *p, const float *src, size_t n) {
     float *d = dalloc<float>(n);
-    if (d) { cudaMemcpy(d, src, n * 4, cudaMemcpyHostToDevice); p->owned.push_back(d); }
+    if (d) { p->owned.push_back(d); if (cudaMemcpy(d, src, n * 4, cudaMemcpyHostToDevice) != cudaSuccess) p->failed = true; }
+    else p->failed = true;
     return d;
 }
 
@@ -1138,6 +1153,7 @@ extern "C" lpbox_policy *lpbox_policy_create(int device, int tokens, int n_layer
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { lpbox_set_error("no CUDA device (there is no CPU fallback)"); return nullptr; }
     if (cudaSetDevice(device) != cudaSuccess) { lpbox_set_error("bad device"); return nullptr; }
     if (!get_encode()) { lpbox_set_error("cuTensorMapEncodeTiled not available"); return nullptr; }
+    if (!policy_prepare_device()) { lpbox_set_error("policy_create: cannot set the shared-memory attributes of the policy kernels on this device"); return nullptr; }
     lpbox_policy *p = new lpbox_policy();
     p->device = device; p->T = tokens; p->L = n_layers; p->chunk = chunk_rows > 0 ? chunk_rows : 16384;
     p->fused_mha = getenv("LPBOX_POLICY_UNFUSED_MHA") == nullptr;
@@ -1168,7 +1184,8 @@ extern "C" lpbox_policy *lpbox_policy_create(int device, int tokens, int n_layer
     const size_t Mt = (size_t)p->chunk * tokens;
     p->h = dalloc<__nv_bfloat16>(Mt * 128); p->h2 = dalloc<__nv_bfloat16>(Mt * 128); p->qkv = dalloc<__nv_bfloat16>(Mt * 384);
     p->ff = dalloc<__nv_bfloat16>(Mt * 512); p->a1 = dalloc<__nv_bfloat16>((size_t)p->chunk * 256); p->a2 = dalloc<__nv_bfloat16>((size_t)p->chunk * 128);
-    for (void *q : {(void *)p->h, (void *)p->h2, (void *)p->qkv, (void *)p->ff, (void *)p->a1, (void *)p->a2}) { if (!q) { lpbox_set_error("policy_create: out of device memory"); return nullptr; } p->owned.push_back(q); }
+    for (void *q : {(void *)p->h, (void *)p->h2, (void *)p->qkv, (void *)p->ff, (void *)p->a1, (void *)p->a2}) { if (q) p->owned.push_back(q); else p->failed = true; }
+    if (p->failed) { lpbox_set_error("policy_create: out of device memory (or a weight upload failed)"); lpbox_policy_destroy(p); return nullptr; }
     return p;
 }
 
@@ -1184,6 +1201,7 @@ extern "C" void lpbox_policy_destroy(lpbox_policy *p) {
 extern "C" int lpbox_policy_forward_dev(lpbox_policy *p, void *stream, const float *input_dev, int64_t rows, float *scores_dev) {
     if (!p || !input_dev || !scores_dev || rows < 0) return LPBOX_E_INVALID;
     if (cudaSetDevice(p->device) != cudaSuccess) return LPBOX_E_CUDA;
+    if (!policy_prepare_device()) return LPBOX_E_CUDA;
     cudaStream_t st = (cudaStream_t)stream;
     const int T = p->T;
     for (int64_t r0 = 0; r0 < rows; r0 += p->chunk) {
@@ -1225,7 +1243,7 @@ extern "C" int64_t lpbox_policy_launch_count(const lpbox_policy *p) { return p ?
 
 // plain GEMM entry for tests: C[M][N] (bf16) = A[M][K] (bf16) . W[N][K]^T (+ bias, ReLU)
 extern "C" int lpbox_gemm_bf16_dev(void *stream, const void *A, const void *W, void *C, int64_t M, int N, int K, const float *bias, int relu) {
-    if (!get_encode()) { lpbox_set_error("cuTensorMapEncodeTiled not available"); return LPBOX_E_CUDA; }
+    if (!get_encode() || !policy_prepare_device()) { lpbox_set_error("cuTensorMapEncodeTiled / kernel attributes not available"); return LPBOX_E_CUDA; }
     return launch_gemm((cudaStream_t)stream, (const __nv_bfloat16 *)A, (const __nv_bfloat16 *)W, (__nv_bfloat16 *)C, M, N, K,
                        Epi{bias, nullptr, nullptr, nullptr, relu});
 }
@@ -1234,7 +1252,7 @@ extern "C" int lpbox_gemm_bf16_dev(void *stream, const void *A, const void *W, v
 // W1 bf16 [512][128], W2 bf16 [128][512]
 extern "C" int lpbox_ff_fused_dev(void *stream, const void *X, const void *W1, const float *b1, const void *W2, const float *b2, const float *scale,
                                   const float *shift, void *out, int64_t M) {
-    if (!get_encode()) { lpbox_set_error("cuTensorMapEncodeTiled not available"); return LPBOX_E_CUDA; }
+    if (!get_encode() || !policy_prepare_device()) { lpbox_set_error("cuTensorMapEncodeTiled / kernel attributes not available"); return LPBOX_E_CUDA; }
     return launch_ff_fused((cudaStream_t)stream, (const __nv_bfloat16 *)X, (const __nv_bfloat16 *)W1, b1, (const __nv_bfloat16 *)W2, b2, scale, shift,
                            (__nv_bfloat16 *)out, M);
 }
@@ -1243,7 +1261,7 @@ extern "C" int lpbox_ff_fused_dev(void *stream, const void *X, const void *W1, c
 // Wqkv bf16 [384][128] (q | k | v, head-major inside each third), Wo bf16 [128][128]; T = 20, 10 or 5
 extern "C" int lpbox_mha_fused_dev(void *stream, const void *X, const void *Wqkv, const void *Wo, const float *scale, const float *shift, void *out,
                                    int64_t M, int T) {
-    if (!get_encode()) { lpbox_set_error("cuTensorMapEncodeTiled not available"); return LPBOX_E_CUDA; }
+    if (!get_encode() || !policy_prepare_device()) { lpbox_set_error("cuTensorMapEncodeTiled / kernel attributes not available"); return LPBOX_E_CUDA; }
     return launch_mha_fused((cudaStream_t)stream, (const __nv_bfloat16 *)X, (const __nv_bfloat16 *)Wqkv, (const __nv_bfloat16 *)Wo, scale, shift,
                             (__nv_bfloat16 *)out, M, T);
 }

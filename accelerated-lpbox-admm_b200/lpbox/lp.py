@@ -41,9 +41,27 @@ def read_instance(root, i, k, j):
 
 class ProblemList(list):
     """A list of problem tuples that may also carry the same instances already concatenated (`packed`), as produced by
-    `gen_auctions`.  Slices and copies are plain lists, so `packed` can never describe a different set of problems --
-    unless the list is mutated in place, which LPBatch detects by the length."""
+    `gen_auctions`.  Slices and copies are plain lists; every in-place mutation drops `packed`, so it can never describe a
+    different set (or order) of problems than the list itself."""
     packed = None
+
+    def _drop(self):
+        self.packed = None
+
+
+def _mutating(name):
+    base = getattr(list, name)
+
+    def method(self, *a, **kw):
+        self._drop()
+        return base(self, *a, **kw)
+    method.__name__ = name
+    return method
+
+
+for _name in ("__setitem__", "__delitem__", "__iadd__", "__imul__", "append", "extend", "insert", "pop", "remove", "clear",
+              "sort", "reverse"):
+    setattr(ProblemList, _name, _mutating(_name))
 
 
 class LPBatch:
@@ -281,7 +299,10 @@ class PyLPboxADMMsolver:
             ret = int(b.iters(i, j)[0])
         finally:
             check(b.L.lpbox_batch_set_record_history(b.h, 0), "set_record_history")
-        done = min((b.get_iter(0) - i + 1) if ret else (j - i), self._hist_cap)      # iterates recorded (the stopping one included)
+        # iterates actually recorded: a stop (y1/y2 test -> ret 0, LP.cpp:934; objective-std test -> ret 1, :977) breaks with the
+        # loop variable still on the stopping iteration, whose iterate was written before the test (:903-909)
+        it = b.get_iter(0)
+        done = min((it - i + 1) if it < j else (j - i), self._hist_cap)
         try:
             with open(self._xiters_path, "w+") as fh:
                 if done > 0:

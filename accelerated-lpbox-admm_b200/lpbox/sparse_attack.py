@@ -170,14 +170,21 @@ def loop(model, images, target_label, epsilon, G, init_params, other_params, B, 
 
 
 def update_G_l2f(model, images, target_label, epsilon, G, init_params, B, noise_Weight, score_net, out_iter=None, f=None, args=None,
-                 windows=3, ws=50, C_thr=0.90):
+                 windows=3, ws=50, C_thr=0.90, reference_return=False, history=None):
     """main_ori.py:376-499: 3 windows of 50 iterations; between windows the policy (tokens = 10 x 5 iterates of the
     window) rewrites G: score > 0.9 -> 1, < 0.1 -> 0, else the window's last iterate.  `score_net` maps a
-    (rows, 10, 5) tensor to (logit, sigmoid) like `GraphAttentionEncoder` (the reference reloads it from disk each call)."""
+    (rows, 10, 5) tensor to (logit, sigmoid) like `GraphAttentionEncoder` (the reference reloads it from disk each call).
+
+    Return value: (G, params).  By default G is the mask AFTER the last window -- what a caller wants.  The reference's own
+    function returns something else: its `loop` never hands the updated G back (main_ori.py:502-623 rebinds a local), so
+    `update_G_l2f` returns the policy-rewritten mask the LAST window STARTED from (:485-499); `reference_return=True` reproduces
+    that (tests/test_sa_gpu.py compares it with the reference's own output).  `history`: optional list that receives the
+    iterate history (N, C, H, W, ws) of every window."""
     L = _capi.lib()
     ip, other, hist = dict(init_params), None, None
     N = G.shape[0]
     fixed = []
+    G_start = G
     for w in range(windows):
         if hist is not None:
             rows = hist.reshape(-1, ws)                                         # (N*C*H*W, ws)   :436-444
@@ -190,8 +197,11 @@ def update_G_l2f(model, images, target_label, epsilon, G, init_params, B, noise_
             check(L.lpbox_sa_apply_policy_dev(stream, last.numel(), _p(sig), _p(last), C_thr, 1 - C_thr, _p(Gn), _p(cnt)), "sa_apply_policy")
             G = Gn.view_as(G)
             fixed.append(cnt)
+        G_start = G.clone() if reference_return else G
         ip, other, G, hist = loop(model, images, target_label, epsilon, G, ip, other, B, noise_Weight, w * ws, (w + 1) * ws, args=args)
-    return G, ip
+        if history is not None:
+            history.append(hist)
+    return (G_start if reference_return else G), ip
 
 
 # ---- the outer loop either side of update_G -------------------------------------------------------------

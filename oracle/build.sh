@@ -7,6 +7,8 @@ mkdir -p _ref
 # C restatement: no FMA contraction, no fast-math, baseline x86-64 (SSE2) like the reference Makefile (-O3, no -march)
 gcc -O2 -std=c11 -fPIC -shared -ffp-contract=off -fno-fast-math -fvisibility=hidden \
     -o liblpbox_oracle.so lpbox_oracle.c seg_oracle.c -lm
+# the benchmark's workload generator as its own library: bench.py's reference arm must not map the product library
+g++ -O2 -std=c++17 -fPIC -shared -o liblpbox_gen.so ../accelerated-lpbox-admm_b200/csrc/auction_gen.cpp -lpthread
 REF=/root/reference/Segmentation/Segmentation/cython/src/liblpbox_solver.so
 if [ -f "$REF" ]; then
   # The reference sources need Eigen 3.4-dev + OpenCV 4.4 headers (absent here, no network) -> unbuildable.

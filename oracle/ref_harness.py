@@ -307,3 +307,58 @@ def unary_cost(image_2d, sigma=0.1, b=0.6, f1=0.2, f2=0.2):
     fn(C.byref(dm), sigma, b, f1, f2, C.byref(out))
     a = np.ctypeslib.as_array(C.cast(out.data, C.POINTER(C.c_double)), shape=(out.rows * out.cols,)).copy()
     return a.reshape((out.rows, out.cols), order="F")
+
+
+# ---- the binary's own member entry points (image front-end -> legacy / early-fix windows -> getters) ------------------------
+class SegMember:
+    """Drives `LPboxADMMsolver(print_info, numNodes, problem)` of the reference binary the way `SEG.pyx` does:
+    `ADMM_bqp_unconstrained_init` (reads ../data/<problem>.jpg through the functional cv stub, builds the graph, SEG.cpp:658-810),
+    then `ADMM_bqp_unconstrained_legacy` (:1200-1380) or windows of `ADMM_bqp_unconstrained_l2f` (:917-1195) with caller-supplied
+    fix vectors, and the getters (:833-893).  The image must be SQUARE (the stub's cv2eigen route) and numNodes == rows * cols."""
+
+    def __init__(self, img_u8, workroot, problem=1, print_info=0):
+        import struct
+        img = np.ascontiguousarray(img_u8, dtype=np.uint8)
+        assert img.ndim == 2 and img.shape[0] == img.shape[1], "square grey image"
+        self.lib = _load()
+        self.n0 = int(img.size)
+        for d in ("data", "result", "xiter", "work"):
+            os.makedirs(os.path.join(workroot, d), exist_ok=True)
+        with open(os.path.join(workroot, "data", "%d.jpg" % problem), "wb") as fh:
+            fh.write(b"LPBXRAW8" + struct.pack("<ii", img.shape[0], img.shape[1]) + img.tobytes())
+        self.cwd = os.path.join(workroot, "work")          # the reference uses ../data, ../result, ../xiter relative to cwd
+        self.buf = (C.c_char * (1 << 20))()
+        self._call(self.lib._ZN15LPboxADMMsolverC1Eiii, None, C.c_int(print_info), C.c_int(self.n0), C.c_int(problem))
+
+    def _call(self, fn, restype, *args):
+        fn.restype = restype
+        old = os.getcwd()
+        os.chdir(self.cwd)
+        saved = _silence_stdout()
+        try:
+            return fn(C.byref(self.buf), *args)
+        finally:
+            _restore_stdout(saved)
+            os.chdir(old)
+
+    def init(self):
+        self._call(self.lib._ZN15LPboxADMMsolver27ADMM_bqp_unconstrained_initEv, None)
+
+    def legacy(self):
+        return self._call(self.lib._ZN15LPboxADMMsolver29ADMM_bqp_unconstrained_legacyEv, C.c_int)
+
+    def l2f(self, start, end, vec, num):
+        v = np.ascontiguousarray(vec, dtype=np.float64)
+        return self._call(self.lib._ZN15LPboxADMMsolver26ADMM_bqp_unconstrained_l2fEiiPdi, C.c_int, C.c_int(int(start)), C.c_int(int(end)),
+                          v.ctypes.data_as(C.POINTER(C.c_double)), C.c_int(int(num)))
+
+    def x_iters(self, rows, ws):
+        p = self._call(self.lib._ZN15LPboxADMMsolver13get_x_iters_dEi, C.POINTER(C.c_double), C.c_int(int(ws)))
+        return np.ctypeslib.as_array(p, shape=(int(rows), int(ws))).copy()
+
+    def x_sol(self):
+        p = self._call(self.lib._ZN15LPboxADMMsolver9get_x_solEv, C.POINTER(C.c_double))
+        return np.ctypeslib.as_array(p, shape=(self.n0,)).copy()
+
+    def final_obj(self):
+        return self._call(self.lib._ZN15LPboxADMMsolver13get_final_objEv, C.c_double)

@@ -80,4 +80,5 @@ if __name__ == "__main__":
         make(s, 100, 500, with_txt=(s == 0))
     make(0, 20, 60, ks=(1, 10, 100))
     make(1, 40, 200)
-    make(0, 400, 2000, ks=(1, 10, 100))
+    make(0, 400, 2000, ks=(1, 10, 100))      # n = 2000: <512,4> kernel variant
+    make(3, 160, 800)                        # n = 800: <256,4> kernel variant

@@ -90,3 +90,17 @@ def test_generator_packed_layout_matches_the_tuples():
     assert np.array_equal(np.concatenate([t[5] for t in p]), pk["b"])
     assert np.array_equal([t[0] for t in p], pk["ms"]) and np.array_equal([t[1] for t in p], pk["ns"])
     assert getattr(p[:10], "packed", None) is None and type(p[:10]) is list
+
+
+def test_problem_list_drops_packed_on_mutation():
+    """`packed` (the pre-concatenated arrays LPBatch trusts) must not survive an in-place change of the list."""
+    import random
+    from lpbox.lp import ProblemList
+    def fresh():
+        p = ProblemList([("a",), ("b",), ("c",)]); p.packed = {"ms": [0, 0, 0]}; return p
+    for mutate in (lambda p: p.reverse(), lambda p: p.sort(), lambda p: random.shuffle(p), lambda p: p.__setitem__(0, ("z",)),
+                   lambda p: p.append(("d",)), lambda p: p.pop(), lambda p: p.insert(0, ("y",)), lambda p: p.extend([("q",)])):
+        p = fresh(); mutate(p)
+        assert p.packed is None
+    p = fresh()
+    assert p.packed is not None and p[1:].__class__ is list

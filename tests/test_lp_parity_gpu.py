@@ -21,6 +21,7 @@ def _same(a, b):
 
 @pytest.mark.parametrize("name,ks", [("auction_20_60_seed0.npz", (1, 10, 100)), ("auction_40_200_seed1.npz", (1, 10, 100, 1000)),
                                      ("auction_100_500_seed0.npz", (1, 10, 100, 1000)),
+                                     ("auction_160_800_seed3.npz", (1, 10, 100, 1000)),
                                      ("auction_400_2000_seed0.npz", (1, 10, 100))])
 def test_iterates_match_reference_binary(name, ks):
     """x after K iterations == the reference's compiled Eigen build (tests/golden, make_golden.py), bit for bit."""
@@ -36,7 +37,7 @@ def test_iterates_match_reference_binary(name, ks):
 
 
 @pytest.mark.parametrize("name", ["auction_100_500_seed0.npz", "auction_100_500_seed1.npz", "auction_100_500_seed2.npz",
-                                  "auction_40_200_seed1.npz"])
+                                  "auction_40_200_seed1.npz", "auction_160_800_seed3.npz", "auction_400_2000_seed0.npz"])
 def test_converged_solution_matches_reference_binary(name):
     import lpbox
     g = load_golden(name)
@@ -50,7 +51,8 @@ def test_converged_solution_matches_reference_binary(name):
     assert s.get_iter() == o.get_iter()
     x = s.get_final_x_sol(g["n"]).ravel()
     assert _same(x, g["x_final"])
-    assert -s.cal_Obj() == pytest.approx(float(g["obj_final"]), rel=0, abs=0)
+    assert s.cal_Obj() == o.cal_Obj()                                       # bit-exact vs the oracle (Eigen summation order)
+    assert -s.cal_Obj() == pytest.approx(float(g["obj_final"]), rel=1e-13, abs=0)   # fixture value: numpy dot of the binary's x
     assert s.check_infeasible_lpbox() >= 0
     assert s.check_infeasible_l2f() == int(g["infeasible_final"])
     xb = s.get_x_sol(g["n"]).ravel()
@@ -187,3 +189,29 @@ def test_reference_output_files(tmp_path, monkeypatch):
     t = lpbox.PyLPboxADMMsolver(0); t.read_File(1, 100, 500); t.solve_init(); t.solve_iter(0, K)
     assert t.get_iter() == s.get_iter() and t.cal_Obj() == s.cal_Obj()
     assert np.array_equal(t._batch.state(0)["x"], s._batch.state(0)["x"])
+
+
+def test_xiters_file_when_the_loop_stops_early(tmp_path, monkeypatch):
+    """print_info == 2 and a solve that ends on the y1/y2 test (ret == 0, LP.cpp:934): the dump holds exactly the iterates
+    that were run -- get_iter() + 1 rows, the last one being the final iterate -- not `j - i` rows padded with zeros
+    (trainer.py's getLabel reads the last row)."""
+    import lpbox
+    g = load_golden("auction_20_60_seed0.npz")
+    d = tmp_path / "instance" / "20_60"
+    d.mkdir(parents=True); (tmp_path / "xiter").mkdir()
+    E_cols = np.repeat(np.arange(g["n"]), np.diff(g["colptr"]))
+    (d / "instance_1_C.txt").write_text("".join("%d,%d,%f\n" % (r + 1, c + 1, 1.0) for r, c in zip(g["rowidx"], E_cols)))
+    (d / "instance_1_b.txt").write_text("".join("%.17g\n" % v for v in g["price"]))
+    monkeypatch.setenv("LPBOX_DATA_ROOT", str(tmp_path))
+    s = lpbox.PyLPboxADMMsolver(2)
+    s.read_File(1, 20, 60); s.solve_init()
+    ret = s.solve_iter(0, 1e4)
+    it = s.get_iter()
+    assert it < 10000 - 1                                    # stopped before max_iters
+    rows = open(tmp_path / "xiter" / "20_60_xiters_1.csv").read().strip().split("\n")
+    assert len(rows) == it + 1 and rows[-1].startswith("Iter%d," % (it + 1))
+    last = np.array([float(v) for v in rows[-1].split(",")[1:]])
+    x = s.get_final_x_sol(s.get_n()).ravel()
+    assert np.abs(last).max() > 0 and np.allclose(last, x, atol=5.1e-7, rtol=0)
+    o = _oracle(g); o.solve_init()
+    assert ret == o.solve_iter(0, 1e4) and it == o.get_iter()

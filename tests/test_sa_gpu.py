@@ -112,3 +112,41 @@ def test_lambda1_search_matches_oracle_per_image():
             assert abs(float(got[k][i]) - ref[k]) <= 1e-3 * max(1.0, abs(ref[k])), (k, i)
         lams.add(ref["lambda1"])
     assert len(lams) > 1            # the images really took different search paths
+
+
+def test_update_G_l2f_matches_the_reference_function():
+    """C2 against the reference itself: tests/golden/sa_l2f_golden.npz holds what the reference's OWN `update_G_l2f`
+    (main_ori.py:376-499, run on CPU with an injected score network, make_golden_sa_l2f.py) computed -- the scores it thresholded
+    after windows 1 and 2, checkpoints of the iterate history of all three windows, its return value and parameters.  Replaying
+    the recorded scores (identical fix decisions by construction) the CUDA driver reproduces history, returned mask and
+    parameters to fp32 accumulation tolerance."""
+    import os
+    from conftest import GOLDEN
+    from lpbox import sparse_attack as sa
+    g = np.load(os.path.join(GOLDEN, "sa_l2f_golden.npz"))
+    model, images, target, eps, G0, B, nw, seg_id = make_problem(seed=3, n_images=1, device="cuda")
+    calls = []
+
+    def replay(x):                                   # x: (3072, 10, 5); the golden scores are in the same variable order
+        s = torch.from_numpy(g["scores"][len(calls)]).to(x.device)
+        calls.append(x)
+        return None, s
+    hist = []
+    G_ret, ip = sa.update_G_l2f(model, images, target, eps, G0.clone(), sa.init_params(), B, nw, replay, reference_return=True, history=hist)
+    assert len(calls) == 2 and len(hist) == 3
+    for w in range(3):
+        ours = hist[w][0][..., [0, 24, 49]]          # (3, 32, 32, 3)
+        ref = torch.from_numpy(g["hist"][w]).cuda()
+        assert _rel(ours, ref) <= 1e-3, (w, float(_rel(ours, ref)))
+    # the policy input of the second call is the second window's history, which already depends on the first rewrite
+    assert _rel(calls[1].reshape(3, 32, 32, 50)[..., 49], torch.from_numpy(g["hist"][1][..., 2]).cuda()) <= 1e-3
+    ref_G = torch.from_numpy(g["G_ret"]).cuda()
+    assert G_ret.shape == ref_G.shape
+    exact = (ref_G == 0.0) | (ref_G == 1.0)         # fixed entries are exact, kept ones carry the iterate
+    assert torch.equal(G_ret[exact], ref_G[exact]) and int(exact.sum()) > 0
+    assert _rel(G_ret, ref_G) <= 1e-3
+    assert np.allclose([ip["cur_step_g"], ip["cur_rho1"], ip["cur_rho2"], ip["cur_rho3"], ip["cur_rho4"]], g["res"], rtol=1e-12)
+    # the default return value is the mask AFTER the last window (documented deviation from the reference's return value)
+    calls.clear()
+    G_last, _ = sa.update_G_l2f(model, images, target, eps, G0.clone(), sa.init_params(), B, nw, replay)
+    assert _rel(G_last[0], torch.from_numpy(g["hist"][2][..., 2]).cuda()) <= 1e-3

@@ -46,3 +46,40 @@ def test_l2f_bookkeeping():
     xs = o2.x_sol()
     assert np.array_equal(xs[idx], vec[idx])
     assert o2.L.sego_get_final_obj(o2.h) == pytest.approx(float(e_plain), abs=30)     # same energy basin
+
+
+@pytest.mark.parametrize("K", [1, 5, 20, 10000])
+def test_full_size_iterates_equal_reference(K):
+    """The oracle at BASELINE configs[2]'s size (375 x 500): bit-identical to the reference binary (SHA-256 of the iterate,
+    tests/golden/seg_full_golden.json from make_golden_seg_full.py)."""
+    import hashlib
+    import json
+    g = json.load(open(os.path.join(GOLDEN, "seg_full_golden.json")))
+    img = synth_image(g["seed"], g["nr"], g["nc"], blobs=g["blobs"])
+    o = OracleSeg()
+    rp, ci, va, b, c = o.build_graph(img)
+    assert len(ci) == g["nnz"] and c == g["c"]
+    o.set_problem(rp, ci, va, b, c); o.init(max_iters=K); o.legacy()
+    x = np.ascontiguousarray(o.state()["x"])
+    assert hashlib.sha256(x.tobytes()).hexdigest() == g["iterates"][str(K)]["sha256"]
+
+
+def test_l2f_windows_equal_reference_binary():
+    """B2 pinned to the reference: the oracle's early-fixing windows (compaction A[keep,keep], b update, post-fix operator
+    patch, history, getters) replay the fix decisions of tests/golden/seg_l2f_golden.npz and reproduce, bit for bit, what the
+    reference binary's OWN `ADMM_bqp_unconstrained_init` + `_l2f` + `get_x_iters_d` + `get_x_sol` + `get_final_obj` produced
+    (make_golden_seg_l2f.py drives them through the functional cv stub)."""
+    g = np.load(os.path.join(GOLDEN, "seg_l2f_golden.npz"))
+    ws = int(g["ws"])
+    o = OracleSeg(); o.set_problem(*o.build_graph(g["img"])); o.init()
+    fixed_any = False
+    for w in range(int(g["windows"])):
+        vec, num = g[f"vec_{w}"], int(g[f"num_{w}"])
+        ret = o.l2f(ws * w, ws * (w + 1), vec if num else np.zeros(1), num)
+        assert ret == int(g[f"ret_{w}"]), w
+        assert o.L.sego_get_n(o.h) == int(g[f"n_{w}"]), w
+        assert np.array_equal(o.x_iters(ws), g[f"xit_{w}"]), w
+        fixed_any |= num > 0
+    assert fixed_any
+    assert np.array_equal(o.x_sol(), g["x_sol"])
+    assert o.L.sego_get_final_obj(o.h) == float(g["final_obj"])

@@ -153,3 +153,59 @@ def test_general_matrix_format_matches_oracle():
         g = bt.graph(0)
         assert np.array_equal(g[1], ci) and np.array_equal(g[2], va_s)
         bt.close()
+
+
+@pytest.fixture(scope="module")
+def gold_full():
+    import json
+    return json.load(open(os.path.join(GOLDEN, "seg_full_golden.json")))
+
+
+@pytest.mark.parametrize("K", [1, 5, 20, 10000])
+def test_full_size_image_matches_reference_binary_and_oracle(gold_full, K):
+    """BASELINE configs[2] at its size: one 375 x 500 image (n = 187 500) through the SHIPPED path -- device graph builder,
+    compact (int16 distance + int8 value) matrix format, 5 CTAs/SM streaming kernel -- after K iterations and at convergence:
+    bit-identical to the reference binary's `ADMM_bqp_unconstrained` (SHA-256 / sum / strided sample of the iterate in
+    tests/golden/seg_full_golden.json, made by make_golden_seg_full.py) and, entry for entry, to the C oracle run here."""
+    import hashlib
+    import lpbox
+    g = gold_full
+    img = synth_image(g["seed"], g["nr"], g["nc"], blobs=g["blobs"])
+    b = lpbox.SegBatch([img])
+    b.set_params(max_iters=K)
+    b.init()
+    b.solve()
+    x = np.ascontiguousarray(b.state(0)["x"])
+    assert x.shape == (g["n"],)
+    ref = g["iterates"][str(K)]
+    assert [float(v) for v in x[::7919][:24]] == ref["sample"]
+    assert float(x.sum()) == ref["sum"] and int((x >= 0.5).sum()) == ref["ones"]
+    assert hashlib.sha256(x.tobytes()).hexdigest() == ref["sha256"]
+    o = OracleSeg()
+    rp, ci, va, bb, c = o.build_graph(img)
+    assert len(ci) == g["nnz"] and c == g["c"]
+    o.set_problem(rp, ci, va, bb, c); o.init(max_iters=K); o.legacy()
+    assert np.array_equal(o.state()["x"], x)
+    assert o.L.sego_get_admm_iters(o.h) == int(b.results()["iters"][0])
+    b.close()
+
+
+def test_l2f_windows_match_reference_binary():
+    """B2 against the reference itself: the CUDA early-fixing windows replay the fix decisions of
+    tests/golden/seg_l2f_golden.npz (made by the reference binary's own _init / _l2f / getters, make_golden_seg_l2f.py) and
+    reproduce its per-window history, return values, assembled binary solution and final energy bit for bit."""
+    import lpbox
+    g = np.load(os.path.join(GOLDEN, "seg_l2f_golden.npz"))
+    ws = int(g["ws"])
+    img = g["img"]
+    s = lpbox.PySegLPboxADMMsolver(0, img.size, 0)
+    s.set_image(img); s.solve_init()
+    for w in range(int(g["windows"])):
+        vec, num = g[f"vec_{w}"], int(g[f"num_{w}"])
+        ret = s.solve_iter_l2f(ws * w, ws * (w + 1), vec if num else np.zeros(1), num)
+        assert ret == int(g[f"ret_{w}"]), w
+        assert s.get_n() == int(g[f"n_{w}"]), w
+        xg = s.get_x_iters_2d(ws)
+        assert xg.shape == g[f"xit_{w}"].shape and np.array_equal(xg, g[f"xit_{w}"]), w
+    assert np.array_equal(s.get_x_sol().ravel(), g["x_sol"])
+    assert s.get_obj() == float(g["final_obj"])
