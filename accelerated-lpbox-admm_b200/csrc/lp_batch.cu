@@ -103,6 +103,9 @@ struct lpbox_batch {
     DevBuf<int> d_work;                         // launch order when pat_smem < max_pat (instances with a spilled image first)
     DevBuf<double> d_park;                      // [grid][PK_COUNT][cap] per-CTA parking lot of the window kernel
     DevBuf<int> d_err;                          // [2]: error flag of the window kernel, result of the shared-window probe
+    DevBuf<float> d_pinp, d_pscore;             // lpbox_batch_solve_l2f: policy input [rows][ws] / scores [rows]
+    DevBuf<L2fMeta> d_meta;
+    int pinp_ws = 0;
     int cap = 0, nwarps = 0;                    // T * EPT and T / 32 of the window-kernel variant
     int max_col_len = 0, tab_len = 0;           // longest column of the batch; entries of the shared 1/diag table (unit case)
     bool fast = false;                          // lpbox_batch_set_mode: tree reductions + FMA (not bit-identical)
@@ -489,7 +492,7 @@ extern "C" void lpbox_batch_destroy(lpbox_batch *h) {
     h->d_x.free_(); h->d_y1.free_(); h->d_y2.free_(); h->d_z1.free_(); h->d_z2.free_(); h->d_b.free_(); h->d_Pd.free_(); h->d_Esq.free_();
     h->d_y3.free_(); h->d_z4.free_(); h->d_f.free_(); h->d_val_r.free_(); h->d_val_c.free_(); h->d_r4v.free_(); h->d_hist.free_();
     h->d_ret_val.free_(); h->d_pow.free_(); h->d_vec.free_(); h->d_pat.free_(); h->d_st.free_(); h->d_left.free_(); h->d_ret_idx.free_();
-    h->d_counter.free_(); h->d_num.free_(); h->d_work.free_(); h->d_park.free_(); h->d_err.free_();
+    h->d_counter.free_(); h->d_num.free_(); h->d_work.free_(); h->d_park.free_(); h->d_err.free_(); h->d_pinp.free_(); h->d_pscore.free_(); h->d_meta.free_();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
@@ -816,7 +819,7 @@ extern "C" int64_t lpbox_batch_policy_input_dev(lpbox_batch *h, int ws, float *o
     CK(cudaMemcpyAsync(h->d_active.p, h->h_active.data(), sizeof(int) * (size_t)na, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_row_off.p, h->h_row_off.data(), sizeof(long long) * (size_t)(na + 1), cudaMemcpyHostToDevice, h->stream));
     dim3 grid((max_rows + 31) / 32, na), block(32, 8);
-    lp_policy_input_kernel<<<grid, block, 0, h->stream>>>(h->bv, h->d_active.p, h->d_row_off.p, ws, out_dev);
+    lp_policy_input_kernel<<<grid, block, 0, h->stream>>>(h->bv, h->d_active.p, h->d_row_off.p, ws, out_dev, nullptr);
     CK(cudaGetLastError());
     h->launches += 1;
     return rows;
@@ -829,7 +832,7 @@ extern "C" int lpbox_batch_apply_scores_dev(lpbox_batch *h, const float *scores_
     CK(cudaMemsetAsync(h->d_num.p, 0, sizeof(int) * (size_t)h->B, h->stream));
     if (na > 0) {
         lp_threshold_kernel<<<na, 256, 0, h->stream>>>(h->bv, h->d_active.p, h->d_row_off.p, scores_dev, hi, lo, min_fix, h->d_vec.p,
-                                                      h->d_off_vec.p, h->d_num.p);
+                                                      h->d_off_vec.p, h->d_num.p, nullptr);
         CK(cudaGetLastError());
         h->launches += 1;
     }
@@ -860,6 +863,72 @@ extern "C" int lpbox_batch_iters_l2f_dev(lpbox_batch *h, int iter_start, int ite
     int active = 0;
     for (int i = 0; i < h->B; ++i) if (!h->h_st[i].done && h->h_st[i].n != 0) active++;
     return active;
+}
+
+
+// ---- the whole early-fixing loop behind one call (LP.trainer:510-545) ------------------------------------------------------
+// for w in range(max_iter / ws): ADMM_lp_iters_l2f(ws*w, ws*(w+1), fix vector of the previous window); stop when every instance
+// returned 1; policy on the window's iterate history; deter_fix_2 (p > hi -> 1, p < lo -> 0, <= min_fix fixes -> none).
+// Everything is enqueued on the handle's stream; the active list and the row offsets of the policy input are built on the
+// device, and the host reads back 24 bytes per window (how many rows the policy has to score).
+extern "C" int lpbox_batch_solve_l2f(lpbox_batch *h, lpbox_policy *policy, int ws, int max_iter, double hi, double lo, int min_fix,
+                                     lpbox_log_row *log, uint8_t *x_bits, int row_stride_bytes, lpbox_l2f_stats *stats) {
+    if (!h || !h->inited || !policy || ws <= 0 || max_iter < ws) { set_err("solve_l2f: bad arguments / call lpbox_batch_init first"); return LPBOX_E_INVALID; }
+    if (ws > h->hist_cap) { set_err("solve_l2f: create the batch with hist_cap >= ws"); return LPBOX_E_INVALID; }
+    if (ws % h->pr.rho_change_step != 0) { set_err("solve_l2f: ws must be a multiple of rho_change_step (LP.cpp:1392-1405)"); return LPBOX_E_INVALID; }
+    CK(cudaSetDevice(h->device));
+    const long long cap_rows = h->off_n[h->B];
+    if (!h->d_pinp.p || h->pinp_ws != ws) {
+        h->d_pinp.free_(); h->d_pscore.free_();
+        CK(h->d_pinp.alloc((size_t)cap_rows * (size_t)ws)); CK(h->d_pscore.alloc((size_t)cap_rows));
+        h->pinp_ws = ws;
+    }
+    if (!h->d_meta.p) CK(h->d_meta.alloc(1));
+    if (!h->d_active.p) { CK(h->d_active.alloc(h->B)); CK(h->d_row_off.alloc((size_t)h->B + 1)); }
+    const int np = (h->max_n + 1) & ~1, mp = (h->max_m + 1) & ~1;
+    const int val_elems = h->all_unit ? 0 : ((h->max_nnz + 1) & ~1);
+    lpbox_l2f_stats st{};
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, h->stream));
+    CK(cudaMemsetAsync(h->d_num.p, 0, sizeof(int) * (size_t)h->B, h->stream));
+    int rc = 0;
+    for (int w = 0; w < max_iter / ws && rc == 0; ++w) {
+        lp_fix_kernel<<<h->B, FIX_T, h->fix_smem, h->stream>>>(h->bv, h->pr, h->d_vec.p, h->d_off_vec.p, h->d_num.p, 1, np, mp, h->max_csr, val_elems);
+        if (w == 0) lp_setup_kernel<<<h->B, 128, 0, h->stream>>>(h->bv, h->pr, 2, 0);     // `if(iter==0) update_expression(0)` (LP.cpp:1380-1381)
+        h->launches += (w == 0) ? 2 : 1;
+        rc = run_window(h, ws * w, ws * (w + 1), 1, 1);
+        if (rc) break;
+        st.windows++;
+        lp_active_scan_kernel<<<1, 1024, 0, h->stream>>>(h->bv, h->d_active.p, h->d_row_off.p, h->d_meta.p);
+        h->launches += 1;
+        L2fMeta meta{};
+        CK(cudaMemcpyAsync(&meta, h->d_meta.p, sizeof(meta), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        h->d2h_bytes += (int64_t)sizeof(meta);
+        if (meta.n_active == 0 || meta.rows == 0) break;
+        dim3 grid((unsigned)((meta.max_n + 31) / 32), (unsigned)meta.n_active), block(32, 8);
+        lp_policy_input_kernel<<<grid, block, 0, h->stream>>>(h->bv, h->d_active.p, h->d_row_off.p, ws, h->d_pinp.p, h->d_meta.p);
+        h->launches += 1;
+        rc = lpbox_policy_forward_dev(policy, (void *)h->stream, h->d_pinp.p, meta.rows, h->d_pscore.p);
+        if (rc) break;
+        st.policy_rows += meta.rows;
+        CK(cudaMemsetAsync(h->d_num.p, 0, sizeof(int) * (size_t)h->B, h->stream));
+        lp_threshold_kernel<<<(unsigned)meta.n_active, 256, 0, h->stream>>>(h->bv, h->d_active.p, h->d_row_off.p, h->d_pscore.p, hi, lo, min_fix,
+                                                                         h->d_vec.p, h->d_off_vec.p, h->d_num.p, h->d_meta.p);
+        h->launches += 1;
+    }
+    if (rc == 0 && cudaGetLastError() != cudaSuccess) { set_err("solve_l2f: kernel launch failed"); rc = LPBOX_E_CUDA; }
+    cudaEventRecord(e1, h->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (rc) return rc;
+    h->last_ms = ms; st.device_ms = ms;
+    rc = sync_states(h); if (rc) return rc;
+    if (stats) *stats = st;
+    if (log || x_bits) return lpbox_batch_results(h, log, x_bits, row_stride_bytes);
+    return 0;
 }
 
 extern "C" int lpbox_batch_config(const lpbox_batch *h, int32_t *out4) {

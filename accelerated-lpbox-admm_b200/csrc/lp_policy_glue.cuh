@@ -7,11 +7,51 @@
 
 namespace lpb {
 
+// Device-side active list of the window loop (LP.trainer:510-535 without a host scan): one CTA compacts the instances that
+// are still running (not done, n > 0) into `active`, their row offsets (exclusive scan of n) into `row_off`, and writes
+// meta = {n_active, total rows, largest n}.  The kernels below take n_active from meta and exit early beyond it, so the host
+// launches them for the worst case and only reads back the 24 bytes of meta per window (to size the policy launch).
+struct L2fMeta { long long n_active, rows, max_n; };
+__global__ void __launch_bounds__(1024) lp_active_scan_kernel(BatchView bv, int *__restrict__ active, long long *__restrict__ row_off,
+                                                              L2fMeta *__restrict__ meta) {
+    __shared__ long long s_rows[1024];
+    __shared__ int s_cnt[1024];
+    __shared__ int s_max;
+    const int tid = threadIdx.x, B = bv.B;
+    const int per = (B + 1023) / 1024;
+    const int beg = min(tid * per, B), end = min(beg + per, B);
+    int cnt = 0, mx = 0;
+    long long rows = 0;
+    for (int i = beg; i < end; ++i) {
+        const InstState &st = bv.st[i];
+        if (!st.done && st.n != 0) { cnt++; rows += st.n; mx = max(mx, st.n); }
+    }
+    s_cnt[tid] = cnt; s_rows[tid] = rows;
+    if (tid == 0) s_max = 0;
+    __syncthreads();
+    atomicMax(&s_max, mx);
+    if (tid == 0) {                                   // 1024 partials: a serial scan is cheap next to a window of ADMM iterations
+        int c = 0; long long r = 0;
+        for (int t = 0; t < 1024; ++t) { const int ct = s_cnt[t]; const long long rt = s_rows[t]; s_cnt[t] = c; s_rows[t] = r; c += ct; r += rt; }
+        meta->n_active = c; meta->rows = r;
+        row_off[c] = r;
+    }
+    __syncthreads();
+    if (tid == 0) meta->max_n = s_max;
+    int c = s_cnt[tid];
+    long long r = s_rows[tid];
+    for (int i = beg; i < end; ++i) {
+        const InstState &st = bv.st[i];
+        if (!st.done && st.n != 0) { active[c] = i; row_off[c] = r; c++; r += st.n; }
+    }
+}
+
 // grid = (ceil(max_rows/32), n_active); block = (32, 8).  Tile transpose through shared memory so that both the reads
 // (along the variable index) and the writes (along the iteration index) are coalesced.
 __global__ void lp_policy_input_kernel(BatchView bv, const int *__restrict__ active, const long long *__restrict__ row_off,
-                                       int ws, float *__restrict__ out) {
+                                       int ws, float *__restrict__ out, const L2fMeta *__restrict__ meta) {
     __shared__ float tile[32][33];
+    if (meta && (long long)blockIdx.y >= meta->n_active) return;       // launched for the worst case (device-side active list)
     const int inst = active[blockIdx.y];
     const InstState *st = bv.st + inst;
     const int n = st->n, n0 = st->n0, cols = min(st->xit_cols, min(ws, bv.hist_cap));
@@ -36,8 +76,9 @@ __global__ void lp_policy_input_kernel(BatchView bv, const int *__restrict__ act
 // one CTA per active instance: vec[i] = 1 if p > hi, 0 if p < lo, else -1; num = #fixed, or 0 when #fixed <= min_fix
 __global__ void lp_threshold_kernel(BatchView bv, const int *__restrict__ active, const long long *__restrict__ row_off,
                                     const float *__restrict__ scores, double hi, double lo, int min_fix, double *__restrict__ vec,
-                                    long long *__restrict__ off_vec, int *__restrict__ num) {
+                                    long long *__restrict__ off_vec, int *__restrict__ num, const L2fMeta *__restrict__ meta) {
     __shared__ int s_cnt;
+    if (meta && (long long)blockIdx.x >= meta->n_active) return;
     const int inst = active[blockIdx.x];
     const int n = bv.st[inst].n;
     const float *p = scores + row_off[blockIdx.x];

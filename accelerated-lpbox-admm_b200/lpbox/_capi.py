@@ -30,6 +30,11 @@ class LogRow(C.Structure):
                 ("cur_bin_obj", C.c_double), ("n_left", C.c_int32), ("infeasible", C.c_int32)]
 
 
+class L2fStats(C.Structure):
+    """lpbox_l2f_stats."""
+    _fields_ = [("windows", C.c_int32), ("policy_rows", C.c_int64), ("device_ms", C.c_double)]
+
+
 LOG_DTYPE = np.dtype([("iters", "<i4"), ("status", "<i4"), ("cg_iters", "<i8"), ("obj", "<f8"), ("cur_bin_obj", "<f8"),
                       ("n_left", "<i4"), ("infeasible", "<i4")])
 assert LOG_DTYPE.itemsize == C.sizeof(LogRow)
@@ -53,6 +58,7 @@ SIGNATURES = {
     "lpbox_batch_iters": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "lpbox_batch_iters_l2f": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "lpbox_batch_solve": (C.c_int, [_vp, C.c_int, _vp]),
+    "lpbox_batch_solve_l2f": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, _vp, _vp, C.c_int, C.POINTER(L2fStats)]),
     "lpbox_batch_size": (C.c_int, [_vp]),
     "lpbox_batch_get_n": (C.c_int, [_vp, C.c_int]),
     "lpbox_batch_get_m": (C.c_int, [_vp, C.c_int]),

@@ -17,9 +17,11 @@ def solve_l2f(batch, score_fn, ws=100, max_iter=10000, tokens=20, hi=0.9, lo=Non
     score_fn: callable (rows, tokens, ws // tokens) float32 CUDA tensor -> (rows,) or (rows, 1) sigmoid scores, e.g.
     `lambda x: net(x)[1]` with a `lpbox.policy.GraphAttentionEncoder`.  Returns (log rows, packed bits, stats dict).
     """
-    import torch
     if lo is None:
         lo = 1 - hi                                             # `data[i] < 1 - C` (LP.trainer:124)
+    if getattr(score_fn, "h", None) is not None and hasattr(score_fn, "T") and score_fn.T * 5 == ws and tokens == score_fn.T:
+        return solve_l2f_native(batch, score_fn, ws=ws, max_iter=max_iter, hi=hi, lo=lo, min_fix=min_fix)
+    import torch
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     L, h = batch.L, batch.h
     check(L.lpbox_batch_set_stream(h, torch.cuda.current_stream(dev).cuda_stream), "set_stream")
@@ -46,3 +48,19 @@ def solve_l2f(batch, score_fn, ws=100, max_iter=10000, tokens=20, hi=0.9, lo=Non
     torch.cuda.current_stream(dev).synchronize()
     log, bits = batch.results()
     return log, bits, stats
+
+
+def solve_l2f_native(batch, policy, ws=100, max_iter=10000, hi=0.9, lo=0.1, min_fix=10):
+    """The same loop entirely behind the C ABI (`lpbox_batch_solve_l2f`): `policy` is a `lpbox.policy_kernel.PolicyKernel`
+    (the bf16 tcgen05 network); window kernel, device-side active list, policy input gather, policy, thresholds and
+    compaction are enqueued by the library on its own stream -- the host reads 24 bytes per window."""
+    from . import _capi
+    import ctypes as C
+    L, h = batch.L, batch.h
+    log = np.zeros(batch.B, dtype=_capi.LOG_DTYPE)
+    stride = (int(batch.org_n.max()) + 7) // 8
+    bits = np.zeros((batch.B, stride), dtype=np.uint8)
+    st = _capi.L2fStats()
+    check(L.lpbox_batch_solve_l2f(h, policy.h, int(ws), int(max_iter), float(hi), float(lo), int(min_fix), _capi.ptr(log), _capi.ptr(bits), stride,
+                                  C.byref(st)), "solve_l2f")
+    return log, bits, dict(windows=int(st.windows), policy_rows=int(st.policy_rows), window_ms=float(st.device_ms), native=True)

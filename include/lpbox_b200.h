@@ -133,6 +133,23 @@ int lpbox_batch_apply_scores_dev(lpbox_batch *h, const float *scores_dev, double
  * was not called since the last window).  Returns the number of instances still active afterwards. */
 int lpbox_batch_iters_l2f_dev(lpbox_batch *h, int iter_start, int iter_end);
 
+/* The whole early-fixing loop of the reference driver (LP.trainer:510-545) in one call: windows of `ws` iterations
+ * (ADMM_lp_iters_l2f), after each window the policy scores every free variable of every running instance from the window's
+ * iterate history (the reshape of LP.trainer:524-530), deter_fix_2 (LP.trainer:101-135: p > hi -> 1, p < lo -> 0; instances
+ * with <= min_fix fixes get none, :533-535) and the compaction of the next window's prologue -- all on the device, on the
+ * handle's stream.  The active list and the policy-input row offsets are built on the device; the host reads 24 bytes per
+ * window.  `policy`: lpbox_policy_create (declared below).  Create the batch with hist_cap >= ws; ws must be a multiple of
+ * rho_change_step.  log / x_bits as lpbox_batch_results (either may be NULL).
+ * Replaces the Python loop around solve_iter_l2f / get_x_iters_2d / deter_fix_2 (LP.trainer:510-545). */
+typedef struct lpbox_policy lpbox_policy;
+typedef struct {
+    int32_t windows;        /* windows run */
+    int64_t policy_rows;    /* variable-windows scored by the policy */
+    double  device_ms;      /* CUDA-event time of the whole loop on the handle's stream */
+} lpbox_l2f_stats;
+int lpbox_batch_solve_l2f(lpbox_batch *h, lpbox_policy *policy, int ws, int max_iter, double hi, double lo, int min_fix,
+                          lpbox_log_row *log, uint8_t *x_bits, int row_stride_bytes, lpbox_l2f_stats *stats);
+
 /* getters; `i` = instance index ---------------------------------------------------------------------------------- */
 int lpbox_batch_size(const lpbox_batch *h);
 int lpbox_batch_get_n(lpbox_batch *h, int i);            /* get_n()      LP.h:392 */
