@@ -106,6 +106,7 @@ struct lpbox_batch {
     DevBuf<float> d_pinp, d_pscore;             // lpbox_batch_solve_l2f: policy input [rows][ws] / scores [rows]
     DevBuf<L2fMeta> d_meta;
     int pinp_ws = 0;
+    bool guard = false;                         // lpbox_batch_set_fix_guard: feasibility guard on fix-to-one decisions (not in the reference)
     int cap = 0, nwarps = 0;                    // T * EPT and T / 32 of the window-kernel variant
     int max_col_len = 0, tab_len = 0;           // longest column of the batch; entries of the shared 1/diag table (unit case)
     bool fast = false;                          // lpbox_batch_set_mode: tree reductions + FMA (not bit-identical)
@@ -508,6 +509,14 @@ extern "C" int lpbox_batch_set_mode(lpbox_batch *h, int mode) {
     return 0;
 }
 
+// Optional extension (off by default = the reference's deter_fix_2): fix-to-one proposals are only applied where the fixed
+// part of the solution stays feasible (see lp_guard_kernel).
+extern "C" int lpbox_batch_set_fix_guard(lpbox_batch *h, int on) {
+    if (!h) return LPBOX_E_INVALID;
+    h->guard = on != 0;
+    return 0;
+}
+
 extern "C" int lpbox_batch_set_params(lpbox_batch *h, const lpbox_params *p, int variant) {
     if (!h || !p) return LPBOX_E_INVALID;
     if (p->history_size < 2 || p->history_size > 16 || p->history_size != floor(p->history_size)) { set_err("history_size must be an integer in [2,16]"); return LPBOX_E_INVALID; }
@@ -676,6 +685,13 @@ extern "C" int lpbox_batch_get_state(lpbox_batch *h, int i, double *x, double *y
     return rc ? LPBOX_E_CUDA : 0;
 }
 
+// left_idx (LP.h:246): original ids of the variables that are still free, n_cur entries (diagnostics of the early-fixing loop)
+extern "C" int lpbox_batch_get_left_idx(lpbox_batch *h, int i, int32_t *out) {
+    CHK_I(h, i);
+    if (!out) return LPBOX_E_INVALID;
+    return d2h(h, out, h->d_left.p + h->off_n[i], sizeof(int) * (size_t)h->h_st[i].n) ? LPBOX_E_CUDA : h->h_st[i].n;
+}
+
 extern "C" int lpbox_batch_get_final_x_sol(lpbox_batch *h, int i, double *out) {
     CHK_I(h, i);
     if (!out) return LPBOX_E_INVALID;
@@ -835,6 +851,12 @@ extern "C" int lpbox_batch_apply_scores_dev(lpbox_batch *h, const float *scores_
                                                       h->d_off_vec.p, h->d_num.p, nullptr);
         CK(cudaGetLastError());
         h->launches += 1;
+        if (h->guard) {
+            lp_guard_kernel<<<na, 256, sizeof(unsigned long long) * (size_t)h->max_m, h->stream>>>(h->bv, h->d_active.p, h->d_row_off.p, scores_dev, min_fix,
+                                                                                          h->d_vec.p, h->d_num.p, nullptr);
+            CK(cudaGetLastError());
+            h->launches += 1;
+        }
     }
     h->dev_fix_pending = true;
     return na;
@@ -917,6 +939,11 @@ extern "C" int lpbox_batch_solve_l2f(lpbox_batch *h, lpbox_policy *policy, int w
         lp_threshold_kernel<<<(unsigned)meta.n_active, 256, 0, h->stream>>>(h->bv, h->d_active.p, h->d_row_off.p, h->d_pscore.p, hi, lo, min_fix,
                                                                          h->d_vec.p, h->d_off_vec.p, h->d_num.p, h->d_meta.p);
         h->launches += 1;
+        if (h->guard) {
+            lp_guard_kernel<<<(unsigned)meta.n_active, 256, sizeof(unsigned long long) * (size_t)h->max_m, h->stream>>>(
+                h->bv, h->d_active.p, h->d_row_off.p, h->d_pscore.p, min_fix, h->d_vec.p, h->d_num.p, h->d_meta.p);
+            h->launches += 1;
+        }
     }
     if (rc == 0 && cudaGetLastError() != cudaSuccess) { set_err("solve_l2f: kernel launch failed"); rc = LPBOX_E_CUDA; }
     cudaEventRecord(e1, h->stream);

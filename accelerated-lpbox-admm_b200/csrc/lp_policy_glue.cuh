@@ -97,4 +97,57 @@ __global__ void lp_threshold_kernel(BatchView bv, const int *__restrict__ active
     if (threadIdx.x == 0) num[inst] = (s_cnt <= min_fix) ? 0 : s_cnt;
 }
 
+// Optional feasibility guard for fix-to-one decisions (NOT in the reference, whose deter_fix_2 trusts the policy; off by
+// default).  One CTA per active instance, after lp_threshold_kernel: a variable proposed for x = 1 is kept only if, in EVERY
+// constraint row it touches, (i) the row still has capacity for it (f_i - E_ij >= 0 with the current right-hand side, which
+// already accounts for earlier fixes, LP.cpp:1276-1278) and (ii) it is the highest-scored proposal of that row (ties: lower
+// index).  Two accepted variables can then never share a row, so the fixed part of the solution satisfies E x <= f by
+// construction; losers fall back to "keep" (-1) and may be proposed again in a later window.  Proposals for x = 0 are always
+// feasible for <= constraints with non-negative E and are left alone.  The <= min_fix rule is applied again afterwards.
+__global__ void __launch_bounds__(256) lp_guard_kernel(BatchView bv, const int *__restrict__ active, const long long *__restrict__ row_off,
+                                                       const float *__restrict__ scores, int min_fix, double *__restrict__ vec,
+                                                       int *__restrict__ num, const L2fMeta *__restrict__ meta) {
+    extern __shared__ unsigned long long s_best[];       // [m] best proposal key per row
+    __shared__ int s_cnt;
+    if (meta && (long long)blockIdx.x >= meta->n_active) return;
+    const int inst = active[blockIdx.x];
+    const InstState *st = bv.st + inst;
+    const int n = st->n, m = st->m;
+    if (num[inst] == 0) return;                          // nothing proposed (or already below the min_fix rule)
+    const CsrLayout PL = csr_layout(st->n0, st->m0, st->nnz0);
+    const unsigned char *pat = bv.csr + bv.off_csr[inst];
+    const u16 *colptr = reinterpret_cast<const u16 *>(pat + PL.o_colptr);
+    const u16 *rowidx = reinterpret_cast<const u16 *>(pat + PL.o_rowidx);
+    const long long ov = bv.off_val ? bv.off_val[inst] : 0;
+    const bool unit = st->unit != 0;
+    const float *p = scores + row_off[blockIdx.x];
+    double *v = vec + bv.off_n[inst];
+    const double *f = bv.f + bv.off_m[inst];
+    for (int i = threadIdx.x; i < m; i += blockDim.x) s_best[i] = 0ull;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    auto key = [&](int j) { return ((unsigned long long)__float_as_uint(p[j]) << 32) | (unsigned long long)(0xffffffffu - (unsigned)j); };   // scores are in (0, 1): bit order = value order
+    for (int j = threadIdx.x; j < n; j += blockDim.x)
+        if (v[j] == 1.0) { const unsigned long long k = key(j); for (int q = colptr[j]; q < colptr[j + 1]; ++q) atomicMax(&s_best[rowidx[q]], k); }
+    __syncthreads();
+    int c = 0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        double t = v[j];
+        if (t == 1.0) {
+            const unsigned long long k = key(j);
+            bool ok = true;
+            for (int q = colptr[j]; q < colptr[j + 1] && ok; ++q) {
+                const int i = rowidx[q];
+                const double e = unit ? 1.0 : bv.val_c[ov + q];
+                ok = (s_best[i] == k) && (f[i] - e >= 0.0);
+            }
+            if (!ok) { t = -1.0; v[j] = t; }
+        }
+        if (t == 1.0 || t == 0.0) c++;
+    }
+    atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) num[inst] = (s_cnt <= min_fix) ? 0 : s_cnt;
+}
+
 }  // namespace lpb

@@ -53,6 +53,7 @@ SIGNATURES = {
     "lpbox_batch_destroy": (None, [_vp]),
     "lpbox_batch_set_params": (C.c_int, [_vp, C.POINTER(Params), C.c_int]),
     "lpbox_batch_set_mode": (C.c_int, [_vp, C.c_int]),
+    "lpbox_batch_set_fix_guard": (C.c_int, [_vp, C.c_int]),
     "lpbox_batch_init": (C.c_int, [_vp, _vp]),
     "lpbox_batch_set_record_history": (C.c_int, [_vp, C.c_int]),
     "lpbox_batch_iters": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
@@ -67,6 +68,7 @@ SIGNATURES = {
     "lpbox_batch_cal_obj": (C.c_double, [_vp, C.c_int]),
     "lpbox_batch_get_cur_bin_obj": (C.c_double, [_vp, C.c_int]),
     "lpbox_batch_get_x_sol": (C.c_int, [_vp, C.c_int, _vp]),
+    "lpbox_batch_get_left_idx": (C.c_int, [_vp, C.c_int, _vp]),
     "lpbox_batch_get_final_x_sol": (C.c_int, [_vp, C.c_int, _vp]),
     "lpbox_batch_get_x_iters": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "lpbox_batch_check_infeasible_lpbox": (C.c_int, [_vp, C.c_int]),

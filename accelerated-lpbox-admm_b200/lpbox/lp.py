@@ -122,6 +122,11 @@ class LPBatch:
         """"parity" (default): bit-identical to the reference; "fast": tree reductions + FMA, NOT bit-identical (opt-in)."""
         check(self.L.lpbox_batch_set_mode(self.h, {"parity": 0, "fast": 1}[mode]), "set_mode")
 
+    def set_fix_guard(self, on=True):
+        """Optional extension (off by default = the reference): only apply fix-to-one decisions that keep the fixed part of the
+        solution feasible (csrc/lp_policy_glue.cuh: lp_guard_kernel)."""
+        check(self.L.lpbox_batch_set_fix_guard(self.h, 1 if on else 0), "set_fix_guard")
+
     def init(self, x0=None):
         x0 = None if x0 is None else _f64(np.concatenate([np.asarray(v) for v in x0]))
         return check(self.L.lpbox_batch_init(self.h, ptr(x0)), "init")

@@ -479,12 +479,14 @@ def run_l2f(ctx):
     score = PolicyKernel(net, device=ctx.local, chunk_rows=32768)      # bf16 tcgen05 kernels (csrc/policy_kernels.cu)
     ref = lpbox.LPBatch(probs, device=ctx.local, hist_cap=0); ref.init(); plog = ref.solve(MAX_ITERS); ref.close()
 
-    def step():
+    def step(guard=not a.l2f_no_guard, max_iter=a.l2f_max_iter):
         lb = lpbox.LPBatch(probs, device=ctx.local, hist_cap=100)
+        if guard:
+            lb.set_fix_guard(True)
         lb.init()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        llog, bits, st = lpbox.solve_l2f(lb, score, ws=100, max_iter=10000)
+        llog, bits, st = lpbox.solve_l2f(lb, score, ws=100, max_iter=max_iter)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         h2d, d2h = lb.h2d_bytes(), lb.d2h_bytes()
@@ -509,6 +511,12 @@ def run_l2f(ctx):
         ctx.barrier(); e2e_ms += 1e3 * (time.perf_counter() - t1)
     e2e_ms /= max(a.e2e_steps, 1)
     gap = (llog["obj"] - plog["obj"]) / np.abs(plog["obj"])
+    # the reference driver's own settings for comparison (LP.trainer:510-545: 1e4 iterations, deter_fix_2 without a guard)
+    rms, rlog, rst, _, _ = step(guard=False, max_iter=10000)
+    rgap = (rlog["obj"] - plog["obj"]) / np.abs(plog["obj"])
+    ref_settings = {"instances_per_sec_this_gpu": B / (rms / 1e3), "objective_gap_mean_vs_plain": float(rgap.mean()),
+                    "infeasible_instances_this_gpu": int((rlog["infeasible"] > 0).sum()), "unconverged_instances_this_gpu": int((rlog["status"] == 0).sum()),
+                    "note": "max_iter 1e4 as in LP.trainer:510, no feasibility guard: instances still running after 100 windows are rounded as they are"}
     (dev_ms, e2e_ms), (tot_B, infeas, gapsum, rows) = ctx.reduce([dev_ms, e2e_ms], [float(B), float((llog["infeasible"] > 0).sum()), float(gap.sum()), float(st["policy_rows"])])
     line = None
     if ctx.rank == 0:
@@ -516,14 +524,16 @@ def run_l2f(ctx):
         line = base_line(ctx, "admm_instances_per_sec", UNIT, tot_B / (ms_per_step / 1e3), ms_per_step, "f64 (ADMM) + bf16 (policy)",
                          f"lp_l2f / configs[1]: {int(tot_B)} synthetic auctions (j={N_ITEMS}, k={N_BIDS}) over {ctx.world} GPU(s) with MHA early fixing: "
                          "windows of 100 iterations, GraphAttentionEncoder policy on the bf16 tcgen05 kernels, deter_fix_2 thresholds 0.9/0.1, "
-                         "device-resident window -> policy -> compaction loop (approximate solutions: see `quality`)",
+                         "device-resident window -> policy -> compaction loop behind lpbox_batch_solve_l2f (approximate solutions: see `quality`)"
+                         + f"; window loop capped at {a.l2f_max_iter} iterations" + ("" if a.l2f_no_guard else "; feasibility guard on fix-to-one decisions ON (extension, not in the reference)"),
                          {"instances_per_gpu": B, "parallelism": f"instances sharded over {ctx.world} GPU(s), no data-path collective"})
         flops = rows * 17.56e6
         line.update({"e2e": {"value": tot_B / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": a.e2e_steps,
                              "note": "wall clock incl. batch creation from host arrays and the read-back of the results"},
                      "gpu_launches": int(st["windows"] * 4 + (score.launch_count() - l0)), "clocks": clocks,
                      "quality": {"objective_gap_mean_vs_plain": gapsum / tot_B, "infeasible_instances": int(infeas), "windows": st["windows"],
-                                 "mean_admm_iters": float(llog["iters"].mean()), "mean_admm_iters_plain": float(plog["iters"].mean())},
+                                 "mean_admm_iters": float(llog["iters"].mean()), "mean_admm_iters_plain": float(plog["iters"].mean()),
+                                 "max_iter": a.l2f_max_iter, "fix_guard": not a.l2f_no_guard, "with_reference_driver_settings": ref_settings},
                      "roofline": {"bound": "tensor", "achieved": flops / 1e12 / (ms_per_step / 1e3) / ctx.world, "peak": ctx.peaks["tf"], "unit": "TFLOP/s",
                                   "frac": flops / 1e12 / (ms_per_step / 1e3) / ctx.world / ctx.peaks["tf"], "traffic": None,
                                   "note": "policy flops (17.56 MFLOP per variable-window) over the WHOLE step (ADMM windows included), per GPU; "
@@ -752,6 +762,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="units per GPU per step (weak) or in total (strong); 0 = the configuration's default")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--sa-iters", type=int, default=50)
+    ap.add_argument("--l2f-no-guard", action="store_true", help="lp_l2f: switch the feasibility guard on fix-to-one decisions off (the guard is an extension, not in the reference)")
+    ap.add_argument("--l2f-max-iter", type=int, default=20000, help="lp_l2f: iteration cap of the window loop (the solver's own cap, LP.cpp:498; the reference trainer stops at 1e4)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -150,6 +150,12 @@ typedef struct {
 int lpbox_batch_solve_l2f(lpbox_batch *h, lpbox_policy *policy, int ws, int max_iter, double hi, double lo, int min_fix,
                           lpbox_log_row *log, uint8_t *x_bits, int row_stride_bytes, lpbox_l2f_stats *stats);
 
+/* Optional extension, OFF by default (= the reference, whose deter_fix_2 trusts the policy): when on, a fix-to-one proposal is
+ * only applied if every constraint row it touches still has capacity for it under the current right-hand side and it is the
+ * best-scored proposal of that row, so the fixed part of the solution satisfies E x <= f by construction; rejected proposals
+ * stay free.  Applies to lpbox_batch_apply_scores_dev and lpbox_batch_solve_l2f. */
+int lpbox_batch_set_fix_guard(lpbox_batch *h, int on);
+
 /* getters; `i` = instance index ---------------------------------------------------------------------------------- */
 int lpbox_batch_size(const lpbox_batch *h);
 int lpbox_batch_get_n(lpbox_batch *h, int i);            /* get_n()      LP.h:392 */
@@ -163,6 +169,8 @@ double lpbox_batch_get_cur_bin_obj(lpbox_batch *h, int i); /* get_curBinObj() LP
 int lpbox_batch_get_x_sol(lpbox_batch *h, int i, double *out);
 /* get_final_x_sol(): relaxed x of the current (compacted) problem, n entries  (LP.cpp:1668-1685) */
 int lpbox_batch_get_final_x_sol(lpbox_batch *h, int i, double *out);
+/* left_idx (LP.h:246): original ids of the variables still free, n entries; returns n */
+int lpbox_batch_get_left_idx(lpbox_batch *h, int i, int32_t *out);
 /* get_x_iters_d(ws): row-major (n_cur x ws) window history  (LP.cpp:1616-1627).  Returns n_cur. */
 int lpbox_batch_get_x_iters(lpbox_batch *h, int i, int ws, double *out);
 int lpbox_batch_check_infeasible_lpbox(lpbox_batch *h, int i);  /* LP.cpp:1577-1591 */
