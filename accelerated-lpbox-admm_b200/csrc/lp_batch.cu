@@ -265,6 +265,103 @@ static int sync_states(lpbox_batch *h) {
     return 0;
 }
 
+
+// ---- bank-aware slot assignment (host, per instance) -------------------------------------------------------------------------
+// The window kernel gathers 8-byte operands from shared memory with addresses that depend on the sparsity pattern; a 64-bit
+// access is served half a warp at a time and two lanes of a half-warp collide when their operands sit in the same 8-byte bank
+// pair (slot mod 16) at different addresses.  Which slot a row / column occupies is free as far as the arithmetic goes (only
+// the order INSIDE each sparse product is the reference's), so it is chosen to avoid collisions:
+//   * columns are grouped 16 at a time (= the lanes of one half-warp) in descending length such that the members of a group
+//     have distinct chain-major staging banks ((2 (j & 3) + (j >> 2)) mod 16, csrc/lp_types.h chain_stride): the scattered
+//     staging stores of the reduction operands become conflict-free;
+//   * inside every group of 16 columns (rows) the positions are permuted so that the columns (rows) that one half-warp gathers
+//     in one step of E v (E^T w) fall into different bank pairs as far as a greedy assignment manages (two sweeps).
+// Group membership fixes which operands are gathered together; the position inside the group only moves the bank -- so the two
+// permutation problems (columns for E v, rows for E^T w) are independent.
+namespace {
+struct GatherSets {          // for one orientation: sets of inner items gathered together by one half-warp in one step
+    std::vector<int> set_ptr, set_mem;          // members (distinct inner items) of set s: set_mem[set_ptr[s] .. set_ptr[s+1])
+    std::vector<int> of_ptr, of_set;            // sets that contain inner item x: of_set[of_ptr[x] .. of_ptr[x+1])
+};
+// outer items in slot order `order` (groups of 16 consecutive slots gather together), lists[o] = inner items of outer item o ascending
+static void build_sets(const std::vector<int> &order, const int *ptr, const int32_t *idx, int n_inner, GatherSets &G) {
+    G.set_ptr.assign(1, 0); G.set_mem.clear();
+    const int n_outer = (int)order.size();
+    std::vector<int> tmp;
+    for (int g0 = 0; g0 < n_outer; g0 += 16) {
+        const int g1 = std::min(g0 + 16, n_outer);
+        int W = 0;
+        for (int s = g0; s < g1; ++s) W = std::max(W, ptr[order[s] + 1] - ptr[order[s]]);
+        for (int k = 0; k < W; ++k) {
+            tmp.clear();
+            for (int s = g0; s < g1; ++s) { const int o = order[s]; if (ptr[o] + k < ptr[o + 1]) tmp.push_back(idx[ptr[o] + k]); }
+            std::sort(tmp.begin(), tmp.end()); tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+            if (tmp.size() < 2) continue;                                   // a single address can not collide
+            G.set_mem.insert(G.set_mem.end(), tmp.begin(), tmp.end());
+            G.set_ptr.push_back((int)G.set_mem.size());
+        }
+    }
+    const int ns = (int)G.set_ptr.size() - 1;
+    G.of_ptr.assign(n_inner + 1, 0);
+    for (int v : G.set_mem) G.of_ptr[v + 1]++;
+    for (int x = 0; x < n_inner; ++x) G.of_ptr[x + 1] += G.of_ptr[x];
+    G.of_set.resize(G.set_mem.size());
+    std::vector<int> fill(G.of_ptr.begin(), G.of_ptr.end() - 1);
+    for (int s2 = 0; s2 < ns; ++s2) for (int q = G.set_ptr[s2]; q < G.set_ptr[s2 + 1]; ++q) G.of_set[fill[G.set_mem[q]]++] = s2;
+}
+// permutes the members of every full group of 16 in `order` (slot order of the INNER items) to lower the bank collisions of G's sets
+static void place_in_groups(std::vector<int> &order, const GatherSets &G, int sweeps) {
+    const int n = (int)order.size();
+    const int ns = (int)G.set_ptr.size() - 1;
+    if (ns == 0 || n < 16) return;
+    std::vector<unsigned char> cnt((size_t)ns * 16, 0);
+    std::vector<int> pos(n, -1);                                           // item -> position (0..15) inside its group, -1 = not placed
+    auto add = [&](int x, int p, int d) { for (int q = G.of_ptr[x]; q < G.of_ptr[x + 1]; ++q) cnt[(size_t)G.of_set[q] * 16 + p] += d; };
+    for (int sw = 0; sw < sweeps; ++sw)
+        for (int g0 = 0; g0 + 16 <= n; g0 += 16) {
+            int mem[16];
+            for (int t = 0; t < 16; ++t) { mem[t] = order[g0 + t]; if (pos[mem[t]] >= 0) { add(mem[t], pos[mem[t]], -1); pos[mem[t]] = -1; } }
+            std::stable_sort(mem, mem + 16, [&](int a, int b) { return G.of_ptr[a + 1] - G.of_ptr[a] > G.of_ptr[b + 1] - G.of_ptr[b]; });
+            bool used[16] = {false};
+            for (int t = 0; t < 16; ++t) {
+                const int x = mem[t];
+                int cost[16] = {0};
+                for (int q = G.of_ptr[x]; q < G.of_ptr[x + 1]; ++q) { const unsigned char *c = &cnt[(size_t)G.of_set[q] * 16]; for (int p = 0; p < 16; ++p) cost[p] += c[p]; }
+                int best = -1;
+                for (int p = 0; p < 16; ++p) if (!used[p] && (best < 0 || cost[p] < cost[best])) best = p;
+                used[best] = true; pos[x] = best; add(x, best, +1);
+            }
+            for (int t = 0; t < 16; ++t) order[g0 + pos[mem[t]]] = mem[t];
+        }
+}
+// descending-length grouping of the columns, 16 at a time, with distinct staging banks inside a group where columns of (almost)
+// the same length allow it
+static void group_columns(const std::vector<int> &cl, std::vector<int> &order) {
+    const int n = (int)cl.size();
+    std::vector<int> sorted(n);
+    for (int j = 0; j < n; ++j) sorted[j] = j;
+    std::stable_sort(sorted.begin(), sorted.end(), [&](int a, int b) { return cl[a] > cl[b]; });
+    std::vector<char> taken(n, 0);
+    order.clear(); order.reserve(n);
+    int first = 0;
+    while ((int)order.size() < n) {
+        while (first < n && taken[first]) ++first;
+        const int Lmax = cl[sorted[first]];
+        bool used[16] = {false};
+        int got = 0;
+        const size_t base = order.size();
+        for (int q = first; q < n && got < 16 && cl[sorted[q]] >= Lmax - 1; ++q) {
+            if (taken[q]) continue;
+            const int j = sorted[q], c = (2 * (j & 3) + (j >> 2)) & 15;
+            if (used[c]) continue;
+            used[c] = true; taken[q] = 1; order.push_back(j); ++got;
+        }
+        for (int q = first; q < n && got < 16; ++q) if (!taken[q]) { taken[q] = 1; order.push_back(sorted[q]); ++got; }   // no distinct bank left
+        std::stable_sort(order.begin() + base, order.end(), [&](int a, int b) { return cl[a] > cl[b]; });
+    }
+}
+}  // namespace
+
 static lpbox_batch *batch_create_impl(int device, int B, const int32_t *m, const int32_t *n, const int32_t *colptr_all,
                                       const int32_t *rowidx_all, const double *val_all, const double *b_all,
                                       const double *f_all, int hist_cap);
@@ -316,26 +413,44 @@ static lpbox_batch *batch_create_impl(int device, int B, const int32_t *m, const
         b_in_off[i + 1] = b_in_off[i] + n[i]; f_in_off[i + 1] = f_in_off[i] + m[i];
         h->max_n = std::max(h->max_n, n[i]); h->max_m = std::max(h->max_m, m[i]); h->max_nnz = std::max(h->max_nnz, h->nnz0[i]);
     }
-    // (2) per instance, in parallel on the host cores: SpMV work assignment -- slots sorted by descending stored length
-    //     (stable) -- and the capacities of the sliced-ELL image
+    // (2) per instance, in parallel on the host cores: SpMV work assignment -- slots in descending stored length, bank-aware
+    //     (see above; LPBOX_PLAIN_SLOTS=1 keeps the plain stable sort) -- and the capacities of the sliced-ELL image
     std::atomic<int> err1(0);
+    static const bool plain_slots = getenv("LPBOX_PLAIN_SLOTS") != nullptr;
     host_parallel_for(B, [&](int i) {
-        const int ni = n[i], mi = m[i];
+        const int ni = n[i], mi = m[i], nz = h->nnz0[i];
         const int32_t *cp = colptr_all + h->h_cp_off[i];
         const int32_t *ri = rowidx_all + h->h_nnz_off[i];
-        std::vector<int> rl(mi, 0), cl(ni), ord(mi);
-        for (int k = 0; k < h->nnz0[i]; ++k) { if (ri[k] < 0 || ri[k] >= mi) { err1.store(1); return; } rl[ri[k]]++; }
+        std::vector<int> rl(mi, 0), cl(ni), rord(mi), cord;
+        for (int k = 0; k < nz; ++k) { if (ri[k] < 0 || ri[k] >= mi) { err1.store(1); return; } rl[ri[k]]++; }
         for (int j = 0; j < ni; ++j) cl[j] = cp[j + 1] - cp[j];
-        for (int r = 0; r < mi; ++r) ord[r] = r;
-        std::stable_sort(ord.begin(), ord.end(), [&](int a, int b2) { return rl[a] > rl[b2]; });
+        for (int r = 0; r < mi; ++r) rord[r] = r;
+        std::stable_sort(rord.begin(), rord.end(), [&](int a, int b2) { return rl[a] > rl[b2]; });
+        if (plain_slots) {
+            cord.resize(ni);
+            for (int j = 0; j < ni; ++j) cord[j] = j;
+            std::stable_sort(cord.begin(), cord.end(), [&](int a, int b2) { return cl[a] > cl[b2]; });
+        } else {
+            group_columns(cl, cord);
+            // row-compressed copy of the pattern (rows gather columns in E v)
+            std::vector<int> rp(mi + 1, 0), cix(nz);
+            for (int r = 0; r < mi; ++r) rp[r + 1] = rp[r] + rl[r];
+            { std::vector<int> fill(rp.begin(), rp.end() - 1); for (int j = 0; j < ni; ++j) for (int k = cp[j]; k < cp[j + 1]; ++k) cix[fill[ri[k]]++] = j; }
+            GatherSets gs;
+            build_sets(rord, rp.data(), cix.data(), ni, gs);         // E v: half-warps of rows gather columns -> place the columns
+            place_in_groups(cord, gs, 2);
+            std::vector<int> cpi(cp, cp + ni + 1);
+            build_sets(cord, cpi.data(), ri, mi, gs);                // E^T w: half-warps of columns gather rows -> place the rows
+            place_in_groups(rord, gs, 2);
+        }
         rperm_all[i].resize(mi);
-        for (int r = 0; r < mi; ++r) { rperm_all[i][r] = (uint16_t)ord[r]; if ((r & 31) == 0) rcap[i] += rl[ord[r]]; }
-        ord.resize(ni);
-        for (int j = 0; j < ni; ++j) ord[j] = j;
-        std::stable_sort(ord.begin(), ord.end(), [&](int a, int b2) { return cl[a] > cl[b2]; });
+        for (int s0 = 0; s0 < mi; s0 += 32) { int w = 0; for (int s2 = s0; s2 < std::min(s0 + 32, mi); ++s2) w = std::max(w, rl[rord[s2]]); rcap[i] += w; }
+        for (int r = 0; r < mi; ++r) rperm_all[i][r] = (uint16_t)rord[r];
         cperm_all[i].resize(ni);
-        for (int j = 0; j < ni; ++j) { cperm_all[i][j] = (uint16_t)ord[j]; if ((j & 31) == 0) ccap[i] += cl[ord[j]]; }
-        maxcl[i] = cl[ord[0]];
+        int mx = 0;
+        for (int s0 = 0; s0 < ni; s0 += 32) { int w = 0; for (int s2 = s0; s2 < std::min(s0 + 32, ni); ++s2) w = std::max(w, cl[cord[s2]]); ccap[i] += w; mx = std::max(mx, w); }
+        for (int j = 0; j < ni; ++j) cperm_all[i][j] = (uint16_t)cord[j];
+        maxcl[i] = mx;
     });
     if (err1.load()) { set_err("row index out of range"); delete h; return nullptr; }
     // (3) serial: offsets that depend on the layouts
