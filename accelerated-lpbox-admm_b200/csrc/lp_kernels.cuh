@@ -290,11 +290,12 @@ __device__ __forceinline__ double ell_dot(uint32_t ia, const u16 *__restrict__ g
             double t0 = lds64(i0 + add), t1 = lds64(i1 + add), t2 = lds64(i2 + add), t3 = lds64(i3 + add);
             if (COEF == 2) { t0 = dM(val[pos], t0); t1 = dM(val[pos + 32], t1); t2 = dM(val[pos + 64], t2); t3 = dM(val[pos + 96], t3); }
             k += 4; pos += 128;
-            const bool more = (k + 4 <= W);
-            if (more) { i0 = ld_idx<GIDX>(ia, gidx, pos); i1 = ld_idx<GIDX>(ia, gidx, pos + 32); i2 = ld_idx<GIDX>(ia, gidx, pos + 64);
-                        i3 = ld_idx<GIDX>(ia, gidx, pos + 96); }
+            // the next batch of offsets is fetched unconditionally (the arrays are followed by slack, lp_types.h ELL_SLACK): past
+            // the end of the slice they are simply not used
+            i0 = ld_idx<GIDX>(ia, gidx, pos); i1 = ld_idx<GIDX>(ia, gidx, pos + 32); i2 = ld_idx<GIDX>(ia, gidx, pos + 64);
+            i3 = ld_idx<GIDX>(ia, gidx, pos + 96);
             acc = dA(acc, t0); acc = dA(acc, t1); acc = dA(acc, t2); acc = dA(acc, t3);
-            if (!more) break;
+            if (k + 4 > W) break;
         }
     }
     if (W & 2) {                                     // W is warp-uniform: straight-line tail

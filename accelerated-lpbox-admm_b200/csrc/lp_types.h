@@ -88,14 +88,17 @@ LPB_HD CsrLayout csr_layout(int n0, int m0, int nnz0) {
 }
 // rcap / ccap: capacity of the row / column ELL index arrays in 32-entry groups (sum of the slice widths at creation;
 // early fixing can only shrink them)
+// the SpMV loops prefetch one batch of offsets (4 steps x 32 lanes x 2 bytes) past the end of a slice without a bounds test:
+// both offset arrays are followed by that much slack
+constexpr int ELL_SLACK = 256;
 LPB_HD EllLayout ell_layout(int n0, int m0, int rcap, int ccap) {
     EllLayout L;
     const int nsr = (m0 + 31) / 32, nsc = (n0 + 31) / 32;
     L.o_rsptr = 0;
     L.o_csptr = a16(2 * (nsr + 1));
     L.o_ridx = L.o_csptr + a16(2 * (nsc + 1));
-    L.o_cidx = L.o_ridx + a16(64 * rcap);
-    L.o_rperm = L.o_cidx + a16(64 * ccap);
+    L.o_cidx = L.o_ridx + a16(64 * rcap) + ELL_SLACK;
+    L.o_rperm = L.o_cidx + a16(64 * ccap) + ELL_SLACK;
     L.o_cperm = L.o_rperm + a16(2 * m0);
     L.bytes = L.o_cperm + a16(2 * n0);
     return L;
