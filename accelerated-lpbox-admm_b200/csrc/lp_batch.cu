@@ -272,7 +272,7 @@ static int sync_states(lpbox_batch *h) {
 // pair (slot mod 16) at different addresses.  Which slot a row / column occupies is free as far as the arithmetic goes (only
 // the order INSIDE each sparse product is the reference's), so it is chosen to avoid collisions:
 //   * columns are grouped 16 at a time (= the lanes of one half-warp) in descending length such that the members of a group
-//     have distinct chain-major staging banks ((2 (j & 3) + (j >> 2)) mod 16, csrc/lp_types.h chain_stride): the scattered
+//     have distinct chain-major staging banks ((CH (j & 3) + (j >> 2)) mod 16, csrc/lp_types.h chain_stride): the scattered
 //     staging stores of the reduction operands become conflict-free;
 //   * inside every group of 16 columns (rows) the positions are permuted so that the columns (rows) that one half-warp gathers
 //     in one step of E v (E^T w) fall into different bank pairs as far as a greedy assignment manages (two sweeps).
@@ -336,7 +336,7 @@ static void place_in_groups(std::vector<int> &order, const GatherSets &G, int sw
 }
 // descending-length grouping of the columns, 16 at a time, with distinct staging banks inside a group where columns of (almost)
 // the same length allow it
-static void group_columns(const std::vector<int> &cl, std::vector<int> &order) {
+static void group_columns(const std::vector<int> &cl, int CH, std::vector<int> &order) {
     const int n = (int)cl.size();
     std::vector<int> sorted(n);
     for (int j = 0; j < n; ++j) sorted[j] = j;
@@ -352,7 +352,7 @@ static void group_columns(const std::vector<int> &cl, std::vector<int> &order) {
         const size_t base = order.size();
         for (int q = first; q < n && got < 16 && cl[sorted[q]] >= Lmax - 1; ++q) {
             if (taken[q]) continue;
-            const int j = sorted[q], c = (2 * (j & 3) + (j >> 2)) & 15;
+            const int j = sorted[q], c = (CH * (j & 3) + (j >> 2)) & 15;
             if (used[c]) continue;
             used[c] = true; taken[q] = 1; order.push_back(j); ++got;
         }
@@ -417,6 +417,7 @@ static lpbox_batch *batch_create_impl(int device, int B, const int32_t *m, const
     //     (see above; LPBOX_PLAIN_SLOTS=1 keeps the plain stable sort) -- and the capacities of the sliced-ELL image
     std::atomic<int> err1(0);
     static const bool plain_slots = getenv("LPBOX_PLAIN_SLOTS") != nullptr;
+    const int np_batch = std::max((h->max_n + 1) & ~1, (h->max_m + 1) & ~1);     // the window kernel's vector stride (configure())
     host_parallel_for(B, [&](int i) {
         const int ni = n[i], mi = m[i], nz = h->nnz0[i];
         const int32_t *cp = colptr_all + h->h_cp_off[i];
@@ -431,7 +432,7 @@ static lpbox_batch *batch_create_impl(int device, int B, const int32_t *m, const
             for (int j = 0; j < ni; ++j) cord[j] = j;
             std::stable_sort(cord.begin(), cord.end(), [&](int a, int b2) { return cl[a] > cl[b2]; });
         } else {
-            group_columns(cl, cord);
+            group_columns(cl, chain_stride(np_batch), cord);
             // row-compressed copy of the pattern (rows gather columns in E v)
             std::vector<int> rp(mi + 1, 0), cix(nz);
             for (int r = 0; r < mi; ++r) rp[r + 1] = rp[r] + rl[r];

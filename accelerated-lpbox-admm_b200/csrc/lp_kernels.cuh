@@ -290,7 +290,7 @@ __device__ __forceinline__ double ell_dot(uint32_t ia, const u16 *__restrict__ g
             double t0 = lds64(i0 + add), t1 = lds64(i1 + add), t2 = lds64(i2 + add), t3 = lds64(i3 + add);
             if (COEF == 2) { t0 = dM(val[pos], t0); t1 = dM(val[pos + 32], t1); t2 = dM(val[pos + 64], t2); t3 = dM(val[pos + 96], t3); }
             k += 4; pos += 128;
-            // the next batch of offsets is fetched unconditionally (the arrays are followed by slack, lp_types.h ELL_SLACK): past
+            // the next batch of offsets is fetched unconditionally (what follows the arrays is readable, lp_types.h): past
             // the end of the slice they are simply not used
             i0 = ld_idx<GIDX>(ia, gidx, pos); i1 = ld_idx<GIDX>(ia, gidx, pos + 32); i2 = ld_idx<GIDX>(ia, gidx, pos + 64);
             i3 = ld_idx<GIDX>(ia, gidx, pos + 96);
@@ -413,7 +413,7 @@ struct Smem {
 __host__ __device__ inline size_t smem_bytes(int cap, int np, int mp, int pat_bytes, int evr_elems, int evc_elems, int nwarps, int tab_len) {
     size_t d = (size_t)((mp + 3) & ~1) + 8 * (size_t)chain_stride(np) + (size_t)((tab_len + 1) & ~1) + 32 * (size_t)nwarps + 16 +
                2 * SB_COUNT + 16 + 2 * 4 * (size_t)nwarps + 2 + (size_t)evr_elems + 2 * (size_t)evc_elems;
-    return (size_t)gather_base(cap) + d * sizeof(double) + (size_t)pat_bytes + 16;
+    return (size_t)gather_base(cap) + d * sizeof(double) + (size_t)pat_bytes + 16 + 256;
 }
 __device__ __forceinline__ Smem carve(unsigned char *base, int cap, int np, int mp, int pat_bytes, int evr_elems, int evc_elems, int nwarps,
                                       int tab_len) {
@@ -437,6 +437,8 @@ __device__ __forceinline__ Smem carve(unsigned char *base, int cap, int np, int 
     s.ev_c = d; d += evc_elems;
     s.r4v = d; d += evc_elems;
     s.pat = reinterpret_cast<unsigned char *>(d);
+    // the image is followed by the mbarrier and 256 readable bytes: the unconditional offset prefetch of the SpMV loops may
+    // read (never use) that far past the image's last array
     s.bar = reinterpret_cast<uint64_t *>(s.pat + pat_bytes);
     return s;
 }

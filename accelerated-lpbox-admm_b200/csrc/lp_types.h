@@ -88,30 +88,31 @@ LPB_HD CsrLayout csr_layout(int n0, int m0, int nnz0) {
 }
 // rcap / ccap: capacity of the row / column ELL index arrays in 32-entry groups (sum of the slice widths at creation;
 // early fixing can only shrink them)
-// the SpMV loops prefetch one batch of offsets (4 steps x 32 lanes x 2 bytes) past the end of a slice without a bounds test:
-// both offset arrays are followed by that much slack
-constexpr int ELL_SLACK = 256;
+// The SpMV loops prefetch one batch of offsets (4 steps x 32 lanes x 2 bytes = 256 bytes) past the end of a slice without a
+// bounds test; what follows the arrays only has to be readable: the row offsets are followed by the column offsets, those by the
+// permutations (global memory) / by 256 spare bytes at the end of the window kernel's shared memory.
 LPB_HD EllLayout ell_layout(int n0, int m0, int rcap, int ccap) {
     EllLayout L;
     const int nsr = (m0 + 31) / 32, nsc = (n0 + 31) / 32;
     L.o_rsptr = 0;
     L.o_csptr = a16(2 * (nsr + 1));
     L.o_ridx = L.o_csptr + a16(2 * (nsc + 1));
-    L.o_cidx = L.o_ridx + a16(64 * rcap) + ELL_SLACK;
-    L.o_rperm = L.o_cidx + a16(64 * ccap) + ELL_SLACK;
+    L.o_cidx = L.o_ridx + a16(64 * rcap);
+    L.o_rperm = L.o_cidx + a16(64 * ccap);
     L.o_cperm = L.o_rperm + a16(2 * m0);
     L.bytes = L.o_cperm + a16(2 * n0);
     return L;
 }
 // Chain-major reduction buffers: element j of an n-vector sits at (j & 3) * CH + (j >> 2) (Eigen's four interleaved
-// chains become four contiguous runs).  CH = 2 (mod 16) doubles: the four chains start 16 bytes apart modulo 128, and
-// two buffers laid out back to back start 64 bytes apart modulo 128 -> eight lanes reading 16 bytes each (two
-// reductions side by side) touch every bank exactly once.
+// chains become four contiguous runs).  CH = 2 (mod 4) doubles: CH * 8 bytes is then an odd multiple of 16 modulo 128, so the
+// four chains start in four different 16-byte bank groups, and two buffers laid out back to back start 64 bytes apart modulo
+// 128 -> eight lanes reading 16 bytes each (two reductions side by side) touch every bank exactly once.
 LPB_HD constexpr int chain_stride(int np) {
     const int c = np / 4 + 3;                  // terms per chain, the slot of the tail elements, two never-written doubles
-    return 16 * ((c - 2 + 15) / 16) + 2;       // (the last two doubles of a buffer stay 0.0: padding operand of the z4 copy)
+    return 4 * ((c - 2 + 3) / 4) + 2;          // (the last two doubles of a buffer stay 0.0: padding operand of the z4 copy)
 }
-// shared-memory map of the window kernel that the image refers to; cap = T * EPT of the kernel variant in use
+// shared-memory map of the window kernel that the image refers to; cap = T * EPT of the kernel variant in use (compile-time in
+// the kernel: runtime region sizes cost registers there)
 LPB_HD constexpr int zero_off(int cap) { return 4 * chain_stride(cap) * 8; }     // the shared 0.0 (end of the G region)
 LPB_HD constexpr int gather_base(int cap) { return zero_off(cap) + 16; }         // T1 starts here
 
@@ -139,7 +140,7 @@ struct BatchView {
     int *ret_idx;                                  // [off_n] fixed original ids (ret_idx_prev)
     double *ret_val;                               // [off_n]
     const double *pow_tab;                         // pow_tab[k] = pow((double)k, 0.5) from the host libm
-    int cap;                                       // T * EPT of the window-kernel variant of this batch (offsets in the ELL image)
+    int cap;                                       // T * EPT of the window-kernel variant of this batch
     int sbase;                                     // shared-window address of the window kernel's dynamic shared memory (lp_probe_kernel)
 };
 

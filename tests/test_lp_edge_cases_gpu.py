@@ -133,7 +133,7 @@ def test_spilled_pattern_image_is_bit_identical(monkeypatch):
         rs = np.sort(np.bincount(ri, minlength=m))[::-1]; cs = np.sort(np.diff(cp))[::-1]
         # staged part of the padded sliced-ELL image (csrc/lp_types.h ell_layout): slice pointers + both offset arrays
         return (a16(2 * ((m + 31) // 32 + 1)) + a16(2 * ((n + 31) // 32 + 1)) + a16(64 * int(rs[::32].sum()))
-                + a16(64 * int(cs[::32].sum())) + 512)        # + the prefetch slack after both arrays
+                + a16(64 * int(cs[::32].sum())))
     sizes = sorted(image_bytes(p) for p in probs)
     monkeypatch.setenv("LPBOX_IMAGE_BUDGET", str(sizes[len(sizes) // 2]))
     b2 = lpbox.LPBatch(probs); b2.init()

@@ -8,8 +8,11 @@ from conftest import load_golden, problem_tuple
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 592
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
-gs = [load_golden(f"auction_100_500_seed{s}.npz") for s in (0, 1, 2)]
-probs = [problem_tuple(gs[i % 3]) for i in range(B)]
+if len(sys.argv) > 3 and sys.argv[3] == "gen":      # the bench's own batch (native generator, seed 0)
+    probs = lpbox.gen_auctions(0, B, 100, 500)
+else:
+    gs = [load_golden(f"auction_100_500_seed{s}.npz") for s in (0, 1, 2)]
+    probs = [problem_tuple(gs[i % 3]) for i in range(B)]
 t = time.time(); b = lpbox.LPBatch(probs); b.init(); print("create+init s", time.time() - t, b.config())
 t = time.time(); log = b.solve(iters); wall = time.time() - t
 ms = b.last_kernel_ms()
