@@ -245,6 +245,13 @@ class PyLPboxADMMsolver:
         # into windows (iteration `iter_start` of ADMM_lp_iters is special, LP.cpp:920-934), so the whole history is kept
         self._hist_cap = 10000 if self.print_info == 2 else 500
         self._file_idx, self._allres_path, self._xiters_path = 0, None, None
+        self._log_path = None
+
+    def set_log_file(self, path):
+        """`set_log_file` (LP.h:572-575): the plain loop then writes the reference's per-iteration text log (LP.cpp:1013-1067:
+        norms of x, y1, y2, y3, z1, z2, z4, `LongkangIter: <it>;  x_sol: ..; dou_obj: ..; bin_obj: ..`, elapsed time).  A debugging
+        aid: the solve is stepped one iteration per launch (same iterates -- see `_solve_logging`), so it is slow."""
+        self._log_path = path
 
     # -- problem in ------------------------------------------------------------------------------------------
     def read_File(self, i, k, j):
@@ -286,7 +293,9 @@ class PyLPboxADMMsolver:
         b = self._need()
         i, j = int(i), int(j)
         t0 = time.time()
-        if self.print_info == 2 and self._xiters_path is not None:
+        if self._log_path is not None:
+            ret = self._solve_logging(b, i, j, t0)
+        elif self.print_info == 2 and self._xiters_path is not None:
             ret = self._solve_dumping_iterates(b, i, j)
         else:
             ret = int(b.iters(i, j)[0])
@@ -296,6 +305,31 @@ class PyLPboxADMMsolver:
                     fh.write("%d,%f,%d,%f\n" % (self._file_idx, -b.cur_bin_obj(0), b.get_iter(0) + 1, int((time.time() - t0) * 1000) / 1000.0))     # `iter+1` of the loop variable
             except OSError:
                 pass
+        return ret
+
+    def _solve_logging(self, b, i, j, t0):
+        """ADMM_lp_iters(i, j) stepped one iteration per launch, writing the reference's log lines after each iteration.  The
+        first step keeps the plain loop's `iter == iter_start` rules (stop test skipped, z4 assigned, LP.cpp:920-934), the later
+        ones run without them -- exactly what iterations iter_start+1.. of one call do -- so the iterates are those of a single
+        `solve_iter(i, j)` (window boundaries carry the whole solver state)."""
+        bvec = np.asarray(self._problem[5], dtype=np.float64)
+        nrm = lambda v: float(np.sqrt(np.dot(v, v)))
+        ret = 0
+        with open(self._log_path, "w+") as fp:
+            for it in range(i, j):
+                b.set_params(variant=3 if it == i else 2)
+                ret = int(b.iters(it, it + 1)[0])
+                st = b.state(0)
+                stopped = b.get_iter(0) == it          # a stop leaves the loop variable on the stopping iteration (no log entry: the
+                if stopped:                            # reference breaks before the logging block)
+                    break
+                x = st["x"]
+                fp.write("norm of x_sol: %.9f\nnorm of y1: %.9f\nnorm of y2: %.9f\nnorm of y3: %.9f\n" % (nrm(x), nrm(st["y1"]), nrm(st["y2"]), nrm(st["y3"])))
+                fp.write("norm of z1: %.9f\nnorm of z2: %.9f\nFor z4\nnorm of z4: %.9f\n" % (nrm(st["z1"]), nrm(st["z2"]), nrm(st["z4"])))
+                fp.write("LongkangIter: %d;  x_sol: %f; dou_obj:%f; bin_obj: %f\n" % (it + 1, nrm(x), float(bvec[:len(x)] @ x) if len(x) == len(bvec) else float("nan"), b.cur_bin_obj(0)))
+                fp.write("Time elapsed: %fs\n-------------------------------------------------\n" % (int((time.time() - t0) * 1000) / 1000.0))
+            fp.write("Time elapsed: %fs\n" % (int((time.time() - t0) * 1000) / 1000.0))
+        b.set_params(variant=3)
         return ret
 
     def _solve_dumping_iterates(self, b, i, j):

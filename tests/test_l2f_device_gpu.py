@@ -99,3 +99,24 @@ def test_native_l2f_loop_equals_the_python_driven_loop():
     assert np.array_equal(log_a, log_b) and np.array_equal(bits_a, bits_b)
     assert (log_a["n_left"] < 500).any()                   # the policy really fixed variables
     a.close(); b.close(); pk.close()
+
+
+def test_policy_training_smoke(tmp_path):
+    """N2: the training pipeline (GPU-produced iterate windows -> weighted BCE, reference recipe LP.trainer:254-299) runs end to
+    end, lowers its loss, and writes a checkpoint in the reference's format that loads into the policy modules and kernels."""
+    import torch
+    from lpbox.train_policy import train_lp_policy
+    from lpbox.policy import load_policy
+    from lpbox.policy_kernel import PolicyKernel
+    out = str(tmp_path / "policy.pt")
+    net, losses = train_lp_policy(n_inst=6, epochs=3, out=out, pos_weight=4.0, n_items=40, n_bids=200, log=lambda s: None)
+    assert len(losses) == 3 and all(np.isfinite(losses)) and losses[-1] < losses[0]
+    ck = torch.load(out)
+    assert set(ck) == {"net", "epoch"} and ck["epoch"] == 3
+    net2 = load_policy(out, device="cuda:0")
+    x = torch.rand(64, 20, 5, device="cuda")
+    with torch.no_grad():
+        ref = net2(x)[1].reshape(-1)
+    pk = PolicyKernel(net2, device=0, chunk_rows=64)
+    assert float((pk(x) - ref).abs().max()) <= 0.02
+    pk.close()

@@ -215,3 +215,28 @@ def test_xiters_file_when_the_loop_stops_early(tmp_path, monkeypatch):
     assert np.abs(last).max() > 0 and np.allclose(last, x, atol=5.1e-7, rtol=0)
     o = _oracle(g); o.solve_init()
     assert ret == o.solve_iter(0, 1e4) and it == o.get_iter()
+
+
+def test_per_iteration_text_log(tmp_path):
+    """`set_log_file` (LP.h:572-575): the reference's per-iteration text log (LP.cpp:1013-1067) -- norms of x, y1, y2, y3, z1, z2,
+    z4 and `LongkangIter: <it>;  x_sol: ..; dou_obj: ..; bin_obj: ..` after every iteration.  The logging solve steps one
+    iteration per launch and must leave exactly the iterates of an un-logged `solve_iter` (compared with the oracle too)."""
+    import lpbox
+    g = load_golden("auction_20_60_seed0.npz")
+    K = 40
+    s = lpbox.PyLPboxADMMsolver(0)
+    s.set_problem(g["m"], g["n"], g["colptr"], g["rowidx"], None, g["b"], g["f"])
+    s.set_log_file(str(tmp_path / "log.txt"))
+    s.solve_init(); s.solve_iter(0, K)
+    t = lpbox.PyLPboxADMMsolver(0)
+    t.set_problem(g["m"], g["n"], g["colptr"], g["rowidx"], None, g["b"], g["f"])
+    t.solve_init(); t.solve_iter(0, K)
+    assert np.array_equal(s._batch.state(0)["x"], t._batch.state(0)["x"]) and s.get_iter() == t.get_iter() and s.cal_Obj() == t.cal_Obj()
+    lines = open(tmp_path / "log.txt").read().strip().split("\n")
+    its = [ln for ln in lines if ln.startswith("LongkangIter:")]
+    assert len(its) == K and its[0].startswith("LongkangIter: 1;") and its[-1].startswith("LongkangIter: %d;" % K)
+    assert sum(ln.startswith("norm of z4:") for ln in lines) == K and lines[-1].startswith("Time elapsed:")
+    o = _oracle(g); o.solve_init(); o.solve_iter(0, K)
+    x = o.state()["x"]
+    assert float(its[-1].split("x_sol:")[1].split(";")[0]) == pytest.approx(np.sqrt(x @ x), abs=1e-6)
+    assert float(its[-1].split("dou_obj:")[1].split(";")[0]) == pytest.approx(float(g["b"] @ x), abs=1e-6)

@@ -14,7 +14,8 @@ probs = lpbox.gen_auctions(4242, B, 100, 500)
 b = lpbox.LPBatch(probs); b.init()
 t = time.time(); plain = b.solve(20000); torch.cuda.synchronize(); t_plain = time.time() - t
 b.close()
-net = load_policy(os.path.join(ROOT, "accelerated-lpbox-admm_b200", "lpbox", "weights", os.environ.get("LPBOX_POLICY", "lp_mha_policy.pt")))
+pol = os.environ.get("LPBOX_POLICY", "lp_mha_policy.pt")
+net = load_policy(pol if os.path.isabs(pol) or os.path.exists(pol) else os.path.join(ROOT, "accelerated-lpbox-admm_b200", "lpbox", "weights", pol))
 if dtype == "kernel":
     from lpbox.policy_kernel import PolicyKernel
     pk = PolicyKernel(net, chunk_rows=32768)
@@ -26,9 +27,12 @@ elif dtype == "bf16":
 else:
     def score(x):
         return net(x)[1]
-b = lpbox.LPBatch(probs, hist_cap=100); b.init()
+b = lpbox.LPBatch(probs, hist_cap=100)
+if os.environ.get("L2F_GUARD", "1") == "1":
+    b.set_fix_guard(True)
+b.init()
 torch.cuda.synchronize(); t = time.time()
-log, bits, stats = lpbox.solve_l2f(b, score, ws=100, max_iter=10000)
+log, bits, stats = lpbox.solve_l2f(b, score, ws=100, max_iter=int(os.environ.get("L2F_MAXIT", "20000")))
 torch.cuda.synchronize(); t_l2f = time.time() - t
 gap = (log["obj"] - plain["obj"]) / np.abs(plain["obj"])       # objectives are minimised (-revenue): positive gap = worse
 print(f"B={B} dtype={dtype} plain: {t_plain:.2f}s ({B/t_plain:.1f} inst/s)  l2f: {t_l2f:.2f}s ({B/t_l2f:.1f} inst/s)  speed-up {t_plain/t_l2f:.2f}x")

@@ -1,80 +1,15 @@
-"""Trains the LP early-fixing policy with the reference recipe (LP.trainer:254-299) on iterates
-produced by the CUDA solver, entirely on the GPU box:
-
-  * instances: native auction generator (j=100, k=500);
-  * data: windows 1..10 of 100 iterates each (first 1000 ADMM iterations) of every variable, label = final x >= 0.5 of
-    the plain solve, sample weight 1/i for window i (LP.trainer:270-297), weighted BCE, Adam 1e-4;
-  * output: accelerated-lpbox-admm_b200/lpbox/weights/lp_mha_policy.pt in the reference's checkpoint format
-    ({'net': state_dict, 'epoch': e}).
-Run:  python tools/train_policy.py [n_instances] [epochs]
-"""
+"""Command-line wrapper of lpbox.train_policy.train_lp_policy (the reference recipe, LP.trainer:254-299, on GPU-produced iterates).
+Run:  python tools/train_policy.py [n_instances] [epochs] [out.pt]   (LPBOX_TRAIN_POS_WEIGHT / LPBOX_TRAIN_NEG_WEIGHT: class weights)"""
 import os
 import sys
-import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "accelerated-lpbox-admm_b200"))
-import numpy as np  # noqa: E402
-import torch  # noqa: E402
-import lpbox  # noqa: E402
-from lpbox.policy import GraphAttentionEncoder  # noqa: E402
+from lpbox.train_policy import train_lp_policy  # noqa: E402
 
-
-def main():
+if __name__ == "__main__":
     n_inst = int(sys.argv[1]) if len(sys.argv) > 1 else 200
     epochs = int(sys.argv[2]) if len(sys.argv) > 2 else 8
     out = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "accelerated-lpbox-admm_b200", "lpbox", "weights", "lp_mha_policy.pt")
-    ws, nwin = 100, 10
-    neg_w = float(os.environ.get("LPBOX_TRAIN_NEG_WEIGHT", "1"))   # > 1: false fix-to-one decisions (the cause of infeasible solutions) cost more
-    torch.manual_seed(19260817)                      # cmd_args.py:11
-    probs = lpbox.gen_auctions(777, n_inst, 100, 500)
-    # labels: plain solve to convergence
-    t0 = time.time()
-    b = lpbox.LPBatch(probs); b.init(); b.solve(20000)
-    labels = np.concatenate([b.x_sol(i) for i in range(n_inst)]).astype(np.float32)
-    b.close()
-    # features: first 10 windows without fixing
-    b = lpbox.LPBatch(probs, hist_cap=ws); b.init()
-    feats = []
-    for w in range(nwin):
-        b.iters_l2f(ws * w, ws * (w + 1))
-        feats.append(np.concatenate([b.x_iters(i, ws) for i in range(n_inst)]).astype(np.float32))
-    b.close()
-    print(f"data: {n_inst} instances, {labels.size} variables, {time.time() - t0:.1f}s, positives {labels.mean():.3f}", flush=True)
-    X = torch.from_numpy(np.stack(feats)).cuda()                      # (nwin, rows, ws)
-    y = torch.from_numpy(labels).cuda()
-    net = GraphAttentionEncoder(tokens=20).cuda()
-    opt = torch.optim.Adam(net.parameters(), lr=1e-4)
-    rows = y.numel()
-    offs = np.concatenate([[0], np.cumsum([p[1] for p in probs])])
-    for ep in range(epochs):
-        net.train()
-        tot, cnt = 0.0, 0
-        for it in np.random.RandomState(ep).permutation(n_inst):
-            a, e = int(offs[it]), int(offs[it + 1])
-            n = e - a
-            # one batch = the 10 windows of one instance, weight 1/i for window i (LP.trainer:270-297)
-            xb = X[:, a:e].reshape(nwin * n, 20, 5)
-            yb = y[a:e].repeat(nwin).view(-1, 1)
-            wb = torch.cat([torch.full((n, 1), 1.0 / (i + 1), device="cuda") for i in range(nwin)])
-            if neg_w != 1.0:
-                wb = wb * torch.where(yb > 0.5, torch.ones_like(yb), torch.full_like(yb, neg_w))
-            logit, _ = net(xb)
-            loss = torch.nn.functional.binary_cross_entropy_with_logits(logit, yb, weight=wb)
-            opt.zero_grad(); loss.backward(); opt.step()
-            tot += float(loss.detach()); cnt += 1
-        if ep % 5 == 4 or ep == epochs - 1:
-            net.eval()
-            with torch.no_grad():
-                for w in (0, 4, 9):
-                    sig = torch.cat([net(X[w, q:q + 20000].view(-1, 20, 5))[1].view(-1) for q in range(0, rows, 20000)])
-                    fix1 = (sig > 0.9); fix0 = (sig < 0.1)
-                    err = ((fix1 & (y < 0.5)) | (fix0 & (y > 0.5))).float().sum().item()
-                    print(f"epoch {ep}: loss {tot / cnt:.4f}  window {w + 1}: fixes {int(fix1.sum() + fix0.sum())}/{rows} ({int(fix1.sum())} ones), wrong {int(err)}", flush=True)
-    os.makedirs(os.path.dirname(out), exist_ok=True)
-    torch.save({"net": {k: v.cpu() for k, v in net.state_dict().items()}, "epoch": epochs}, out)
-    print("saved", out)
-
-
-if __name__ == "__main__":
-    main()
+    train_lp_policy(n_inst, epochs, out, pos_weight=float(os.environ.get("LPBOX_TRAIN_POS_WEIGHT", "1")),
+                    neg_weight=float(os.environ.get("LPBOX_TRAIN_NEG_WEIGHT", "1")), log=lambda s: print(s, flush=True))
