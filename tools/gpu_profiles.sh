@@ -9,4 +9,4 @@ ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,
     --clock-control none -k regex:lp_admm_window -c 1 --csv --log-file gpurun_out/r02_window_traffic.csv python tools/quick_bench.py 10000 20000 gen > gpurun_out/r02_ncu_traffic.log 2>&1
 # 3. launch list of a whole (short) bench run
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_bench.csv python bench.py --batch 2072 --steps 1 --warmup 1 --e2e-steps 1 --no-cpu-baseline > gpurun_out/r02_ncu_launches.log 2>&1
-tail -2 gpurun_out/r02_ncu_window.log gpurun_out/r02_ncu_traffic.log gpurun_out/r02_ncu_launches.log
+for f in window traffic launches; do tail -n 2 gpurun_out/r02_ncu_$f.log; done
