@@ -103,6 +103,8 @@ struct lpbox_batch {
     DevBuf<int> d_work;                         // launch order when pat_smem < max_pat (instances with a spilled image first)
     DevBuf<double> d_park;                      // [grid][PK_COUNT][cap] per-CTA parking lot of the window kernel
     DevBuf<int> d_err;                          // [2]: error flag of the window kernel, result of the shared-window probe
+    DevBuf<int> d_ring;                         // sliced work queue of plain batch solves: [0] tail, [1] finished, [2..] ring
+    int ring_cap = 0;
     DevBuf<float> d_pinp, d_pscore;             // lpbox_batch_solve_l2f: policy input [rows][ws] / scores [rows]
     DevBuf<L2fMeta> d_meta;
     int pinp_ws = 0;
@@ -233,7 +235,7 @@ static int configure(lpbox_batch *h) {
     return 0;
 }
 
-static int run_window(lpbox_batch *h, int iter_start, int iter_end, int l2f, int skip_done) {
+static int run_window(lpbox_batch *h, int iter_start, int iter_end, int l2f, int skip_done, int slice = 0) {
     Launch la{};
     la.iter_start = iter_start; la.iter_end = iter_end; la.l2f = l2f; la.skip_done = skip_done; la.record = h->record_plain ? 1 : 0;
     la.n_work = h->B; la.work = h->d_work.p; la.counter = h->d_counter.p;
@@ -242,6 +244,22 @@ static int run_window(lpbox_batch *h, int iter_start, int iter_end, int l2f, int
     static const bool no_rotate = getenv("LPBOX_NO_ROTATE") != nullptr;     // experiments: reduction warp fixed to the last warp
     la.sm_rank = no_rotate ? nullptr : h->d_counter.p + 1; la.park = h->d_park.p; la.fast = h->fast ? 1 : 0; la.error = h->d_err.p;
     CK(cudaMemsetAsync(h->d_counter.p, 0, sizeof(int) * (1 + SM_RANK_SLOTS), h->stream));
+    const bool slice_force = getenv("LPBOX_SLICE_FORCE") != nullptr;      // tests: slice small batches too
+    if (slice > 0 && (h->B >= 2 * h->grid || slice_force) && iter_end > iter_start) {
+        // sliced queue: every instance can be re-queued once per slice of its (at most iter_end - iter_start) iterations
+        const long long cap = (long long)h->B * ((iter_end - iter_start + slice - 1) / slice + 1);
+        if (cap < (1ll << 30)) {
+            if (!h->d_ring.p || h->ring_cap < (int)cap) { h->d_ring.free_(); CK(h->d_ring.alloc((size_t)cap + 2)); h->ring_cap = (int)cap; }
+            CK(cudaMemsetAsync(h->d_ring.p, 0xff, sizeof(int) * ((size_t)h->ring_cap + 2), h->stream));      // -1 = not produced yet
+            std::vector<int> head(h->B + 2);
+            head[0] = h->B; head[1] = 0;                                                                     // tail, finished
+            for (int i = 0; i < h->B; ++i) head[2 + i] = i;
+            if (h->d_work.p) CK(cudaMemcpyAsync(h->d_ring.p + 2, h->d_work.p, sizeof(int) * (size_t)h->B, cudaMemcpyDeviceToDevice, h->stream));
+            CK(cudaMemcpyAsync(h->d_ring.p, head.data(), sizeof(int) * (h->d_work.p ? 2 : (size_t)h->B + 2), cudaMemcpyHostToDevice, h->stream));
+            CK(cudaStreamSynchronize(h->stream));                                                            // `head` is a local
+            la.slice = slice; la.ring = h->d_ring.p + 2; la.ring_cap = h->ring_cap; la.tail = h->d_ring.p; la.finished = h->d_ring.p + 1;
+        }
+    }
     bool u = h->all_unit;
     switch (h->tcfg) {
         case 0: u ? launch_window<128, 4, true>(h, la, h->grid) : launch_window<128, 4, false>(h, la, h->grid); break;
@@ -609,7 +627,7 @@ extern "C" void lpbox_batch_destroy(lpbox_batch *h) {
     h->d_x.free_(); h->d_y1.free_(); h->d_y2.free_(); h->d_z1.free_(); h->d_z2.free_(); h->d_b.free_(); h->d_Pd.free_(); h->d_Esq.free_();
     h->d_y3.free_(); h->d_z4.free_(); h->d_f.free_(); h->d_val_r.free_(); h->d_val_c.free_(); h->d_r4v.free_(); h->d_hist.free_();
     h->d_ret_val.free_(); h->d_pow.free_(); h->d_vec.free_(); h->d_pat.free_(); h->d_st.free_(); h->d_left.free_(); h->d_ret_idx.free_();
-    h->d_counter.free_(); h->d_num.free_(); h->d_work.free_(); h->d_park.free_(); h->d_err.free_(); h->d_pinp.free_(); h->d_pscore.free_(); h->d_meta.free_();
+    h->d_counter.free_(); h->d_num.free_(); h->d_work.free_(); h->d_park.free_(); h->d_err.free_(); h->d_pinp.free_(); h->d_pscore.free_(); h->d_meta.free_(); h->d_ring.free_();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
@@ -755,7 +773,11 @@ extern "C" int lpbox_batch_solve(lpbox_batch *h, int max_iters, lpbox_log_row *l
     lp_setup_kernel<<<h->B, 128, 0, h->stream>>>(h->bv, h->pr, 2, 0);
     CK(cudaGetLastError());
     h->launches += 1;
-    int rc = run_window(h, 0, max_iters, 0, 1);
+    // Sliced (breadth-first) work queue: opt-in.  Measured on 4144 instances: 870 instances/s with slices of 250 or 500 iterations
+    // against 927 with one instance per CTA until it stops -- when every instance advances at the same pace the launch ends with
+    // ALL the long instances still alive and too few of them to fill the GPU, which costs more than the depth-first tail.
+    const int slice_env = getenv("LPBOX_SLICE") ? atoi(getenv("LPBOX_SLICE")) : 0;
+    int rc = run_window(h, 0, max_iters, 0, 1, h->record_plain ? 0 : slice_env);
     if (rc) return rc;
     rc = time_end(h); if (rc) return rc;
     rc = sync_states(h); if (rc) return rc;

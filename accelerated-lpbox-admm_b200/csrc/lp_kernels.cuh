@@ -406,14 +406,14 @@ struct Smem {
     double *blk;     // [2][SB_COUNT] ADMM-level scalars (rho's, gamma, objective bookkeeping), double-buffered per iteration
     double *ring;    // [16]    tail of obj_list
     double *part;    // [2][4*NW] fast-mode partial sums
-    int *ctl;        // [4]     work item, reduction-warp index, status of the iteration
+    int *ctl;        // [8]     work item, reduction-warp index, status of the iteration, PCG code, end of the slice
     double *ev_r, *ev_c, *r4v;    // ELL-order values: [evr_elems], [evc_elems], [evc_elems] (non-unit only)
     unsigned char *pat;
     uint64_t *bar;
 };
 __host__ __device__ inline size_t smem_bytes(int cap, int np, int mp, int pat_bytes, int evr_elems, int evc_elems, int nwarps, int tab_len) {
     size_t d = (size_t)((mp + 3) & ~1) + 8 * (size_t)chain_stride(np) + (size_t)((tab_len + 1) & ~1) + 32 * (size_t)nwarps + 16 +
-               2 * SB_COUNT + 16 + 2 * 4 * (size_t)nwarps + 2 + (size_t)evr_elems + 2 * (size_t)evc_elems;
+               2 * SB_COUNT + 16 + 2 * 4 * (size_t)nwarps + 4 + (size_t)evr_elems + 2 * (size_t)evc_elems;
     return (size_t)gather_base(cap) + d * sizeof(double) + (size_t)pat_bytes + 16 + 256;
 }
 __device__ __forceinline__ Smem carve(unsigned char *base, int cap, int np, int mp, int pat_bytes, int evr_elems, int evc_elems, int nwarps,
@@ -433,7 +433,7 @@ __device__ __forceinline__ Smem carve(unsigned char *base, int cap, int np, int 
     s.blk = d; d += 2 * SB_COUNT;
     s.ring = d; d += 16;
     s.part = d; d += 2 * 4 * nwarps;
-    s.ctl = reinterpret_cast<int *>(d); d += 2;
+    s.ctl = reinterpret_cast<int *>(d); d += 4;
     s.ev_r = d; d += evr_elems;
     s.ev_c = d; d += evc_elems;
     s.r4v = d; d += evc_elems;
@@ -552,6 +552,7 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
     if (tid == 0) {
         mbar_init(S.bar, 1); fence_mbar_init();
         S.ctl[1] = la.sm_rank ? (atomicAdd(la.sm_rank + smid(), 1) & (NW - 1)) : (NW - 1);
+        S.ctl[5] = -2;                                                                  // sliced queue: nothing to hand back yet
         sts64(S.G + zero_off(CAP), 0.0); sts64(S.G + zero_off(CAP) + 8, 0.0);         // the shared padding operand
         sts64(S.R1 - 16, 0.0); sts64(S.R1 - 8, 0.0);                                  // padding operand of the z4 copy (zero + z4_add)
     }
@@ -570,14 +571,42 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
     (void)part_sel; (void)rq; (void)g3_off; (void)r1_off;
 
     for (;;) {
-        if (tid == 0) S.ctl[0] = atomicAdd(la.counter, 1);
+        // Work items.  Plain mode: ticket w of the atomic counter is instance work[w].  SLICED mode (la.slice > 0, plain solves of a
+        // whole batch): the queue is a ring of instance ids; a CTA runs at most `slice` iterations of the instance it popped and, if
+        // the instance is still running, appends it to the ring again -- every instance advances at about the same pace, so when
+        // the queue drains the CTAs finish within one slice of each other instead of one whole solve (the tail of a launch with
+        // thousands of iterations per instance).  The window boundary carries the full solver state, so the iterates do not change.
+        if (tid == 0) {
+            if (la.slice > 0) {                                    // hand back / retire the instance this CTA has just left
+                const int again = S.ctl[5];
+                if (again >= 0) { const int slot = atomicAdd(la.tail, 1); if (slot < la.ring_cap) atomicExch(la.ring + slot, again); }
+                else if (again == -1) atomicAdd(la.finished, 1);
+                S.ctl[5] = -2;
+            }
+            const int t = atomicAdd(la.counter, 1);
+            int item = -1;
+            if (la.slice <= 0) { if (t < la.n_work) item = la.work ? la.work[t] : t; }
+            else if (t < la.ring_cap) {
+                volatile int *rg = la.ring;
+                for (;;) {
+                    const int v = rg[t];
+                    if (v >= 0) { item = v; break; }
+                    if (*(volatile int *)la.finished >= la.n_work) break;      // every instance is done: no more tickets will come
+                    __nanosleep(256);
+                }
+                __threadfence();                                               // acquire: the producer's state writes are visible
+            }
+            S.ctl[0] = item;
+        }
         __syncthreads();
-        const int w = S.ctl[0];
+        const int inst = S.ctl[0];
         __syncthreads();
-        if (w >= la.n_work) break;
-        const int inst = la.work ? la.work[w] : w;
+        if (inst < 0) break;
         InstState *stp = bv.st + inst;
-        if ((la.skip_done && stp->done) || stp->n == 0) continue;   // uniform per CTA
+        if ((la.skip_done && __ldcg(&stp->done)) || stp->n == 0) {          // uniform per CTA
+            if (la.slice > 0 && tid == 0) atomicAdd(la.finished, 1);
+            continue;
+        }
 
         // ---------------- stage the instance --------------------------------------------------------------------
         const int n = stp->n, m = stp->m;
@@ -603,8 +632,9 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
             const bool in = s < n;
             const int j = in ? (int)g_cperm[s] : 0;
             cpk[e >> 1] |= ((uint32_t)((j & 3) * CH + (j >> 2)) * 8u) << (16 * (e & 1));
-            x[e] = in ? bv.x[on + j] : 0.0;
-            const double pd = in ? bv.Pd[on + j] : 1.0;
+            // (mutable solver state is read past the L1: with the sliced queue another SM may have written it since this SM last saw it)
+            x[e] = in ? __ldcg(bv.x + on + j) : 0.0;
+            const double pd = in ? __ldcg(bv.Pd + on + j) : 1.0;
             const double iv = (pd != 0.0) ? dD(1.0, pd) : 1.0;   // value in use when rhoUpdated == 0 (Eigen: zero diagonal -> 1)
             if (UNIT) {
                 const uint32_t L = in ? (uint32_t)bv.Esq[on + j] : 0u;      // unit case: Esq_j = number of stored entries of column j
@@ -612,13 +642,13 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                 if (in) sts64(S.tab + 8u * L, iv);                            // same value from every column of that length
             } else invd[UNIT ? 0 : e] = iv;
             if (in) {
-                park[PK_Y1 * CAP + e * T] = bv.y1[on + j]; park[PK_Y2 * CAP + e * T] = bv.y2[on + j];
-                park[PK_Z1 * CAP + e * T] = bv.z1[on + j]; park[PK_Z2 * CAP + e * T] = bv.z2[on + j];
+                park[PK_Y1 * CAP + e * T] = __ldcg(bv.y1 + on + j); park[PK_Y2 * CAP + e * T] = __ldcg(bv.y2 + on + j);
+                park[PK_Z1 * CAP + e * T] = __ldcg(bv.z1 + on + j); park[PK_Z2 * CAP + e * T] = __ldcg(bv.z2 + on + j);
                 park[PK_B * CAP + e * T] = bv.b[on + j];
             }
             if (s < m) {
                 const int i = g_rperm[s];
-                park[PK_Y3 * CAP + e * T] = bv.y3[om + i]; park[PK_Z4 * CAP + e * T] = bv.z4[om + i]; park[PK_F * CAP + e * T] = bv.f[om + i];
+                park[PK_Y3 * CAP + e * T] = __ldcg(bv.y3 + om + i); park[PK_Z4 * CAP + e * T] = __ldcg(bv.z4 + om + i); park[PK_F * CAP + e * T] = bv.f[om + i];
             }
         }
         sts_u32x2(S.cst + 8u * (uint32_t)tid, make_uint2(cpk[0], cpk[1]));   // read back (by this thread only) at every staging step
@@ -629,22 +659,23 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                      LPB_FOR_E cst[e] = S.R0 + (((((e) >> 1) ? cw_.y : cw_.x) >> (16 * ((e) & 1))) & 0xffffu); }      \
         else { LPB_FOR_E cst[e] = 0u; }
 #define LPB_INVD(e) (UNIT ? lds64(S.tab + 8u * ((lens >> (8 * (e))) & 0xffu)) : invd[UNIT ? 0 : (e)])
-        double D = stp->D, r4s = stp->r4s;
-        int rhoUpdated = stp->rhoUpdated;
+        double D = __ldcg(&stp->D), r4s = __ldcg(&stp->r4s);
+        int rhoUpdated = __ldcg(&stp->rhoUpdated);
         int cg_total = 0, admm_total = 0;
         int cur = 0;                                          // which scalar block the iteration about to start reads
         if (tid == 0) {
             double *b0 = S.blk;
-            b0[SB_RHO1] = stp->rho1; b0[SB_RHO2] = stp->rho2; b0[SB_RHO4] = stp->rho4; b0[SB_PRHO1] = stp->prho1; b0[SB_PRHO2] = stp->prho2;
-            b0[SB_PRHO4] = stp->prho4; b0[SB_GAMMA] = stp->gamma; b0[SB_RATIO] = stp->ratio; b0[SB_STD] = stp->std_obj; b0[SB_CUR] = stp->cur_obj;
-            b0[SB_BEST] = stp->best_bin_obj; b0[SB_OBJLEN] = __longlong_as_double(stp->obj_len);
+            b0[SB_RHO1] = __ldcg(&stp->rho1); b0[SB_RHO2] = __ldcg(&stp->rho2); b0[SB_RHO4] = __ldcg(&stp->rho4); b0[SB_PRHO1] = __ldcg(&stp->prho1);
+            b0[SB_PRHO2] = __ldcg(&stp->prho2); b0[SB_PRHO4] = __ldcg(&stp->prho4); b0[SB_GAMMA] = __ldcg(&stp->gamma); b0[SB_RATIO] = __ldcg(&stp->ratio);
+            b0[SB_STD] = __ldcg(&stp->std_obj); b0[SB_CUR] = __ldcg(&stp->cur_obj); b0[SB_BEST] = __ldcg(&stp->best_bin_obj);
+            b0[SB_OBJLEN] = __longlong_as_double(__ldcg(&stp->obj_len));
         }
-        if (tid < 16) S.ring[tid] = stp->obj_ring[tid];
+        if (tid < 16) S.ring[tid] = __ldcg(&stp->obj_ring[tid]);
         const int evr_used = UNIT ? 0 : 32 * stp->rcap, evc_used = UNIT ? 0 : 32 * stp->ccap;
         if (!UNIT) {
             const long long er = bv.off_evr[inst], ec = bv.off_evc[inst];
             for (int k = tid; k < evr_used; k += T) S.ev_r[k] = bv.ev_r[er + k];
-            for (int k = tid; k < evc_used; k += T) { S.ev_c[k] = bv.ev_c[ec + k]; S.r4v[k] = bv.r4v[ec + k]; }
+            for (int k = tid; k < evc_used; k += T) { S.ev_c[k] = bv.ev_c[ec + k]; S.r4v[k] = __ldcg(bv.r4v + ec + k); }
         }
         mbar_wait(S.bar, tma_phase); tma_phase ^= 1;
         const uint32_t pat_a = smem_u32(S.pat);
@@ -683,7 +714,9 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
     do { block_sum<K, NW>(V, S.part + part_sel * 4 * NW); part_sel ^= 1; } while (0)
 
         int status = RUNNING;
-        int iter = la.iter_start;
+        int iter = la.slice > 0 ? __ldcg(&stp->iter) : la.iter_start;          // sliced: continue where the previous slice of this instance stopped
+        if (tid == 0) S.ctl[4] = la.slice > 0 ? min(iter + la.slice, la.iter_end) : la.iter_end;   // end of this slice (read from shared memory: registers are scarce)
+#define it_end (*(volatile int *)(S.ctl + 4))
         int cc = 0;
         const bool lp_plain = (!la.l2f) && pr.guard_first_iter;
         double ynorm2 = 0.0;                                  // ||x + z2/rho2 - 1/2||^2 of the iteration about to start
@@ -691,7 +724,7 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
         // ---- window prologue: E x -> T1 and ||y||^2 for the first iteration (later iterations get both from the tail
         //      of the previous one: same operands, same order -> same bits) ---------------------------------------------
         __syncthreads();                                      // image, ring, scalar block visible; previous instance's smem reads done
-        if (iter < la.iter_end) {
+        if (iter < it_end) {
             double ysq[1] = {0.0};
             const double rho2 = S.blk[SB_RHO2];
             LPB_CST_LOAD();
@@ -712,7 +745,7 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
             if (!FAST) ynorm2 = S.sc[5];
         }
 
-        for (; iter < la.iter_end; ++iter) {
+        for (; iter < it_end; ++iter) {
             const double *blk = S.blk + cur * SB_COUNT;      // read-only during the iteration
             // ---- operator patch after a rho step (:851-866) first: the rhs uses the patched rho4 E^T --------------------
             if (iter != 0 && rhoUpdated) {
@@ -724,7 +757,7 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                     const int s = vt + e * T;
                     if (s < n) {
                         const int j = g_cperm[s];
-                        double pd = bv.Pd[on + j];
+                        double pd = __ldcg(bv.Pd + on + j);
                         pd = dA(pd, c12);
                         pd = dA(pd, dM(c4, bv.Esq[on + j]));
                         bv.Pd[on + j] = pd;
@@ -736,7 +769,7 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
             if (rhoUpdated) {                                                // preconditioner refresh (:883-890)
                 LPB_FOR_E {
                     const int s = vt + e * T;
-                    const double pd = (s < n) ? bv.Pd[on + g_cperm[s]] : 1.0;
+                    const double pd = (s < n) ? __ldcg(bv.Pd + on + g_cperm[s]) : 1.0;
                     const double iv = (pd != 0.0) ? dD(1.0, pd) : 1.0;
                     if (UNIT) { if (s < n) sts64(S.tab + 8u * ((lens >> (8 * e)) & 0xffu), iv); }
                     else invd[UNIT ? 0 : e] = iv;
@@ -1062,18 +1095,22 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
             stp->prho4 = fb[SB_PRHO4]; stp->gamma = fb[SB_GAMMA]; stp->ratio = fb[SB_RATIO]; stp->std_obj = fb[SB_STD];
             stp->cur_obj = fb[SB_CUR]; stp->best_bin_obj = fb[SB_BEST]; stp->obj_len = __double_as_longlong(fb[SB_OBJLEN]);
             stp->D = D; stp->r4s = r4s; stp->rhoUpdated = rhoUpdated;
-            stp->cg_iters += cg_total; stp->admm_iters += admm_total;
+            stp->cg_iters = __ldcg(&stp->cg_iters) + cg_total; stp->admm_iters = __ldcg(&stp->admm_iters) + admm_total;
             stp->iter = iter; stp->status = status;
             int ret;
-            if (la.l2f) ret = (status != RUNNING || stp->norm_small) ? 1 : 0;    // :1505, :1542, :1452, :1223
+            if (la.l2f) ret = (status != RUNNING || __ldcg(&stp->norm_small)) ? 1 : 0;    // :1505, :1542, :1452, :1223
             else ret = (status == STOP_STD) ? 1 : 0;                             // :978
             stp->last_ret = ret;
             // the window driver stops calling once a call returned 1 (LP.trainer:521); the plain driver calls once
             stp->done = la.l2f ? ret : (status != RUNNING);
             if (la.l2f || la.record) { stp->xit_cols = cc; if (!la.l2f) stp->xit_rows = n; }
+            S.ctl[5] = (status == RUNNING && iter < la.iter_end) ? inst : -1;   // sliced queue: ticket to append once the state is out
         }
+        if (la.slice > 0) __threadfence();                                     // every thread's state writes precede the ticket
         __syncthreads();
+        // (the ticket is appended at the top of the loop, before the next pop)
     }
+#undef it_end
 #undef LPB_ROW_SPMV
 #undef LPB_COL_DOT
 #undef LPB_BLOCK_SUM

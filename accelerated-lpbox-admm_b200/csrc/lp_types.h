@@ -156,6 +156,10 @@ struct Launch {
     int pat_bytes;           // shared-memory bytes reserved for the sliced-ELL blob
     int evr_elems, evc_elems; // shared-memory doubles reserved for the ELL-order value arrays (0 when unit)
     int tab_len;             // unit case: entries of the shared 1/diag table (longest column of the batch + 1)
+    int slice;               // > 0: sliced queue -- at most `slice` iterations per pop, running instances are re-queued (plain batch solves)
+    int *ring;               // [ring_cap] sliced queue: instance ids, -1 = not produced yet; the first n_work entries are pre-filled
+    int ring_cap;
+    int *tail, *finished;    // sliced queue: next free ring slot; number of instances that are done
     int *sm_rank;            // [#SMs] zeroed per launch: arrival order of the CTAs of one SM (rotates the reduction warp)
     double *park;            // [grid][8][cap] per-CTA parking lot (L2-resident) for vectors that are not touched inside PCG
     int *error;              // device flag: set when the shared-window base differs from BatchView::sbase

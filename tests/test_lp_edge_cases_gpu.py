@@ -4,7 +4,7 @@ spot-checked against the oracle, and re-solving (determinism)."""
 import numpy as np
 import pytest
 
-from conftest import synth_auction
+from conftest import load_golden, problem_tuple, synth_auction
 
 pytestmark = pytest.mark.gpu
 
@@ -161,3 +161,24 @@ def test_spilled_pattern_image_is_bit_identical(monkeypatch):
     assert np.array_equal(spilled[0], plain[0])
     for a, c in zip(spilled[1], plain[1]):
         assert np.array_equal(a, c)
+
+
+def test_sliced_work_queue_is_bit_identical(monkeypatch):
+    """Plain batch solves can run with a SLICED work queue (opt-in, LPBOX_SLICE: a CTA leaves an instance after `slice` iterations
+    and re-queues it; csrc/lp_kernels.cuh).  Forced onto a small batch with a slice that splits every solve into many pieces --
+    across CTAs and SMs -- it must give exactly the log rows, iterates and solutions of the unsliced launch."""
+    import lpbox
+    probs = lpbox.gen_auctions(9, 48, 100, 500) + [problem_tuple(load_golden("auction_40_200_seed1.npz"))]
+    monkeypatch.setenv("LPBOX_SLICE", "0")
+    a = lpbox.LPBatch(probs); a.init(); ref = a.solve(20000).copy(); xa = [a.state(i)["x"].copy() for i in (0, 17, 48)]; _, bits_a = a.results()
+    a.close()
+    for sl in ("137", "500"):
+        monkeypatch.setenv("LPBOX_SLICE", sl); monkeypatch.setenv("LPBOX_SLICE_FORCE", "1")
+        b = lpbox.LPBatch(probs); b.init(); got = b.solve(20000)
+        assert np.array_equal(got, ref), sl
+        for k, i in enumerate((0, 17, 48)):
+            assert np.array_equal(b.state(i)["x"], xa[k]), (sl, i)
+        assert np.array_equal(b.results()[1], bits_a)
+        # a second solve on the same handle (re-init) reuses the queue buffers
+        b.init(); assert np.array_equal(b.solve(20000), ref)
+        b.close()
