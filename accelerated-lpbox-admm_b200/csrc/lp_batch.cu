@@ -183,6 +183,7 @@ static int configure(lpbox_batch *h) {
     CK(occ_at(h->smem, &occ));
     h->pat_smem = h->max_pat;
     h->d_work.free_();
+    int spill_budget = -1;
     // Shared memory is sized for the LARGEST sliced-ELL image of the batch; a few instances with a wide pattern can cost the
     // whole batch one resident CTA per SM.  When that happens the image budget is cut to what full occupancy allows and the
     // (few) instances above it keep their last array -- the column index array -- in global memory (L2) instead.
@@ -207,11 +208,7 @@ static int configure(lpbox_batch *h) {
         if (head_max <= budget && budget < h->max_pat && (forced || fit >= (h->B * 9) / 10)) {
             h->pat_smem = budget;
             h->smem = smem_bytes(h->cap, np, mp, budget, 0, 0, h->nwarps, h->tab_len);
-            std::vector<int> order;
-            for (int i = 0; i < h->B; ++i) if (h->pat_bytes_i[i] > budget) order.push_back(i);
-            for (int i = 0; i < h->B; ++i) if (h->pat_bytes_i[i] <= budget) order.push_back(i);
-            CK(h->d_work.alloc(order.size()));
-            CK(cudaMemcpy(h->d_work.p, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice));
+            spill_budget = budget;
             if (getenv("LPBOX_DEBUG")) fprintf(stderr, "[lpbox] image budget %d B (largest %d B): %d of %d instances keep their column indices in L2\n", budget, h->max_pat, h->B - fit, h->B);
         }
         CK(occ_at(h->smem, &occ));
@@ -219,6 +216,23 @@ static int configure(lpbox_batch *h) {
     CK(cudaFuncSetAttribute(lp_fix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fix_smem));
     if (occ < 1) occ = 1;
     h->grid = std::max(1, std::min(h->B, sms * occ));
+    // Launch order.  A CTA keeps an instance until it stops, so a launch of more than one wave ends with the instances that were
+    // started last: start the ones with the most stored entries first (they tend to run longest: corr(nnz, CG iterations) = 0.5 on
+    // the auction batches, tools/dump_iters.py) -- longest-processing-time-first list scheduling with a free predictor.
+    // Instances whose image does not fit the shared-memory budget (the widest patterns) lead in any case.
+    static const bool no_sort = getenv("LPBOX_NO_SORT") != nullptr;         // experiments
+    if (spill_budget >= 0 || (h->B > h->grid && !no_sort && (int)h->nnz0.size() == h->B)) {
+        std::vector<int> order(h->B);
+        for (int i = 0; i < h->B; ++i) order[i] = i;
+        auto spilled = [&](int i) { return spill_budget >= 0 && h->pat_bytes_i[i] > spill_budget; };
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            const bool sa = spilled(a), sb = spilled(b);
+            if (sa != sb) return sa;
+            return (h->B > h->grid && !no_sort) ? h->nnz0[a] > h->nnz0[b] : false;
+        });
+        CK(h->d_work.alloc(order.size()));
+        CK(cudaMemcpy(h->d_work.p, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice));
+    }
     h->d_park.free_();
     CK(h->d_park.alloc((size_t)h->grid * PK_COUNT * (size_t)h->cap));
     // the ELL image stores absolute shared-window addresses: ask where the dynamic shared memory of a kernel without static

@@ -51,6 +51,8 @@ struct lpbox_seg_batch {
     std::vector<SegInst> h_st;
     bool inited = false;
     int grid = 0;
+    int threads = 0;                            // launch shape of seg_admm_kernel (SegCfg): 256, 192 or 160
+    size_t smem_admm = 0;
     size_t smem = 0;
     double last_ms = 0;
     int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
@@ -146,6 +148,17 @@ extern "C" void lpbox_seg_destroy(lpbox_seg_batch *h) {
 }
 
 // allocation + kernel configuration shared by both constructors; CSR / b are filled afterwards (H2D or the device graph builder)
+// Opt-in shared memory + resident CTAs per SM of one launch shape of seg_admm_kernel.
+template <int T>
+static cudaError_t seg_shape_query(bool compact, int *occ, size_t *smem) {
+    *smem = sizeof(double) * (SegCfg<T>::BUF + 8 + 16);
+    cudaError_t e = compact ? cudaFuncSetAttribute(seg_admm_kernel<true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem)
+                            : cudaFuncSetAttribute(seg_admm_kernel<false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem);
+    if (e != cudaSuccess) return e;
+    return compact ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, seg_admm_kernel<true, T>, T, *smem)
+                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, seg_admm_kernel<false, T>, T, *smem);
+}
+
 static lpbox_seg_batch *seg_new(int device, int B, const int32_t *n, const int *nnz, const double *c, int hist_cap, bool compact) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { lpbox_set_error("no CUDA device (there is no CPU fallback)"); return nullptr; }
@@ -206,18 +219,30 @@ static lpbox_seg_batch *seg_new(int device, int B, const int32_t *n, const int *
     for (int k = 0; k < 2; ++k) { v.b[k] = h->d_b[k].p; v.rowptr[k] = h->d_rp[k].p; v.colidx[k] = h->d_ci[k].p; v.val[k] = h->d_val[k].p; }
     v.kidx = h->d_kidx.p; v.cnt = h->d_cnt.p; v.pow_tab = h->d_powtab.p;
     v.st = h->d_st.p; v.hist = h->d_hist.p; v.left_idx = h->d_left.p; v.ret_idx = h->d_ret_idx.p; v.ret_val = h->d_ret_val.p; v.powv = h->d_powv.p;
-    h->smem = sizeof(double) * (SEG_BUF_DOUBLES + 8 + 16);
-    int sms = 0, occ = 1;
-    if (cudaFuncSetAttribute(seg_admm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess ||
-        cudaFuncSetAttribute(seg_admm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess ||
-        cudaFuncSetAttribute(seg_setup_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess ||
+    h->smem = sizeof(double) * (SEG_BUF_DOUBLES + 8 + 16);                     // set-up kernel
+    int sms = 0;
+    if (cudaFuncSetAttribute(seg_setup_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess ||
         cudaFuncSetAttribute(seg_setup_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem) != cudaSuccess ||
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
-        (compact ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seg_admm_kernel<true>, SEG_T, h->smem)
-                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seg_admm_kernel<false>, SEG_T, h->smem)) != cudaSuccess) {
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
         lpbox_set_error("seg kernel configuration failed"); lpbox_seg_destroy(h); return nullptr;
     }
-    h->grid = std::max(1, std::min(B, sms * std::max(occ, 1)));
+    // Launch shape (SegCfg): an image is solved by one CTA from start to end, so a launch takes `waves` x (time of one image),
+    // and one image advances in proportion to its CTA's staging threads.  Pick the shape with the smallest waves / staging threads.
+    const int shapes[3] = {256, 192, 160};
+    double best = 0.0;
+    const char *force = getenv("LPBOX_SEG_T");                                  // experiments
+    for (int k = 0; k < 3; ++k) {
+        int occ = 0; size_t sm = 0;
+        const cudaError_t e = shapes[k] == 256 ? seg_shape_query<256>(compact, &occ, &sm)
+                            : shapes[k] == 192 ? seg_shape_query<192>(compact, &occ, &sm) : seg_shape_query<160>(compact, &occ, &sm);
+        if (e != cudaSuccess || occ < 1) { lpbox_set_error("seg kernel configuration failed"); lpbox_seg_destroy(h); return nullptr; }
+        const int slots = sms * occ;
+        const double cost = (double)((B + slots - 1) / slots) / (shapes[k] - 32);
+        if (force ? atoi(force) == shapes[k] : (h->threads == 0 || cost < best)) {
+            best = cost; h->threads = shapes[k]; h->smem_admm = sm; h->grid = std::max(1, std::min(B, slots));
+        }
+    }
+    if (h->threads == 0) { lpbox_set_error("LPBOX_SEG_T must be 256, 192 or 160"); lpbox_seg_destroy(h); return nullptr; }
     return h;
 }
 
@@ -549,13 +574,22 @@ extern "C" int lpbox_seg_init(lpbox_seg_batch *h, const double *x0_all) {
     return 0;
 }
 
+template <int T>
+static void seg_launch_admm(lpbox_seg_batch *h, const SegLaunch &la) {
+    if (h->compact) seg_admm_kernel<true, T><<<h->grid, T, h->smem_admm, h->stream>>>(h->sv, h->pr, la);
+    else seg_admm_kernel<false, T><<<h->grid, T, h->smem_admm, h->stream>>>(h->sv, h->pr, la);
+}
+
 static int seg_run(lpbox_seg_batch *h, int iter_start, int iter_end, int l2f, int skip_done) {
     SegLaunch la{};
     la.iter_start = iter_start; la.iter_end = iter_end; la.l2f = l2f; la.skip_done = skip_done; la.n_work = h->B; la.counter = h->d_counter.p;
     SCK(cudaMemsetAsync(h->d_counter.p, 0, sizeof(int), h->stream));
     SCK(cudaEventRecord(h->ev0, h->stream));
-    if (h->compact) seg_admm_kernel<true><<<h->grid, SEG_T, h->smem, h->stream>>>(h->sv, h->pr, la);
-    else seg_admm_kernel<false><<<h->grid, SEG_T, h->smem, h->stream>>>(h->sv, h->pr, la);
+    switch (h->threads) {
+        case 256: seg_launch_admm<256>(h, la); break;
+        case 192: seg_launch_admm<192>(h, la); break;
+        default:  seg_launch_admm<160>(h, la); break;
+    }
     SCK(cudaGetLastError());
     h->launches += 1;
     SCK(cudaEventRecord(h->ev1, h->stream));

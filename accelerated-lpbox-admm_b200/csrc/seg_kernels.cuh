@@ -61,10 +61,23 @@ struct SegLaunch {
     int *counter;
 };
 
-constexpr int SEG_T = 256;
-constexpr int SEG_CH = 256;     // products staged per reduction per chunk
+constexpr int SEG_T = 256;      // threads of the set-up / early-fix kernels and of the wide ADMM variant
 constexpr int SEG_RMAX = 7;
-constexpr int SEG_BUF_DOUBLES = (2 * 7 * 256 > 2 * 5 * 448) ? 2 * 7 * 256 : 2 * 5 * 448;   // max(block_redux ring, fused-pass ring)
+
+// Launch shapes of seg_admm_kernel (one chain warp + T/32 - 1 staging warps per CTA; 40-42 resident warps per SM each):
+//   T = 256: 5 CTAs/SM (740 images resident on 148 SMs), 224 staging threads per image, 48 registers -- fastest per image;
+//   T = 192: 7 CTAs/SM (1036 resident), 160 staging threads per image, 40 registers (42 warps do not fit at 48);
+//   T = 160: 8 CTAs/SM (1184 resident), 128 staging threads per image, 48 registers.
+// The host picks the shape that needs fewer waves (e.g. the 1024-image batch of configs[2]: one wave instead of 1.38).
+// BUF = doubles of the double-buffered product ring; a fused pass with R reductions stages FCH<R> elements per chunk (a multiple
+// of the staging thread count): few reductions -> long chunks -> more rows in flight per thread between two barriers.
+template <int T> struct SegCfg {
+    static constexpr int STG = T - 32;
+    static constexpr int MINB = (T == 256) ? 5 : (T == 192) ? 7 : 8;
+    static constexpr int BUF = (T == 256) ? 4480 : (T == 192) ? 3840 : 3328;
+    static constexpr int CH = (BUF / (2 * SEG_RMAX) < 256 ? BUF / (2 * SEG_RMAX) : 256) & ~3;   // seg_block_redux: products per reduction per chunk
+};
+constexpr int SEG_BUF_DOUBLES = SegCfg<SEG_T>::BUF;
 
 // Storage format of A.  COMPACT = 3 bytes per stored entry instead of 12: the column index as int16 distance from the row and the
 // value as int8 (exact: both conversions are lossless for the graphs of the reference's builder and for any user matrix the host
@@ -85,6 +98,22 @@ __device__ __forceinline__ double seg_row_dot(const int *__restrict__ rp, const 
         const int c = seg_col<CMP>(ci, k, i);
         double m = (double)av[k];
         if (DIAG) m = (c == i) ? md[i] : dM(2.0, m);
+        acc = dA(acc, dM(m, v[c]));
+    }
+    return acc;
+}
+
+// Same with the row bounds [s, e) already in registers (the fused passes prefetch them one element ahead, which takes the
+// rowptr load out of the dependent chain rowptr -> column offsets -> operands) and the diagonal entry md[i] loaded once.
+template <bool DIAG, bool CMP>
+__device__ __forceinline__ double seg_row_dot_se(int s, int e, const typename SegFmt<CMP>::CI *__restrict__ ci,
+                                                 const typename SegFmt<CMP>::AV *__restrict__ av, double mdi,
+                                                 const double *__restrict__ v, int i) {
+    double acc = 0.0;
+    for (int k = s; k < e; ++k) {
+        const int c = seg_col<CMP>(ci, k, i);
+        double m = (double)av[k];
+        if (DIAG) m = (c == i) ? mdi : dM(2.0, m);
         acc = dA(acc, dM(m, v[c]));
     }
     return acc;
@@ -113,21 +142,21 @@ __device__ __forceinline__ double seg_chain(const double *src, int i, int lim, d
 }
 
 // Block-cooperative Eigen-order reduction of R product streams prod(q, i), i < n.  Results in sc[0..R).
-// buf: shared, 2 * R * SEG_CH doubles.  All SEG_T threads must call.
-template <int R, typename F>
+// buf: shared, 2 * R * SegCfg<T>::CH doubles.  All T threads must call.
+template <int R, int T = SEG_T, typename F>
 __device__ __forceinline__ void seg_block_redux(F prod, int n, double *buf, double *sc) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int RW = SEG_T / 32 - 1;
+    constexpr int RW = T / 32 - 1, CH = SegCfg<T>::CH;
     const int a2 = n & ~3, a1 = n & ~1;
     const int q = lane >> 2, k = lane & 3;
-    const int nch = (a2 + SEG_CH - 1) / SEG_CH;
+    const int nch = (a2 + CH - 1) / CH;
     auto stage = [&](int c) {
-        double *dst = buf + (size_t)(c & 1) * R * SEG_CH;
-        const int base = c * SEG_CH;
-        const int lim = min(SEG_CH, a2 - base);
-        for (int idx = tid; idx < R * SEG_CH; idx += SEG_T - 32) {      // every warp but the reduction warp
-            const int qq = idx / SEG_CH, i = idx - qq * SEG_CH;
-            if (i < lim) dst[qq * SEG_CH + i] = prod(qq, base + i);
+        double *dst = buf + (size_t)(c & 1) * R * CH;
+        const int base = c * CH;
+        const int lim = min(CH, a2 - base);
+        for (int idx = tid; idx < R * CH; idx += T - 32) {          // every warp but the reduction warp
+            const int qq = idx / CH, i = idx - qq * CH;
+            if (i < lim) dst[qq * CH + i] = prod(qq, base + i);
         }
     };
     double acc = 0.0;
@@ -138,8 +167,8 @@ __device__ __forceinline__ void seg_block_redux(F prod, int n, double *buf, doub
         for (int c = 0; c < nch; ++c) {
             if (warp != RW) { if (c + 1 < nch) stage(c + 1); }
             else if (q < R) {
-                const double *src = buf + (size_t)(c & 1) * R * SEG_CH + q * SEG_CH;
-                const int lim = min(SEG_CH, a2 - c * SEG_CH);
+                const double *src = buf + (size_t)(c & 1) * R * CH + q * CH;
+                const int lim = min(CH, a2 - c * CH);
                 int i = k;
                 if (c == 0) { acc = src[k]; i = 4 + k; }
                 acc = seg_chain(src, i, lim, acc);
@@ -167,29 +196,37 @@ __device__ __forceinline__ void seg_block_redux(F prod, int n, double *buf, doub
     __syncthreads();
 }
 
-// Fused streaming pass + Eigen-order reductions.  body(i, v) is called EXACTLY ONCE for every i < n (in chunk order) by the
-// staging warps: it performs the element's work (global loads / stores) and returns the R products of element i.  The
-// products go to a double-buffered shared-memory ring; the reduction warp walks the four chains of each reduction one
-// chunk behind the producers, so the streaming work and the sequential chains overlap.  Results in sc[0..R).
-constexpr int SEG_FCH = 448;            // elements per chunk = 2 per staging thread (multiple of 4)
-constexpr int SEG_FR = 5;               // max reductions per fused pass
-template <int R, typename Body>
-__device__ __forceinline__ void seg_fused_pass(Body body, int n, double *buf, double *sc) {
+// Fused streaming pass + Eigen-order reductions.  body(i, s, e, v) is called EXACTLY ONCE for every i < n (in chunk order) by
+// the staging warps: it performs the element's work (global loads / stores) and returns the R products of element i; with
+// ROWS, [s, e) are the bounds of row i of A (loaded one element ahead).  The products go to a double-buffered shared-memory
+// ring; the reduction warp walks the four chains of each reduction one chunk behind the producers, so the streaming work and
+// the sequential chains overlap.  Results in sc[0..R).  The chunk length only decides how the work is staged, never the order
+// of the additions.
+template <int T, int R, bool ROWS, typename Body>
+__device__ __forceinline__ void seg_fused_pass(Body body, const int *__restrict__ rp, int n, double *buf, double *sc) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int RW = SEG_T / 32 - 1;
+    constexpr int RW = T / 32 - 1, STG = T - 32;
+    constexpr int FCH = (SegCfg<T>::BUF / (2 * R)) / STG * STG;
+    // short vectors: at least 8 chunks (so that staging and chain overlap), at least two elements per staging thread
+    const int fch = (n >= 8 * FCH) ? FCH : max(2 * STG, (n / 8) / STG * STG);
     const int a2 = n & ~3, a1 = n & ~1;
     const int q = lane >> 2, k = lane & 3;
-    const int nch = (n + SEG_FCH - 1) / SEG_FCH;
+    const int nch = (n + fch - 1) / fch;
     auto stage = [&](int c) {
-        double *dst = buf + (size_t)(c & 1) * R * SEG_FCH;
-        const int base = c * SEG_FCH;
-        const int lim = min(SEG_FCH, n - base);
+        double *dst = buf + (size_t)(c & 1) * R * fch;
+        const int base = c * fch;
+        const int lim = min(fch, n - base);
+        int idx = tid, s = 0, e = 0;
+        if (ROWS && idx < lim) { s = rp[base + idx]; e = rp[base + idx + 1]; }
 #pragma unroll 2
-        for (int idx = tid; idx < lim; idx += SEG_T - 32) {
+        for (; idx < lim; idx += STG) {
+            int s2 = 0, e2 = 0;
+            if (ROWS && idx + STG < lim) { s2 = rp[base + idx + STG]; e2 = rp[base + idx + STG + 1]; }
             double v[R];
-            body(base + idx, v);
+            body(base + idx, s, e, v);
 #pragma unroll
-            for (int r = 0; r < R; ++r) dst[r * SEG_FCH + idx] = v[r];
+            for (int r = 0; r < R; ++r) dst[r * fch + idx] = v[r];
+            s = s2; e = e2;
         }
     };
     double acc = 0.0;
@@ -199,8 +236,8 @@ __device__ __forceinline__ void seg_fused_pass(Body body, int n, double *buf, do
     for (int c = 0; c < nch; ++c) {
         if (warp != RW) { if (c + 1 < nch) stage(c + 1); }
         else if (q < R && a1 > 2) {
-            const double *src = buf + (size_t)(c & 1) * R * SEG_FCH + q * SEG_FCH;
-            const int lim = min(SEG_FCH, a2 - c * SEG_FCH);     // chain part only (elements < a2)
+            const double *src = buf + (size_t)(c & 1) * R * fch + q * fch;
+            const int lim = min(fch, a2 - c * fch);             // chain part only (elements < a2)
             int i = k;
             if (c == 0) { acc = src[k]; i = 4 + k; }
             acc = seg_chain(src, i, lim, acc);
@@ -210,7 +247,7 @@ __device__ __forceinline__ void seg_fused_pass(Body body, int n, double *buf, do
     if (warp == RW) {
         // products of the tail elements (index >= a2) sit in the ring slot of the chunk that contains them
         const int qq = q < R ? q : 0;
-        auto at = [&](int i) { const int c = i / SEG_FCH; return buf[(size_t)(c & 1) * R * SEG_FCH + qq * SEG_FCH + (i - c * SEG_FCH)]; };
+        auto at = [&](int i) { const int c = i / fch; return buf[(size_t)(c & 1) * R * fch + qq * fch + (i - c * fch)]; };
         // only the last two chunks are still resident: all indices >= a2 - and, for n < 4, indices 0..n-1 - are in them
         double res;
         if (a1 > 2) {
@@ -230,14 +267,14 @@ __device__ __forceinline__ void seg_fused_pass(Body body, int n, double *buf, do
     __syncthreads();
 }
 
-template <bool CMP>
-__global__ void __launch_bounds__(SEG_T, 5)
+template <bool CMP, int T>
+__global__ void __launch_bounds__(T, SegCfg<T>::MINB)
 seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
     using CI = typename SegFmt<CMP>::CI;
     using AV = typename SegFmt<CMP>::AV;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *buf = reinterpret_cast<double *>(smem_raw);                 // [2][SEG_RMAX][SEG_CH]
-    double *sc = buf + SEG_BUF_DOUBLES;                                 // [8]
+    double *buf = reinterpret_cast<double *>(smem_raw);                 // product ring, SegCfg<T>::BUF doubles
+    double *sc = buf + SegCfg<T>::BUF;                                 // [8]
     double *ring = sc + 8;                                              // [16]
     __shared__ int s_work;
     const int tid = threadIdx.x;
@@ -269,20 +306,20 @@ seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
         int status = RUNNING, iter = la.iter_start, cc = 0;
         for (; iter < la.iter_end; ++iter) {
             // ---- pass 1: y1, y2 pre-image (SEG.cpp:1223-1234) + ||y||^2 ---------------------------------------------
-            seg_fused_pass<1>([&](int i, double (&v)[1]) {
+            seg_fused_pass<T, 1, false>([&](int i, int, int, double (&v)[1]) {
                 const double xi = x[i];
                 double tt = dA(xi, dD(z1[i], rho1));
                 y1[i] = (tt > 1.0) ? 1.0 : ((tt < 0.0) ? 0.0 : tt);
                 const double sh = dS(dA(xi, dD(z2[i], rho2)), 0.5);
                 y2[i] = sh;
                 v[0] = dM(sh, sh);
-            }, n, buf, sc);
+            }, rp, n, buf, sc);
             const double den = dM(2.0, sqrt(sc[0]));
             // ---- pass 2 (no reduction): diagonal patch (:1240-1243), preconditioner (:1252-1255), y2, rhs (:1246), x = y1 ----
             const bool patch = (iter != 0 && rhoUpdated);
             const double dpatch = dM(dA(prho1, prho2), ratio);
 #pragma unroll 4
-            for (int i = tid; i < n; i += SEG_T) {
+            for (int i = tid; i < n; i += T) {
                 if (patch) md[i] = dA(md[i], dpatch);
                 if (rhoUpdated) { const double d = md[i]; invd[i] = (d != 0.0) ? dD(1.0, d) : 1.0; }
                 const double y1i = y1[i];
@@ -293,17 +330,17 @@ seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
             }
             rhoUpdated = 0;
             // ---- PCG (SEG.cpp:272-342).  pass 3: r = rhs - M x, p = invd r; rhs.rhs, r.r, r.p ---------------------------
-            seg_fused_pass<3>([&](int i, double (&v)[3]) {
+            seg_fused_pass<T, 3, true>([&](int i, int s, int e, double (&v)[3]) {
                 const double rhs = w[i];
-                const double rr = dS(rhs, seg_row_dot<true, CMP>(rp, ci, av, md, x, i));
+                const double rr = dS(rhs, seg_row_dot_se<true, CMP>(s, e, ci, av, md[i], x, i));
                 const double pp = dM(invd[i], rr);
                 r[i] = rr; p[i] = pp;
                 v[0] = dM(rhs, rhs); v[1] = dM(rr, rr); v[2] = dM(rr, pp);
-            }, n, buf, sc);
+            }, rp, n, buf, sc);
             const double rhsNorm2 = sc[0];
             int cg_it = 0;
             if (rhsNorm2 == 0.0) {
-                for (int i = tid; i < n; i += SEG_T) x[i] = 0.0;
+                for (int i = tid; i < n; i += T) x[i] = 0.0;
             } else {
                 double threshold = dM(dM(pr.pcg_tol, pr.pcg_tol), rhsNorm2);
                 if (!(threshold > DBL_MIN)) threshold = DBL_MIN;
@@ -311,27 +348,27 @@ seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
                 if (!(r2 < threshold)) {
                     while (cg_it < pr.pcg_maxiters) {
                         // tmp = M p fused with p.dot(tmp)
-                        seg_fused_pass<1>([&](int i, double (&v)[1]) {
-                            const double ti = seg_row_dot<true, CMP>(rp, ci, av, md, p, i);
+                        seg_fused_pass<T, 1, true>([&](int i, int s, int e, double (&v)[1]) {
+                            const double ti = seg_row_dot_se<true, CMP>(s, e, ci, av, md[i], p, i);
                             t[i] = ti;
                             v[0] = dM(p[i], ti);
-                        }, n, buf, sc);
+                        }, rp, n, buf, sc);
                         const double alpha = dD(absNew, sc[0]);
                         // x += alpha p; r -= alpha tmp; z = invd r fused with r.r and r.z
-                        seg_fused_pass<2>([&](int i, double (&v)[2]) {
+                        seg_fused_pass<T, 2, false>([&](int i, int, int, double (&v)[2]) {
                             x[i] = dA(x[i], dM(alpha, p[i]));
                             const double rr = dS(r[i], dM(alpha, t[i]));
                             const double zz = dM(invd[i], rr);
                             r[i] = rr; t[i] = zz;
                             v[0] = dM(rr, rr); v[1] = dM(rr, zz);
-                        }, n, buf, sc);
+                        }, rp, n, buf, sc);
                         r2 = sc[0];
                         if (r2 < threshold) { cg_it++; break; }
                         const double absOld = absNew;
                         absNew = sc[1];
                         const double beta = dD(absNew, absOld);
 #pragma unroll 4
-                        for (int i = tid; i < n; i += SEG_T) p[i] = dA(t[i], dM(beta, p[i]));
+                        for (int i = tid; i < n; i += T) p[i] = dA(t[i], dM(beta, p[i]));
                         cg_it++;
                     }
                 }
@@ -342,24 +379,24 @@ seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
             if (la.l2f && sv.hist_cap > 0) { if (cc < sv.hist_cap) h = sv.hist + sv.off_hist[inst] + (long long)cc * st->n0; cc++; }
             {
                 const double g1 = dM(gamma, rho1), g2 = dM(gamma, rho2);
-                seg_fused_pass<5>([&](int i, double (&v)[5]) {
+                seg_fused_pass<T, 5, true>([&](int i, int s, int e, double (&v)[5]) {
                     const double xi = x[i];
                     if (h) h[i] = xi;
                     const double d1 = dS(xi, y1[i]), d2 = dS(xi, y2[i]);
                     z1[i] = dA(z1[i], dM(g1, d1));
                     z2[i] = dA(z2[i], dM(g2, d2));
                     w[i] = (xi >= 0.5) ? 1.0 : 0.0;
-                    const double ax = seg_row_dot<false, CMP>(rp, ci, av, md, x, i);
+                    const double ax = seg_row_dot_se<false, CMP>(s, e, ci, av, 0.0, x, i);
                     v[0] = dM(xi, xi); v[1] = dM(d1, d1); v[2] = dM(d2, d2); v[3] = dM(xi, ax); v[4] = dM(b[i], xi);
-                }, n, buf, sc);
+                }, rp, n, buf, sc);
             }
             const double nx2 = sc[0], d12 = sc[1], d22 = sc[2], obj_val = dA(sc[3], sc[4]);   // compute_cost: val + val2
             // ---- pass: A 1[x >= 0.5]; idx.A idx, b.idx  (SEG.cpp:1323-1326) -------------------------------------------
-            seg_fused_pass<2>([&](int i, double (&v)[2]) {
+            seg_fused_pass<T, 2, true>([&](int i, int s, int e, double (&v)[2]) {
                 const double wi = w[i];
-                v[0] = dM(wi, seg_row_dot<false, CMP>(rp, ci, av, md, w, i));
+                v[0] = dM(wi, seg_row_dot_se<false, CMP>(s, e, ci, av, 0.0, w, i));
                 v[1] = dM(b[i], wi);
-            }, n, buf, sc);
+            }, rp, n, buf, sc);
             const double bin_val = dA(sc[0], sc[1]);
             {
                 double temp0 = sqrt(nx2);
@@ -392,11 +429,11 @@ seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
         __syncthreads();
         if (!la.l2f) {
             // legacy epilogue (SEG.cpp:1366-1367): cur_obj = compute_cost(1[x >= 0.5])
-            for (int i = tid; i < n; i += SEG_T) w[i] = (x[i] >= 0.5) ? 1.0 : 0.0;
+            for (int i = tid; i < n; i += T) w[i] = (x[i] >= 0.5) ? 1.0 : 0.0;
             __syncthreads();
-            for (int i = tid; i < n; i += SEG_T) r[i] = seg_row_dot<false, CMP>(rp, ci, av, md, w, i);
+            for (int i = tid; i < n; i += T) r[i] = seg_row_dot<false, CMP>(rp, ci, av, md, w, i);
             __syncthreads();
-            seg_block_redux<2>([&](int q, int i) { return dM(q == 0 ? w[i] : b[i], q == 0 ? r[i] : w[i]); }, n, buf, sc);
+            seg_block_redux<2, T>([&](int q, int i) { return dM(q == 0 ? w[i] : b[i], q == 0 ? r[i] : w[i]); }, n, buf, sc);
             cur_obj = dA(sc[0], sc[1]);
         }
         if (tid < 16) st->obj_ring[tid] = ring[tid];

@@ -1,6 +1,8 @@
 """GPU test of the device-resident window loop (window kernel -> policy input gather -> scores -> threshold kernel ->
 compaction kernel; LP.trainer:510-535) against the CPU oracle driven by the reference's Python loop shape, with an
 EXACT surrogate policy (score = last iterate of the window as float32) so that fix decisions are identical."""
+import os
+
 import numpy as np
 import pytest
 
@@ -120,3 +122,42 @@ def test_policy_training_smoke(tmp_path):
     pk = PolicyKernel(net2, device=0, chunk_rows=64)
     assert float((pk(x) - ref).abs().max()) <= 0.02
     pk.close()
+
+
+def test_bf16_policy_kernel_decisions_vs_fp32_module_on_real_windows():
+    """The bf16 tcgen05 policy kernels agree with the fp32 PyTorch module to |d sigmoid| <= 0.02; what matters downstream is the
+    DECISION deter_fix_2 takes from the score (fix to 1 above 0.9, to 0 below 0.1, LP.trainer:121-132).  Count the decisions that
+    differ on real policy inputs -- the first iterate window of 64 generated auctions, 32 000 variables, shipped checkpoint."""
+    import ctypes
+    import torch
+    import lpbox
+    from lpbox.policy import load_policy
+    from lpbox.policy_kernel import PolicyKernel
+    w = os.path.join(os.path.dirname(lpbox.__file__), "weights", "lp_mha_policy.pt")
+    net = load_policy(w, device="cuda:0")
+    pk = PolicyKernel(net, device=0, chunk_rows=8192)
+    ws = 100
+    batch = lpbox.LPBatch(lpbox.gen_auctions(5, 64, 100, 500), hist_cap=ws)
+    batch.init()
+    batch.iters_l2f(0, ws)
+    rows = batch.L.lpbox_batch_policy_input_dev(batch.h, ws, None, 0)
+    inp = torch.zeros((rows, ws), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    assert batch.L.lpbox_batch_policy_input_dev(batch.h, ws, ctypes.c_void_p(inp.data_ptr()), rows) == rows
+    batch.get_iter(0)                                       # a getter synchronises the library's stream
+    x = inp.view(rows, 20, 5)
+    with torch.no_grad():
+        ref = net(x)[1].reshape(-1)
+    got = pk(x).reshape(-1)
+    torch.cuda.synchronize()
+    assert (got - ref).abs().max().item() <= 0.02
+
+    def decide(s):
+        return torch.where(s > 0.9, 1, torch.where(s < 0.1, 0, -1))
+    dk, dr = decide(got), decide(ref)
+    differ = int((dk != dr).sum().item())
+    opposite = int(((dk >= 0) & (dr >= 0) & (dk != dr)).sum().item())
+    assert opposite == 0                                    # never fix to the other value
+    assert differ <= rows // 200, (differ, rows)            # borderline scores only: <= 0.5 % of the variables
+    assert int((dr >= 0).sum().item()) > 0                  # the window does produce decisions
+    batch.close(); pk.close()

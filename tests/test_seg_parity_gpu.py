@@ -53,6 +53,28 @@ def test_iterates_match_reference_binary(gold, K):
     assert np.array_equal(b.state(0)["x"], gold[f"x_K{K}"])
 
 
+@pytest.mark.parametrize("T", [256, 192, 160])
+def test_launch_shapes_are_bit_identical(gold, T, monkeypatch):
+    """The three launch shapes of seg_admm_kernel (SegCfg: 256 threads x 5 CTAs/SM, 192 x 7, 160 x 8; the host picks by batch
+    size) stage the products in chunks of different length but add them in the same order: same bits as the reference binary
+    (general matrix format) and as each other on device-built graphs (compact format, ragged sizes)."""
+    import lpbox
+    monkeypatch.setenv("LPBOX_SEG_T", str(T))
+    for K in (20, 10000):
+        b = lpbox.SegBatch([(gold["rowptr"], gold["colidx"], gold["val"], gold["b"], float(gold["c"]))])
+        b.set_params(max_iters=K); b.init(); b.solve()
+        assert np.array_equal(b.state(0)["x"], gold[f"x_K{K}"]), K
+    imgs = [synth_image(s, nr, nc) for s, (nr, nc) in enumerate([(24, 30), (37, 41), (1, 17), (2, 2), (75, 100), (120, 161)])]
+    b = lpbox.SegBatch(imgs); b.set_params(max_iters=60); b.init(); e = b.solve()
+    monkeypatch.setenv("LPBOX_SEG_T", "256")
+    r = lpbox.SegBatch(imgs); r.set_params(max_iters=60); r.init(); er = r.solve()
+    assert np.array_equal(e, er)
+    for i in range(len(imgs)):
+        sb, sr = b.state(i), r.state(i)
+        for k in sr:
+            assert np.array_equal(sb[k], sr[k]), (i, k)
+
+
 def test_batch_of_images_matches_oracle():
     import lpbox
     imgs = [synth_image(s, nr, nc) for s, (nr, nc) in enumerate([(24, 30), (37, 41), (50, 64), (33, 29), (64, 48)])]
