@@ -46,6 +46,9 @@ struct lpbox_seg_batch {
     SBuf<double> vecs[11], d_b[2], d_val[2], d_hist, d_ret_val, d_powv, d_powtab, d_vec, d_b_org, d_val_org;
     SBuf<int> d_rp[2], d_ci[2], d_left, d_ret_idx, d_counter, d_kidx, d_cnt, d_num, d_rp_org, d_ci_org;
     SBuf<long long> d_off_vec;
+    SBuf<uint4> d_ell_c;                        // compact format: row image the ADMM kernel reads (seg_ell_build_kernel)
+    SBuf<uint2> d_ell_a;
+    SBuf<int> d_ell_flag;
     int max_n = 0;
     SBuf<SegInst> d_st;
     std::vector<SegInst> h_st;
@@ -141,6 +144,7 @@ extern "C" void lpbox_seg_destroy(lpbox_seg_batch *h) {
     for (int k = 0; k < 2; ++k) { h->d_b[k].free_(); h->d_val[k].free_(); h->d_rp[k].free_(); h->d_ci[k].free_(); }
     h->d_hist.free_(); h->d_ret_val.free_(); h->d_powv.free_(); h->d_powtab.free_(); h->d_vec.free_(); h->d_b_org.free_(); h->d_val_org.free_();
     h->d_kidx.free_(); h->d_cnt.free_(); h->d_num.free_(); h->d_rp_org.free_(); h->d_ci_org.free_(); h->d_off_vec.free_(); h->d_left.free_(); h->d_ret_idx.free_(); h->d_counter.free_(); h->d_st.free_();
+    h->d_ell_c.free_(); h->d_ell_a.free_(); h->d_ell_flag.free_();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -152,11 +156,20 @@ extern "C" void lpbox_seg_destroy(lpbox_seg_batch *h) {
 template <int T>
 static cudaError_t seg_shape_query(bool compact, int *occ, size_t *smem) {
     *smem = sizeof(double) * (SegCfg<T>::BUF + 8 + 16);
-    cudaError_t e = compact ? cudaFuncSetAttribute(seg_admm_kernel<true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem)
-                            : cudaFuncSetAttribute(seg_admm_kernel<false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem);
-    if (e != cudaSuccess) return e;
-    return compact ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, seg_admm_kernel<true, T>, T, *smem)
-                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, seg_admm_kernel<false, T>, T, *smem);
+    const int sm = (int)*smem;
+    cudaError_t e;
+    if (compact) {
+        e = cudaFuncSetAttribute(seg_admm_kernel<true, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(seg_admm_kernel<true, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        int o2 = 0;
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, seg_admm_kernel<true, T, true>, T, *smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, seg_admm_kernel<true, T, false>, T, *smem);
+        if (e == cudaSuccess) *occ = std::min(*occ, o2);
+    } else {
+        e = cudaFuncSetAttribute(seg_admm_kernel<false, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, seg_admm_kernel<false, T, false>, T, *smem);
+    }
+    return e;
 }
 
 static lpbox_seg_batch *seg_new(int device, int B, const int32_t *n, const int *nnz, const double *c, int hist_cap, bool compact) {
@@ -199,6 +212,7 @@ static lpbox_seg_batch *seg_new(int device, int B, const int32_t *n, const int *
     A(h->d_hist.alloc((size_t)h->off_hist[B])); A(h->d_ret_val.alloc(NN)); A(h->d_powv.alloc(B)); A(h->d_left.alloc(NN)); A(h->d_ret_idx.alloc(NN));
     A(h->d_counter.alloc(1)); A(h->d_st.alloc(B));
     A(h->d_kidx.alloc(NN)); A(h->d_cnt.alloc(NN)); A(h->d_num.alloc(B)); A(h->d_off_vec.alloc(B + 1)); A(h->d_vec.alloc(NN)); A(h->d_powtab.alloc((size_t)h->max_n + 1));
+    if (compact) { A(h->d_ell_c.alloc(NN)); A(h->d_ell_a.alloc(NN)); A(h->d_ell_flag.alloc(1)); }
     A(h->d_rp_org.alloc(NN + 4 * (size_t)B)); A(h->d_ci_org.alloc(ZCI)); A(h->d_val_org.alloc(ZVA)); A(h->d_b_org.alloc(NN));
     if (!ok) { lpbox_seg_destroy(h); return nullptr; }
     auto H2D = [&](void *d, const void *s, size_t bytes) { if (bytes) { A(cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, h->stream)); h->h2d_bytes += (int64_t)bytes; } };
@@ -217,6 +231,7 @@ static lpbox_seg_batch *seg_new(int device, int B, const int32_t *n, const int *
     double **vp[11] = {&v.x, &v.y1, &v.y2, &v.z1, &v.z2, &v.md, &v.invd, &v.r, &v.p, &v.t, &v.w};
     for (int k = 0; k < 11; ++k) *vp[k] = h->vecs[k].p;
     for (int k = 0; k < 2; ++k) { v.b[k] = h->d_b[k].p; v.rowptr[k] = h->d_rp[k].p; v.colidx[k] = h->d_ci[k].p; v.val[k] = h->d_val[k].p; }
+    v.ell_c = h->d_ell_c.p; v.ell_a = h->d_ell_a.p; v.use_ell = 0;
     v.kidx = h->d_kidx.p; v.cnt = h->d_cnt.p; v.pow_tab = h->d_powtab.p;
     v.st = h->d_st.p; v.hist = h->d_hist.p; v.left_idx = h->d_left.p; v.ret_idx = h->d_ret_idx.p; v.ret_val = h->d_ret_val.p; v.powv = h->d_powv.p;
     h->smem = sizeof(double) * (SEG_BUF_DOUBLES + 8 + 16);                     // set-up kernel
@@ -552,6 +567,26 @@ extern "C" int lpbox_seg_set_params(lpbox_seg_batch *h, const lpbox_params *p) {
     return 0;
 }
 
+// (Re)build the row image the ADMM kernel reads from the current CSR arrays (compact format).  `check`: decide whether the batch
+// qualifies (every row <= 8 entries) -- once, at init; early fixing only ever removes entries from a row.
+static int seg_build_rows(lpbox_seg_batch *h, int skip_done, bool check) {
+    const bool off = getenv("LPBOX_SEG_NO_ROWIMG") != nullptr;      // experiments / tests: keep reading the CSR arrays
+    if (!h->compact || off) return 0;
+    if (check) { h->sv.use_ell = 1; SCK(cudaMemsetAsync(h->d_ell_flag.p, 0, sizeof(int), h->stream)); }
+    if (!h->sv.use_ell) return 0;
+    const dim3 grid((unsigned)std::max(1, std::min(64, (h->max_n + SEG_T - 1) / SEG_T)), (unsigned)h->B);
+    seg_ell_build_kernel<<<grid, SEG_T, 0, h->stream>>>(h->sv, skip_done, h->d_ell_flag.p);
+    SCK(cudaGetLastError());
+    h->launches += 1;
+    if (check) {
+        int flag = 0;
+        SCK(cudaMemcpyAsync(&flag, h->d_ell_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        SCK(cudaStreamSynchronize(h->stream));
+        if (flag) h->sv.use_ell = 0;
+    }
+    return 0;
+}
+
 extern "C" int lpbox_seg_init(lpbox_seg_batch *h, const double *x0_all) {
     if (!h) return LPBOX_E_INVALID;
     SCK(cudaSetDevice(h->device));
@@ -567,8 +602,9 @@ extern "C" int lpbox_seg_init(lpbox_seg_batch *h, const double *x0_all) {
     else seg_setup_kernel<false><<<h->B, SEG_T, h->smem, h->stream>>>(h->sv, h->pr, x0_all ? 1 : 0);
     SCK(cudaGetLastError());
     h->launches += 1;
+    int rc = seg_build_rows(h, 0, true); if (rc) return rc;
     SCK(cudaEventRecord(h->ev1, h->stream));
-    int rc = seg_sync_states(h); if (rc) return rc;
+    rc = seg_sync_states(h); if (rc) return rc;
     float ms = 0; SCK(cudaEventElapsedTime(&ms, h->ev0, h->ev1)); h->last_ms = ms;
     h->inited = true;
     return 0;
@@ -576,8 +612,9 @@ extern "C" int lpbox_seg_init(lpbox_seg_batch *h, const double *x0_all) {
 
 template <int T>
 static void seg_launch_admm(lpbox_seg_batch *h, const SegLaunch &la) {
-    if (h->compact) seg_admm_kernel<true, T><<<h->grid, T, h->smem_admm, h->stream>>>(h->sv, h->pr, la);
-    else seg_admm_kernel<false, T><<<h->grid, T, h->smem_admm, h->stream>>>(h->sv, h->pr, la);
+    if (h->compact && h->sv.use_ell) seg_admm_kernel<true, T, true><<<h->grid, T, h->smem_admm, h->stream>>>(h->sv, h->pr, la);
+    else if (h->compact) seg_admm_kernel<true, T, false><<<h->grid, T, h->smem_admm, h->stream>>>(h->sv, h->pr, la);
+    else seg_admm_kernel<false, T, false><<<h->grid, T, h->smem_admm, h->stream>>>(h->sv, h->pr, la);
 }
 
 static int seg_run(lpbox_seg_batch *h, int iter_start, int iter_end, int l2f, int skip_done) {
@@ -637,7 +674,9 @@ extern "C" int lpbox_seg_iters_l2f(lpbox_seg_batch *h, int iter_start, int iter_
     else seg_fix_kernel<false><<<h->B, SEG_T, 0, h->stream>>>(h->sv, h->pr, h->d_vec.p, h->d_off_vec.p, h->d_num.p, skip_done);
     SCK(cudaGetLastError());
     h->launches += 1;
-    int rc = seg_run(h, iter_start, iter_end, 1, skip_done);
+    int rc = seg_build_rows(h, skip_done, false);
+    if (rc) return rc;
+    rc = seg_run(h, iter_start, iter_end, 1, skip_done);
     if (rc) return rc;
     if (ret) for (int i = 0; i < h->B; ++i) ret[i] = h->h_st[i].last_ret;
     return h->h_st[0].last_ret;

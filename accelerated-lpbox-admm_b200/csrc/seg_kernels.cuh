@@ -50,6 +50,9 @@ struct SegView {
     double *ret_val;
     const double *pow_tab;     // pow_tab[k] = std::pow(k, 0.5) from the host libm, k <= max n0
     double *powv;              // [B] std::pow(n, 0.5) of the CURRENT n, refreshed by the early-fix kernel
+    uint4 *ell_c;              // [off_n] compact format only: the row image the ADMM kernel reads -- 8 x int16 column distances
+    uint2 *ell_a;              // [off_n]   (SEG_ELL_PAD = no entry) and 8 x int8 values per row, built from the CSR arrays (SegRowRef)
+    int use_ell;               // every row has <= 8 stored entries: seg_admm_kernel<., ., true> reads ell_c / ell_a instead of the CSR arrays
     int *kidx;                 // [off_n] scratch: new index of a kept variable
     int *cnt;                  // [off_n] scratch: kept entries per new row / misc
 };
@@ -71,9 +74,18 @@ constexpr int SEG_RMAX = 7;
 // The host picks the shape that needs fewer waves (e.g. the 1024-image batch of configs[2]: one wave instead of 1.38).
 // BUF = doubles of the double-buffered product ring; a fused pass with R reductions stages FCH<R> elements per chunk (a multiple
 // of the staging thread count): few reductions -> long chunks -> more rows in flight per thread between two barriers.
+// Staging elements a thread works on side by side.  Measured on 375x500 images: 1 beats 2, 3 and 4 for every shape (+5 %): the
+// row prefetch already overlaps the loads of consecutive elements and a second element in flight costs spills.
+#ifndef SEG_UNROLL_W
+#define SEG_UNROLL_W 1
+#endif
+#ifndef SEG_UNROLL_N
+#define SEG_UNROLL_N 1
+#endif
 template <int T> struct SegCfg {
     static constexpr int STG = T - 32;
     static constexpr int MINB = (T == 256) ? 5 : (T == 192) ? 7 : 8;
+    static constexpr int UNROLL = (T == 256) ? SEG_UNROLL_W : SEG_UNROLL_N;
     static constexpr int BUF = (T == 256) ? 4480 : (T == 192) ? 3840 : 3328;
     static constexpr int CH = (BUF / (2 * SEG_RMAX) < 256 ? BUF / (2 * SEG_RMAX) : 256) & ~3;   // seg_block_redux: products per reduction per chunk
 };
@@ -103,18 +115,51 @@ __device__ __forceinline__ double seg_row_dot(const int *__restrict__ rp, const 
     return acc;
 }
 
-// Same with the row bounds [s, e) already in registers (the fused passes prefetch them one element ahead, which takes the
-// rowptr load out of the dependent chain rowptr -> column offsets -> operands) and the diagonal entry md[i] loaded once.
+// What a staging thread holds of one row of A while it works on it, loaded ONE ELEMENT AHEAD by the fused passes so that the
+// dependent chain of a row product is just "operands" instead of "rowptr -> column offsets / values -> operands":
+//   general / compact CSR: the row bounds [s, e);
+//   row image (compact format, every row <= 8 entries -- the reference builder's graphs have <= 7): the whole row, one 16-byte
+//   and one 8-byte load: 8 x int16 column distance (SEG_ELL_PAD marks "no entry", padding sits at the end) + 8 x int8 value.
+constexpr int SEG_ELL_PAD = -32768;
+template <bool ELL> struct SegRowRef { int s, e; };
+template <> struct SegRowRef<true> { uint4 c; uint2 a; };
+template <bool ELL> struct SegRowSrc {
+    const int *__restrict__ rp;
+    __device__ __forceinline__ SegRowRef<false> load(int i) const { SegRowRef<false> r; r.s = rp[i]; r.e = rp[i + 1]; return r; }
+};
+template <> struct SegRowSrc<true> {
+    const uint4 *__restrict__ c; const uint2 *__restrict__ a;
+    __device__ __forceinline__ SegRowRef<true> load(int i) const { SegRowRef<true> r; r.c = __ldg(c + i); r.a = __ldg(a + i); return r; }
+};
+
+// y_i = ((0 + m_i1 v_j1) + m_i2 v_j2) + ... with the row already referenced by `rw`; mdi = md[i] (DIAG only).
 template <bool DIAG, bool CMP>
-__device__ __forceinline__ double seg_row_dot_se(int s, int e, const typename SegFmt<CMP>::CI *__restrict__ ci,
-                                                 const typename SegFmt<CMP>::AV *__restrict__ av, double mdi,
-                                                 const double *__restrict__ v, int i) {
+__device__ __forceinline__ double seg_row_dot_ref(const SegRowRef<false> &rw, const typename SegFmt<CMP>::CI *__restrict__ ci,
+                                                  const typename SegFmt<CMP>::AV *__restrict__ av, double mdi,
+                                                  const double *__restrict__ v, int i) {
     double acc = 0.0;
-    for (int k = s; k < e; ++k) {
+    for (int k = rw.s; k < rw.e; ++k) {
         const int c = seg_col<CMP>(ci, k, i);
         double m = (double)av[k];
         if (DIAG) m = (c == i) ? mdi : dM(2.0, m);
         acc = dA(acc, dM(m, v[c]));
+    }
+    return acc;
+}
+template <bool DIAG, bool CMP>
+__device__ __forceinline__ double seg_row_dot_ref(const SegRowRef<true> &rw, const typename SegFmt<CMP>::CI *__restrict__,
+                                                  const typename SegFmt<CMP>::AV *__restrict__, double mdi,
+                                                  const double *__restrict__ v, int i) {
+    const unsigned cw[4] = {rw.c.x, rw.c.y, rw.c.z, rw.c.w}, aw[2] = {rw.a.x, rw.a.y};
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int d = (int)(short)(cw[k >> 1] >> (16 * (k & 1)));
+        if (d != SEG_ELL_PAD) {                                  // same entries in the same order as the CSR walk
+            double m = (double)(int)(signed char)(aw[k >> 2] >> (8 * (k & 3)));
+            if (DIAG) m = (d == 0) ? mdi : dM(2.0, m);
+            acc = dA(acc, dM(m, v[i + d]));
+        }
     }
     return acc;
 }
@@ -196,14 +241,14 @@ __device__ __forceinline__ void seg_block_redux(F prod, int n, double *buf, doub
     __syncthreads();
 }
 
-// Fused streaming pass + Eigen-order reductions.  body(i, s, e, v) is called EXACTLY ONCE for every i < n (in chunk order) by
+// Fused streaming pass + Eigen-order reductions.  body(i, rw, v) is called EXACTLY ONCE for every i < n (in chunk order) by
 // the staging warps: it performs the element's work (global loads / stores) and returns the R products of element i; with
-// ROWS, [s, e) are the bounds of row i of A (loaded one element ahead).  The products go to a double-buffered shared-memory
+// ROWS, rw references row i of A (SegRowRef, loaded one element ahead).  The products go to a double-buffered shared-memory
 // ring; the reduction warp walks the four chains of each reduction one chunk behind the producers, so the streaming work and
 // the sequential chains overlap.  Results in sc[0..R).  The chunk length only decides how the work is staged, never the order
 // of the additions.
-template <int T, int R, bool ROWS, typename Body>
-__device__ __forceinline__ void seg_fused_pass(Body body, const int *__restrict__ rp, int n, double *buf, double *sc) {
+template <int T, int R, bool ROWS, bool ELL, typename Body>
+__device__ __forceinline__ void seg_fused_pass(Body body, const SegRowSrc<ELL> &rows, int n, double *buf, double *sc) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int RW = T / 32 - 1, STG = T - 32;
     constexpr int FCH = (SegCfg<T>::BUF / (2 * R)) / STG * STG;
@@ -216,17 +261,18 @@ __device__ __forceinline__ void seg_fused_pass(Body body, const int *__restrict_
         double *dst = buf + (size_t)(c & 1) * R * fch;
         const int base = c * fch;
         const int lim = min(fch, n - base);
-        int idx = tid, s = 0, e = 0;
-        if (ROWS && idx < lim) { s = rp[base + idx]; e = rp[base + idx + 1]; }
-#pragma unroll 2
+        int idx = tid;
+        SegRowRef<ELL> rw{};
+        if (ROWS && idx < lim) rw = rows.load(base + idx);
+#pragma unroll (SegCfg<T>::UNROLL)
         for (; idx < lim; idx += STG) {
-            int s2 = 0, e2 = 0;
-            if (ROWS && idx + STG < lim) { s2 = rp[base + idx + STG]; e2 = rp[base + idx + STG + 1]; }
+            SegRowRef<ELL> nx{};
+            if (ROWS && idx + STG < lim) nx = rows.load(base + idx + STG);
             double v[R];
-            body(base + idx, s, e, v);
+            body(base + idx, rw, v);
 #pragma unroll
             for (int r = 0; r < R; ++r) dst[r * fch + idx] = v[r];
-            s = s2; e = e2;
+            rw = nx;
         }
     };
     double acc = 0.0;
@@ -267,9 +313,11 @@ __device__ __forceinline__ void seg_fused_pass(Body body, const int *__restrict_
     __syncthreads();
 }
 
-template <bool CMP, int T>
+template <bool CMP, int T, bool ELL>
 __global__ void __launch_bounds__(T, SegCfg<T>::MINB)
 seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
+    static_assert(CMP || !ELL, "the row image exists for the compact format only");
+    using Row = SegRowRef<ELL>;
     using CI = typename SegFmt<CMP>::CI;
     using AV = typename SegFmt<CMP>::AV;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -295,6 +343,8 @@ seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
         const int *__restrict__ rp = sv.rowptr[cur] + on + 4 * inst;      // n0r + 4 ints reserved per instance
         const CI *__restrict__ ci = reinterpret_cast<const CI *>(sv.colidx[cur]) + oz;
         const AV *__restrict__ av = reinterpret_cast<const AV *>(sv.val[cur]) + oz;
+        SegRowSrc<ELL> rows;
+        if constexpr (ELL) { rows.c = sv.ell_c + on; rows.a = sv.ell_a + on; } else { rows.rp = rp; }
         double rho1 = st->rho1, rho2 = st->rho2, prho1 = st->prho1, prho2 = st->prho2, gamma = st->gamma, ratio = st->ratio,
                std_obj = st->std_obj, cur_obj = st->cur_obj, best_bin_obj = st->best_bin_obj;
         int rhoUpdated = st->rhoUpdated;
@@ -306,14 +356,14 @@ seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
         int status = RUNNING, iter = la.iter_start, cc = 0;
         for (; iter < la.iter_end; ++iter) {
             // ---- pass 1: y1, y2 pre-image (SEG.cpp:1223-1234) + ||y||^2 ---------------------------------------------
-            seg_fused_pass<T, 1, false>([&](int i, int, int, double (&v)[1]) {
+            seg_fused_pass<T, 1, false, ELL>([&](int i, const Row &, double (&v)[1]) {
                 const double xi = x[i];
                 double tt = dA(xi, dD(z1[i], rho1));
                 y1[i] = (tt > 1.0) ? 1.0 : ((tt < 0.0) ? 0.0 : tt);
                 const double sh = dS(dA(xi, dD(z2[i], rho2)), 0.5);
                 y2[i] = sh;
                 v[0] = dM(sh, sh);
-            }, rp, n, buf, sc);
+            }, rows, n, buf, sc);
             const double den = dM(2.0, sqrt(sc[0]));
             // ---- pass 2 (no reduction): diagonal patch (:1240-1243), preconditioner (:1252-1255), y2, rhs (:1246), x = y1 ----
             const bool patch = (iter != 0 && rhoUpdated);
@@ -330,13 +380,13 @@ seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
             }
             rhoUpdated = 0;
             // ---- PCG (SEG.cpp:272-342).  pass 3: r = rhs - M x, p = invd r; rhs.rhs, r.r, r.p ---------------------------
-            seg_fused_pass<T, 3, true>([&](int i, int s, int e, double (&v)[3]) {
+            seg_fused_pass<T, 3, true, ELL>([&](int i, const Row &rw, double (&v)[3]) {
                 const double rhs = w[i];
-                const double rr = dS(rhs, seg_row_dot_se<true, CMP>(s, e, ci, av, md[i], x, i));
+                const double rr = dS(rhs, seg_row_dot_ref<true, CMP>(rw, ci, av, md[i], x, i));
                 const double pp = dM(invd[i], rr);
                 r[i] = rr; p[i] = pp;
                 v[0] = dM(rhs, rhs); v[1] = dM(rr, rr); v[2] = dM(rr, pp);
-            }, rp, n, buf, sc);
+            }, rows, n, buf, sc);
             const double rhsNorm2 = sc[0];
             int cg_it = 0;
             if (rhsNorm2 == 0.0) {
@@ -348,20 +398,20 @@ seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
                 if (!(r2 < threshold)) {
                     while (cg_it < pr.pcg_maxiters) {
                         // tmp = M p fused with p.dot(tmp)
-                        seg_fused_pass<T, 1, true>([&](int i, int s, int e, double (&v)[1]) {
-                            const double ti = seg_row_dot_se<true, CMP>(s, e, ci, av, md[i], p, i);
+                        seg_fused_pass<T, 1, true, ELL>([&](int i, const Row &rw, double (&v)[1]) {
+                            const double ti = seg_row_dot_ref<true, CMP>(rw, ci, av, md[i], p, i);
                             t[i] = ti;
                             v[0] = dM(p[i], ti);
-                        }, rp, n, buf, sc);
+                        }, rows, n, buf, sc);
                         const double alpha = dD(absNew, sc[0]);
                         // x += alpha p; r -= alpha tmp; z = invd r fused with r.r and r.z
-                        seg_fused_pass<T, 2, false>([&](int i, int, int, double (&v)[2]) {
+                        seg_fused_pass<T, 2, false, ELL>([&](int i, const Row &, double (&v)[2]) {
                             x[i] = dA(x[i], dM(alpha, p[i]));
                             const double rr = dS(r[i], dM(alpha, t[i]));
                             const double zz = dM(invd[i], rr);
                             r[i] = rr; t[i] = zz;
                             v[0] = dM(rr, rr); v[1] = dM(rr, zz);
-                        }, rp, n, buf, sc);
+                        }, rows, n, buf, sc);
                         r2 = sc[0];
                         if (r2 < threshold) { cg_it++; break; }
                         const double absOld = absNew;
@@ -379,24 +429,24 @@ seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
             if (la.l2f && sv.hist_cap > 0) { if (cc < sv.hist_cap) h = sv.hist + sv.off_hist[inst] + (long long)cc * st->n0; cc++; }
             {
                 const double g1 = dM(gamma, rho1), g2 = dM(gamma, rho2);
-                seg_fused_pass<T, 5, true>([&](int i, int s, int e, double (&v)[5]) {
+                seg_fused_pass<T, 5, true, ELL>([&](int i, const Row &rw, double (&v)[5]) {
                     const double xi = x[i];
                     if (h) h[i] = xi;
                     const double d1 = dS(xi, y1[i]), d2 = dS(xi, y2[i]);
                     z1[i] = dA(z1[i], dM(g1, d1));
                     z2[i] = dA(z2[i], dM(g2, d2));
                     w[i] = (xi >= 0.5) ? 1.0 : 0.0;
-                    const double ax = seg_row_dot_se<false, CMP>(s, e, ci, av, 0.0, x, i);
+                    const double ax = seg_row_dot_ref<false, CMP>(rw, ci, av, 0.0, x, i);
                     v[0] = dM(xi, xi); v[1] = dM(d1, d1); v[2] = dM(d2, d2); v[3] = dM(xi, ax); v[4] = dM(b[i], xi);
-                }, rp, n, buf, sc);
+                }, rows, n, buf, sc);
             }
             const double nx2 = sc[0], d12 = sc[1], d22 = sc[2], obj_val = dA(sc[3], sc[4]);   // compute_cost: val + val2
             // ---- pass: A 1[x >= 0.5]; idx.A idx, b.idx  (SEG.cpp:1323-1326) -------------------------------------------
-            seg_fused_pass<T, 2, true>([&](int i, int s, int e, double (&v)[2]) {
+            seg_fused_pass<T, 2, true, ELL>([&](int i, const Row &rw, double (&v)[2]) {
                 const double wi = w[i];
-                v[0] = dM(wi, seg_row_dot_se<false, CMP>(s, e, ci, av, 0.0, w, i));
+                v[0] = dM(wi, seg_row_dot_ref<false, CMP>(rw, ci, av, 0.0, w, i));
                 v[1] = dM(b[i], wi);
-            }, rp, n, buf, sc);
+            }, rows, n, buf, sc);
             const double bin_val = dA(sc[0], sc[1]);
             {
                 double temp0 = sqrt(nx2);
@@ -487,6 +537,35 @@ seg_setup_kernel(SegView sv, Params pr, int use_x0) {
         st->std_obj = 1.0; st->cur_obj = 0.0; st->best_bin_obj = dA(sc[0], sc[1]); st->obj_len = 0; st->cg_iters = 0; st->admm_iters = 0;
         st->iter = 0; st->status = RUNNING; st->done = 0; st->last_ret = 0; st->n_ret = 0; st->xit_rows = 0; st->xit_cols = 0;
         for (int k = 0; k < 16; ++k) st->obj_ring[k] = 0.0;
+    }
+}
+
+// Row image of the compact format (SegRowRef<true>) from the current CSR arrays: one thread per row.  *flag is set when a row
+// has more than 8 stored entries or a distance equal to the padding marker (the batch then keeps using the CSR arrays).
+__global__ void __launch_bounds__(SEG_T)
+seg_ell_build_kernel(SegView sv, int skip_done, int *flag) {
+    const int inst = blockIdx.y;
+    const SegInst *st = sv.st + inst;
+    if (skip_done && st->done) return;
+    const int n = st->n, cur = st->cur;
+    const long long on = sv.off_n[inst], oz = sv.off_nnz[inst];
+    const int *__restrict__ rp = sv.rowptr[cur] + on + 4 * inst;
+    const short *__restrict__ ci = reinterpret_cast<const short *>(sv.colidx[cur]) + oz;
+    const signed char *__restrict__ av = reinterpret_cast<const signed char *>(sv.val[cur]) + oz;
+    for (int i = blockIdx.x * SEG_T + threadIdx.x; i < n; i += gridDim.x * SEG_T) {
+        const int s = rp[i];
+        int len = rp[i + 1] - s;
+        if (len > 8) { *flag = 1; len = 8; }
+        unsigned cw[4] = {0, 0, 0, 0}, aw[2] = {0, 0};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            int d = SEG_ELL_PAD, a = 0;
+            if (k < len) { d = ci[s + k]; a = av[s + k]; if (d == SEG_ELL_PAD) *flag = 1; }
+            cw[k >> 1] |= (unsigned)(d & 0xffff) << (16 * (k & 1));
+            aw[k >> 2] |= (unsigned)(a & 0xff) << (8 * (k & 3));
+        }
+        sv.ell_c[on + i] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+        sv.ell_a[on + i] = make_uint2(aw[0], aw[1]);
     }
 }
 

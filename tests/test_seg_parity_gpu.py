@@ -57,7 +57,8 @@ def test_iterates_match_reference_binary(gold, K):
 def test_launch_shapes_are_bit_identical(gold, T, monkeypatch):
     """The three launch shapes of seg_admm_kernel (SegCfg: 256 threads x 5 CTAs/SM, 192 x 7, 160 x 8; the host picks by batch
     size) stage the products in chunks of different length but add them in the same order: same bits as the reference binary
-    (general matrix format) and as each other on device-built graphs (compact format, ragged sizes)."""
+    (general matrix format) and as each other on device-built graphs (compact format, ragged sizes) -- with the 8-entry row image
+    (SegRowRef<true>, the default for the compact format) and with the CSR walk."""
     import lpbox
     monkeypatch.setenv("LPBOX_SEG_T", str(T))
     for K in (20, 10000):
@@ -67,6 +68,7 @@ def test_launch_shapes_are_bit_identical(gold, T, monkeypatch):
     imgs = [synth_image(s, nr, nc) for s, (nr, nc) in enumerate([(24, 30), (37, 41), (1, 17), (2, 2), (75, 100), (120, 161)])]
     b = lpbox.SegBatch(imgs); b.set_params(max_iters=60); b.init(); e = b.solve()
     monkeypatch.setenv("LPBOX_SEG_T", "256")
+    monkeypatch.setenv("LPBOX_SEG_NO_ROWIMG", "1")          # reference run: the kernel walks the CSR arrays instead of the row image
     r = lpbox.SegBatch(imgs); r.set_params(max_iters=60); r.init(); er = r.solve()
     assert np.array_equal(e, er)
     for i in range(len(imgs)):
