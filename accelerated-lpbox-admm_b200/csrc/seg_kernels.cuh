@@ -164,6 +164,37 @@ __device__ __forceinline__ double seg_row_dot_ref(const SegRowRef<true> &rw, con
     return acc;
 }
 
+// Two products with one walk over row i of A: ax = (A x)_i and aw = (A 1[x >= 0.5])_i, each accumulated in row order.
+template <bool CMP>
+__device__ __forceinline__ void seg_row_dot2_ref(const SegRowRef<false> &rw, const typename SegFmt<CMP>::CI *__restrict__ ci,
+                                                 const typename SegFmt<CMP>::AV *__restrict__ av, const double *__restrict__ v, int i,
+                                                 double &ax, double &aw) {
+    double a0 = 0.0, a1 = 0.0;
+    for (int k = rw.s; k < rw.e; ++k) {
+        const double m = (double)av[k], xc = v[seg_col<CMP>(ci, k, i)];
+        a0 = dA(a0, dM(m, xc));
+        a1 = dA(a1, dM(m, (xc >= 0.5) ? 1.0 : 0.0));
+    }
+    ax = a0; aw = a1;
+}
+template <bool CMP>
+__device__ __forceinline__ void seg_row_dot2_ref(const SegRowRef<true> &rw, const typename SegFmt<CMP>::CI *__restrict__,
+                                                 const typename SegFmt<CMP>::AV *__restrict__, const double *__restrict__ v, int i,
+                                                 double &ax, double &aw) {
+    const unsigned cw[4] = {rw.c.x, rw.c.y, rw.c.z, rw.c.w}, aws[2] = {rw.a.x, rw.a.y};
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int d = (int)(short)(cw[k >> 1] >> (16 * (k & 1)));
+        if (d != SEG_ELL_PAD) {
+            const double m = (double)(int)(signed char)(aws[k >> 2] >> (8 * (k & 3))), xc = v[i + d];
+            a0 = dA(a0, dM(m, xc));
+            a1 = dA(a1, dM(m, (xc >= 0.5) ? 1.0 : 0.0));
+        }
+    }
+    ax = a0; aw = a1;
+}
+
 // Walks one Eigen chain: adds src[i], src[i+4], ... (indices < lim) to acc IN ORDER.  The next four terms are fetched into
 // loop-carried registers before the four dependent adds; otherwise ptxas, short of registers (5 CTAs/SM), serialises
 // load -> add -> load on one register and every step pays the shared-memory latency on top of the fp64 add latency.
@@ -252,27 +283,29 @@ __device__ __forceinline__ void seg_fused_pass(Body body, const SegRowSrc<ELL> &
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int RW = T / 32 - 1, STG = T - 32;
     constexpr int FCH = (SegCfg<T>::BUF / (2 * R)) / STG * STG;
-    // short vectors: at least 8 chunks (so that staging and chain overlap), at least two elements per staging thread
-    const int fch = (n >= 8 * FCH) ? FCH : max(2 * STG, (n / 8) / STG * STG);
+    static_assert(FCH >= STG, "product ring too small for one element per staging thread");
+    // short vectors: about 8 chunks (so that staging and chain overlap), at least one element per staging thread
+    const int fch = (n >= 8 * FCH) ? FCH : min(FCH, max(STG, (n / 8) / STG * STG));
     const int a2 = n & ~3, a1 = n & ~1;
     const int q = lane >> 2, k = lane & 3;
     const int nch = (n + fch - 1) / fch;
+    // A staging thread works on the elements tid, tid + STG, tid + 2 STG, ... (fch is a multiple of STG, so the sequence runs on
+    // across chunk boundaries); the row of the NEXT element is requested before the current one is processed.
+    SegRowRef<ELL> nx{};
+    if (ROWS && warp != RW && tid < n) nx = rows.load(tid);
     auto stage = [&](int c) {
         double *dst = buf + (size_t)(c & 1) * R * fch;
         const int base = c * fch;
         const int lim = min(fch, n - base);
-        int idx = tid;
-        SegRowRef<ELL> rw{};
-        if (ROWS && idx < lim) rw = rows.load(base + idx);
 #pragma unroll (SegCfg<T>::UNROLL)
-        for (; idx < lim; idx += STG) {
-            SegRowRef<ELL> nx{};
-            if (ROWS && idx + STG < lim) nx = rows.load(base + idx + STG);
+        for (int idx = tid; idx < lim; idx += STG) {
+            const int i = base + idx;
+            const SegRowRef<ELL> rw = nx;
+            if (ROWS && i + STG < n) nx = rows.load(i + STG);
             double v[R];
-            body(base + idx, rw, v);
+            body(i, rw, v);
 #pragma unroll
             for (int r = 0; r < R; ++r) dst[r * fch + idx] = v[r];
-            rw = nx;
         }
     };
     double acc = 0.0;
@@ -365,28 +398,26 @@ seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
                 v[0] = dM(sh, sh);
             }, rows, n, buf, sc);
             const double den = dM(2.0, sqrt(sc[0]));
-            // ---- pass 2 (no reduction): diagonal patch (:1240-1243), preconditioner (:1252-1255), y2, rhs (:1246), x = y1 ----
-            const bool patch = (iter != 0 && rhoUpdated);
+            // ---- pass 2+3: diagonal patch (:1240-1243), preconditioner (:1252-1255), y2, rhs (:1246), warm start x = y1, and the
+            // PCG prologue (SEG.cpp:272-342) r = rhs - M x, p = invd r with rhs.rhs, r.r, r.p.  One pass: every quantity of element i
+            // but the row product depends on element i only, and the row product gathers x = y1, which pass 1 has completed.
+            const bool patch = (iter != 0 && rhoUpdated), refresh = rhoUpdated != 0;
             const double dpatch = dM(dA(prho1, prho2), ratio);
-#pragma unroll 4
-            for (int i = tid; i < n; i += T) {
-                if (patch) md[i] = dA(md[i], dpatch);
-                if (rhoUpdated) { const double d = md[i]; invd[i] = (d != 0.0) ? dD(1.0, d) : 1.0; }
+            seg_fused_pass<T, 3, true, ELL>([&](int i, const Row &rw, double (&v)[3]) {
+                double mdi = md[i];
+                if (patch) { mdi = dA(mdi, dpatch); md[i] = mdi; }
+                double idi;
+                if (refresh) { idi = (mdi != 0.0) ? dD(1.0, mdi) : 1.0; invd[i] = idi; } else idi = invd[i];
                 const double y1i = y1[i];
                 const double y2v = dA(dD(dM(y2[i], pow_n), den), 0.5);
                 y2[i] = y2v;
-                w[i] = dS(dA(dM(rho1, y1i), dM(rho2, y2v)), dA(dA(b[i], z1[i]), z2[i]));
-                x[i] = y1i;
-            }
-            rhoUpdated = 0;
-            // ---- PCG (SEG.cpp:272-342).  pass 3: r = rhs - M x, p = invd r; rhs.rhs, r.r, r.p ---------------------------
-            seg_fused_pass<T, 3, true, ELL>([&](int i, const Row &rw, double (&v)[3]) {
-                const double rhs = w[i];
-                const double rr = dS(rhs, seg_row_dot_ref<true, CMP>(rw, ci, av, md[i], x, i));
-                const double pp = dM(invd[i], rr);
-                r[i] = rr; p[i] = pp;
+                const double rhs = dS(dA(dM(rho1, y1i), dM(rho2, y2v)), dA(dA(b[i], z1[i]), z2[i]));
+                const double rr = dS(rhs, seg_row_dot_ref<true, CMP>(rw, ci, av, mdi, y1, i));
+                const double pp = dM(idi, rr);
+                x[i] = y1i; r[i] = rr; p[i] = pp;
                 v[0] = dM(rhs, rhs); v[1] = dM(rr, rr); v[2] = dM(rr, pp);
             }, rows, n, buf, sc);
+            rhoUpdated = 0;
             const double rhsNorm2 = sc[0];
             int cg_it = 0;
             if (rhsNorm2 == 0.0) {
@@ -429,25 +460,22 @@ seg_admm_kernel(SegView sv, Params pr, SegLaunch la) {
             if (la.l2f && sv.hist_cap > 0) { if (cc < sv.hist_cap) h = sv.hist + sv.off_hist[inst] + (long long)cc * st->n0; cc++; }
             {
                 const double g1 = dM(gamma, rho1), g2 = dM(gamma, rho2);
-                seg_fused_pass<T, 5, true, ELL>([&](int i, const Row &rw, double (&v)[5]) {
+                // one walk over row i yields (A x)_i and (A 1[x >= 0.5])_i: the second product (SEG.cpp:1323-1326) needs no pass of its own
+                seg_fused_pass<T, 7, true, ELL>([&](int i, const Row &rw, double (&v)[7]) {
                     const double xi = x[i];
                     if (h) h[i] = xi;
                     const double d1 = dS(xi, y1[i]), d2 = dS(xi, y2[i]);
                     z1[i] = dA(z1[i], dM(g1, d1));
                     z2[i] = dA(z2[i], dM(g2, d2));
-                    w[i] = (xi >= 0.5) ? 1.0 : 0.0;
-                    const double ax = seg_row_dot_ref<false, CMP>(rw, ci, av, 0.0, x, i);
-                    v[0] = dM(xi, xi); v[1] = dM(d1, d1); v[2] = dM(d2, d2); v[3] = dM(xi, ax); v[4] = dM(b[i], xi);
+                    const double wi = (xi >= 0.5) ? 1.0 : 0.0, bi = b[i];
+                    double ax, aw;
+                    seg_row_dot2_ref<CMP>(rw, ci, av, x, i, ax, aw);
+                    v[0] = dM(xi, xi); v[1] = dM(d1, d1); v[2] = dM(d2, d2); v[3] = dM(xi, ax); v[4] = dM(bi, xi);
+                    v[5] = dM(wi, aw); v[6] = dM(bi, wi);
                 }, rows, n, buf, sc);
             }
             const double nx2 = sc[0], d12 = sc[1], d22 = sc[2], obj_val = dA(sc[3], sc[4]);   // compute_cost: val + val2
-            // ---- pass: A 1[x >= 0.5]; idx.A idx, b.idx  (SEG.cpp:1323-1326) -------------------------------------------
-            seg_fused_pass<T, 2, true, ELL>([&](int i, const Row &rw, double (&v)[2]) {
-                const double wi = w[i];
-                v[0] = dM(wi, seg_row_dot_ref<false, CMP>(rw, ci, av, 0.0, w, i));
-                v[1] = dM(b[i], wi);
-            }, rows, n, buf, sc);
-            const double bin_val = dA(sc[0], sc[1]);
+            const double bin_val = dA(sc[5], sc[6]);                                         // idx.A idx + b.idx
             {
                 double temp0 = sqrt(nx2);
                 if (!(temp0 > 2.2204e-16)) temp0 = 2.2204e-16;
