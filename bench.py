@@ -605,8 +605,16 @@ def run_seg(ctx):
                      "e2e": {"value": tot_B / (e2e_ms / 1e3), "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": a.e2e_steps},
                      "gpu_launches": int(tot_launch), "clocks": clocks,
                      "roofline": {"bound": "hbm", "achieved": ach, "peak": ctx.peaks["hbm"], "unit": "GB/s", "frac": ach / ctx.peaks["hbm"], "traffic": None,
-                                  "traffic_source": "see profiles/ (ncu --set full of seg_admm_kernel)", "kernel": "seg_admm_kernel", "peak_source": ctx.peaks["src"],
-                                  "algorithmic_bytes_per_launch": int(abytes)}})
+                                  "traffic_source": None, "kernel": "seg_admm_kernel", "peak_source": ctx.peaks["src"],
+                                  "algorithmic_bytes_per_launch": int(abytes),
+                                  "note": "algorithmic bytes = SURVEY.md 8d streaming model (12 B per stored entry of A, every vector access counted); the kernel "
+                                          "stores A in 3 B per entry and fuses passes, so its physical DRAM traffic (`traffic`) is below the model"}})
+        tp = os.path.join(ROOT, "profiles", "r02_seg_kernel_traffic.json")
+        if os.path.exists(tp) and int(tot_B) == 1024 * ctx.world and nr * nc == 187500:
+            tj = json.load(open(tp))
+            line["roofline"]["traffic"] = int(tj["dram_bytes_read"] + tj["dram_bytes_write"])
+            line["roofline"]["traffic_source"] = "static: profiles/r02_seg_kernel_traffic.json (ncu metrics pass over this launch configuration)"
+            line["roofline"]["physical_frac_in_capture"] = tj["dram_GBps_in_capture"] / ctx.peaks["hbm"]
         if ctx.world == 1 and not a.no_cpu_baseline:
             procs = host_procs()
             sample = max(4, min(procs, 16, distinct))

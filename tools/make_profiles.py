@@ -115,16 +115,35 @@ def seg():
             "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
             "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
             "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"]
+    f = lambda k: float(m[k][1]) if k in m else float("nan")
+    unit = lambda k: {"Gbyte": 1e9, "Tbyte": 1e12, "Mbyte": 1e6, "byte": 1.0}.get(m[k][0], 1.0)
+    dram = f("dram__bytes_read.sum") * unit("dram__bytes_read.sum") + f("dram__bytes_write.sum") * unit("dram__bytes_write.sum")
+    dur = f("gpu__time_duration.sum") * {"s": 1.0, "ms": 1e-3, "us": 1e-6, "ns": 1e-9}.get(m["gpu__time_duration.sum"][0], 1.0)
     with open(os.path.join(P, "r02_seg_kernel_ncu.txt"), "w") as fh:
-        fh.write("# r02 seg_admm_kernel<compact> -- the SHIPPED 5-CTA/SM kernel with the compact (int16 + int8) matrix format\n"
-                 "# ncu --set full --import-source on --clock-control none -k regex:seg_admm -c 1 python tools/quick_bench_seg.py 740 375 500 30   (740 images 375x500, 30 ADMM iterations)\n"
-                 "# algorithmic bytes of this launch (SURVEY 8d model, 12 B per stored entry): 3579 GB/s x 1.2895 s = 4.61 TB;  physical DRAM = read + write below = 4.13 TB (0.90x: the\n"
-                 "# compact matrix storage moves 3 B per entry) -> 3.2 TB/s = 49 % of the measured 6.53 TB/s copy bandwidth; no wasted re-reads; the kernel is latency-bound\n"
-                 "# (long_scoreboard 24 per issue at 40 resident warps/SM).\n")
+        fh.write("# r02 seg_admm_kernel<compact, 256 threads, row image> -- FINAL kernel of round 2 (5 CTAs/SM, 8-entry row image, fused passes, L2 prefetch)\n"
+                 "# ncu --set full --import-source on --clock-control none -k regex:seg_admm -c 1 python tools/quick_bench_seg.py 740 375 500 30   (740 images 375x500 = one full wave, 30 ADMM iterations)\n"
+                 f"# physical DRAM traffic of this launch = read + write below = {dram / 1e12:.3f} TB in {dur:.4f} s -> {dram / dur / 1e12:.2f} TB/s = {100 * dram / dur / 6534.1e9:.0f} % of the measured 6.53 TB/s copy bandwidth\n")
         for k in want + sorted(h for h in m if "issue_stalled" in h and "per_issue_active" in h):
             if k in m:
                 fh.write(f"{k:90s} {m[k][0]:16s} {m[k][1]}\n")
     print("seg written")
+
+
+def seg_traffic():
+    p = os.path.join(G, "r02_seg_traffic.csv")
+    if not os.path.exists(p):
+        return
+    rows = [r for r in csv.reader(open(p)) if len(r) > 14]
+    m = {r[12]: float(r[14]) for r in rows[1:]}
+    out = {"kernel": rows[1][4].split("(")[0], "launch": f"tools/quick_bench_seg.py 1024 375 500 10000 64 = the launch of `bench.py --config seg` (1024 images 375x500 to convergence, 64 distinct images cycled, grid {rows[1][8]} x {rows[1][7]} threads)",
+           "command": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,... --clock-control none -k regex:seg_admm -c 1 (tools/gpu_profiles.sh)",
+           "dram_bytes_read": int(m["dram__bytes_read.sum"]), "dram_bytes_write": int(m["dram__bytes_write.sum"]), "lts_bytes": int(m["lts__t_bytes.sum"]),
+           "l2_hit_rate_pct": m.get("lts__t_sector_hit_rate.pct"), "duration_ns": int(m["gpu__time_duration.sum"]), "warp_instructions": int(m["smsp__inst_executed.sum"]),
+           "source": "profiles/r02_seg_kernel_traffic_b1024.csv"}
+    out["dram_GBps_in_capture"] = (out["dram_bytes_read"] + out["dram_bytes_write"]) / out["duration_ns"]
+    json.dump(out, open(os.path.join(P, "r02_seg_kernel_traffic.json"), "w"), indent=1)
+    open(os.path.join(P, "r02_seg_kernel_traffic_b1024.csv"), "w").write(open(p).read())
+    print("seg traffic:", out)
 
 
 def bench_lines():
@@ -135,4 +154,4 @@ def bench_lines():
 
 
 if __name__ == "__main__":
-    window_kernel(); traffic(); launches(); seg(); bench_lines()
+    window_kernel(); traffic(); launches(); seg(); seg_traffic(); bench_lines()

@@ -9,7 +9,8 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 296
 nr = int(sys.argv[2]) if len(sys.argv) > 2 else 375
 nc = int(sys.argv[3]) if len(sys.argv) > 3 else 500
 iters = int(sys.argv[4]) if len(sys.argv) > 4 else 10000
-imgs = [synth_image(s % 16, nr, nc, blobs=5) for s in range(min(B, 16))]
+distinct = int(sys.argv[5]) if len(sys.argv) > 5 else 16      # 64 = the images of `bench.py --config seg` on rank 0
+imgs = [synth_image(s, nr, nc, blobs=5) for s in range(min(B, distinct))]
 imgs = [imgs[i % len(imgs)] for i in range(B)]
 t = time.time(); b = lpbox.SegBatch(imgs); print("create s", time.time() - t); b.set_params(max_iters=iters); b.init()
 t = time.time(); e = b.solve(); wall = time.time() - t
