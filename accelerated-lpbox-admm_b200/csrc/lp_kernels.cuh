@@ -75,6 +75,7 @@ __device__ __forceinline__ double2 lds128(uint32_t a) {
     double2 v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a)); return v;
 }
 // (a 32-bit destination: ld.u16 zero-extends, so no separate widening instructions follow the load)
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint2 lds_u32x2(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
 __device__ __forceinline__ void sts_u32x2(uint32_t a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory"); }
@@ -274,39 +275,45 @@ __device__ __forceinline__ void block_sum(double (&v)[K], double *part) {
 // ahead; the gathers of a batch are independent; only the adds form the dependent chain.  W is warp-uniform.
 // `idx` entries are ABSOLUTE shared-window addresses of the operands (lp_types.h).  GIDX: the index array is read from global
 // memory (gidx, element index pos) instead of shared memory (address ia + 2 pos) -- images above the shared-memory budget.
+// Offsets are stored in PAIRS (lp_types.h: ell_pos): one 32-bit load per lane fetches the offsets of two consecutive entries, so a
+// warp reads 128 bytes = one full shared-memory wavefront per two entries instead of one 64-byte wavefront per entry.
+template <bool GIDX>
+__device__ __forceinline__ uint32_t ld_pair(uint32_t ia, const u16 *__restrict__ gidx, int pos) {   // pos: even u16 index
+    return GIDX ? *reinterpret_cast<const uint32_t *>(gidx + pos) : lds32(ia + 2u * (uint32_t)pos);
+}
 template <bool GIDX>
 __device__ __forceinline__ uint32_t ld_idx(uint32_t ia, const u16 *__restrict__ gidx, int pos) {
     return GIDX ? (uint32_t)gidx[pos] : lds16(ia + 2u * (uint32_t)pos);
 }
+// base: u16 index of the slice (32 * sptr[w]); W: width of the slice (warp-uniform)
 template <int COEF, bool GIDX>
-__device__ __forceinline__ double ell_dot(uint32_t ia, const u16 *__restrict__ gidx, const double *__restrict__ val, int pos, int W,
+__device__ __forceinline__ double ell_dot(uint32_t ia, const u16 *__restrict__ gidx, const double *__restrict__ val, int base, int lane, int W,
                                           uint32_t add) {
     double acc = 0.0;
-    int k = 0;
+    int k = 0, pp = base + 2 * lane;                 // this lane's pair of entries (k, k + 1)
     if (W >= 4) {
-        uint32_t i0 = ld_idx<GIDX>(ia, gidx, pos), i1 = ld_idx<GIDX>(ia, gidx, pos + 32), i2 = ld_idx<GIDX>(ia, gidx, pos + 64),
-                 i3 = ld_idx<GIDX>(ia, gidx, pos + 96);
+        uint32_t p0 = ld_pair<GIDX>(ia, gidx, pp), p1 = ld_pair<GIDX>(ia, gidx, pp + 64);
 #pragma unroll 1
         for (;;) {
-            double t0 = lds64(i0 + add), t1 = lds64(i1 + add), t2 = lds64(i2 + add), t3 = lds64(i3 + add);
-            if (COEF == 2) { t0 = dM(val[pos], t0); t1 = dM(val[pos + 32], t1); t2 = dM(val[pos + 64], t2); t3 = dM(val[pos + 96], t3); }
-            k += 4; pos += 128;
-            // the next batch of offsets is fetched unconditionally (what follows the arrays is readable, lp_types.h): past
-            // the end of the slice they are simply not used
-            i0 = ld_idx<GIDX>(ia, gidx, pos); i1 = ld_idx<GIDX>(ia, gidx, pos + 32); i2 = ld_idx<GIDX>(ia, gidx, pos + 64);
-            i3 = ld_idx<GIDX>(ia, gidx, pos + 96);
+            double t0 = lds64((p0 & 0xffffu) + add), t1 = lds64((p0 >> 16) + add), t2 = lds64((p1 & 0xffffu) + add), t3 = lds64((p1 >> 16) + add);
+            if (COEF == 2) { t0 = dM(val[pp], t0); t1 = dM(val[pp + 1], t1); t2 = dM(val[pp + 64], t2); t3 = dM(val[pp + 65], t3); }
+            k += 4; pp += 128;
+            // the next two pairs are fetched unconditionally (what follows the arrays is readable, lp_types.h): past the end of
+            // the slice they are simply not used
+            p0 = ld_pair<GIDX>(ia, gidx, pp); p1 = ld_pair<GIDX>(ia, gidx, pp + 64);
             acc = dA(acc, t0); acc = dA(acc, t1); acc = dA(acc, t2); acc = dA(acc, t3);
             if (k + 4 > W) break;
         }
     }
     if (W & 2) {                                     // W is warp-uniform: straight-line tail
-        const uint32_t i0 = ld_idx<GIDX>(ia, gidx, pos), i1 = ld_idx<GIDX>(ia, gidx, pos + 32);
-        double t0 = lds64(i0 + add), t1 = lds64(i1 + add);
-        if (COEF == 2) { t0 = dM(val[pos], t0); t1 = dM(val[pos + 32], t1); }
+        const uint32_t p0 = ld_pair<GIDX>(ia, gidx, pp);
+        double t0 = lds64((p0 & 0xffffu) + add), t1 = lds64((p0 >> 16) + add);
+        if (COEF == 2) { t0 = dM(val[pp], t0); t1 = dM(val[pp + 1], t1); }
         acc = dA(acc, t0); acc = dA(acc, t1);
-        pos += 64;
+        pp += 64;
     }
-    if (W & 1) {
+    if (W & 1) {                                     // the odd last entry of a slice is stored alone, one u16 per lane
+        const int pos = pp - lane;
         double t = lds64(ld_idx<GIDX>(ia, gidx, pos) + add);
         if (COEF == 2) t = dM(val[pos], t);
         acc = dA(acc, t);
@@ -316,23 +323,25 @@ __device__ __forceinline__ double ell_dot(uint32_t ia, const u16 *__restrict__ g
 // two products over the same pattern (the two column products of the rhs, LP.cpp:875-878): operands at idx and idx + add2
 template <int COEF, bool GIDX>
 __device__ __forceinline__ void ell_dot2(uint32_t ia, const u16 *__restrict__ gidx, const double *__restrict__ val1,
-                                         const double *__restrict__ val2, int pos, int W, uint32_t add2, double &o1, double &o2) {
+                                         const double *__restrict__ val2, int base, int lane, int W, uint32_t add2, double &o1, double &o2) {
     double acc1 = 0.0, acc2 = 0.0;
-    int k = 0;
+    int k = 0, pp = base + 2 * lane;
     if (W >= 2) {
-        uint32_t i0 = ld_idx<GIDX>(ia, gidx, pos), i1 = ld_idx<GIDX>(ia, gidx, pos + 32);
+        uint32_t p0 = ld_pair<GIDX>(ia, gidx, pp);
 #pragma unroll 1
         for (;;) {
+            const uint32_t i0 = p0 & 0xffffu, i1 = p0 >> 16;
             double t0 = lds64(i0), t1 = lds64(i1), u0 = lds64(i0 + add2), u1 = lds64(i1 + add2);
-            if (COEF == 2) { t0 = dM(val1[pos], t0); t1 = dM(val1[pos + 32], t1); u0 = dM(val2[pos], u0); u1 = dM(val2[pos + 32], u1); }
-            k += 2; pos += 64;
+            if (COEF == 2) { t0 = dM(val1[pp], t0); t1 = dM(val1[pp + 1], t1); u0 = dM(val2[pp], u0); u1 = dM(val2[pp + 1], u1); }
+            k += 2; pp += 64;
             const bool more = (k + 2 <= W);
-            if (more) { i0 = ld_idx<GIDX>(ia, gidx, pos); i1 = ld_idx<GIDX>(ia, gidx, pos + 32); }
+            if (more) p0 = ld_pair<GIDX>(ia, gidx, pp);
             acc1 = dA(acc1, t0); acc2 = dA(acc2, u0); acc1 = dA(acc1, t1); acc2 = dA(acc2, u1);
             if (!more) break;
         }
     }
     if (k < W) {
+        const int pos = pp - lane;
         const uint32_t i0 = ld_idx<GIDX>(ia, gidx, pos);
         double t0 = lds64(i0), u0 = lds64(i0 + add2);
         if (COEF == 2) { t0 = dM(val1[pos], t0); u0 = dM(val2[pos], u0); }
@@ -364,10 +373,11 @@ __device__ __forceinline__ void build_ell(const u16 *ptr, const u16 *idx, const 
     for (int s = threadIdx.x; s < ns * 32; s += blockDim.x) {
         const int w = s >> 5;
         const int W = s_w[w + 1] - s_w[w];
-        int pos = s_w[w] * 32 + (s & 31);
+        const int slice0 = s_w[w] * 32, l = s & 31;
         int L = 0, beg = 0;
         if (s < count) { const int o = perm[s]; beg = ptr[o]; L = ptr[o + 1] - beg; }
-        for (int k = 0; k < W; ++k, pos += 32) {
+        for (int k = 0; k < W; ++k) {
+            const int pos = ell_pos(slice0, l, k, W);
             if (k < L) { o_idx[pos] = (u16)(base + 8 * (int)inv[idx[beg + k]]); if (o_val) o_val[pos] = val[beg + k]; }
             else { o_idx[pos] = (u16)zoff; if (o_val) o_val[pos] = 0.0; }
         }
@@ -692,7 +702,7 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
             const int sl = vw + e * NW;                                                                               \
             if (sl < nsr) {                                                                                           \
                 const int w0 = lds16(rsptr + 2 * sl), W = LPB_UNIFORM((int)lds16(rsptr + 2 * sl + 2) - w0);           \
-                double acc = ell_dot<CE, false>(ridx, nullptr, S.ev_r, w0 * 32 + lane, W, 0u);                        \
+                double acc = ell_dot<CE, false>(ridx, nullptr, S.ev_r, w0 * 32, lane, W, 0u);                        \
                 if (SCALE) acc = dM(r4s, acc);                                                                        \
                 if (vt + e * T < m) sts64(S.T1 + 8u * (uint32_t)(vt + e * T), acc);                                   \
             }                                                                                                         \
@@ -705,8 +715,8 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
         OUT = 0.0;                                                                                                    \
         if (sl < nsc) {                                                                                               \
             const int w0 = lds16(csptr + 2 * sl), W = LPB_UNIFORM((int)lds16(csptr + 2 * sl + 2) - w0);               \
-            OUT = spill ? ell_dot<CE, true>(0u, gcidx, S.r4v, w0 * 32 + lane, W, 0u)                                  \
-                        : ell_dot<CE, false>(cidx, nullptr, S.r4v, w0 * 32 + lane, W, 0u);                            \
+            OUT = spill ? ell_dot<CE, true>(0u, gcidx, S.r4v, w0 * 32, lane, W, 0u)                                  \
+                        : ell_dot<CE, false>(cidx, nullptr, S.r4v, w0 * 32, lane, W, 0u);                            \
         }                                                                                                             \
     } while (0)
         // fast-mode CTA-wide sums (alternating partial buffers: one barrier per call)
@@ -808,8 +818,8 @@ lp_admm_window_kernel(BatchView bv, Params pr, Launch la) {
                     const int sl = vw + e * NW;
                     if (sl < nsc) {
                         const int w0 = lds16(csptr + 2 * sl), W = LPB_UNIFORM((int)lds16(csptr + 2 * sl + 2) - w0);
-                        if (spill) ell_dot2<CE, true>(0u, gcidx, S.r4v, S.ev_c, w0 * 32 + lane, W, z4_add, a, c);
-                        else ell_dot2<CE, false>(cidx, nullptr, S.r4v, S.ev_c, w0 * 32 + lane, W, z4_add, a, c);
+                        if (spill) ell_dot2<CE, true>(0u, gcidx, S.r4v, S.ev_c, w0 * 32, lane, W, z4_add, a, c);
+                        else ell_dot2<CE, false>(cidx, nullptr, S.r4v, S.ev_c, w0 * 32, lane, W, z4_add, a, c);
                     }
                     if (s < n) {
                         const double z1 = park[PK_Z1 * CAP + e * T], z2 = park[PK_Z2 * CAP + e * T], bj = park[PK_B * CAP + e * T];

@@ -62,7 +62,9 @@ struct InstState {
 //     orientations in PADDED SLICED-ELL form.  "Slot" s is the work item AND the home of row rperm[s] (column
 //     cperm[s]): the thread that owns slot s keeps that row's / column's vector entries and computes its sparse
 //     product.  Slots are sorted by descending stored length; a slice = 32 consecutive slots, stored column-major and
-//     padded to the length of its longest slot: entry k of lane l of slice w sits at idx[(sptr[w] + k) * 32 + l].
+//     padded to the length of its longest slot: entry k of lane l of slice w sits at idx[ell_pos(32 sptr[w], l, k, W)] -- the
+//     entries of a lane are stored in PAIRS (k, k + 1), pair-column-major, so that one 32-bit load fetches two offsets; an odd
+//     last entry forms a final plain column (the slice still takes 32 W entries).
 //     An entry is not an index but the SHARED-WINDOW ADDRESS of the operand it gathers (sbase = start of the window
 //     kernel's dynamic shared memory): sbase + 8 * (slot of that column) for the row image (operand vector G at offset
 //     0), sbase + gather_base(cap) + 8 * (slot of that row) for the column image (operand vector T1); padding entries
@@ -91,6 +93,10 @@ LPB_HD CsrLayout csr_layout(int n0, int m0, int nnz0) {
 // The SpMV loops prefetch one batch of offsets (4 steps x 32 lanes x 2 bytes = 256 bytes) past the end of a slice without a
 // bounds test; what follows the arrays only has to be readable: the row offsets are followed by the column offsets, those by the
 // permutations (global memory) / by 256 spare bytes at the end of the window kernel's shared memory.
+// position (in entries) of entry k of lane l in a slice of width W that starts at entry `base`
+LPB_HD constexpr int ell_pos(int base, int l, int k, int W) {
+    return k < (W & ~1) ? base + (k >> 1) * 64 + 2 * l + (k & 1) : base + (W >> 1) * 64 + l;
+}
 LPB_HD EllLayout ell_layout(int n0, int m0, int rcap, int ccap) {
     EllLayout L;
     const int nsr = (m0 + 31) / 32, nsc = (n0 + 31) / 32;
