@@ -392,6 +392,78 @@ static void group_columns(const std::vector<int> &cl, int CH, std::vector<int> &
         std::stable_sort(order.begin() + base, order.end(), [&](int a, int b) { return cl[a] > cl[b]; });
     }
 }
+// Slot order of the rows (rord) and columns (cord) of one instance.  mode 0: descending stored length (stable); 1: bank-aware.
+static void assign_slots(int ni, int mi, int nz, const int32_t *cp, const int32_t *ri, const std::vector<int> &rl, const std::vector<int> &cl,
+                         int mode, int np_batch, std::vector<int> &rord, std::vector<int> &cord) {
+    static const int sweeps = getenv("LPBOX_PLACE_SWEEPS") ? atoi(getenv("LPBOX_PLACE_SWEEPS")) : 2;
+    rord.resize(mi);
+    for (int r = 0; r < mi; ++r) rord[r] = r;
+    std::stable_sort(rord.begin(), rord.end(), [&](int a, int b2) { return rl[a] > rl[b2]; });
+    if (mode == 0) {
+        cord.resize(ni);
+        for (int j = 0; j < ni; ++j) cord[j] = j;
+        std::stable_sort(cord.begin(), cord.end(), [&](int a, int b2) { return cl[a] > cl[b2]; });
+        return;
+    }
+    group_columns(cl, chain_stride(np_batch), cord);
+    // row-compressed copy of the pattern (rows gather columns in E v)
+    std::vector<int> rp(mi + 1, 0), cix(nz);
+    for (int r = 0; r < mi; ++r) rp[r + 1] = rp[r] + rl[r];
+    { std::vector<int> fill(rp.begin(), rp.end() - 1); for (int j = 0; j < ni; ++j) for (int k = cp[j]; k < cp[j + 1]; ++k) cix[fill[ri[k]]++] = j; }
+    GatherSets gs;
+    build_sets(rord, rp.data(), cix.data(), ni, gs);         // E v: half-warps of rows gather columns -> place the columns
+    place_in_groups(cord, gs, sweeps);
+    std::vector<int> cpi(cp, cp + ni + 1);
+    build_sets(cord, cpi.data(), ri, mi, gs);                // E^T w: half-warps of columns gather rows -> place the rows
+    place_in_groups(rord, gs, sweeps);
+}
+}  // namespace
+
+// Diagnostic (host only, no device needed): shared-memory wavefronts of the operand gathers of one E v and one E^T w of an instance
+// under the slot assignment `mode` (see assign_slots) -- a 64-bit access is served half a warp at a time, a half-warp takes as many
+// wavefronts as the largest number of DISTINCT addresses that share one 8-byte bank pair.  out = {E v actual, E v ideal (one wavefront
+// per half-warp and step), E^T w actual, E^T w ideal}.  cap = T * EPT of the kernel shape (512 for n <= 512).
+extern "C" int lpbox_debug_gather_wavefronts(int m, int n, const int32_t *colptr, const int32_t *rowidx, int cap, int mode, int64_t *out) {
+    if (m <= 0 || n <= 0 || !colptr || !rowidx || !out || cap < std::max(m, n)) return LPBOX_E_INVALID;
+    const int nz = colptr[n];
+    std::vector<int> rl(m, 0), cl(n), rord, cord;
+    for (int k = 0; k < nz; ++k) { if (rowidx[k] < 0 || rowidx[k] >= m) return LPBOX_E_INVALID; rl[rowidx[k]]++; }
+    for (int j = 0; j < n; ++j) cl[j] = colptr[j + 1] - colptr[j];
+    assign_slots(n, m, nz, colptr, rowidx, rl, cl, mode, std::max((n + 1) & ~1, (m + 1) & ~1), rord, cord);
+    std::vector<int> rinv(m), cinv(n);
+    for (int s = 0; s < m; ++s) rinv[rord[s]] = s;
+    for (int s = 0; s < n; ++s) cinv[cord[s]] = s;
+    std::vector<int> rp(m + 1, 0), cix(nz);
+    for (int r = 0; r < m; ++r) rp[r + 1] = rp[r] + rl[r];
+    { std::vector<int> fill(rp.begin(), rp.end() - 1); for (int j = 0; j < n; ++j) for (int k = colptr[j]; k < colptr[j + 1]; ++k) cix[fill[rowidx[k]]++] = j; }
+    const int zero_word = zero_off(cap) / 8, t1_word = gather_base(cap) / 8;
+    auto count = [&](const std::vector<int> &order, const int *ptr, const int *idx, const std::vector<int> &inv, int word0, int64_t &act, int64_t &ideal) {
+        const int cnt = (int)order.size();
+        act = ideal = 0;
+        for (int s0 = 0; s0 < cnt; s0 += 32) {
+            int W = 0;
+            for (int s = s0; s < std::min(s0 + 32, cnt); ++s) W = std::max(W, ptr[order[s] + 1] - ptr[order[s]]);
+            for (int k = 0; k < W; ++k)
+                for (int h0 = s0; h0 < s0 + 32; h0 += 16) {
+                    std::vector<int> addr[16];
+                    for (int s = h0; s < h0 + 16; ++s) {
+                        int w = zero_word;
+                        if (s < cnt) { const int o = order[s]; if (ptr[o] + k < ptr[o + 1]) w = word0 + inv[idx[ptr[o] + k]]; }
+                        auto &v = addr[w & 15];
+                        if (std::find(v.begin(), v.end(), w) == v.end()) v.push_back(w);
+                    }
+                    size_t mx = 1;
+                    for (auto &v : addr) mx = std::max(mx, v.size());
+                    act += (int64_t)mx; ideal += 1;
+                }
+        }
+    };
+    std::vector<int> cpv(colptr, colptr + n + 1), riv(rowidx, rowidx + nz);
+    count(rord, rp.data(), cix.data(), cinv, 0, out[0], out[1]);
+    count(cord, cpv.data(), riv.data(), rinv, t1_word, out[2], out[3]);
+    return 0;
+}
+namespace {
 }  // namespace
 
 static lpbox_batch *batch_create_impl(int device, int B, const int32_t *m, const int32_t *n, const int32_t *colptr_all,
@@ -454,28 +526,10 @@ static lpbox_batch *batch_create_impl(int device, int B, const int32_t *m, const
         const int ni = n[i], mi = m[i], nz = h->nnz0[i];
         const int32_t *cp = colptr_all + h->h_cp_off[i];
         const int32_t *ri = rowidx_all + h->h_nnz_off[i];
-        std::vector<int> rl(mi, 0), cl(ni), rord(mi), cord;
+        std::vector<int> rl(mi, 0), cl(ni), rord, cord;
         for (int k = 0; k < nz; ++k) { if (ri[k] < 0 || ri[k] >= mi) { err1.store(1); return; } rl[ri[k]]++; }
         for (int j = 0; j < ni; ++j) cl[j] = cp[j + 1] - cp[j];
-        for (int r = 0; r < mi; ++r) rord[r] = r;
-        std::stable_sort(rord.begin(), rord.end(), [&](int a, int b2) { return rl[a] > rl[b2]; });
-        if (plain_slots) {
-            cord.resize(ni);
-            for (int j = 0; j < ni; ++j) cord[j] = j;
-            std::stable_sort(cord.begin(), cord.end(), [&](int a, int b2) { return cl[a] > cl[b2]; });
-        } else {
-            group_columns(cl, chain_stride(np_batch), cord);
-            // row-compressed copy of the pattern (rows gather columns in E v)
-            std::vector<int> rp(mi + 1, 0), cix(nz);
-            for (int r = 0; r < mi; ++r) rp[r + 1] = rp[r] + rl[r];
-            { std::vector<int> fill(rp.begin(), rp.end() - 1); for (int j = 0; j < ni; ++j) for (int k = cp[j]; k < cp[j + 1]; ++k) cix[fill[ri[k]]++] = j; }
-            GatherSets gs;
-            build_sets(rord, rp.data(), cix.data(), ni, gs);         // E v: half-warps of rows gather columns -> place the columns
-            place_in_groups(cord, gs, 2);
-            std::vector<int> cpi(cp, cp + ni + 1);
-            build_sets(cord, cpi.data(), ri, mi, gs);                // E^T w: half-warps of columns gather rows -> place the rows
-            place_in_groups(rord, gs, 2);
-        }
+        assign_slots(ni, mi, nz, cp, ri, rl, cl, plain_slots ? 0 : 1, np_batch, rord, cord);
         rperm_all[i].resize(mi);
         for (int s0 = 0; s0 < mi; s0 += 32) { int w = 0; for (int s2 = s0; s2 < std::min(s0 + 32, mi); ++s2) w = std::max(w, rl[rord[s2]]); rcap[i] += w; }
         for (int r = 0; r < mi; ++r) rperm_all[i][r] = (uint16_t)rord[r];

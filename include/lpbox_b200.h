@@ -313,6 +313,12 @@ void lpbox_free(void *p);
  * Own random stream (not numpy's): same distribution, different instances.  Outputs are malloc()ed, concatenated in
  * the layout lpbox_batch_create takes (colptr: count x (n_bids+1); price: count x n_bids, POSITIVE bid prices --
  * negate for b); release with lpbox_free().  threads <= 0: all host cores. */
+/* Diagnostic, host only (no device needed): shared-memory wavefronts of the operand gathers of one E v and one E^T w of an instance
+ * under the window kernel's slot assignment (mode 0: slots by descending stored length; 1: the bank-aware assignment the library uses).
+ * out[4] = {E v actual, E v conflict-free, E^T w actual, E^T w conflict-free}; cap = 512 / 1024 / 2048 (slots of the kernel shape).
+ * No counterpart in the reference (it has no GPU path); used by tests/ and tools/ to track the quality of the assignment. */
+int lpbox_debug_gather_wavefronts(int m, int n, const int32_t *colptr, const int32_t *rowidx, int cap, int mode, int64_t *out);
+
 int lpbox_gen_auctions(uint64_t seed, int count, int n_items, int n_bids, double add_item_prob, int threads,
                        int32_t **m_out, int32_t **colptr_out, int32_t **rowidx_out, double **price_out);
 

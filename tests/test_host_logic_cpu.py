@@ -104,3 +104,25 @@ def test_problem_list_drops_packed_on_mutation():
         assert p.packed is None
     p = fresh()
     assert p.packed is not None and p[1:].__class__ is list
+
+
+def test_bank_aware_slot_assignment_lowers_gather_wavefronts():
+    """Host-only diagnostic of the window kernel's slot assignment (csrc/lp_batch.cu: assign_slots): the bank-aware assignment must
+    cost fewer shared-memory wavefronts per E v + E^T w than slots in plain length order, on generated k = 500 auctions."""
+    import lpbox
+    from lpbox import _capi
+    L = _capi.lib()
+    L.lpbox_debug_gather_wavefronts.restype = C.c_int
+    L.lpbox_debug_gather_wavefronts.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    tot = np.zeros((2, 4))
+    for p in lpbox.gen_auctions(3, 24, 100, 500):
+        cp, ri = np.ascontiguousarray(p[2], dtype=np.int32), np.ascontiguousarray(p[3], dtype=np.int32)
+        for mode in (0, 1):
+            out = np.zeros(4, dtype=np.int64)
+            assert L.lpbox_debug_gather_wavefronts(int(p[0]), int(p[1]), cp.ctypes.data, ri.ctypes.data, 512, mode, out.ctypes.data) == 0
+            tot[mode] += out
+    ratio = (tot[:, 0] + tot[:, 2]) / (tot[:, 1] + tot[:, 3])
+    assert np.array_equal(tot[0, [1, 3]] > 0, [True, True])
+    assert ratio[1] < 0.9 * ratio[0] and ratio[1] < 1.95, ratio          # measured: 1.80 x conflict-free against 2.25 x
+    bad = np.zeros(4, dtype=np.int64)
+    assert L.lpbox_debug_gather_wavefronts(0, 5, None, None, 512, 1, bad.ctypes.data) < 0
