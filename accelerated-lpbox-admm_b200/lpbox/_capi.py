@@ -125,6 +125,7 @@ SIGNATURES = {
     "lpbox_free": (None, [_vp]),
     "lpbox_gen_auctions": (C.c_int, [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(_ip),
                                      C.POINTER(_ip), C.POINTER(_ip), C.POINTER(_dp)]),
+    "lpbox_debug_gather_wavefronts": (C.c_int, [C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp]),
 }
 
 _lib = None

@@ -112,8 +112,6 @@ def test_bank_aware_slot_assignment_lowers_gather_wavefronts():
     import lpbox
     from lpbox import _capi
     L = _capi.lib()
-    L.lpbox_debug_gather_wavefronts.restype = C.c_int
-    L.lpbox_debug_gather_wavefronts.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     tot = np.zeros((2, 4))
     for p in lpbox.gen_auctions(3, 24, 100, 500):
         cp, ri = np.ascontiguousarray(p[2], dtype=np.int32), np.ascontiguousarray(p[3], dtype=np.int32)

@@ -6,8 +6,6 @@ import numpy as np
 import lpbox
 from lpbox import _capi
 L = _capi.lib()
-L.lpbox_debug_gather_wavefronts.restype = C.c_int
-L.lpbox_debug_gather_wavefronts.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 probs = lpbox.gen_auctions(0, B, 100, 500)
 for mode in (0, 1):
