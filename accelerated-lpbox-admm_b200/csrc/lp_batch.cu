@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <string>
 #include <atomic>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -489,6 +490,14 @@ static lpbox_batch *batch_create_impl(int device, int B, const int32_t *m, const
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { set_err("no CUDA device (there is no CPU fallback)"); return nullptr; }
     if (device < 0 || device >= ndev) { set_err("bad device index"); return nullptr; }
     if (cudaSetDevice(device) != cudaSuccess) { set_err("cudaSetDevice failed"); return nullptr; }
+    const bool dbg_t = getenv("LPBOX_DEBUG") != nullptr;                         // stage timings of the set-up on stderr
+    auto t_prev = std::chrono::steady_clock::now();
+    auto stage = [&](const char *what) {
+        if (!dbg_t) return;
+        const auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[lpbox] create: %-28s %7.1f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count());
+        t_prev = t;
+    };
     lpbox_batch *h = new lpbox_batch();
     h->device = device; h->B = B; h->hist_cap = hist_cap;
     h->n0.assign(n, n + B); h->m0.assign(m, m + B); h->nnz0.resize(B);
@@ -517,6 +526,7 @@ static lpbox_batch *batch_create_impl(int device, int B, const int32_t *m, const
         b_in_off[i + 1] = b_in_off[i] + n[i]; f_in_off[i + 1] = f_in_off[i] + m[i];
         h->max_n = std::max(h->max_n, n[i]); h->max_m = std::max(h->max_m, m[i]); h->max_nnz = std::max(h->max_nnz, h->nnz0[i]);
     }
+    stage("sizes / validation");
     // (2) per instance, in parallel on the host cores: SpMV work assignment -- slots in descending stored length, bank-aware
     //     (see above; LPBOX_PLAIN_SLOTS=1 keeps the plain stable sort) -- and the capacities of the sliced-ELL image
     std::atomic<int> err1(0);
@@ -540,6 +550,7 @@ static lpbox_batch *batch_create_impl(int device, int B, const int32_t *m, const
         maxcl[i] = mx;
     });
     if (err1.load()) { set_err("row index out of range"); delete h; return nullptr; }
+    stage("slot assignment (parallel)");
     // (3) serial: offsets that depend on the layouts
     for (int i = 0; i < B; ++i) {
         EllLayout EL = ell_layout(n[i], m[i], rcap[i], ccap[i]);
@@ -569,6 +580,7 @@ static lpbox_batch *batch_create_impl(int device, int B, const int32_t *m, const
         h->all_unit = false;
         if (!val_all) { ones.assign((size_t)tot_nnz, 1.0); val_all = ones.data(); h->h_val = ones; }
     }
+    stage("layout offsets / host copies");
     // build pattern blobs (+ values in both orders) on the host
     std::vector<unsigned char> pat((size_t)h->off_pat[B], 0), csr((size_t)h->off_csr[B], 0);
     std::vector<double> val_r, val_c;
@@ -633,6 +645,7 @@ static lpbox_batch *batch_create_impl(int device, int B, const int32_t *m, const
     A(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     A(cudaEventCreate(&h->ev0)); A(cudaEventCreate(&h->ev1));
     size_t NN = (size_t)h->off_n[B], MM = (size_t)h->off_m[B];
+    stage("pattern blobs (parallel)");
     A(h->d_off_n.alloc(B + 1)); A(h->d_off_m.alloc(B + 1)); A(h->d_off_pat.alloc(B + 1)); A(h->d_off_val.alloc(B + 1));
     A(h->d_off_csr.alloc(B + 1)); A(h->d_off_evr.alloc(B + 1)); A(h->d_off_evc.alloc(B + 1)); A(h->d_csr.alloc((size_t)h->off_csr[B]));
     A(h->d_off_hist.alloc(B + 1)); A(h->d_off_vec.alloc(B + 1));
@@ -651,6 +664,7 @@ static lpbox_batch *batch_create_impl(int device, int B, const int32_t *m, const
     A(h->d_st.alloc(B)); A(h->d_counter.alloc(1 + SM_RANK_SLOTS)); A(h->d_num.alloc(B));
     A(h->d_pow.alloc((size_t)h->max_n + 1));
     if (!ok) { lpbox_batch_destroy(h); return nullptr; }
+    stage("device allocation");
     std::vector<double> powtab((size_t)h->max_n + 1);
     for (int k = 0; k <= h->max_n; ++k) powtab[k] = pow((double)k, 1.0 / 2);   // std::pow(n, 1.0/p), LP.cpp:427 (host libm)
     auto H2D = [&](void *d, const void *s, size_t bytes) { if (bytes) { A(cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, h->stream)); h->h2d_bytes += (int64_t)bytes; } };
@@ -679,10 +693,13 @@ static lpbox_batch *batch_create_impl(int device, int B, const int32_t *m, const
     v.y3 = h->d_y3.p; v.z4 = h->d_z4.p; v.f = h->d_f.p; v.pat = h->d_pat.p;
     v.val_r = h->d_val_r.p; v.val_c = h->d_val_c.p; v.r4v = h->d_r4v.p; v.st = h->d_st.p; v.hist = h->d_hist.p;
     v.left_idx = h->d_left.p; v.ret_idx = h->d_ret_idx.p; v.ret_val = h->d_ret_val.p; v.pow_tab = h->d_pow.p;
+    stage("H2D");
     if (configure(h) != 0) { lpbox_batch_destroy(h); return nullptr; }
+    stage("configure");
     lp_setup_kernel<<<B, 128, 0, h->stream>>>(h->bv, h->pr, 4, 0);     // build the sliced-ELL images on the device
     if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess) { set_err("ELL build kernel failed"); lpbox_batch_destroy(h); return nullptr; }
     h->launches += 1;
+    stage("image build kernel");
     return h;
 }
 

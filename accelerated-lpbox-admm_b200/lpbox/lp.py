@@ -153,8 +153,11 @@ class LPBatch:
         check(self.L.lpbox_batch_iters_l2f(self.h, int(start), int(end), ptr(vec), ptr(nums), ptr(ret)), "iters_l2f")
         return ret
 
-    def solve(self, max_iters=20000):
-        log = np.zeros(self.B, dtype=_capi.LOG_DTYPE)
+    def solve(self, max_iters=20000, want_log=True):
+        """ADMM_lp_iters_init state -> ADMM_lp_iters(0, max_iters) for every instance.  want_log=False skips the per-instance log
+        rows (objective / feasibility of the rounded solution, computed on the host from a read-back of x): call `results()` once
+        afterwards instead of paying for them twice."""
+        log = np.zeros(self.B, dtype=_capi.LOG_DTYPE) if want_log else None
         check(self.L.lpbox_batch_solve(self.h, int(max_iters), ptr(log)), "solve")
         return log
 

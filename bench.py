@@ -356,7 +356,7 @@ def run_lp(ctx, fast=False, large=False):
         if fast:
             bb.set_mode("fast")
         bb.init()
-        bb.solve(MAX_ITERS)
+        bb.solve(MAX_ITERS, want_log=False)       # the log rows and packed solutions are read back once, by results()
         elog, bits = bb.results()
         if ctx.dist is not None:   # the final gather of packed solutions over NVLink
             tb = torch.from_numpy(bits).cuda()

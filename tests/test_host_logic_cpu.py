@@ -124,3 +124,30 @@ def test_bank_aware_slot_assignment_lowers_gather_wavefronts():
     assert ratio[1] < 0.9 * ratio[0] and ratio[1] < 1.95, ratio          # measured: 1.80 x conflict-free against 2.25 x
     bad = np.zeros(4, dtype=np.int64)
     assert L.lpbox_debug_gather_wavefronts(0, 5, None, None, 512, 1, bad.ctypes.data) < 0
+
+
+def test_native_generator_matches_the_reference_distribution():
+    """csrc/auction_gen.cpp restates the reference generator with its own RNG: individual instances differ, the DISTRIBUTION must not.
+    1 000 native instances against statistics of 1 000 instances of the reference's own `generate_cauctions` (fixture
+    tests/golden/gen_stats_100_500.json, made by tests/golden/make_golden_gen_stats.py): rows m, stored entries, column- and
+    row-length distributions, bid prices."""
+    import json
+    import lpbox
+    ref = json.load(open(os.path.join(GOLDEN, "gen_stats_100_500.json")))
+    probs = lpbox.gen_auctions(12345, 1000, 100, 500)
+    ms = np.array([p[0] for p in probs]); nnz = np.array([len(p[3]) for p in probs])
+    cl = np.concatenate([np.diff(p[2]) for p in probs])
+    rl = np.concatenate([np.bincount(p[3], minlength=p[0]) for p in probs])
+    price = np.concatenate([-np.asarray(p[5]) for p in probs])
+    q = ref["quantile_levels"]
+    assert abs(ms.mean() - ref["m_mean"]) < 0.6 and abs(ms.std() - ref["m_std"]) < 0.5           # measured: 192.7 / 3.34 vs 192.9 / 3.29
+    assert ref["m_min"] - 4 <= ms.min() and ms.max() <= ref["m_max"] + 4
+    assert abs(nnz.mean() / ref["nnz_mean"] - 1) < 0.01 and abs(nnz.std() / ref["nnz_std"] - 1) < 0.12
+    hist = np.bincount(cl, minlength=24)[:24] / len(cl)
+    assert np.abs(hist - np.array(ref["col_len_hist"])).sum() < 0.03, hist                       # L1 distance of the column-length histograms
+    assert abs(cl.mean() - ref["col_len_mean"]) < 0.05 and cl.min() >= 1
+    assert np.all(np.abs(np.percentile(rl, q) - np.array(ref["row_len_quantiles"])) <= 1.0)
+    assert abs(rl.mean() - ref["row_len_mean"]) < 0.15
+    pq = np.percentile(price, q)
+    assert np.all(np.abs(pq / np.array(ref["price_quantiles"]) - 1) < 0.05), pq
+    assert abs(price.mean() / ref["price_mean"] - 1) < 0.02
