@@ -179,6 +179,56 @@ def test_general_matrix_format_matches_oracle():
         bt.close()
 
 
+def test_rows_with_more_than_eight_entries_fall_back_to_the_csr_walk():
+    """The 8-entry row image of the compact format only holds graphs with <= 8 stored entries per row (the reference builder's have
+    <= 7).  A qualifying CSR input (small integer weights, near neighbours) with WIDER rows must be detected at init and solved by
+    walking the CSR arrays -- bit-exact vs the oracle, incl. an early-fix window -- and mixing it into a batch must not disturb a
+    builder graph next to it."""
+    import lpbox
+    rng = np.random.default_rng(11)
+    n = 700
+    A = np.zeros((n, n))
+    for i in range(n):                                   # banded symmetric integer matrix: 11 entries per interior row
+        for d in (1, 2, 3, 17, 40):
+            if i + d < n:
+                w = float(rng.integers(-3, 4))
+                A[i, i + d] = A[i + d, i] = w
+        A[i, i] = float(rng.integers(4, 9))
+    rows, cols = np.nonzero(A)
+    rp = np.zeros(n + 1, dtype=np.int32); np.add.at(rp, rows + 1, 1); rp = np.cumsum(rp).astype(np.int32)
+    ci = cols.astype(np.int32); va = A[rows, cols].astype(np.float64)
+    assert (np.diff(rp) > 8).any()
+    b = rng.integers(-20, 21, n).astype(np.float64)
+    img = synth_image(4, 20, 27)
+    o_img = OracleSeg(); g_img = o_img.build_graph(img)
+    probs = [(rp, ci, va, b, 0.0), g_img]
+    bt = lpbox.SegBatch(probs, hist_cap=10); bt.init()
+    orcs = []
+    for p in probs:
+        o = OracleSeg(); o.set_problem(*p); o.init(); orcs.append(o)
+    vecs, nums = None, None
+    for w in range(3):
+        rg = bt.iters_l2f(10 * w, 10 * (w + 1), vecs, nums)
+        nxt_v, nxt_n = [], []
+        for i, o in enumerate(orcs):
+            v_i = np.zeros(1) if vecs is None else vecs[i]
+            n_i = 0 if nums is None else nums[i]
+            ro = o.l2f(10 * w, 10 * (w + 1), v_i, n_i)
+            assert ro == int(rg[i]), (w, i)
+            so, sg = o.state(), bt.state(i)
+            for k in so:
+                assert np.array_equal(so[k], sg[k]), (w, i, k)
+            x = so["x"]
+            if w == 0:
+                idx = np.argsort(-np.abs(x - 0.5))[: len(x) // 4]
+                v = -np.ones(len(x)); v[idx] = (x[idx] >= 0.5) * 1.0
+                nxt_v.append(v); nxt_n.append(len(idx))
+            else:
+                nxt_v.append(-np.ones(len(x))); nxt_n.append(0)
+        vecs, nums = nxt_v, nxt_n
+    bt.close()
+
+
 @pytest.fixture(scope="module")
 def gold_full():
     import json
