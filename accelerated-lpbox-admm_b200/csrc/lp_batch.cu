@@ -308,7 +308,7 @@ static int sync_states(lpbox_batch *h) {
 //     have distinct chain-major staging banks ((CH (j & 3) + (j >> 2)) mod 16, csrc/lp_types.h chain_stride): the scattered
 //     staging stores of the reduction operands become conflict-free;
 //   * inside every group of 16 columns (rows) the positions are permuted so that the columns (rows) that one half-warp gathers
-//     in one step of E v (E^T w) fall into different bank pairs as far as a greedy assignment manages (two sweeps).
+//     in one step of E v (E^T w) fall into different bank pairs as far as a greedy assignment manages (one sweep).
 // Group membership fixes which operands are gathered together; the position inside the group only moves the bank -- so the two
 // permutation problems (columns for E v, rows for E^T w) are independent.
 namespace {
@@ -396,7 +396,9 @@ static void group_columns(const std::vector<int> &cl, int CH, std::vector<int> &
 // Slot order of the rows (rord) and columns (cord) of one instance.  mode 0: descending stored length (stable); 1: bank-aware.
 static void assign_slots(int ni, int mi, int nz, const int32_t *cp, const int32_t *ri, const std::vector<int> &rl, const std::vector<int> &cl,
                          int mode, int np_batch, std::vector<int> &rord, std::vector<int> &cord) {
-    static const int sweeps = getenv("LPBOX_PLACE_SWEEPS") ? atoi(getenv("LPBOX_PLACE_SWEEPS")) : 2;
+    // one greedy sweep: a second one does not lower the wavefront count any further (1.78 x the conflict-free count after one sweep, 1.80 x
+    // after two, tools/eval_placement.py) and costs as much host time as the first
+    static const int sweeps = getenv("LPBOX_PLACE_SWEEPS") ? atoi(getenv("LPBOX_PLACE_SWEEPS")) : 1;
     rord.resize(mi);
     for (int r = 0; r < mi; ++r) rord[r] = r;
     std::stable_sort(rord.begin(), rord.end(), [&](int a, int b2) { return rl[a] > rl[b2]; });
@@ -568,8 +570,12 @@ static lpbox_batch *batch_create_impl(int device, int B, const int32_t *m, const
         h->pat_bytes_i.push_back(EL.o_rperm); h->pat_head_i.push_back(EL.o_cidx);   // staged bytes with / without the column offsets
     }
     long long tot_nnz = h->h_nnz_off[B];
-    h->h_colptr.assign(colptr_all, colptr_all + h->h_cp_off[B]);
-    h->h_rowidx.assign(rowidx_all, rowidx_all + tot_nnz);
+    // the host copies of the pattern (getters, feasibility checks) are made by a helper thread while the blobs are packed
+    struct Joiner { std::thread t; ~Joiner() { if (t.joinable()) t.join(); } } copier;
+    copier.t = std::thread([h, colptr_all, rowidx_all, tot_nnz, B]() {
+        h->h_colptr.assign(colptr_all, colptr_all + h->h_cp_off[B]);
+        h->h_rowidx.assign(rowidx_all, rowidx_all + tot_nnz);
+    });
     std::vector<double> ones;
     if (val_all) {
         h->h_val.assign(val_all, val_all + tot_nnz);
@@ -582,10 +588,20 @@ static lpbox_batch *batch_create_impl(int device, int B, const int32_t *m, const
     }
     stage("layout offsets / host copies");
     // build pattern blobs (+ values in both orders) on the host
-    std::vector<unsigned char> pat((size_t)h->off_pat[B], 0), csr((size_t)h->off_csr[B], 0);
+    // The big staging buffers are allocated UNINITIALISED and every instance clears / fills its own part inside the parallel loop
+    // (a value-initialised std::vector would zero ~340 MB for 10 000 instances on one core first: 70 ms of the set-up).
+    struct RawBuf {
+        unsigned char *p = nullptr; size_t n = 0;
+        explicit RawBuf(size_t bytes) : p(static_cast<unsigned char *>(::operator new(std::max<size_t>(bytes, 1)))), n(bytes) {}
+        ~RawBuf() { ::operator delete(p); }
+        RawBuf(const RawBuf &) = delete; RawBuf &operator=(const RawBuf &) = delete;
+        unsigned char *data() { return p; } size_t size() const { return n; }
+    };
+    RawBuf pat((size_t)h->off_pat[B]), csr((size_t)h->off_csr[B]);
     std::vector<double> val_r, val_c;
     if (!h->all_unit) { val_r.assign((size_t)h->off_val[B], 0.0); val_c.assign((size_t)h->off_val[B], 0.0); }
-    std::vector<double> fvec((size_t)h->off_m[B], 1.0), bvec((size_t)h->off_n[B], 0.0);
+    RawBuf fraw(sizeof(double) * (size_t)h->off_m[B]), braw(sizeof(double) * (size_t)h->off_n[B]);
+    double *const fvec = reinterpret_cast<double *>(fraw.data()), *const bvec = reinterpret_cast<double *>(braw.data());
     std::vector<InstState> st(B);
     std::atomic<int> err2(0);
     host_parallel_for(B, [&](int i) {
@@ -596,9 +612,11 @@ static lpbox_batch *batch_create_impl(int device, int B, const int32_t *m, const
         const double *va = val_all ? val_all + h->h_nnz_off[i] : nullptr;
         CsrLayout PL = csr_layout(ni, mi, nz);
         unsigned char *blob = csr.data() + h->off_csr[i];
+        memset(blob, 0, (size_t)(h->off_csr[i + 1] - h->off_csr[i]));
         {
             EllLayout EL = ell_layout(ni, mi, rcap[i], ccap[i]);
             unsigned char *eb = pat.data() + h->off_pat[i];
+            memset(eb, 0, (size_t)(h->off_pat[i + 1] - h->off_pat[i]));
             memcpy(eb + EL.o_rperm, rperm_all[i].data(), sizeof(uint16_t) * (size_t)mi);
             memcpy(eb + EL.o_cperm, cperm_all[i].data(), sizeof(uint16_t) * (size_t)ni);
         }
@@ -626,12 +644,16 @@ static lpbox_batch *batch_create_impl(int device, int B, const int32_t *m, const
                 colidx[q] = (uint16_t)j;
                 if (!h->all_unit) { val_r[(size_t)h->off_val[i] + q] = va[k]; val_c[(size_t)h->off_val[i] + k] = va[k]; }
             }
-        memcpy(bvec.data() + h->off_n[i], b_all + boff, sizeof(double) * (size_t)ni);
-        if (f_all) memcpy(fvec.data() + h->off_m[i], f_all + foff, sizeof(double) * (size_t)mi);
+        memcpy(bvec + h->off_n[i], b_all + boff, sizeof(double) * (size_t)ni);
+        for (long long k = h->off_n[i] + ni; k < h->off_n[i + 1]; ++k) bvec[k] = 0.0;                  // stride padding
+        if (f_all) memcpy(fvec + h->off_m[i], f_all + foff, sizeof(double) * (size_t)mi);
+        else for (int r = 0; r < mi; ++r) fvec[h->off_m[i] + r] = 1.0;                                // f = 1 (LP.cpp:2522)
+        for (long long k = h->off_m[i] + mi; k < h->off_m[i + 1]; ++k) fvec[k] = 1.0;
         InstState &s = st[i];
         memset(&s, 0, sizeof(s));
         s.n0 = s.n = ni; s.m0 = s.m = mi; s.nnz0 = s.nnz = nz; s.rcap = rcap[i]; s.ccap = ccap[i]; s.unit = h->all_unit ? 1 : 0; s.std_obj = 1.0; s.rhoUpdated = 1;
     });
+    copier.t.join();
     if (err2.load()) { set_err(err2.load() == 1 ? "bad colptr" : "row indices must be in range and strictly ascending within each column"); delete h; return nullptr; }
     h->h_st = st;
     lpbox_params lp; lpbox_params_lp(&lp);
@@ -677,8 +699,8 @@ static lpbox_batch *batch_create_impl(int device, int B, const int32_t *m, const
     H2D(h->d_off_evc.p, h->off_evc.data(), sizeof(long long) * (B + 1));
     H2D(h->d_csr.p, csr.data(), csr.size());
     H2D(h->d_off_hist.p, h->off_hist.data(), sizeof(long long) * (B + 1));
-    H2D(h->d_b.p, bvec.data(), sizeof(double) * NN);
-    H2D(h->d_f.p, fvec.data(), sizeof(double) * MM);
+    H2D(h->d_b.p, bvec, sizeof(double) * NN);
+    H2D(h->d_f.p, fvec, sizeof(double) * MM);
     H2D(h->d_pat.p, pat.data(), pat.size());
     if (!h->all_unit) { H2D(h->d_val_r.p, val_r.data(), sizeof(double) * val_r.size()); H2D(h->d_val_c.p, val_c.data(), sizeof(double) * val_c.size()); }
     H2D(h->d_st.p, st.data(), sizeof(InstState) * (size_t)B);

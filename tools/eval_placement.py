@@ -16,5 +16,5 @@ for mode in (0, 1):
         rc = L.lpbox_debug_gather_wavefronts(int(m), int(n), cp.ctypes.data, ri.ctypes.data, 512, mode, out.ctypes.data)
         assert rc == 0, rc
         tot += out
-    print(f"mode {mode} sweeps {os.environ.get('LPBOX_PLACE_SWEEPS', '2')}: E v {tot[0] / tot[1]:.3f} x ideal ({tot[0] / B:.0f} vs {tot[1] / B:.0f}),  E^T w {tot[2] / tot[3]:.3f} x ideal "
+    print(f"mode {mode} sweeps {os.environ.get('LPBOX_PLACE_SWEEPS', '1')}: E v {tot[0] / tot[1]:.3f} x ideal ({tot[0] / B:.0f} vs {tot[1] / B:.0f}),  E^T w {tot[2] / tot[3]:.3f} x ideal "
           f"({tot[2] / B:.0f} vs {tot[3] / B:.0f}),  both {(tot[0] + tot[2]) / (tot[1] + tot[3]):.3f}")
