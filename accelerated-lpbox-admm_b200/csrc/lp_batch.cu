@@ -428,6 +428,8 @@ static void assign_slots(int ni, int mi, int nz, const int32_t *cp, const int32_
 // per half-warp and step), E^T w actual, E^T w ideal}.  cap = T * EPT of the kernel shape (512 for n <= 512).
 extern "C" int lpbox_debug_gather_wavefronts(int m, int n, const int32_t *colptr, const int32_t *rowidx, int cap, int mode, int64_t *out) {
     if (m <= 0 || n <= 0 || !colptr || !rowidx || !out || cap < std::max(m, n)) return LPBOX_E_INVALID;
+    if (colptr[0] != 0) return LPBOX_E_INVALID;
+    for (int j = 0; j < n; ++j) if (colptr[j + 1] < colptr[j]) return LPBOX_E_INVALID;
     const int nz = colptr[n];
     std::vector<int> rl(m, 0), cl(n), rord, cord;
     for (int k = 0; k < nz; ++k) { if (rowidx[k] < 0 || rowidx[k] >= m) return LPBOX_E_INVALID; rl[rowidx[k]]++; }

@@ -574,7 +574,7 @@ static int seg_build_rows(lpbox_seg_batch *h, int skip_done, bool check) {
     if (!h->compact || off) return 0;
     if (check) { h->sv.use_ell = 1; SCK(cudaMemsetAsync(h->d_ell_flag.p, 0, sizeof(int), h->stream)); }
     if (!h->sv.use_ell) return 0;
-    const dim3 grid((unsigned)std::max(1, std::min(64, (h->max_n + SEG_T - 1) / SEG_T)), (unsigned)h->B);
+    const dim3 grid((unsigned)h->B, (unsigned)std::max(1, std::min(64, (h->max_n + SEG_T - 1) / SEG_T)));
     seg_ell_build_kernel<<<grid, SEG_T, 0, h->stream>>>(h->sv, skip_done, h->d_ell_flag.p);
     SCK(cudaGetLastError());
     h->launches += 1;

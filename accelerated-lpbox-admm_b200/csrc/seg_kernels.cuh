@@ -585,7 +585,7 @@ seg_setup_kernel(SegView sv, Params pr, int use_x0) {
 // has more than 8 stored entries or a distance equal to the padding marker (the batch then keeps using the CSR arrays).
 __global__ void __launch_bounds__(SEG_T)
 seg_ell_build_kernel(SegView sv, int skip_done, int *flag) {
-    const int inst = blockIdx.y;
+    const int inst = blockIdx.x;                         // grid = (images, row chunks): the x dimension holds any batch size
     const SegInst *st = sv.st + inst;
     if (skip_done && st->done) return;
     const int n = st->n, cur = st->cur;
@@ -593,7 +593,7 @@ seg_ell_build_kernel(SegView sv, int skip_done, int *flag) {
     const int *__restrict__ rp = sv.rowptr[cur] + on + 4 * inst;
     const short *__restrict__ ci = reinterpret_cast<const short *>(sv.colidx[cur]) + oz;
     const signed char *__restrict__ av = reinterpret_cast<const signed char *>(sv.val[cur]) + oz;
-    for (int i = blockIdx.x * SEG_T + threadIdx.x; i < n; i += gridDim.x * SEG_T) {
+    for (int i = blockIdx.y * SEG_T + threadIdx.x; i < n; i += gridDim.y * SEG_T) {
         const int s = rp[i];
         int len = rp[i + 1] - s;
         if (len > 8) { *flag = 1; len = 8; }
