@@ -476,7 +476,7 @@ def run_l2f(ctx):
         probs = lpbox.gen_auctions(a.seed + 1000003 * ctx.rank, B, N_ITEMS, N_BIDS)
     wpath = os.path.join(PKG, "lpbox", "weights", "lp_mha_policy.pt")
     net = load_policy(wpath, device=f"cuda:{ctx.local}")
-    score = PolicyKernel(net, device=ctx.local, chunk_rows=32768)      # bf16 tcgen05 kernels (csrc/policy_kernels.cu)
+    score = PolicyKernel(net, device=ctx.local, chunk_rows=131072)     # bf16 tcgen05 kernels (csrc/policy_kernels.cu)
     ref = lpbox.LPBatch(probs, device=ctx.local, hist_cap=0); ref.init(); plog = ref.solve(MAX_ITERS); ref.close()
 
     def step(guard=not a.l2f_no_guard, max_iter=a.l2f_max_iter):
@@ -713,7 +713,7 @@ def run_policy(ctx):
     torch.manual_seed(0)
     dev = torch.device("cuda", ctx.local)
     net = GraphAttentionEncoder(tokens=20).to(dev).eval()
-    pk = PolicyKernel(net, device=ctx.local, chunk_rows=32768)
+    pk = PolicyKernel(net, device=ctx.local, chunk_rows=131072)   # 504 TFLOP/s; 462 at 32768, 427 at 16384 (tools/quick_bench_policy_chunks.py)
     h_x = torch.rand(rows, 20, 5).pin_memory()
     x = h_x.to(dev)
     for _ in range(a.warmup):
