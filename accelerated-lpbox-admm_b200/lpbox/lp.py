@@ -41,12 +41,28 @@ def read_instance(root, i, k, j):
 
 class ProblemList(list):
     """A list of problem tuples that may also carry the same instances already concatenated (`packed`), as produced by
-    `gen_auctions`.  Slices and copies are plain lists; every in-place mutation drops `packed`, so it can never describe a
+    `gen_auctions`.  Contiguous slices stay packed, other slices and copies are plain lists; every in-place mutation drops `packed`, so it can never describe a
     different set (or order) of problems than the list itself."""
     packed = None
 
     def _drop(self):
         self.packed = None
+
+    def __getitem__(self, key):
+        """A contiguous slice of a packed list stays packed (a rank's shard under strong scaling); anything else is a plain list."""
+        if not isinstance(key, slice):
+            return list.__getitem__(self, key)
+        lo, hi, step = key.indices(len(self))
+        if self.packed is None or step != 1 or not all(k in self.packed for k in ("ms", "ns", "colptr", "rowidx", "b")):
+            return list.__getitem__(self, key)
+        out = ProblemList(list.__getitem__(self, key))
+        pk = self.packed
+        cp_off = np.concatenate([[0], np.cumsum(pk["ns"].astype(np.int64) + 1)])
+        n_off = np.concatenate([[0], np.cumsum(pk["ns"].astype(np.int64))])
+        nz_off = np.concatenate([[0], np.cumsum(pk["colptr"][cp_off[1:] - 1].astype(np.int64))])     # last colptr entry of an instance = its nnz
+        out.packed = dict(ms=pk["ms"][lo:hi].copy(), ns=pk["ns"][lo:hi].copy(), colptr=pk["colptr"][cp_off[lo]:cp_off[hi]].copy(),
+                          rowidx=pk["rowidx"][nz_off[lo]:nz_off[hi]].copy(), b=pk["b"][n_off[lo]:n_off[hi]].copy())
+        return out
 
 
 def _mutating(name):

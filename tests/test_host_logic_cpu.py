@@ -81,7 +81,7 @@ def test_policy_pack_layout_reproduces_the_module():
 
 def test_generator_packed_layout_matches_the_tuples():
     """`gen_auctions` returns problem tuples plus the same data concatenated (`packed`, what LPBatch hands to the C ABI);
-    slices are plain lists without it."""
+    strided slices are plain lists without it (contiguous ones stay packed: next test but one)."""
     import lpbox
     p = lpbox.gen_auctions(3, 40, 20, 60)
     pk = p.packed
@@ -89,7 +89,7 @@ def test_generator_packed_layout_matches_the_tuples():
     assert np.array_equal(np.concatenate([np.asarray(t[3]) for t in p]), pk["rowidx"])
     assert np.array_equal(np.concatenate([t[5] for t in p]), pk["b"])
     assert np.array_equal([t[0] for t in p], pk["ms"]) and np.array_equal([t[1] for t in p], pk["ns"])
-    assert getattr(p[:10], "packed", None) is None and type(p[:10]) is list
+    assert getattr(p[::3], "packed", None) is None and type(p[::3]) is list
 
 
 def test_problem_list_drops_packed_on_mutation():
@@ -103,7 +103,25 @@ def test_problem_list_drops_packed_on_mutation():
         p = fresh(); mutate(p)
         assert p.packed is None
     p = fresh()
-    assert p.packed is not None and p[1:].__class__ is list
+    assert p.packed is not None and p[1:].__class__ is list and p[::2].__class__ is list
+
+
+def test_contiguous_slices_of_a_generated_list_stay_packed():
+    """A rank's shard under strong scaling (`probs[lo:hi]`) keeps the concatenated arrays, cut at the right offsets."""
+    import lpbox
+    a = lpbox.gen_auctions(3, 50, 20, 60)
+    s = a[10:30]
+    pk = s.packed
+    assert pk is not None and len(s) == 20 and type(a[::2]) is list and len(a[50:50]) == 0
+    o = oc = 0
+    for i, p in enumerate(s):
+        assert pk["ms"][i] == p[0] and pk["ns"][i] == p[1]
+        assert np.array_equal(pk["colptr"][oc:oc + p[1] + 1], p[2]); oc += p[1] + 1
+        assert np.array_equal(pk["rowidx"][o:o + len(p[3])], p[3]); o += len(p[3])
+        assert np.array_equal(pk["b"][i * 60:(i + 1) * 60], p[5])
+    assert o == len(pk["rowidx"]) and oc == len(pk["colptr"])
+    s.append(a[0])
+    assert s.packed is None and a.packed is not None
 
 
 def test_bank_aware_slot_assignment_lowers_gather_wavefronts():
