@@ -132,11 +132,13 @@ static void host_parallel_for(int count, F f) {
     for (auto &th : pool) th.join();
 }
 
+// The opt-in limit of a kernel is one value per function and context, NOT per handle: it is always raised to the device maximum, so
+// that handles with different shared-memory needs can be alive (and launch from different host threads) at the same time.
 template <int T, int EPT, bool UNIT>
-static cudaError_t prep_kernel(size_t smem, int *occ) {
-    cudaError_t e = cudaFuncSetAttribute(lp_admm_window_kernel<T, EPT, UNIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+static cudaError_t prep_kernel(size_t smem, int smem_optin_max, int *occ) {
+    cudaError_t e = cudaFuncSetAttribute(lp_admm_window_kernel<T, EPT, UNIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_max);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(lp_admm_window_kernel<T, EPT, UNIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(lp_admm_window_kernel<T, EPT, UNIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_max);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, lp_admm_window_kernel<T, EPT, UNIT, false>, T, smem);
 }
@@ -172,11 +174,11 @@ static int configure(lpbox_batch *h) {
     bool u = h->all_unit;
     auto occ_at = [&](size_t smem, int *occ) -> cudaError_t {
         switch (h->tcfg) {
-            case 0: return u ? prep_kernel<128, 4, true>(smem, occ) : prep_kernel<128, 4, false>(smem, occ);
-            case 1: return u ? prep_kernel<256, 4, true>(smem, occ) : prep_kernel<256, 4, false>(smem, occ);
-            case 3: return u ? prep_kernel<256, 2, true>(smem, occ) : prep_kernel<256, 2, false>(smem, occ);
-            case 4: return u ? prep_kernel<512, 2, true>(smem, occ) : prep_kernel<512, 2, false>(smem, occ);
-            default: return u ? prep_kernel<512, 4, true>(smem, occ) : prep_kernel<512, 4, false>(smem, occ);
+            case 0: return u ? prep_kernel<128, 4, true>(smem, dev_smem, occ) : prep_kernel<128, 4, false>(smem, dev_smem, occ);
+            case 1: return u ? prep_kernel<256, 4, true>(smem, dev_smem, occ) : prep_kernel<256, 4, false>(smem, dev_smem, occ);
+            case 3: return u ? prep_kernel<256, 2, true>(smem, dev_smem, occ) : prep_kernel<256, 2, false>(smem, dev_smem, occ);
+            case 4: return u ? prep_kernel<512, 2, true>(smem, dev_smem, occ) : prep_kernel<512, 2, false>(smem, dev_smem, occ);
+            default: return u ? prep_kernel<512, 4, true>(smem, dev_smem, occ) : prep_kernel<512, 4, false>(smem, dev_smem, occ);
         }
     };
     int occ = 1, occ_reg = 1;
@@ -214,7 +216,7 @@ static int configure(lpbox_batch *h) {
         }
         CK(occ_at(h->smem, &occ));
     }
-    CK(cudaFuncSetAttribute(lp_fix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fix_smem));
+    CK(cudaFuncSetAttribute(lp_fix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
     if (occ < 1) occ = 1;
     h->grid = std::max(1, std::min(h->B, sms * occ));
     // Launch order.  A CTA keeps an instance until it stops, so a launch of more than one wave ends with the instances that were
@@ -1162,12 +1164,18 @@ extern "C" int lpbox_batch_solve_l2f(lpbox_batch *h, lpbox_policy *policy, int w
     CK(cudaEventRecord(e0, h->stream));
     CK(cudaMemsetAsync(h->d_num.p, 0, sizeof(int) * (size_t)h->B, h->stream));
     int rc = 0;
+    const bool dbg_t = getenv("LPBOX_DEBUG") != nullptr;          // phase timings (fix / window / scan+gather / policy+threshold) on stderr
+    std::vector<cudaEvent_t> evs;
+    auto mark = [&]() { if (dbg_t) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, h->stream); evs.push_back(e); } };
     for (int w = 0; w < max_iter / ws && rc == 0; ++w) {
+        mark();
         lp_fix_kernel<<<h->B, FIX_T, h->fix_smem, h->stream>>>(h->bv, h->pr, h->d_vec.p, h->d_off_vec.p, h->d_num.p, 1, np, mp, h->max_csr, val_elems);
         if (w == 0) lp_setup_kernel<<<h->B, 128, 0, h->stream>>>(h->bv, h->pr, 2, 0);     // `if(iter==0) update_expression(0)` (LP.cpp:1380-1381)
         h->launches += (w == 0) ? 2 : 1;
+        mark();
         rc = run_window(h, ws * w, ws * (w + 1), 1, 1);
         if (rc) break;
+        mark();
         st.windows++;
         lp_active_scan_kernel<<<1, 1024, 0, h->stream>>>(h->bv, h->d_active.p, h->d_row_off.p, h->d_meta.p);
         h->launches += 1;
@@ -1179,6 +1187,7 @@ extern "C" int lpbox_batch_solve_l2f(lpbox_batch *h, lpbox_policy *policy, int w
         dim3 grid((unsigned)((meta.max_n + 31) / 32), (unsigned)meta.n_active), block(32, 8);
         lp_policy_input_kernel<<<grid, block, 0, h->stream>>>(h->bv, h->d_active.p, h->d_row_off.p, ws, h->d_pinp.p, h->d_meta.p);
         h->launches += 1;
+        mark();
         rc = lpbox_policy_forward_dev(policy, (void *)h->stream, h->d_pinp.p, meta.rows, h->d_pscore.p);
         if (rc) break;
         st.policy_rows += meta.rows;
@@ -1196,6 +1205,15 @@ extern "C" int lpbox_batch_solve_l2f(lpbox_batch *h, lpbox_policy *policy, int w
     cudaEventRecord(e1, h->stream);
     cudaEventSynchronize(e1);
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    if (dbg_t && rc == 0) {
+        // marks per complete window: [fix | window | scan + gather | policy + threshold (+ guard)]; the last window may stop after its scan
+        double ph[4] = {0, 0, 0, 0};
+        for (size_t i = 0; i + 1 < evs.size(); ++i) { float t = 0; cudaEventElapsedTime(&t, evs[i], evs[i + 1]); ph[i & 3] += t; }
+        if (!evs.empty()) { float t = 0; cudaEventElapsedTime(&t, evs.back(), e1); ph[(evs.size() - 1) & 3] += t; }
+        fprintf(stderr, "[lpbox] solve_l2f: %d windows, %.1f ms: fix %.1f, window kernel %.1f, scan + input gather %.1f, policy + thresholds %.1f\n",
+                (int)st.windows, ms, ph[0], ph[1], ph[2], ph[3]);
+    }
+    for (cudaEvent_t e : evs) cudaEventDestroy(e);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (rc) return rc;
     h->last_ms = ms; st.device_ms = ms;

@@ -182,3 +182,34 @@ def test_sliced_work_queue_is_bit_identical(monkeypatch):
         # a second solve on the same handle (re-init) reuses the queue buffers
         b.init(); assert np.array_equal(b.solve(20000), ref)
         b.close()
+
+
+def test_handles_of_different_shapes_alive_at_once_and_on_two_host_threads():
+    """The dynamic shared-memory opt-in of a kernel is one value per function, not per handle: a second (smaller) batch created
+    while a first one is alive must not lower it under the first one's need -- sequentially and from two host threads at once
+    (ctypes releases the GIL in the C calls; every handle has its own stream)."""
+    import threading
+    import lpbox
+    big = [problem_tuple(load_golden(f"auction_100_500_seed{s}.npz")) for s in (0, 1)]
+    small = [problem_tuple(load_golden("auction_20_60_seed0.npz"))]
+    ref_big = lpbox.LPBatch(big); ref_big.init(); want_big = ref_big.solve(300); xb = ref_big.state(0)["x"].copy(); ref_big.close()
+    ref_small = lpbox.LPBatch(small); ref_small.init(); want_small = ref_small.solve(300); xs = ref_small.state(0)["x"].copy(); ref_small.close()
+    a = lpbox.LPBatch(big); a.init()
+    b = lpbox.LPBatch(small); b.init()                     # configured after `a`, needs far less shared memory
+    got_a = a.solve(300)
+    got_b = b.solve(300)
+    assert np.array_equal(got_a, want_big) and np.array_equal(got_b, want_small)
+    assert np.array_equal(a.state(0)["x"], xb) and np.array_equal(b.state(0)["x"], xs)
+    a.close(); b.close()
+    out, err = {}, []
+    def run(name, probs):
+        try:
+            h = lpbox.LPBatch(probs); h.init(); out[name] = (h.solve(300), h.state(0)["x"].copy()); h.close()
+        except Exception as e:                              # noqa: BLE001 -- reported below
+            err.append((name, e))
+    for _ in range(3):
+        th = [threading.Thread(target=run, args=("big", big)), threading.Thread(target=run, args=("small", small))]
+        [t.start() for t in th]; [t.join() for t in th]
+        assert not err, err
+        assert np.array_equal(out["big"][0], want_big) and np.array_equal(out["big"][1], xb)
+        assert np.array_equal(out["small"][0], want_small) and np.array_equal(out["small"][1], xs)
