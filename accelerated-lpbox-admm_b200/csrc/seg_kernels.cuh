@@ -1,15 +1,17 @@
 // Unconstrained Lp-Box ADMM (graph-cut segmentation, `min x'Ax + b'x`) for sm_100a -- streaming variant.
 //
-// An image-sized problem (n = 187 500 for 375x500) does not fit on chip: per image ~12 fp64 n-vectors + A (<= 7 stored
+// An image-sized problem (n = 187 500 for 375x500) does not fit on chip: per image 11 fp64 n-vectors + A (<= 7 stored
 // entries per row).  One CTA owns one image for a whole window and streams its vectors through L2/HBM with coalesced
-// accesses; there is NO inter-CTA synchronisation, so a batch of images fills the GPU with independent CTAs
-// (2 per SM: while one CTA sits in a sequential reduction chain the other streams).
+// accesses; there is NO inter-CTA synchronisation, so a batch of images fills the GPU with independent CTAs (5, 7 or 8 per SM,
+// SegCfg below: while some CTAs sit in a barrier or a sequential reduction chain the others stream).
 //
 // PARITY MODE: the arithmetic follows the reference's compiled Eigen code (SEG.cpp =
 // Segmentation/Segmentation/cython/src/LPboxADMMsolver.cpp): no FMA, row-sequential SpMV in ascending column order,
-// reductions in Eigen's SSE2 order.  A reduction over n elements is four dependent chains of n/4 adds; the CTA streams
-// the products into a double-buffered shared-memory ring (all warps) while one warp walks the chains (up to 8
-// reductions side by side, 4 lanes each).
+// reductions in Eigen's SSE2 order.  A reduction over n elements is four dependent chains of n/4 adds; the staging warps
+// stream the products into a double-buffered shared-memory ring while ONE warp walks the chains (up to 7 reductions side by
+// side, 4 lanes each).  What makes it fast: the matrix is read through an 8-entry row image fetched one element
+// ahead (SegRowRef), element-wise passes are fused with the reductions that consume them (seg_fused_pass), and the streamed
+// operands of the next element are prefetched into L2 (seg_pf).
 //
 // The CG matrix `temp_mat = 2A + (rho1+rho2) I` (SEG.cpp:784-786) is never materialised: off-diagonal entries are
 // 2*a_ij (exact), the diagonal lives in `md` and is patched additively like the reference (SEG.cpp:1240-1243).
