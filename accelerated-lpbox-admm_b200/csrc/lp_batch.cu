@@ -349,28 +349,46 @@ static void place_in_groups(std::vector<int> &order, const GatherSets &G, int sw
     const int n = (int)order.size();
     const int ns = (int)G.set_ptr.size() - 1;
     if (ns == 0 || n < 16) return;
-    std::vector<unsigned char> cnt((size_t)ns * 16, 0);
+    // cnt[s][p]: members of set s placed at position p so far; mx[s] = max_p cnt[s][p] = the wavefronts set s costs.  An item goes to the
+    // free position that raises the fewest maxima (the true cost), ties broken by the fewest members already there (pairwise collisions).
+    static const bool pairwise_only = getenv("LPBOX_PLACE_PAIRWISE") != nullptr;      // experiments: the round-2a cost function
+    std::vector<unsigned char> cnt((size_t)ns * 16, 0), mx(ns, 0);
     std::vector<int> pos(n, -1);                                           // item -> position (0..15) inside its group, -1 = not placed
-    auto add = [&](int x, int p, int d) { for (int q = G.of_ptr[x]; q < G.of_ptr[x + 1]; ++q) cnt[(size_t)G.of_set[q] * 16 + p] += d; };
+    auto add = [&](int x, int p) {
+        for (int q = G.of_ptr[x]; q < G.of_ptr[x + 1]; ++q) { const int s2 = G.of_set[q]; const unsigned char c = ++cnt[(size_t)s2 * 16 + p]; if (c > mx[s2]) mx[s2] = c; }
+    };
+    auto remove = [&](int x, int p) {
+        for (int q = G.of_ptr[x]; q < G.of_ptr[x + 1]; ++q) {
+            const int s2 = G.of_set[q];
+            unsigned char *c = &cnt[(size_t)s2 * 16];
+            --c[p];
+            unsigned char m2 = 0;
+            for (int r = 0; r < 16; ++r) m2 = std::max(m2, c[r]);
+            mx[s2] = m2;
+        }
+    };
     for (int sw = 0; sw < sweeps; ++sw)
         for (int g0 = 0; g0 + 16 <= n; g0 += 16) {
             int mem[16];
-            for (int t = 0; t < 16; ++t) { mem[t] = order[g0 + t]; if (pos[mem[t]] >= 0) { add(mem[t], pos[mem[t]], -1); pos[mem[t]] = -1; } }
+            for (int t = 0; t < 16; ++t) { mem[t] = order[g0 + t]; if (pos[mem[t]] >= 0) { remove(mem[t], pos[mem[t]]); pos[mem[t]] = -1; } }
             std::stable_sort(mem, mem + 16, [&](int a, int b) { return G.of_ptr[a + 1] - G.of_ptr[a] > G.of_ptr[b + 1] - G.of_ptr[b]; });
             bool used[16] = {false};
             for (int t = 0; t < 16; ++t) {
                 const int x = mem[t];
                 int cost[16] = {0};
-                for (int q = G.of_ptr[x]; q < G.of_ptr[x + 1]; ++q) { const unsigned char *c = &cnt[(size_t)G.of_set[q] * 16]; for (int p = 0; p < 16; ++p) cost[p] += c[p]; }
+                for (int q = G.of_ptr[x]; q < G.of_ptr[x + 1]; ++q) {
+                    const int s2 = G.of_set[q];
+                    const unsigned char *c = &cnt[(size_t)s2 * 16];
+                    const int m2 = pairwise_only ? 255 : mx[s2];
+                    for (int p = 0; p < 16; ++p) cost[p] += c[p] + (c[p] >= m2 ? 64 : 0);     // 64 > any sum of counts of one item's sets / position
+                }
                 int best = -1;
                 for (int p = 0; p < 16; ++p) if (!used[p] && (best < 0 || cost[p] < cost[best])) best = p;
-                used[best] = true; pos[x] = best; add(x, best, +1);
+                used[best] = true; pos[x] = best; add(x, best);
             }
             for (int t = 0; t < 16; ++t) order[g0 + pos[mem[t]]] = mem[t];
         }
 }
-// descending-length grouping of the columns, 16 at a time, with distinct staging banks inside a group where columns of (almost)
-// the same length allow it
 static void group_columns(const std::vector<int> &cl, int CH, std::vector<int> &order) {
     const int n = (int)cl.size();
     std::vector<int> sorted(n);
@@ -398,8 +416,9 @@ static void group_columns(const std::vector<int> &cl, int CH, std::vector<int> &
 // Slot order of the rows (rord) and columns (cord) of one instance.  mode 0: descending stored length (stable); 1: bank-aware.
 static void assign_slots(int ni, int mi, int nz, const int32_t *cp, const int32_t *ri, const std::vector<int> &rl, const std::vector<int> &cl,
                          int mode, int np_batch, std::vector<int> &rord, std::vector<int> &cord) {
-    // one greedy sweep: a second one does not lower the wavefront count any further (1.78 x the conflict-free count after one sweep, 1.80 x
-    // after two, tools/eval_placement.py) and costs as much host time as the first
+    // one greedy sweep: further sweeps do not lower the wavefront count (1.74 x the conflict-free count after one sweep, 1.76 x after two,
+    // tools/eval_placement.py; even 200 000 random improving swaps per instance only reach 1.65 x -- the rest is decided by which rows and
+    // columns share a half-warp, not by the positions inside a group) and cost as much host time as the first
     static const int sweeps = getenv("LPBOX_PLACE_SWEEPS") ? atoi(getenv("LPBOX_PLACE_SWEEPS")) : 1;
     rord.resize(mi);
     for (int r = 0; r < mi; ++r) rord[r] = r;
